@@ -1,0 +1,157 @@
+"""Pin oracle/sddc_oracle.py against vectors produced by the unmodified reference
+(tests/golden/make_golden.py) and against the reference's transform known-answer tests
+(Transforms.py:132-374).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+from oracle import sddc_oracle as orc
+
+CASES = ["small_nosym", "small_sym", "cfg1_nosym", "cfg1_sym", "cfg3_member"]
+TOL_CALL = 5e-13   # single operator call, relative L2
+TOL_STEPS = 1e-10  # north_star tolerance after 100 steps
+
+
+def _ops(g):
+    return orc.Operators(int(g["N_fm"]), int(g["N_r"]), float(g["d"]), float(g["dt"]), float(g["Pr"]), float(g["Tau"]))
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    g = load_golden(request.param)
+    return g, _ops(g)
+
+
+def test_transforms_match_reference():
+    g = load_golden("transforms")
+    for K in (16, 48):
+        M = 3 * K // 2
+        a, gr = g["in_hat_%d" % K], g["in_grid_%d" % K]
+        assert rel_l2(orc.grid(M), g["grid_%d" % K]) < 1e-15
+        assert rel_l2(orc.IDCT(a, n=M), g["IDCT_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDST(a, n=M), g["IDST_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDCT(a), g["IDCT_same_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDST(a), g["IDST_same_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDCT(a, n=3 * K), g["IDCT_3x_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDST(a, n=3 * K), g["IDST_3x_%d" % K]) < 1e-13
+        assert rel_l2(orc.DCT(gr), g["DCT_%d" % K]) < 1e-13
+        assert rel_l2(orc.DST(gr), g["DST_%d" % K]) < 1e-13
+        assert rel_l2(orc.DCT(gr, n=K), g["DCT_trunc_%d" % K]) < 1e-13
+        assert rel_l2(orc.DST(gr, n=K), g["DST_trunc_%d" % K]) < 1e-13
+
+
+@pytest.mark.parametrize("k", [0, 1, 5, 100, 255])
+def test_transform_known_answers(k):
+    """Single-mode known answers of Transforms.test_Cosine_Transform / test_Sine_Transform (N=256)."""
+    N = 256
+    x = orc.grid(N)
+    e = np.zeros(N)
+    e[k] = 1.0
+    assert np.allclose(orc.IDCT(e), np.cos(k * x), atol=1e-12)
+    assert np.allclose(orc.DCT(np.cos(k * x)), e, atol=1e-12)
+    if k > 0:
+        assert np.allclose(orc.IDST(e), np.sin(k * x), atol=1e-12)
+        assert np.allclose(orc.DST(np.sin(k * x)), e, atol=1e-12)
+
+
+def test_transform_products_dealiased():
+    """Product identities of Transforms.test_*_NL through the 3/2-padded path."""
+    N = 256
+    M = 3 * N // 2
+    k1, k2 = 40, 75
+    a = np.zeros(N); a[k1] = 1.0
+    b = np.zeros(N); b[k2] = 1.0
+    cc = orc.DCT(orc.IDCT(a, n=M) * orc.IDCT(b, n=M), n=N)
+    exp = np.zeros(N); exp[k2 - k1] += 0.5; exp[k1 + k2] += 0.5
+    assert np.allclose(cc, exp, atol=1e-12)
+    ss = orc.DCT(orc.IDST(a, n=M) * orc.IDST(b, n=M), n=N)
+    exp = np.zeros(N); exp[k2 - k1] += 0.5; exp[k1 + k2] -= 0.5
+    assert np.allclose(ss, exp, atol=1e-12)
+    sc = orc.DST(orc.IDST(a, n=M) * orc.IDCT(b, n=M), n=N)
+    exp = np.zeros(N); exp[k1 + k2] += 0.5; exp[k2 - k1] -= 0.5
+    assert np.allclose(sc, exp, atol=1e-12)
+
+
+def test_operator_build_matches_reference():
+    g = load_golden("small_nosym")
+    op = _ops(g)
+    assert rel_l2(op.D, g["op_D"]) < 1e-14
+    assert rel_l2(op.R, g["op_R"]) < 1e-15
+    assert rel_l2(op.D2, g["op_D2"]) < 1e-13
+    assert rel_l2(op.IR2, g["op_IR2"]) < 1e-15
+    assert rel_l2(op.IR4, g["op_IR4"]) < 1e-15
+    assert rel_l2(op.dT0, g["op_DT0"]) < 1e-15
+    # inverses of ill-conditioned matrices: compare loosely entrywise, tightly through their action below
+    assert rel_l2(op.Linv_A4, g["op_L4"]) < 1e-8
+    assert rel_l2(op.Linv_T, g["op_LT"]) < 1e-10
+    assert rel_l2(op.Linv_S, g["op_LS"]) < 1e-10
+
+
+def test_linear_pieces(case):
+    g, op = case
+    K, n, sym = op.K, op.n, bool(g["symmetric"])
+    Xb = g["Xb"].reshape(3, K, n)
+    assert rel_l2(orc.J_theta_RT(Xb[0], sym), g["J_theta_RT"]) < TOL_CALL
+    assert rel_l2(orc.DT0_theta(Xb[0], op.dT0, sym), g["DT0_theta"]) < TOL_CALL
+    assert rel_l2(orc.A2_SINE(Xb[0], op, sym), g["A2_SINE"]) < TOL_CALL
+    assert rel_l2(orc.A2_SINE_R2(Xb[0], op, sym), g["A2_SINE_R2"]) < TOL_CALL
+    assert rel_l2(orc.buoyancy(Xb[1], op), g["kGR"]) < TOL_CALL
+    assert rel_l2((op.r ** 2)[None, :] * Xb[1], g["R2"]) < TOL_CALL
+
+
+def test_nonlinear_term_and_jvp(case):
+    g, op = case
+    sym = bool(g["symmetric"])
+    assert rel_l2(orc.NLIN_FX(g["Xb"], op, sym), g["NLIN_FX"]) < TOL_CALL
+    assert rel_l2(orc.NLIN_DFX(g["dv"], g["Xb"], op, sym), g["NLIN_DFX"]) < TOL_CALL
+
+
+def test_solves(case):
+    g, op = case
+    K, n, sym = op.K, op.n, bool(g["symmetric"])
+    Xb = g["Xb"].reshape(3, K, n)
+    # cond(L) reaches ~1e6 for the fourth-order operator
+    assert rel_l2(orc.A4_BSub(Xb[0], op.Linv_A4, op, op.Pr * op.dt, sym), g["A4_BSub"]) < 1e-9
+    assert rel_l2(orc.NAB2_BSub(Xb[1], op.Linv_T, op.dt, sym), g["NAB2_BSub_T"]) < 1e-11
+    assert rel_l2(orc.NAB2_BSub(Xb[2], op.Linv_S, op.Tau * op.dt, sym), g["NAB2_BSub_S"]) < 1e-11
+
+
+def test_step_jvp_dmu(case):
+    g, op = case
+    sym = bool(g["symmetric"])
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    assert rel_l2(orc.step(g["Xb"], op, Ra, Ra_s, sym), g["step_Xb"]) < 1e-10
+    assert rel_l2(orc.jvp(g["dv"], g["Xb"], op, Ra, Ra_s, sym), g["jvp_Xb"]) < 1e-10
+    assert rel_l2(orc.dF_dRa(g["Xb"], op, sym), g["dmu_Xb"]) < 1e-10
+
+
+def test_diagnostics(case):
+    g, op = case
+    K, n, sym = op.K, op.n, bool(g["symmetric"])
+    Xb = g["Xb"]
+    Xs = Xb * orc.sym_mask(K, n).reshape(-1) if sym else Xb
+    assert abs(orc.kinetic_energy(Xs, op, sym) / float(g["KE_Xb"]) - 1) < 1e-12
+    X3 = Xb.reshape(3, K, n)
+    assert abs(orc.nusselt(X3[1], op) / float(g["NuT_Xb"]) - 1) < 1e-12
+    assert abs(orc.nusselt(X3[2], op) / float(g["NuS_Xb"]) - 1) < 1e-12
+
+
+def test_time_stepping_parity(case):
+    """The north-star bar: relative L2 <= 1e-10 after the golden run's n_steps (100 for the BASELINE configs)."""
+    g, op = case
+    sym = bool(g["symmetric"])
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    n_steps = int(g["n_steps"])
+    X = g["X0"].copy()
+    mask = orc.sym_mask(op.K, op.n).reshape(-1) if sym else 1.0
+    hist = []
+    for it in range(n_steps):
+        Xn = orc.step(X, op, Ra, Ra_s, sym)
+        if it + 1 in (1, 10):
+            assert rel_l2(Xn, g["X_step%d" % (it + 1)]) < TOL_STEPS
+        if it % max(1, n_steps // 5) == 0:
+            hist.append((it, orc.diagnostics(Xn, op, sym)))
+        X = mask * Xn
+    assert rel_l2(Xn, g["X_step%d" % n_steps]) < TOL_STEPS
+    for it, dg in hist:
+        assert np.allclose(dg, g["diag_hist"][it], rtol=1e-9, atol=0)
