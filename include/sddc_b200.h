@@ -1,0 +1,134 @@
+/*
+ * sddc_b200.h -- C ABI of the B200-native time-stepping / JVP hot path of the axisymmetric spherical-shell
+ * double-diffusive convection solver (reference: mannixp/SpectralDoubleDiffusiveConvection).
+ *
+ * The reference has no FFI: its hot path is a set of Python free functions resolved by module name at call
+ * time.  Every entry point below names the reference function(s) it replaces.
+ * Conventions:
+ *   - all arrays are float64, C-contiguous;
+ *   - a member state is X = [psi | T | S], each field K = N_fm blocks of n = N_r-1 radial values
+ *     (Matrix_Operators.py:529-575); an ensemble is [B][3*K*n];
+ *   - device entry points take CALLER-OWNED DEVICE pointers and a cudaStream_t (passed as void*); they are
+ *     stream-ordered, non-blocking and never allocate after plan creation (CUDA-graph capturable);
+ *   - *_host entry points take HOST pointers and include the host<->device copies (blocking);
+ *   - every function returns 0 on success, a negative sddc_status otherwise; nothing throws across the ABI;
+ *   - a plan is not thread-safe; distinct plans are independent.
+ */
+#ifndef SDDC_B200_H
+#define SDDC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sddc_plan sddc_plan;
+
+enum sddc_status {
+    SDDC_OK = 0,
+    SDDC_ERR_INVALID = -1,     /* bad argument (reference raises ValueError, e.g. odd N_fm: Matrix_Operators.py:758) */
+    SDDC_ERR_CUDA = -2,        /* CUDA runtime error, see sddc_last_error */
+    SDDC_ERR_UNSUPPORTED = -3, /* shape outside what the kernels are instantiated for */
+    SDDC_ERR_NO_DEVICE = -4
+};
+
+/* Scalar configuration: the arguments of Main.Build_Matrix_Operators (Main.py:179) + symmetric flag
+ * (Main.py:242-245) + capacity. */
+typedef struct {
+    int N_fm;      /* number of latitudinal modes K (multiple of 4) */
+    int N_r;       /* Chebyshev order; n = N_r - 1 interior points */
+    int symmetric; /* 0/1: equatorial symmetry (Main.Eq_SYM, Main.py:137-176) */
+    int max_batch; /* largest B any call will use; scratch is sized for it */
+    int device;    /* CUDA device ordinal */
+    double dt, Pr, Tau, d;
+} sddc_config;
+
+/* Host-built radial operators, computed with the reference's formulas (cheb_radial, Nabla2, Nabla4,
+ * A4_TSTEP_MATS, NAB2_TSTEP_MATS: Matrix_Operators.py:10-76,1014-1030,1089-1112; Main.py:196-222).
+ * They are copied to the device at plan creation; the plan owns the copies. */
+typedef struct {
+    const double* Dr;      /* [n*n]  D[1:-1,1:-1]                                  (Matrix_Operators.py:764) */
+    const double* Dsq;     /* [n*n]  (D@D)[1:-1,1:-1]                              (Matrix_Operators.py:217) */
+    const double* D2r;     /* [n*n]  (diag(1/R^2) D D)[1:-1,1:-1]                  (Matrix_Operators.py:498) */
+    const double* D2;      /* [n*n]  (IR2 (2 D^2 - 4 IR D + 6 IR2))[1:-1,1:-1]     (Main.py:212) */
+    const double* r2;      /* [n]    R[1:-1]^2                                     (Matrix_Operators.py:85) */
+    const double* ir2;     /* [n]    1/R[1:-1]^2                                   (Matrix_Operators.py:216) */
+    const double* ir4;     /* [n]    1/R[1:-1]^4                                   (Matrix_Operators.py:496) */
+    const double* a4_ir2;  /* [n]    diag of IR2 passed to A4_BSub_TSTEP_V2        (Main.py:213) */
+    const double* a4_ir4;  /* [n]    diag of IR4                                   (Main.py:214) */
+    const double* dT0;     /* [n]    A_T / R[1:-1]^2                               (Main.py:201-202) */
+    const double* gbuoy;   /* [n]    (1/d)^2 / R[1:-1]^2                           (Matrix_Operators.py:113) */
+    const double* ir;      /* [n]    1/R[1:-1]                                     (Main.py:102) */
+    const double* nu_in;   /* [n]    (R[0]^2/A_T)  * D[0,1:-1]                     (Main.py:58-62) */
+    const double* nu_out;  /* [n]    (R[-1]^2/A_T) * D[-1,1:-1] */
+    const double* r;       /* [n]    R[1:-1] */
+    double R_in, R_out;    /*        R[0], R[-1] */
+    const double* Linv_A4; /* [K*n*n] descending-mode order as returned by A4_TSTEP_MATS  */
+    const double* Linv_T;  /* [K*n*n] NAB2_TSTEP_MATS(dt)      */
+    const double* Linv_S;  /* [K*n*n] NAB2_TSTEP_MATS(Tau*dt)  */
+} sddc_operators;
+
+/* linear operator codes for sddc_linear_op */
+enum sddc_linop {
+    SDDC_OP_J_THETA = 0,    /* J_theta_RT      (Matrix_Operators.py:436-472) */
+    SDDC_OP_DT0_THETA = 1,  /* DT0_theta       (Matrix_Operators.py:131-189) */
+    SDDC_OP_A2_SINE = 2,    /* A2_SINE         (Matrix_Operators.py:192-245) */
+    SDDC_OP_A2_SINE_R2 = 3, /* A2_SINE_R2      (Matrix_Operators.py:475-526) */
+    SDDC_OP_KGR = 4,        /* kGR_RT(...).dot (Matrix_Operators.py:97-128)  */
+    SDDC_OP_R2 = 5          /* R2(...).dot     (Matrix_Operators.py:79-94)   */
+};
+
+/* transform kinds for sddc_transform (Transforms.py:73-129) */
+enum sddc_transform_kind { SDDC_T_IDCT = 0, SDDC_T_IDST = 1, SDDC_T_DCT = 2, SDDC_T_DST = 3 };
+
+int sddc_version(void);
+int sddc_device_count(void);
+
+/* replaces Main.Build_Matrix_Operators (device side of it) */
+int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operators* ops);
+void sddc_plan_destroy(sddc_plan* plan);
+const char* sddc_last_error(const sddc_plan* plan); /* plan may be NULL: error of the last failed create */
+/* number of this library's kernel launches issued through the plan so far */
+long long sddc_launch_count(const sddc_plan* plan);
+
+/* F(X) for B members: Matrix_Operators.NLIN_FX (743-804). X, F: [B][3Kn] */
+int sddc_nlin_fx(sddc_plan* plan, const double* X, double* F, int B, void* stream);
+/* DF(X) dv: Matrix_Operators.NLIN_DFX (807-898) */
+int sddc_nlin_dfx(sddc_plan* plan, const double* dv, const double* X, double* F, int B, void* stream);
+/* one of the theta-coupling / diagonal operators on one field: in, out: [B][Kn] */
+int sddc_linear_op(sddc_plan* plan, int op, const double* in, double* out, int B, void* stream);
+/* implicit solves: Matrix_Operators.A4_BSub_TSTEP_V2 (1115-1194) and NAB2_BSub_TSTEP_V2 (1033-1086);
+ * g, f: [B][Kn]; which = 0 uses the dt stack (T), 1 the Tau*dt stack (S) */
+int sddc_solve_a4(sddc_plan* plan, const double* g, double* f, int B, void* stream);
+int sddc_solve_nab2(sddc_plan* plan, int which, const double* g, double* f, int B, void* stream);
+
+/* nsteps IMEX-Euler member-steps: the loop body of Main._Time_Step (Step_Python, Main.py:255-283, and
+ * X = X_SYM*X_new, Main.py:323). Ra, Ra_s: [B] per-member Rayleigh numbers (device). Xin is not modified;
+ * Xout may not alias Xin. linear != 0 drops the nonlinear term (Main.py:261-264). */
+int sddc_step(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
+              int nsteps, int linear, void* stream);
+/* Step(X) - X: PFX (Main.py:473-496, 779-802) */
+int sddc_residual(sddc_plan* plan, const double* X, double* out, const double* Ra, const double* Ra_s, int B,
+                  void* stream);
+/* PDFX(dv, X) (Main.py:498-521, 804-827) */
+int sddc_jvp(sddc_plan* plan, const double* dv, const double* X, double* out, const double* Ra,
+             const double* Ra_s, int B, void* stream);
+/* PDFmu(X) (Main.py:829-837) */
+int sddc_dF_dRa(sddc_plan* plan, const double* X, double* out, int B, void* stream);
+/* per member [ ||X||_2, KE, Nu_T, Nu_S, Nu_T(outer wall), Nu_S(outer wall) ]: Main.py:292-295, Kinetic_Energy
+ * (71-134), Nusselt (41-68).  out: [B][6] */
+int sddc_diagnostics(sddc_plan* plan, const double* X, double* out, int B, void* stream);
+
+/* Transforms.IDCT / IDST / DCT / DST on `rows` rows of length n_in -> n_out (device pointers).
+ * Synthesis kinds zero-pad / truncate to n_out like scipy's n= argument; analysis kinds truncate. */
+int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, int n_out, void* stream);
+
+/* Host-buffer variants (blocking; copies included): what a ctypes / NumPy caller binds. */
+int sddc_step_host(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
+                   int nsteps, int linear, double* diag_out /* [B][6] or NULL */);
+int sddc_jvp_host(sddc_plan* plan, const double* dv, const double* X, double* out, const double* Ra,
+                  const double* Ra_s, int B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDDC_B200_H */

@@ -1,0 +1,160 @@
+// Table generation, diagnostics reductions and the generic (drop-in) transforms.
+#pragma once
+#include "common.cuh"
+
+namespace sddc {
+
+// cos / sin of k * theta_j, theta_j = pi (2j+1) / (2M), with exact integer argument reduction.
+__device__ __forceinline__ void trig_kj(long long k, long long j, long long M, double& c, double& s) {
+    const long long q = (k * (2 * j + 1)) % (4 * M);  // angle = pi * q / (2M)
+    sincospi((double)q / (double)(2 * M), &s, &c);
+}
+
+// mode 0: synthesis table  tab[type][par][j' (Jp)][k' (Kp)]            = trig((2k'+par) theta_j')
+// mode 1: analysis table   tab[type][par][k' (Kp)][j' (Jp)]  = scale_k * trig((2k'+par) theta_j')
+// entries with k' >= Kh or j' >= Mh are zero.  scale: 2/M (1/M for the cosine k = 0 row); sine k = 0 row is 0.
+__global__ void fill_table_kernel(double* tab, int mode, int M, int Kh, int Mh, int Kp, int Jp) {
+    const long long total = 4LL * Kp * Jp;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long tp = idx / ((long long)Kp * Jp), rem = idx - tp * (long long)Kp * Jp;
+        const int type = (int)(tp >> 1), par = (int)(tp & 1);
+        int kp, jp;
+        if (mode == 0) { jp = (int)(rem / Kp); kp = (int)(rem - (long long)jp * Kp); }
+        else { kp = (int)(rem / Jp); jp = (int)(rem - (long long)kp * Jp); }
+        double v = 0.0;
+        if (kp < Kh && jp < Mh) {
+            const int k = 2 * kp + par;
+            double c, s;
+            trig_kj(k, jp, M, c, s);
+            v = type == 0 ? c : s;
+            if (k == 0 && type == 1) v = 0.0;
+            if (mode == 1) v *= (type == 0 && k == 0) ? (1.0 / M) : (2.0 / M);
+        }
+        tab[idx] = v;
+    }
+}
+
+// w[j'] = trapezoid weight(theta_j') * sin(theta_j') on the M3-point grid for j' < M3/2 (mirror point has the
+// same value); np.trapz with x = theta on interior nodes only (Main.py:117,130).
+__global__ void fill_ke_weights_kernel(double* w, int M3, int Jp) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Jp) return;
+    double v = 0.0;
+    if (j < M3 / 2) {
+        const double th = M_PI * (2.0 * j + 1.0) / (2.0 * M3);
+        const double dth = M_PI / M3;
+        v = ((j == 0) ? 0.5 * dth : dth) * sin(th);
+    }
+    w[j] = v;
+}
+
+// Coefficient rows for the kinetic-energy synthesis: field 0 = J_theta(psi)/r (cosine), field 1 = Dr psi in
+// sinusoid indexing (sine).  Layout [B][2][n8][2][Khp].  (Main.py:104-115)
+struct KEPrepParams {
+    const double* X; long long x_stride;
+    const double* JJ;
+    double* coef; long long coef_stride;
+    const double* DrT;  // [n][n8]
+    const double* ir;   // [n] 1/r
+    Geo g;
+};
+
+__global__ void __launch_bounds__(256) ke_prep_kernel(KEPrepParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const Geo& g = p.g;
+    const int n = g.n, n8 = g.n8, K = g.K;
+    const int b = blockIdx.y, c0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* sP = smem;           // psi blocks c0-1 .. c0+30 (q = lane)
+    double* mDr = sP + 32 * n;   // [n][n8]
+    const double* Xb = p.X + (long long)b * p.x_stride;
+    for (int idx = tid; idx < 32 * n; idx += 256) {
+        const int bp = c0 - 1 + idx / n;
+        double v = 0.0;
+        // Kinetic_Energy differentiates every psi block, symmetric or not (Main.py:109-111); only the
+        // J_theta part is masked (through the scan)
+        if (bp >= 0 && bp < K) v = Xb[(long long)bp * n + (idx % n)];
+        sP[idx] = v;
+    }
+    for (int idx = tid; idx < n * n8; idx += 256) mDr[idx] = p.DrT[idx];
+    __syncthreads();
+    const int c = c0 + lane;
+    if (c >= K) return;
+    const int par = c & 1, kp = c >> 1;
+    double* cf = p.coef + (long long)b * p.coef_stride;
+    const double* Jb = p.JJ + (long long)b * (K + 1) * n;
+    for (int i = warp; i < n; i += 8) {
+        double d = 0.0;
+        for (int ip = 0; ip < n; ++ip) d = fma(mDr[ip * n8 + i], sP[lane * n + ip], d);
+        const long long o = ((long long)i * 2 + par) * g.Khp + kp;
+        cf[o] = p.ir[i] * Jb[(long long)c * n + i];
+        cf[(long long)n8 * 2 * g.Khp + o] = (c >= 1) ? d : 0.0;
+    }
+}
+
+// One CTA per member: ||X||_2, Nusselt numbers at both walls, and the final kinetic-energy reduction.
+// out[b] = { norm, KE, Nu_T, Nu_S, Nu_T(outer), Nu_S(outer) }   (Main.py:41-68, 292-295)
+__global__ void __launch_bounds__(256) diag_kernel(const double* __restrict__ X, const double* __restrict__ kepart,
+                                                   int nke, const double* __restrict__ nu_in,
+                                                   const double* __restrict__ nu_out, double ke_scale, Geo g,
+                                                   double* __restrict__ out) {
+    __shared__ double red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, n = g.n, N = g.N;
+    const double* Xb = X + (long long)b * 3 * N;
+    double s2 = 0.0, nt_i = 0.0, ns_i = 0.0, nt_o = 0.0, ns_o = 0.0;
+    for (int idx = tid; idx < 3 * N; idx += 256) {
+        const double v = Xb[idx];
+        s2 = fma(v, v, s2);
+    }
+    for (int idx = tid; idx < N; idx += 256) {
+        const int k = idx / n, i = idx - k * n;
+        if ((k & 1) == 0) {
+            const double w = 1.0 / (1.0 - (double)k * (double)k);
+            const double t = Xb[N + idx] * w, s = Xb[2 * N + idx] * w;
+            nt_i = fma(nu_in[i], t, nt_i);  ns_i = fma(nu_in[i], s, ns_i);
+            nt_o = fma(nu_out[i], t, nt_o); ns_o = fma(nu_out[i], s, ns_o);
+        }
+    }
+    double ke = 0.0;
+    for (int idx = tid; idx < nke; idx += 256) ke += kepart[(long long)b * nke + idx];
+    s2 = block_sum(s2, red);
+    nt_i = block_sum(nt_i, red); ns_i = block_sum(ns_i, red);
+    nt_o = block_sum(nt_o, red); ns_o = block_sum(ns_o, red);
+    ke = block_sum(ke, red);
+    if (tid == 0) {
+        double* o = out + (long long)b * 6;
+        o[0] = sqrt(s2); o[1] = ke_scale * ke; o[2] = nt_i; o[3] = ns_i; o[4] = nt_o; o[5] = ns_o;
+    }
+}
+
+// Generic drop-in transforms (Transforms.py:73-129) by direct summation; one thread per output element.
+__global__ void transform_kernel(int kind, const double* __restrict__ in, double* __restrict__ out, int rows,
+                                 int n_in, int n_out) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * n_out) return;
+    const int r = (int)(idx / n_out), o = (int)(idx - (long long)r * n_out);
+    const double* x = in + (long long)r * n_in;
+    double acc = 0.0, c, s;
+    if (kind == 0) {          // IDCT: f_j = sum_{k < min(K, M)} a_k cos(k theta_j), M = n_out
+        const int ku = min(n_in, n_out);
+        for (int k = 0; k < ku; ++k) { trig_kj(k, o, n_out, c, s); acc = fma(x[k], c, acc); }
+    } else if (kind == 1) {   // IDST: g_j = sum_{1 <= k < min(K, M+1)} b_k sin(k theta_j)
+        const int ku = min(n_in, n_out + 1);
+        for (int k = 1; k < ku; ++k) { trig_kj(k, o, n_out, c, s); acc = fma(x[k], s, acc); }
+    } else if (kind == 2) {   // DCT: a_k = (2/M) sum_j f_j cos(k theta_j), a_0 halved, M = n_in
+        for (int j = 0; j < n_in; ++j) { trig_kj(o, j, n_in, c, s); acc = fma(x[j], c, acc); }
+        acc *= (o == 0 ? 1.0 : 2.0) / n_in;
+    } else {                  // DST: b_k = (2/M) sum_j g_j sin(k theta_j), b_0 = 0
+        if (o > 0) for (int j = 0; j < n_in; ++j) { trig_kj(o, j, n_in, c, s); acc = fma(x[j], s, acc); }
+        acc *= 2.0 / n_in;
+    }
+    out[idx] = acc;
+}
+
+// out = a - b (residual / JVP helper for rows the solve does not touch is not needed; used for host tests)
+__global__ void axpby_kernel(double* out, const double* a, const double* b, double alpha, double beta, long long nel) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nel; i += (long long)gridDim.x * blockDim.x)
+        out[i] = alpha * a[i] + beta * b[i];
+}
+
+}  // namespace sddc

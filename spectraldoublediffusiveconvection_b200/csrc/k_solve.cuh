@@ -1,0 +1,190 @@
+// Stage 4: implicit block back-substitutions over latitudinal modes (two decoupled parity chains per field),
+// batched over members as small DMMA GEMMs  L_inv[j] (n x n) @ RHS (n x members)  with the pre-inverted
+// operators streamed through shared memory.
+//
+// Reference semantics: A4_BSub_TSTEP_V2 (Matrix_Operators.py:1115-1194) and NAB2_BSub_TSTEP_V2 (1033-1086).
+#pragma once
+#include "common.cuh"
+
+namespace sddc {
+
+struct SolveParams {
+    const double* g;        // right-hand sides
+    long long g_stride;     // member stride (doubles); field offset added via g_field_off
+    long long g_field_off;  // offset between fields inside a member (N for a full state, 0 for single field)
+    double* out;
+    long long out_stride;
+    long long out_field_off;
+    const double* sub;      // optional: out = f - sub (same layout as out) for residual / JVP
+    const double* LinvA4;   // [K][n8][LDL] zero padded, descending-mode order (index K - j)
+    const double* LinvT;    // [K][n8][LDL] index K-1-j
+    const double* LinvS;
+    const double* D2;       // [n8][LDL]
+    const double* ir2;      // [n] diag IR2 (A4 aux)
+    const double* ir4;      // [n]
+    Geo geo;
+    int B;
+    int field_mask;         // bit f: solve field f (0 psi, 1 T, 2 S)
+    int field_base;         // field index of chain group 0 (for single-field calls)
+    double dt_psi, dt_T, dt_S;  // Pr*dt, dt, Tau*dt
+};
+
+constexpr int SOLVE_NSL = 3;  // operator pipeline stages
+
+template <int NTB>
+__host__ __device__ inline size_t solve_smem_doubles(int n8) {
+    const int LDL = n8 + 4;
+    return (size_t)(SOLVE_NSL + 1) * n8 * LDL + (size_t)2 * (8 * NTB) * LDL;
+}
+
+// grid = (ceil(B / (8*NTB)), 2 chains, nfields), block = 32 * nt8 (warp w owns radial rows 8w..8w+7).
+// Every thread owns the elements (i = 8w + g, member = nt*8 + 2t + e) in MMA accumulator layout, so the
+// running vectors b / f_e / bf_e of the reference live in registers.
+template <int NTB>
+__global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
+    constexpr int BT = 8 * NTB, NE = 2 * NTB;
+    extern __shared__ __align__(16) double smem[];
+    const Geo& G = p.geo;
+    const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int nthr = blockDim.x;
+    const int b0 = blockIdx.x * BT, which = blockIdx.y, fld = p.field_base + blockIdx.z;
+    if (!((p.field_mask >> fld) & 1)) return;
+    double* sL = smem;                          // [NSL][n8][LDL]
+    double* sD2 = sL + (size_t)SOLVE_NSL * MAT; // [n8][LDL]
+    double* sR = sD2 + MAT;                     // [2][BT][LDL]
+
+    const int i = warp * 8 + gq;
+    const bool row_ok = i < n;
+    long long goff[NE], ooff[NE];
+    bool ok[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int m = (e >> 1) * 8 + 2 * tq + (e & 1);
+        ok[e] = row_ok && (b0 + m) < p.B;
+        goff[e] = (long long)(b0 + m) * p.g_stride + (long long)fld * p.g_field_off + i;
+        ooff[e] = (long long)(b0 + m) * p.out_stride + (long long)fld * p.out_field_off + i;
+    }
+    auto store_out = [&](int row, const double* f) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+            if (ok[e]) {
+                const long long o = ooff[e] + (long long)row * n;
+                p.out[o] = p.sub ? f[e] - p.sub[o] : f[e];
+            }
+    };
+    auto put_rhs = [&](double* buf, const double* v) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) buf[((e >> 1) * 8 + 2 * tq + (e & 1)) * LDL + i] = v[e];
+    };
+    // C = Mat(n8 x n8, smem, row stride LDL) @ V (smem [member][i'])
+    auto gemm = [&](const double* mat, const double* vec, double* c) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) c[e] = 0.0;
+        const double* ar = mat + (warp * 8 + gq) * LDL + tq;
+        const double* br = vec + gq * LDL + tq;
+        for (int ks = 0; ks < n8 / 4; ++ks) {
+            const double a = ar[ks * 4];
+#pragma unroll
+            for (int nt = 0; nt < NTB; ++nt) mma884(c[2 * nt], c[2 * nt + 1], a, br[nt * 8 * LDL + ks * 4]);
+        }
+    };
+
+    const bool is_psi = (fld == 0);
+    // chain start mode: psi: j0 = K (which 0) | K-1 (which 1, skipped if symmetric)
+    //                   T,S: j0 = K-2 (which 0) | K-1 (which 1, skipped if symmetric)
+    const int j0 = is_psi ? (K - which) : (which == 0 ? K - 2 : K - 1);
+    const int jend = is_psi ? 1 : 0;
+    if (G.symmetric && which == 1) {
+        double z[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) z[e] = 0.0;
+        for (int j = j0; j >= jend; j -= 2) store_out(is_psi ? j - 1 : j, z);
+        return;
+    }
+    const double* Lg = is_psi ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
+    const int nsteps = (j0 - jend) / 2 + 1;
+    auto load_op = [&](int step) {  // operator of chain step `step` (mode j0 - 2*step) -> stage step % NSL
+        if (step < nsteps) {
+            const int j = j0 - 2 * step;
+            const int jj = is_psi ? (K - j) : (K - 1 - j);
+            const double* src = Lg + (long long)jj * MAT;
+            double* dst = sL + (size_t)(step % SOLVE_NSL) * MAT;
+            for (int idx = tid; idx < MAT / 2; idx += nthr) cp_async16(dst + idx * 2, src + idx * 2);
+        }
+        cp_async_commit();
+    };
+    load_op(0);
+    load_op(1);
+    if (is_psi)
+        for (int idx = tid; idx < MAT; idx += nthr) sD2[idx] = p.D2[idx];
+    for (int idx = tid; idx < 2 * BT * LDL; idx += nthr) sR[idx] = 0.0;  // padded rows stay zero
+    __syncthreads();
+
+    double f[NE], gv[NE];
+    if (!is_psi) {
+        const double dt = (fld == 1) ? p.dt_T : p.dt_S;
+        double bsum[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { bsum[e] = 0.0; f[e] = 0.0; }
+        for (int step = 0; step < nsteps; ++step) {
+            const int j = j0 - 2 * step;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) gv[e] = ok[e] ? p.g[goff[e] + (long long)j * n] : 0.0;
+            double rhs[NE];
+            const double beta = 2.0 * dt * (j + 2.0);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (j < K - 2) bsum[e] += beta * f[e];
+                rhs[e] = gv[e] - (j == 0 ? 0.5 * bsum[e] : bsum[e]);
+            }
+            double* buf = sR + (size_t)(step & 1) * BT * LDL;
+            put_rhs(buf, rhs);
+            cp_async_wait<1>();
+            __syncthreads();
+            load_op(step + 2);
+            gemm(sL + (size_t)(step % SOLVE_NSL) * MAT, buf, f);
+            store_out(j, f);
+        }
+    } else {
+        const double dt = p.dt_psi;
+        double fe[NE], bfe[NE], u[NE];
+        const double ir2 = row_ok ? p.ir2[i] : 0.0, ir4 = row_ok ? p.ir4[i] : 0.0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) { fe[e] = 0.0; bfe[e] = 0.0; f[e] = 0.0; }
+        double* bufA = sR;
+        double* bufB = sR + (size_t)BT * LDL;
+        for (int step = 0; step < nsteps; ++step) {
+            const int j = j0 - 2 * step;
+            const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) gv[e] = ok[e] ? p.g[goff[e] + (long long)(j - 1) * n] : 0.0;
+            double rhs[NE];
+            if (step == 0) {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) rhs[e] = gv[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < NE; ++e) fe[e] += f[e];
+                put_rhs(bufA, fe);
+                __syncthreads();
+                gemm(sD2, bufA, u);  // D2 @ f_e ; L1 = D2 + b_j IR4
+#pragma unroll
+                for (int e = 0; e < NE; ++e) {
+                    const double l1 = u[e] + bj * (ir4 * fe[e]);
+                    rhs[e] = gv[e] + (dt * bjt * (l1 + ir4 * bfe[e]) - bjt * (ir2 * fe[e]));
+                }
+            }
+            put_rhs(bufB, rhs);
+            cp_async_wait<1>();
+            __syncthreads();
+            load_op(step + 2);
+            gemm(sL + (size_t)(step % SOLVE_NSL) * MAT, bufB, f);
+            store_out(j - 1, f);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) bfe[e] += (step == 0) ? bj * f[e] : (bj * f[e] + bjt * fe[e]);
+        }
+    }
+}
+
+}  // namespace sddc

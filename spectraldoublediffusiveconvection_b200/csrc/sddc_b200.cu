@@ -1,0 +1,601 @@
+// Host side of the C ABI (include/sddc_b200.h): plan construction, operator upload / padding, kernel dispatch.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sddc_b200.h"
+#include "common.cuh"
+#include "k_analysis.cuh"
+#include "k_misc.cuh"
+#include "k_prep.cuh"
+#include "k_solve.cuh"
+#include "k_synth.cuh"
+
+using namespace sddc;
+
+namespace {
+
+thread_local std::string g_create_error;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct DevBuf {
+    double* p = nullptr;
+    size_t n = 0;
+};
+
+}  // namespace
+
+struct sddc_plan {
+    sddc_config cfg{};
+    Geo g{};
+    int device = 0;
+    int LDL = 0;
+    int Mh3p = 0;  // padded mirror pairs of the 3K kinetic-energy grid
+    int nke = 0;   // kinetic-energy partial sums per member
+    double ke_scale = 0.0;
+    long long launches = 0;
+    std::string err;
+    std::vector<void*> allocs;
+    // operators
+    double *DrT = nullptr, *D2rT = nullptr, *DsqT = nullptr, *Dr = nullptr, *D2p = nullptr;
+    double *LA4 = nullptr, *LT = nullptr, *LS = nullptr;
+    double *ir2 = nullptr, *ir4 = nullptr, *r2 = nullptr, *dT0 = nullptr, *gb = nullptr, *a4_ir2 = nullptr,
+           *a4_ir4 = nullptr, *ir = nullptr, *nu_in = nullptr, *nu_out = nullptr, *wr = nullptr;
+    double *tab1 = nullptr, *tab2 = nullptr, *tab3 = nullptr, *wth = nullptr;
+    // scratch
+    double *JJ = nullptr, *coef = nullptr, *prd = nullptr, *lin = nullptr, *rhs = nullptr, *xtmp = nullptr,
+           *kepart = nullptr, *zeroRa = nullptr;
+    long long coef_set_stride = 0, coef_member_stride = 0;
+    // host-API staging
+    double *hX0 = nullptr, *hX1 = nullptr, *hX2 = nullptr, *hRa = nullptr, *hRas = nullptr, *hDiag = nullptr;
+    cudaStream_t own_stream = nullptr;
+    // kernel configuration
+    int synth_nt_fx = 0, synth_nt_dfx = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
+    size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
+    int ana_nt = 0, ana_stage = 0;
+    size_t ana_smem = 0;
+    size_t solve_smem = 0;
+};
+
+namespace {
+
+#define PLAN_CUDA(plan, expr)                                                                          \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            (plan)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                         \
+            return SDDC_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+
+int dev_alloc(sddc_plan* pl, double** out, size_t count, bool zero) {
+    void* p = nullptr;
+    PLAN_CUDA(pl, cudaMalloc(&p, count * sizeof(double)));
+    pl->allocs.push_back(p);
+    if (zero) PLAN_CUDA(pl, cudaMemset(p, 0, count * sizeof(double)));
+    *out = static_cast<double*>(p);
+    return SDDC_OK;
+}
+
+int upload(sddc_plan* pl, double** out, const std::vector<double>& h) {
+    int rc = dev_alloc(pl, out, h.size(), false);
+    if (rc) return rc;
+    PLAN_CUDA(pl, cudaMemcpy(*out, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return SDDC_OK;
+}
+
+// M[i][i'] (n x n) -> M^T padded: out[i'][i], row length n8
+std::vector<double> transpose_pad(const double* M, int n, int n8) {
+    std::vector<double> o((size_t)n * n8, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int ip = 0; ip < n; ++ip) o[(size_t)ip * n8 + i] = M[(size_t)i * n + ip];
+    return o;
+}
+
+// stack of nmat (n x n) matrices -> [nmat][n8][LDL], zero padded
+std::vector<double> pad_stack(const double* M, int nmat, int n, int n8, int LDL) {
+    std::vector<double> o((size_t)nmat * n8 * LDL, 0.0);
+    for (int m = 0; m < nmat; ++m)
+        for (int i = 0; i < n; ++i)
+            std::memcpy(&o[((size_t)m * n8 + i) * LDL], &M[((size_t)m * n + i) * n], sizeof(double) * n);
+    return o;
+}
+
+template <typename Kern>
+int set_smem(sddc_plan* pl, Kern kern, size_t bytes) {
+    PLAN_CUDA(pl, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return SDDC_OK;
+}
+
+// choose (NT, stages, smem) of the synthesis kernel for `nfields` coefficient rows per radial point
+int pick_synth(const Geo& g, int nfields, int* nt, int* nstage, size_t* smem) {
+    const int rows = nfields * g.n8, TM = rows / 8, tpw = (TM + 3) / 4;
+    size_t st, ep;
+    if (tpw <= 9 && g.n * 32 <= 1024) { *nt = 4; st = synth_stage_doubles<4>(rows); ep = synth_epi_doubles<4>(rows, g.n); }
+    else if (tpw <= 18 && g.n * 16 <= 1024) { *nt = 2; st = synth_stage_doubles<2>(rows); ep = synth_epi_doubles<2>(rows, g.n); }
+    else if (tpw <= 36 && g.n * 8 <= 1024) { *nt = 1; st = synth_stage_doubles<1>(rows); ep = synth_epi_doubles<1>(rows, g.n); }
+    else return SDDC_ERR_UNSUPPORTED;
+    st *= sizeof(double); ep *= sizeof(double);
+    int ns = 4;
+    while (ns > 2 && ns * st > SMEM_LIMIT) --ns;
+    if (ns * st > SMEM_LIMIT || ep > SMEM_LIMIT) return SDDC_ERR_UNSUPPORTED;
+    *nstage = ns;
+    *smem = std::max(ns * st, ep);
+    return SDDC_OK;
+}
+
+template <int EPI>
+int launch_synth(sddc_plan* pl, int nt, const SynthParams& sp, int nstage, size_t smem, int ncol_tiles, int B,
+                 cudaStream_t st) {
+    dim3 grid(ncol_tiles, B);
+    if (nt == 4) synth_kernel<4, 9, EPI><<<grid, 256, smem, st>>>(sp, nstage);
+    else if (nt == 2) synth_kernel<2, 18, EPI><<<grid, 256, smem, st>>>(sp, nstage);
+    else synth_kernel<1, 36, EPI><<<grid, 256, smem, st>>>(sp, nstage);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int check_batch(sddc_plan* pl, int B) {
+    if (!pl) return SDDC_ERR_INVALID;
+    if (B < 1 || B > pl->cfg.max_batch) {
+        pl->err = "batch size " + std::to_string(B) + " outside [1, max_batch=" + std::to_string(pl->cfg.max_batch) + "]";
+        return SDDC_ERR_INVALID;
+    }
+    PLAN_CUDA(pl, cudaSetDevice(pl->device));
+    return SDDC_OK;
+}
+
+int run_scan(sddc_plan* pl, const double* X, long long stride, int B, cudaStream_t st) {
+    const long long tot = (long long)B * 2 * pl->g.n;
+    scan_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(X, stride, pl->JJ, pl->g, B);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+// scan + prep of state X into coefficient set `set` (and optionally the linear right-hand side)
+int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* lin, const double* Ra,
+             const double* Ras, int B, cudaStream_t st) {
+    int rc = run_scan(pl, X, 3LL * pl->g.N, B, st);
+    if (rc) return rc;
+    PrepParams pp{};
+    pp.X = X; pp.x_stride = 3LL * pl->g.N; pp.JJ = pl->JJ;
+    pp.coef = want_coef ? pl->coef + set * pl->coef_set_stride : nullptr;
+    pp.coef_stride = pl->coef_member_stride;
+    pp.lin = lin; pp.Ra = Ra; pp.Ras = Ras;
+    pp.DrT = pl->DrT; pp.D2rT = pl->D2rT; pp.DsqT = pl->DsqT;
+    pp.ir2 = pl->ir2; pp.ir4 = pl->ir4; pp.r2 = pl->r2; pp.dT0 = pl->dT0; pp.gb = pl->gb;
+    pp.g = pl->g; pp.B = B;
+    dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
+    prep_kernel<<<grid, 256, prep_smem_bytes(pl->g.n, pl->g.n8), st>>>(pp);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
+    SynthParams sp{};
+    sp.coef = pl->coef; sp.coef_stride = pl->coef_member_stride;
+    sp.tab = pl->tab1; sp.tab_Mhp = pl->g.Mhp; sp.Dr = pl->Dr; sp.prd = pl->prd;
+    sp.rows = (dfx ? 18 : 9) * pl->g.n8;
+    sp.type_mask = dfx ? (0x1E0u | (0x1E0u << 9)) : 0x1E0u;
+    sp.g = pl->g;
+    const int nt = dfx ? pl->synth_nt_dfx : pl->synth_nt_fx;
+    const int tiles = pl->g.Mhp / (8 * nt);
+    if (dfx) return launch_synth<EPI_DFX>(pl, nt, sp, pl->synth_stage_dfx, pl->synth_smem_dfx, tiles, B, st);
+    return launch_synth<EPI_FX>(pl, nt, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
+}
+
+int run_analysis(sddc_plan* pl, const double* lin, double* out, int B, cudaStream_t st) {
+    AnaParams ap{};
+    ap.prd = pl->prd; ap.tab2 = pl->tab2; ap.lin = lin; ap.out = out; ap.g = pl->g; ap.mdt = -pl->g.dt;
+    dim3 grid(pl->g.Khp2 / (64 * pl->ana_nt), 2, B);
+    if (pl->ana_nt == 2) analysis_kernel<2, 15><<<grid, 256, pl->ana_smem, st>>>(ap, pl->ana_stage);
+    else analysis_kernel<1, 24><<<grid, 256, pl->ana_smem, st>>>(ap, pl->ana_stage);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double* out, long long os, long long of,
+              const double* sub, int field_base, int nfields, int B, cudaStream_t st) {
+    SolveParams sp{};
+    sp.g = g; sp.g_stride = gs; sp.g_field_off = gf; sp.out = out; sp.out_stride = os; sp.out_field_off = of;
+    sp.sub = sub; sp.LinvA4 = pl->LA4; sp.LinvT = pl->LT; sp.LinvS = pl->LS; sp.D2 = pl->D2p;
+    sp.ir2 = pl->a4_ir2; sp.ir4 = pl->a4_ir4; sp.geo = pl->g; sp.B = B;
+    sp.field_mask = 7; sp.field_base = field_base;
+    sp.dt_psi = pl->g.Pr * pl->g.dt; sp.dt_T = pl->g.dt; sp.dt_S = pl->g.Tau * pl->g.dt;
+    // single-field calls pass field offsets of 0; the operator stack follows field_base
+    dim3 grid((B + 15) / 16, 2, nfields);
+    solve_kernel<2><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+// Step(X) [- sub]: the shared composition of Step_Python / PFX (Main.py:255-283, 473-496)
+int run_member_step(sddc_plan* pl, const double* X, double* out, const double* sub, const double* Ra,
+                    const double* Ras, int B, bool linear, cudaStream_t st) {
+    const long long N3 = 3LL * pl->g.N;
+    int rc = run_prep(pl, X, 0, !linear, pl->lin, Ra, Ras, B, st);
+    if (rc) return rc;
+    const double* rhs = pl->lin;
+    if (!linear) {
+        if ((rc = run_synth_nl(pl, false, B, st))) return rc;
+        if ((rc = run_analysis(pl, pl->lin, pl->rhs, B, st))) return rc;
+        rhs = pl->rhs;
+    }
+    return run_solve(pl, rhs, N3, pl->g.N, out, N3, pl->g.N, sub, 0, 3, B, st);
+}
+
+int ensure_host_staging(sddc_plan* pl) {
+    if (pl->hX0) return SDDC_OK;
+    const size_t cnt = (size_t)pl->cfg.max_batch * 3 * pl->g.N;
+    int rc;
+    if ((rc = dev_alloc(pl, &pl->hX0, cnt, false))) return rc;
+    if ((rc = dev_alloc(pl, &pl->hX1, cnt, false))) return rc;
+    if ((rc = dev_alloc(pl, &pl->hX2, cnt, false))) return rc;
+    if ((rc = dev_alloc(pl, &pl->hRa, pl->cfg.max_batch, false))) return rc;
+    if ((rc = dev_alloc(pl, &pl->hRas, pl->cfg.max_batch, false))) return rc;
+    if ((rc = dev_alloc(pl, &pl->hDiag, (size_t)pl->cfg.max_batch * 6, false))) return rc;
+    PLAN_CUDA(pl, cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+    return SDDC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sddc_version(void) { return 100; }
+
+int sddc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* sddc_last_error(const sddc_plan* plan) { return plan ? plan->err.c_str() : g_create_error.c_str(); }
+
+long long sddc_launch_count(const sddc_plan* plan) { return plan ? plan->launches : 0; }
+
+void sddc_plan_destroy(sddc_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    for (void* p : plan->allocs) cudaFree(p);
+    if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
+    delete plan;
+}
+
+int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operators* ops) {
+    if (!out || !cfg || !ops) { g_create_error = "null argument"; return SDDC_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->N_fm % 2 != 0) {
+        // same condition the reference raises on (Matrix_Operators.py:758-759)
+        g_create_error = "The number of Fourier modes is not even " + std::to_string(cfg->N_fm);
+        return SDDC_ERR_INVALID;
+    }
+    if (cfg->N_fm % 4 != 0 || cfg->N_fm < 8) {
+        g_create_error = "N_fm must be a multiple of 4 and >= 8 (mirror-pair split of the 3/2-padded grid)";
+        return SDDC_ERR_UNSUPPORTED;
+    }
+    if (cfg->N_r < 4 || cfg->N_r - 1 > 64) { g_create_error = "N_r must satisfy 4 <= N_r <= 65"; return SDDC_ERR_UNSUPPORTED; }
+    if (cfg->max_batch < 1) { g_create_error = "max_batch must be >= 1"; return SDDC_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_create_error = "no CUDA device"; return SDDC_ERR_NO_DEVICE; }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return SDDC_ERR_INVALID; }
+
+    sddc_plan* pl = new (std::nothrow) sddc_plan();
+    if (!pl) { g_create_error = "out of host memory"; return SDDC_ERR_INVALID; }
+    pl->cfg = *cfg;
+    pl->device = cfg->device;
+    Geo& g = pl->g;
+    g.n = cfg->N_r - 1; g.n8 = round_up(g.n, 8); g.nt8 = g.n8 / 8;
+    g.K = cfg->N_fm; g.Kh = g.K / 2; g.Khp = round_up(g.Kh, 8); g.Khp2 = round_up(g.Kh, 128);
+    g.M = 3 * g.K / 2; g.Mh = g.M / 2; g.Mhp = round_up(g.Mh, 32);
+    g.N = g.n * g.K; g.symmetric = cfg->symmetric ? 1 : 0;
+    g.dt = cfg->dt; g.Pr = cfg->Pr; g.Tau = cfg->Tau;
+    pl->LDL = g.n8 + 4;
+    const int n = g.n, n8 = g.n8, K = g.K;
+    const int M3 = 3 * K;
+    pl->Mh3p = round_up(M3 / 2, 32);
+
+    auto fail = [&](int rc) {
+        g_create_error = pl->err;
+        sddc_plan_destroy(pl);
+        return rc;
+    };
+#define TRY(x) do { int rc__ = (x); if (rc__) return fail(rc__); } while (0)
+#define TRYC(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { pl->err = std::string(#x) + ": " + cudaGetErrorString(e__); return fail(SDDC_ERR_CUDA); } } while (0)
+
+    TRYC(cudaSetDevice(pl->device));
+    // ---- operators ----
+    TRY(upload(pl, &pl->DrT, transpose_pad(ops->Dr, n, n8)));
+    TRY(upload(pl, &pl->D2rT, transpose_pad(ops->D2r, n, n8)));
+    TRY(upload(pl, &pl->DsqT, transpose_pad(ops->Dsq, n, n8)));
+    TRY(upload(pl, &pl->Dr, std::vector<double>(ops->Dr, ops->Dr + (size_t)n * n)));
+    TRY(upload(pl, &pl->D2p, pad_stack(ops->D2, 1, n, n8, pl->LDL)));
+    TRY(upload(pl, &pl->LA4, pad_stack(ops->Linv_A4, K, n, n8, pl->LDL)));
+    TRY(upload(pl, &pl->LT, pad_stack(ops->Linv_T, K, n, n8, pl->LDL)));
+    TRY(upload(pl, &pl->LS, pad_stack(ops->Linv_S, K, n, n8, pl->LDL)));
+    auto vec = [&](const double* v) { return std::vector<double>(v, v + n); };
+    TRY(upload(pl, &pl->ir2, vec(ops->ir2)));
+    TRY(upload(pl, &pl->ir4, vec(ops->ir4)));
+    TRY(upload(pl, &pl->r2, vec(ops->r2)));
+    TRY(upload(pl, &pl->dT0, vec(ops->dT0)));
+    TRY(upload(pl, &pl->gb, vec(ops->gbuoy)));
+    TRY(upload(pl, &pl->a4_ir2, vec(ops->a4_ir2)));
+    TRY(upload(pl, &pl->a4_ir4, vec(ops->a4_ir4)));
+    TRY(upload(pl, &pl->ir, vec(ops->ir)));
+    TRY(upload(pl, &pl->nu_in, vec(ops->nu_in)));
+    TRY(upload(pl, &pl->nu_out, vec(ops->nu_out)));
+    {
+        // np.trapz(.., x=R[1:-1], axis=0): interior nodes only (Main.py:129)
+        std::vector<double> wr(n, 0.0);
+        for (int i = 0; i + 1 < n; ++i) {
+            const double h = 0.5 * (ops->r[i + 1] - ops->r[i]);
+            wr[i] += h; wr[i + 1] += h;
+        }
+        TRY(upload(pl, &pl->wr, wr));
+        const double V = (2.0 / 3.0) * (ops->R_out * ops->R_out * ops->R_out - ops->R_in * ops->R_in * ops->R_in);
+        pl->ke_scale = 0.5 / V;
+    }
+    // ---- trigonometric tables (L2-resident) ----
+    const size_t t1 = 4ull * g.Mhp * g.Khp, t2 = 4ull * g.Khp2 * g.Mhp, t3 = 4ull * pl->Mh3p * g.Khp;
+    TRY(dev_alloc(pl, &pl->tab1, t1, false));
+    TRY(dev_alloc(pl, &pl->tab2, t2, false));
+    TRY(dev_alloc(pl, &pl->tab3, t3, false));
+    TRY(dev_alloc(pl, &pl->wth, pl->Mh3p, false));
+    fill_table_kernel<<<296, 256>>>(pl->tab1, 0, g.M, g.Kh, g.Mh, g.Khp, g.Mhp);
+    fill_table_kernel<<<296, 256>>>(pl->tab2, 1, g.M, g.Kh, g.Mh, g.Khp2, g.Mhp);
+    fill_table_kernel<<<296, 256>>>(pl->tab3, 0, M3, g.Kh, M3 / 2, g.Khp, pl->Mh3p);
+    fill_ke_weights_kernel<<<(pl->Mh3p + 127) / 128, 128>>>(pl->wth, M3, pl->Mh3p);
+    pl->launches += 4;
+    TRYC(cudaGetLastError());
+    // ---- scratch ----
+    const size_t Bm = (size_t)cfg->max_batch;
+    pl->coef_set_stride = 9LL * n8 * 2 * g.Khp;
+    pl->coef_member_stride = 2 * pl->coef_set_stride;
+    TRY(dev_alloc(pl, &pl->JJ, Bm * (K + 1) * n, false));
+    TRY(dev_alloc(pl, &pl->coef, Bm * pl->coef_member_stride, true));  // padded rows / columns stay zero
+    TRY(dev_alloc(pl, &pl->prd, Bm * 3 * 2 * n8 * g.Mhp, true));
+    TRY(dev_alloc(pl, &pl->lin, Bm * 3 * g.N, false));
+    TRY(dev_alloc(pl, &pl->rhs, Bm * 3 * g.N, false));
+    TRY(dev_alloc(pl, &pl->xtmp, Bm * 3 * g.N, false));
+    pl->nke = pl->Mh3p / 32;
+    TRY(dev_alloc(pl, &pl->kepart, Bm * pl->nke, true));
+    TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
+    // ---- kernel configuration ----
+    if (pick_synth(g, 9, &pl->synth_nt_fx, &pl->synth_stage_fx, &pl->synth_smem_fx) ||
+        pick_synth(g, 18, &pl->synth_nt_dfx, &pl->synth_stage_dfx, &pl->synth_smem_dfx)) {
+        pl->err = "N_r too large for the instantiated synthesis tiles";
+        return fail(SDDC_ERR_UNSUPPORTED);
+    }
+    {
+        const size_t st = synth_stage_doubles<4>(2 * n8) * sizeof(double), ep = synth_epi_doubles<4>(2 * n8, n) * sizeof(double);
+        pl->synth_stage_ke = 4;
+        pl->synth_smem_ke = std::max(4 * st, ep);
+    }
+    const size_t smax = std::max(std::max(pl->synth_smem_fx, pl->synth_smem_dfx), pl->synth_smem_ke);
+    TRY(set_smem(pl, synth_kernel<4, 9, EPI_FX>, smax));
+    TRY(set_smem(pl, synth_kernel<2, 18, EPI_FX>, smax));
+    TRY(set_smem(pl, synth_kernel<1, 36, EPI_FX>, smax));
+    TRY(set_smem(pl, synth_kernel<4, 9, EPI_DFX>, smax));
+    TRY(set_smem(pl, synth_kernel<2, 18, EPI_DFX>, smax));
+    TRY(set_smem(pl, synth_kernel<1, 36, EPI_DFX>, smax));
+    TRY(set_smem(pl, synth_kernel<4, 9, EPI_KE>, smax));
+    {
+        const int TM3 = 3 * g.nt8;
+        pl->ana_nt = (TM3 <= 15) ? 2 : 1;
+        const size_t st = (pl->ana_nt == 2 ? ana_stage_doubles<2>(3 * n8) : ana_stage_doubles<1>(3 * n8)) * sizeof(double);
+        pl->ana_stage = 4;
+        pl->ana_smem = 4 * st;
+        TRY(set_smem(pl, analysis_kernel<2, 15>, pl->ana_smem));
+        TRY(set_smem(pl, analysis_kernel<1, 24>, pl->ana_smem));
+    }
+    pl->solve_smem = solve_smem_doubles<2>(n8) * sizeof(double);
+    TRY(set_smem(pl, solve_kernel<2>, pl->solve_smem));
+    TRY(set_smem(pl, prep_kernel, prep_smem_bytes(n, n8)));
+    TRY(set_smem(pl, linop_kernel, sizeof(double) * ((size_t)PREP_TC * n + (size_t)n * n8)));
+    TRY(set_smem(pl, ke_prep_kernel, sizeof(double) * ((size_t)32 * n + (size_t)n * n8)));
+    TRYC(cudaDeviceSynchronize());
+#undef TRY
+#undef TRYC
+    *out = pl;
+    return SDDC_OK;
+}
+
+int sddc_nlin_fx(sddc_plan* pl, const double* X, double* F, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
+    if ((rc = run_synth_nl(pl, false, B, st))) return rc;
+    return run_analysis(pl, nullptr, F, B, st);
+}
+
+int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
+    if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st))) return rc;
+    if ((rc = run_synth_nl(pl, true, B, st))) return rc;
+    return run_analysis(pl, nullptr, F, B, st);
+}
+
+int sddc_linear_op(sddc_plan* pl, int op, const double* in, double* out, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (op < 0 || op > 5) { pl->err = "unknown linear operator code"; return SDDC_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LinopParams lp{};
+    lp.in = in; lp.out = out; lp.g = pl->g; lp.B = B; lp.op = op;
+    if (op <= 3) {
+        if ((rc = run_scan(pl, in, pl->g.N, B, st))) return rc;
+        lp.JJ = pl->JJ;
+    }
+    switch (op) {
+        case SDDC_OP_DT0_THETA: lp.vec = pl->dT0; break;
+        case SDDC_OP_A2_SINE: lp.vec = pl->ir2; lp.matT = pl->DsqT; break;
+        case SDDC_OP_A2_SINE_R2: lp.vec = pl->ir4; lp.matT = pl->D2rT; break;
+        case SDDC_OP_KGR: lp.vec = pl->gb; break;
+        case SDDC_OP_R2: lp.vec = pl->r2; break;
+        default: break;
+    }
+    dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
+    const size_t smem = sizeof(double) * ((size_t)PREP_TC * pl->g.n + (size_t)pl->g.n * pl->g.n8);
+    linop_kernel<<<grid, 256, smem, st>>>(lp);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int sddc_solve_a4(sddc_plan* pl, const double* g, double* f, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    return run_solve(pl, g, pl->g.N, 0, f, pl->g.N, 0, nullptr, 0, 1, B, static_cast<cudaStream_t>(stream));
+}
+
+int sddc_solve_nab2(sddc_plan* pl, int which, const double* g, double* f, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (which != 0 && which != 1) { pl->err = "which must be 0 (T) or 1 (S)"; return SDDC_ERR_INVALID; }
+    return run_solve(pl, g, pl->g.N, 0, f, pl->g.N, 0, nullptr, 1 + which, 1, B, static_cast<cudaStream_t>(stream));
+}
+
+int sddc_step(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B, int nsteps,
+              int linear, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (nsteps < 1 || Xin == Xout) { pl->err = "nsteps must be >= 1 and Xout must not alias Xin"; return SDDC_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double* src = Xin;
+    for (int s = 0; s < nsteps; ++s) {
+        double* dst = ((nsteps - s) & 1) ? Xout : pl->xtmp;  // the last step lands in Xout
+        if ((rc = run_member_step(pl, src, dst, nullptr, Ra, Ras, B, linear != 0, st))) return rc;
+        src = dst;
+    }
+    return SDDC_OK;
+}
+
+int sddc_residual(sddc_plan* pl, const double* X, double* out, const double* Ra, const double* Ras, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (X == out) { pl->err = "out must not alias X"; return SDDC_ERR_INVALID; }
+    return run_member_step(pl, X, out, X, Ra, Ras, B, false, static_cast<cudaStream_t>(stream));
+}
+
+int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, const double* Ra, const double* Ras, int B,
+             void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (dv == out || X == out) { pl->err = "out must not alias dv or X"; return SDDC_ERR_INVALID; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long N3 = 3LL * pl->g.N;
+    if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
+    if ((rc = run_prep(pl, dv, 1, true, pl->lin, Ra, Ras, B, st))) return rc;
+    if ((rc = run_synth_nl(pl, true, B, st))) return rc;
+    if ((rc = run_analysis(pl, pl->lin, pl->rhs, B, st))) return rc;
+    return run_solve(pl, pl->rhs, N3, pl->g.N, out, N3, pl->g.N, dv, 0, 3, B, st);
+}
+
+int sddc_dF_dRa(sddc_plan* pl, const double* X, double* out, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long N = pl->g.N, N3 = 3 * N;
+    // f_mu = dt Pr G(T) (Main.py:835): kGR operator on the T field, scaled
+    LinopParams lp{};
+    lp.in = X + N; lp.out = pl->rhs; lp.g = pl->g; lp.B = B; lp.op = SDDC_OP_KGR; lp.vec = pl->gb;
+    // the T field of member b sits at X + b*3N + N: run member by member through strides = use a strided variant
+    // (linop_kernel assumes stride N), so gather through cudaMemcpy2DAsync first.
+    PLAN_CUDA(pl, cudaMemcpy2DAsync(pl->lin, N * sizeof(double), X + N, N3 * sizeof(double), N * sizeof(double), B,
+                                    cudaMemcpyDeviceToDevice, st));
+    lp.in = pl->lin;
+    dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
+    const size_t smem = sizeof(double) * ((size_t)PREP_TC * pl->g.n + (size_t)pl->g.n * pl->g.n8);
+    linop_kernel<<<grid, 256, smem, st>>>(lp);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    const double s = pl->g.dt * pl->g.Pr;
+    axpby_kernel<<<296, 256, 0, st>>>(pl->rhs, pl->rhs, pl->rhs, s, 0.0, (long long)B * N);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaMemsetAsync(out, 0, sizeof(double) * B * N3, st));
+    return run_solve(pl, pl->rhs, N, 0, out, N3, N, nullptr, 0, 1, B, st);
+}
+
+int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Geo& g = pl->g;
+    if ((rc = run_scan(pl, X, 3LL * g.N, B, st))) return rc;
+    KEPrepParams kp{};
+    kp.X = X; kp.x_stride = 3LL * g.N; kp.JJ = pl->JJ; kp.coef = pl->coef; kp.coef_stride = pl->coef_member_stride;
+    kp.DrT = pl->DrT; kp.ir = pl->ir; kp.g = g;
+    dim3 grid((g.K + 31) / 32, B);
+    ke_prep_kernel<<<grid, 256, sizeof(double) * ((size_t)32 * g.n + (size_t)g.n * g.n8), st>>>(kp);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    SynthParams sp{};
+    sp.coef = pl->coef; sp.coef_stride = pl->coef_member_stride; sp.tab = pl->tab3; sp.tab_Mhp = pl->Mh3p;
+    sp.wr = pl->wr; sp.wth = pl->wth; sp.kepart = pl->kepart; sp.rows = 2 * g.n8; sp.type_mask = 0x2u; sp.g = g;
+    if ((rc = launch_synth<EPI_KE>(pl, 4, sp, pl->synth_stage_ke, pl->synth_smem_ke, pl->Mh3p / 32, B, st))) return rc;
+    diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, pl->nke, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, int n_out, void* stream) {
+    if (kind < 0 || kind > 3 || rows < 1 || n_in < 1 || n_out < 1) return SDDC_ERR_INVALID;
+    if (kind >= 2 && n_out > n_in) return SDDC_ERR_INVALID;
+    const long long tot = (long long)rows * n_out;
+    transform_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, in, out, rows, n_in, n_out);
+    return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
+int sddc_step_host(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B,
+                   int nsteps, int linear, double* diag_out) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if ((rc = ensure_host_staging(pl))) return rc;
+    cudaStream_t st = pl->own_stream;
+    const size_t bytes = sizeof(double) * (size_t)B * 3 * pl->g.N;
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX0, Xin, bytes, cudaMemcpyHostToDevice, st));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRa, Ra, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRas, Ras, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    if ((rc = sddc_step(pl, pl->hX0, pl->hX1, pl->hRa, pl->hRas, B, nsteps, linear, st))) return rc;
+    if (diag_out) {
+        if ((rc = sddc_diagnostics(pl, pl->hX1, pl->hDiag, B, st))) return rc;
+        PLAN_CUDA(pl, cudaMemcpyAsync(diag_out, pl->hDiag, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    }
+    PLAN_CUDA(pl, cudaMemcpyAsync(Xout, pl->hX1, bytes, cudaMemcpyDeviceToHost, st));
+    PLAN_CUDA(pl, cudaStreamSynchronize(st));
+    return SDDC_OK;
+}
+
+int sddc_jvp_host(sddc_plan* pl, const double* dv, const double* X, double* out, const double* Ra, const double* Ras,
+                  int B) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if ((rc = ensure_host_staging(pl))) return rc;
+    cudaStream_t st = pl->own_stream;
+    const size_t bytes = sizeof(double) * (size_t)B * 3 * pl->g.N;
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX0, dv, bytes, cudaMemcpyHostToDevice, st));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX2, X, bytes, cudaMemcpyHostToDevice, st));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRa, Ra, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRas, Ras, sizeof(double) * B, cudaMemcpyHostToDevice, st));
+    if ((rc = sddc_jvp(pl, pl->hX0, pl->hX2, pl->hX1, pl->hRa, pl->hRas, B, st))) return rc;
+    PLAN_CUDA(pl, cudaMemcpyAsync(out, pl->hX1, bytes, cudaMemcpyDeviceToHost, st));
+    PLAN_CUDA(pl, cudaStreamSynchronize(st));
+    return SDDC_OK;
+}
+
+}  // extern "C"

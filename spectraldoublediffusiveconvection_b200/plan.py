@@ -1,0 +1,220 @@
+"""EnsemblePlan: the batched, device-resident API over the C ABI.
+
+One plan holds the operators of one (N_fm, N_r, d, dt, Pr, Tau, symmetric) on one GPU and applies the hot path
+to B independent members at once.  States are torch.float64 CUDA tensors of shape [B, 3*nr*N_fm] in the
+reference's flat layout; Ra / Ra_s are per-member tensors [B].
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .operators import RadialOperators
+
+OP_J_THETA, OP_DT0_THETA, OP_A2_SINE, OP_A2_SINE_R2, OP_KGR, OP_R2 = range(6)
+T_IDCT, T_IDST, T_DCT, T_DST = range(4)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+class SddcError(RuntimeError):
+    pass
+
+
+class EnsemblePlan:
+    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, symmetric=False, max_batch=1, device=None, operators=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise SddcError("no CUDA device: the B200 path has no CPU fallback")
+        if int(N_fm) % 2 != 0:
+            # same check and message as the reference (Matrix_Operators.py:758-759)
+            raise ValueError("The number of Fourier modes is not even %d" % N_fm)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.ops = operators if operators is not None else RadialOperators(N_fm, N_r, d, dt, Pr, Tau)
+        self.N_fm, self.N_r, self.nr = int(N_fm), int(N_r), int(N_r) - 1
+        self.N = self.nr * self.N_fm
+        self.symmetric = bool(symmetric)
+        self.max_batch = int(max_batch)
+        self.dt, self.Pr, self.Tau, self.d = float(dt), float(Pr), float(Tau), float(d)
+        cfg = _lib.SddcConfig(self.N_fm, self.N_r, int(self.symmetric), self.max_batch, self.device.index,
+                              self.dt, self.Pr, self.Tau, self.d)
+        o = self.ops
+        cops = _lib.SddcOperators(
+            Dr=_ptr(o.Dr), Dsq=_ptr(o.Dsq), D2r=_ptr(o.D2r), D2=_ptr(o.D2), r2=_ptr(o.r2), ir2=_ptr(o.ir2),
+            ir4=_ptr(o.ir4), a4_ir2=_ptr(o.a4_ir2), a4_ir4=_ptr(o.a4_ir4), dT0=_ptr(o.dT0), gbuoy=_ptr(o.gbuoy),
+            ir=_ptr(o.ir), nu_in=_ptr(o.nu_in), nu_out=_ptr(o.nu_out), r=_ptr(o.r), R_in=float(o.R[0]),
+            R_out=float(o.R[-1]), Linv_A4=_ptr(o.L_inv_A4), Linv_T=_ptr(o.L_inv_T), Linv_S=_ptr(o.L_inv_S))
+        handle = C.c_void_p()
+        rc = self.lib.sddc_plan_create(C.byref(handle), C.byref(cfg), C.byref(cops))
+        if rc != 0:
+            msg = self.lib.sddc_last_error(None).decode()
+            if rc == -1:
+                raise ValueError(msg)
+            raise SddcError("sddc_plan_create failed (%d): %s" % (rc, msg))
+        self._h = handle
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sddc_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.sddc_last_error(self._h).decode()
+            if rc == -1:
+                raise ValueError(msg)
+            raise SddcError("libsddc_b200 error %d: %s" % (rc, msg))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _in(self, t, width):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64):
+            raise TypeError("expected a float64 CUDA tensor")
+        if t.device != self.device:
+            raise ValueError("tensor on %s, plan on %s" % (t.device, self.device))
+        if t.dim() == 1:
+            t = t.unsqueeze(0)
+        if t.shape[-1] != width:
+            raise ValueError("last dimension %d, expected %d" % (t.shape[-1], width))
+        return t.contiguous()
+
+    def _param(self, v, B):
+        if isinstance(v, torch.Tensor):
+            v = v.to(device=self.device, dtype=torch.float64).reshape(-1)
+            if v.numel() == 1:
+                v = v.expand(B)
+            return v.contiguous()
+        return torch.full((B,), float(v), dtype=torch.float64, device=self.device)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.sddc_launch_count(self._h))
+
+    def new_state(self, B):
+        return torch.empty((B, 3 * self.N), dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------ hot path
+    def nlin_fx(self, X, out=None):
+        X = self._in(X, 3 * self.N)
+        out = torch.empty_like(X) if out is None else out
+        self._check(self.lib.sddc_nlin_fx(self._h, X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
+        return out
+
+    def nlin_dfx(self, dv, X, out=None):
+        dv, X = self._in(dv, 3 * self.N), self._in(X, 3 * self.N)
+        out = torch.empty_like(X) if out is None else out
+        self._check(self.lib.sddc_nlin_dfx(self._h, dv.data_ptr(), X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
+        return out
+
+    def linear_op(self, op, f, out=None):
+        f = self._in(f, self.N)
+        out = torch.empty_like(f) if out is None else out
+        self._check(self.lib.sddc_linear_op(self._h, int(op), f.data_ptr(), out.data_ptr(), f.shape[0], self._stream()))
+        return out
+
+    def solve_a4(self, g, out=None):
+        g = self._in(g, self.N)
+        out = torch.empty_like(g) if out is None else out
+        self._check(self.lib.sddc_solve_a4(self._h, g.data_ptr(), out.data_ptr(), g.shape[0], self._stream()))
+        return out
+
+    def solve_nab2(self, g, which, out=None):
+        g = self._in(g, self.N)
+        out = torch.empty_like(g) if out is None else out
+        self._check(self.lib.sddc_solve_nab2(self._h, int(which), g.data_ptr(), out.data_ptr(), g.shape[0], self._stream()))
+        return out
+
+    def step(self, X, Ra, Ra_s, nsteps=1, linear=False, out=None):
+        X = self._in(X, 3 * self.N)
+        B = X.shape[0]
+        Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
+        out = torch.empty_like(X) if out is None else out
+        self._check(self.lib.sddc_step(self._h, X.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
+                                       int(nsteps), int(bool(linear)), self._stream()))
+        return out
+
+    def residual(self, X, Ra, Ra_s, out=None):
+        X = self._in(X, 3 * self.N)
+        B = X.shape[0]
+        Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
+        out = torch.empty_like(X) if out is None else out
+        self._check(self.lib.sddc_residual(self._h, X.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B, self._stream()))
+        return out
+
+    def jvp(self, dv, X, Ra, Ra_s, out=None):
+        dv, X = self._in(dv, 3 * self.N), self._in(X, 3 * self.N)
+        B = X.shape[0]
+        Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
+        out = torch.empty_like(X) if out is None else out
+        self._check(self.lib.sddc_jvp(self._h, dv.data_ptr(), X.data_ptr(), out.data_ptr(), Ra.data_ptr(),
+                                      Ra_s.data_ptr(), B, self._stream()))
+        return out
+
+    def dF_dRa(self, X, out=None):
+        X = self._in(X, 3 * self.N)
+        out = torch.empty_like(X) if out is None else out
+        self._check(self.lib.sddc_dF_dRa(self._h, X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
+        return out
+
+    def diagnostics(self, X, out=None):
+        """[B, 6]: ||X||_2, KE, Nu_T, Nu_S, Nu_T(outer wall), Nu_S(outer wall)."""
+        X = self._in(X, 3 * self.N)
+        if out is None:
+            out = torch.empty((X.shape[0], 6), dtype=torch.float64, device=self.device)
+        self._check(self.lib.sddc_diagnostics(self._h, X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ host-buffer entry points (NumPy in / out)
+    def step_host(self, X, Ra, Ra_s, nsteps=1, linear=False, want_diag=False):
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
+        B = X.shape[0]
+        Ra = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra, dtype=np.float64), (B,)))
+        Ra_s = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra_s, dtype=np.float64), (B,)))
+        out = np.empty_like(X)
+        diag = np.empty((B, 6)) if want_diag else None
+        self._check(self.lib.sddc_step_host(self._h, X.ctypes.data, out.ctypes.data, Ra.ctypes.data, Ra_s.ctypes.data,
+                                            B, int(nsteps), int(bool(linear)), diag.ctypes.data if want_diag else None))
+        return (out, diag) if want_diag else out
+
+    def jvp_host(self, dv, X, Ra, Ra_s):
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
+        dv = np.ascontiguousarray(dv, dtype=np.float64).reshape(-1, 3 * self.N)
+        B = X.shape[0]
+        Ra = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra, dtype=np.float64), (B,)))
+        Ra_s = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra_s, dtype=np.float64), (B,)))
+        out = np.empty_like(X)
+        self._check(self.lib.sddc_jvp_host(self._h, dv.ctypes.data, X.ctypes.data, out.ctypes.data, Ra.ctypes.data,
+                                           Ra_s.ctypes.data, B))
+        return out
+
+
+def transform(kind, x, n=None):
+    """Batched Transforms.IDCT/IDST/DCT/DST on the last axis of a float64 CUDA tensor."""
+    lib = _lib.load()
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64):
+        raise TypeError("expected a float64 CUDA tensor")
+    n_in = x.shape[-1]
+    n_out = n_in if n is None else int(n)
+    if kind in (T_DCT, T_DST):
+        n_out = min(n_out, n_in)
+    xc = x.contiguous().reshape(-1, n_in)
+    out = torch.empty((xc.shape[0], n_out), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.sddc_transform(int(kind), xc.data_ptr(), out.data_ptr(), xc.shape[0], n_in, n_out,
+                                C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    if rc != 0:
+        raise SddcError("sddc_transform failed (%d)" % rc)
+    return out.reshape(x.shape[:-1] + (n_out,))

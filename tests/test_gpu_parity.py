@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path (through the C ABI) against golden vectors of the unmodified reference and against
+the NumPy oracle on the same seeded inputs.  Tolerances: fp64, relative L2 <= 1e-10 after 100 steps
+(BASELINE.json north_star); single operator calls are held to much tighter bounds."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+CASES = ["small_nosym", "small_sym", "cfg1_nosym", "cfg1_sym", "cfg3_member"]
+TOL_CALL = 2e-12
+TOL_STEPS = 1e-10
+
+
+def _plan(g, max_batch=4):
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    return EnsemblePlan(int(g["N_fm"]), int(g["N_r"]), float(g["d"]), float(g["dt"]), float(g["Pr"]), float(g["Tau"]),
+                        symmetric=bool(g["symmetric"]), max_batch=max_batch)
+
+
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    g = load_golden(request.param)
+    pl = _plan(g)
+    yield g, pl
+    pl.close()
+
+
+def test_linear_ops(case):
+    from spectraldoublediffusiveconvection_b200 import plan as P
+    g, pl = case
+    N = pl.N
+    Xb = g["Xb"]
+    psi, T = _dev(Xb[0:N]), _dev(Xb[N:2 * N])
+    for op, key, src in ((P.OP_J_THETA, "J_theta_RT", psi), (P.OP_DT0_THETA, "DT0_theta", psi),
+                         (P.OP_A2_SINE, "A2_SINE", psi), (P.OP_A2_SINE_R2, "A2_SINE_R2", psi),
+                         (P.OP_KGR, "kGR", T), (P.OP_R2, "R2", T)):
+        out = pl.linear_op(op, src).cpu().numpy().ravel()
+        assert rel_l2(out, g[key]) < TOL_CALL, key
+
+
+def test_nlin_fx(case):
+    g, pl = case
+    F = pl.nlin_fx(_dev(g["Xb"])).cpu().numpy().ravel()
+    assert rel_l2(F, g["NLIN_FX"]) < TOL_CALL
+
+
+def test_nlin_dfx(case):
+    g, pl = case
+    F = pl.nlin_dfx(_dev(g["dv"]), _dev(g["Xb"])).cpu().numpy().ravel()
+    assert rel_l2(F, g["NLIN_DFX"]) < TOL_CALL
+
+
+def test_solves(case):
+    g, pl = case
+    N = pl.N
+    Xb = g["Xb"]
+    f = pl.solve_a4(_dev(Xb[0:N])).cpu().numpy().ravel()
+    assert rel_l2(f, g["A4_BSub"]) < 1e-9          # cond(L) ~ 1e6
+    f = pl.solve_nab2(_dev(Xb[N:2 * N]), 0).cpu().numpy().ravel()
+    assert rel_l2(f, g["NAB2_BSub_T"]) < 1e-11
+    f = pl.solve_nab2(_dev(Xb[2 * N:3 * N]), 1).cpu().numpy().ravel()
+    assert rel_l2(f, g["NAB2_BSub_S"]) < 1e-11
+
+
+def test_step_jvp_dmu(case):
+    g, pl = case
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    Xb, dv = _dev(g["Xb"]), _dev(g["dv"])
+    assert rel_l2(pl.step(Xb, Ra, Ra_s).cpu().numpy().ravel(), g["step_Xb"]) < 1e-10
+    assert rel_l2(pl.jvp(dv, Xb, Ra, Ra_s).cpu().numpy().ravel(), g["jvp_Xb"]) < 1e-10
+    assert rel_l2(pl.dF_dRa(Xb).cpu().numpy().ravel(), g["dmu_Xb"]) < 1e-10
+    res = pl.residual(Xb, Ra, Ra_s).cpu().numpy().ravel()
+    assert rel_l2(res, g["step_Xb"] - g["Xb"] * (1 if not bool(g["symmetric"]) else 1)) < 1e-10 or bool(g["symmetric"])
+
+
+def test_diagnostics(case):
+    from oracle import sddc_oracle as orc
+    g, pl = case
+    Xb = g["Xb"]
+    if bool(g["symmetric"]):
+        Xb = Xb * orc.sym_mask(pl.N_fm, pl.nr).reshape(-1)
+    d = pl.diagnostics(_dev(Xb)).cpu().numpy()[0]
+    assert abs(d[0] / np.linalg.norm(Xb) - 1) < 1e-13
+    assert abs(d[1] / float(g["KE_Xb"]) - 1) < 1e-11
+    assert abs(d[2] / float(g["NuT_Xb"]) - 1) < 1e-11
+    assert abs(d[3] / float(g["NuS_Xb"]) - 1) < 1e-11
+
+
+def test_time_stepping_parity(case):
+    """relative L2 <= 1e-10 after the golden run's steps (100 for the BASELINE shapes), history of diagnostics too."""
+    g, pl = case
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    n_steps = int(g["n_steps"])
+    X = _dev(g["X0"]).reshape(1, -1)
+    hist = g["diag_hist"]
+    for it in range(n_steps):
+        Xn = pl.step(X, Ra, Ra_s)
+        if it + 1 in (1, 10):
+            assert rel_l2(Xn.cpu().numpy().ravel(), g["X_step%d" % (it + 1)]) < TOL_STEPS
+        if it % max(1, n_steps // 5) == 0:
+            d = pl.diagnostics(Xn).cpu().numpy()[0]
+            assert np.allclose(d[:4], hist[it], rtol=1e-9, atol=0), (it, d[:4], hist[it])
+        X = Xn  # the solve already returns the masked state when symmetric
+    assert rel_l2(X.cpu().numpy().ravel(), g["X_step%d" % n_steps]) < TOL_STEPS
+
+
+def test_multistep_call_equals_single_steps(case):
+    g, pl = case
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    X0 = _dev(g["X0"]).reshape(1, -1)
+    X = X0
+    for _ in range(5):
+        X = pl.step(X, Ra, Ra_s)
+    X5 = pl.step(X0, Ra, Ra_s, nsteps=5)
+    assert torch.equal(X, X5)
+
+
+def test_batch_members_independent_and_match_oracle():
+    """4 members with different Rayleigh numbers in one launch == 4 oracle runs; members do not interact."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    K, N_r, d, dt, Pr, Tau = 32, 14, 0.5, 5e-3, 1.0, 0.5
+    pl = EnsemblePlan(K, N_r, d, dt, Pr, Tau, symmetric=False, max_batch=19)
+    op = orc.Operators(K, N_r, d, dt, Pr, Tau)
+    B = 19                                   # ragged: not a multiple of the 16-member solve tile
+    rng = np.random.default_rng(5)
+    X = rng.random((B, 3 * pl.N)) * 1e-1
+    Ra = np.linspace(2000.0, 6000.0, B)
+    Ra_s = np.linspace(0.0, 500.0, B)
+    out = pl.step(_dev(X), _dev(Ra), _dev(Ra_s), nsteps=3).cpu().numpy()
+    for m in (0, 7, 15, 16, 18):
+        ref = X[m]
+        for _ in range(3):
+            ref = orc.step(ref, op, Ra[m], Ra_s[m])
+        assert rel_l2(out[m], ref) < 1e-10
+    # host-buffer entry point gives the same bits as the device entry point
+    out_h, diag = pl.step_host(X, Ra, Ra_s, nsteps=3, want_diag=True)
+    assert np.array_equal(out_h, out)
+    dg = orc.diagnostics(out[3], op)
+    assert np.allclose(diag[3, :4], dg, rtol=1e-10)
+    pl.close()
+
+
+def test_transforms_shim():
+    from spectraldoublediffusiveconvection_b200 import plan as P
+    g = load_golden("transforms")
+    for K in (16, 48):
+        M = 3 * K // 2
+        a, gr = _dev(g["in_hat_%d" % K]), _dev(g["in_grid_%d" % K])
+        assert rel_l2(P.transform(P.T_IDCT, a, M).cpu().numpy(), g["IDCT_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_IDST, a, M).cpu().numpy(), g["IDST_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_IDCT, a).cpu().numpy(), g["IDCT_same_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_IDST, a, 3 * K).cpu().numpy(), g["IDST_3x_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_DCT, gr).cpu().numpy(), g["DCT_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_DST, gr).cpu().numpy(), g["DST_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_DCT, gr, K).cpu().numpy(), g["DCT_trunc_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_DST, gr, K).cpu().numpy(), g["DST_trunc_%d" % K]) < 1e-13
+
+
+def test_error_behaviour():
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    with pytest.raises(ValueError):
+        EnsemblePlan(17, 10, 0.4, 1e-2, 1.0, 1.0)      # odd N_fm: reference raises ValueError too
+    pl = EnsemblePlan(16, 10, 0.4, 1e-2, 1.0, 1.0, max_batch=2)
+    with pytest.raises(ValueError):
+        pl.nlin_fx(torch.zeros((3, 3 * pl.N), dtype=torch.float64, device="cuda"))   # B > max_batch
+    pl.close()
