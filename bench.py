@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the time-stepping hot path: member-steps/s at N_r=30, N_theta=256 (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # CPU arm: the oracle port on all host cores
+
+One bench "step" = one IMEX-Euler member-step (Step_Python, Main.py:255-283) of every ensemble member of the
+batch.  Workload = the per-GPU shard of BASELINE.json configs[2]: 512 members per GPU of the Ra_T sweep at
+N_r=30, N_theta=256 (weak scaling: 512*N members on N GPUs), synthetic random initial conditions.
+Under torchrun (N>1) every rank owns its members; there is no data-path collective (members are independent);
+the per-step diagnostics all-gather is measured separately ("with_diagnostics").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# fp64 tensor-pipe (DMMA) peak measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak.txt);
+# MEASURED_PEAKS.json carries no fp64 figure.
+FP64_DMMA_PEAK_TFLOPS = 37.18
+HBM_FALLBACK_GBS = 6650.0
+
+PHYS = dict(d=0.31325, Tau=1.0, Pr=1.0, Ra_s=0.0, dt=1e-3)   # Main.Time_Step literals (Main.py:359-376,425)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members-per-gpu", type=int, default=512)
+    ap.add_argument("--N_r", type=int, default=30)
+    ap.add_argument("--N_fm", type=int, default=256)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+
+
+def make_ics(first, count, width):
+    """member m: default_rng(2000+m).random(3N) normalised to 1e-3."""
+    X = np.empty((count, width))
+    for i in range(count):
+        v = np.random.default_rng(2000 + first + i).random(width)
+        X[i] = 1e-3 * v / np.linalg.norm(v)
+    return X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def window_begin(self):
+        self.t0 = time.perf_counter()
+
+    def window_end(self):
+        self.t1 = time.perf_counter()
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside = [ln for (t, ln) in self.lines if self.t0 is None or (self.t0 <= t <= (self.t1 or t))]
+        if not inside:      # very short timed region: fall back to every sample taken under load
+            inside = [ln for (_, ln) in self.lines]
+        for ln in inside:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def _cpu_worker(args):
+    """One host process: advance one member `nsteps` steps with the oracle port; returns seconds."""
+    N_fm, N_r, seed, nsteps, warm = args
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import sddc_oracle as orc
+    orc.set_transform_backend("fft")
+    orc.set_accel(True)
+    op = orc.Operators(N_fm, N_r, PHYS["d"], PHYS["dt"], PHYS["Pr"], PHYS["Tau"])
+    X = make_ics(seed, 1, 3 * op.n * op.K)[0]
+    for _ in range(warm):
+        X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_single(N_fm, N_r, seconds):
+    """Oracle port, one member, one core, bounded to about `seconds` of CPU work."""
+    from oracle import sddc_oracle as orc
+    orc.set_transform_backend("fft")
+    orc.set_accel(True)
+    op = orc.Operators(N_fm, N_r, PHYS["d"], PHYS["dt"], PHYS["Pr"], PHYS["Tau"])
+    X = make_ics(0, 1, 3 * op.n * op.K)[0]
+    for _ in range(3):
+        X = orc.step(X, op, 3750.0, PHYS["Ra_s"])     # JIT + cache warm-up
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and n < 20000:
+        X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
+        n += 1
+    el = time.perf_counter() - t0
+    orc.set_accel(False)
+    orc.set_transform_backend("dense")
+    return {"value": n / el, "unit": "member-steps/s", "cores": 1, "kind": "port",
+            "sample": "1 member, %d IMEX steps at N_r=%d N_theta=%d (%.1f s) with oracle/sddc_oracle.py "
+                      "(scipy.fft transforms + numba-compiled back-substitution loops), 1 thread" % (n, N_r, N_fm, el)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, 1, 2) for i in range(cores)])          # spawn + JIT warm-up
+        # all workers run concurrently; each times its own K steps after its own W warm-up steps
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, a.steps, a.warmup) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    el = max(times)
+    value = cores * a.steps / el
+    sample = ("%d host processes (1 thread each) x 1 member x %d IMEX steps at N_r=%d N_theta=%d; oracle port "
+              "(scipy.fft + numba loops); the reference itself is pure Python and does not travel to the GPU box"
+              % (cores, a.steps, a.N_r, a.N_fm))
+    line = {"impl": "reference", "metric": "member-steps/sec at N_r=%d,N_theta=%d" % (a.N_r, a.N_fm),
+            "value": value, "unit": "member-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * el / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Ra_T sweep shard, N_r=%d N_theta=%d, one member per host core" % (a.N_r, a.N_fm),
+                       "members": cores, **PHYS},
+            "cpu_baseline": {"value": value, "unit": "member-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "member-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s_all_workers": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    Bl = a.members_per_gpu
+    Btot = Bl * world
+    plan = EnsemblePlan(a.N_fm, a.N_r, PHYS["d"], PHYS["dt"], PHYS["Pr"], PHYS["Tau"], symmetric=False,
+                        max_batch=Bl, device=local)
+    W = 3 * plan.N
+    Xh = make_ics(rank * Bl, Bl, W)
+    Ra_all = np.linspace(2000.0, 6000.0, Btot)
+    Ra = torch.as_tensor(Ra_all[rank * Bl:(rank + 1) * Bl]).to(dev)
+    Ras = torch.full((Bl,), PHYS["Ra_s"], dtype=torch.float64, device=dev)
+    A = torch.as_tensor(Xh).to(dev)
+    Bf = torch.empty_like(A)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(3, a.warmup)):
+        plan.step(A, Ra, Ras, out=Bf)
+        A, Bf = Bf, A
+    # ---- timed region: K member-steps of every member, state resident in HBM ----
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.window_begin()
+    l0 = plan.launch_count
+    e0.record()
+    for _ in range(a.steps):
+        plan.step(A, Ra, Ras, out=Bf)
+        A, Bf = Bf, A
+    e1.record()
+    barrier()
+    sampler.window_end()
+    clocks = sampler.stop()
+    launches = (plan.launch_count - l0) * world
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    value = Btot * a.steps / (ms * 1e-3)
+
+    # ---- per-kernel roofline: CUDA events around each kernel on the launching stream ----
+    plan.profile_begin()
+    nprof = 5
+    for _ in range(nprof):
+        plan.step(A, Ra, Ras, out=Bf)
+        A, Bf = Bf, A
+    prof = plan.profile_end()
+    stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
+    nr, K = plan.nr, plan.N_fm
+    M = 3 * K // 2
+    # algorithmic flops of the dominant kernel per member: 9 syntheses as mirror-split dense contractions
+    # (2 flops x 9n rows x K/2 modes x M/2 mirror pairs x 2 parities) + products + the Dr@ grid mat-vec
+    synth_flops = 2.0 * 9 * nr * (K // 2) * (M // 2) * 2 + 2.0 * nr * nr * M + 30.0 * nr * M
+    synth_tflops = Bl * synth_flops / (stage_ms["synth"] * 1e-3) / 1e12 if stage_ms["synth"] > 0 else 0.0
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "synth_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "synth_kernel (fused synthesis + products, DMMA m8n8k4)", "bound": "tensor",
+                "achieved": synth_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": synth_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": traffic,
+                "peak_source": "fp64 DMMA peak measured with tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.txt); "
+                               "MEASURED_PEAKS.json has no fp64 entry",
+                "launch_ms": stage_ms["synth"], "members_per_launch": Bl, "flops_per_member": synth_flops}
+    step_bytes = 48.0 * nr * K   # read X once, write X once
+    per_gpu_rate = value / world
+    hbm_view = {"bound": "hbm", "achieved": per_gpu_rate * step_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": per_gpu_rate * step_bytes / 1e9 / hbm_peak, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_member_step": step_bytes}
+
+    # ---- with per-step diagnostics (+ all-gather over NVLink when N > 1) ----
+    dg = torch.empty((Bl, 6), dtype=torch.float64, device=dev)
+    gathered = torch.empty((Btot, 6), dtype=torch.float64, device=dev) if world > 1 else None
+    nd = max(5, a.steps // 10)
+    barrier()
+    e0.record()
+    for _ in range(nd):
+        plan.step(A, Ra, Ras, out=Bf)
+        plan.diagnostics(Bf, out=dg)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, dg)
+        A, Bf = Bf, A
+    e1.record()
+    barrier()
+    ms_d = max_over_ranks(e0.elapsed_time(e1))
+    with_diag = Btot * nd / (ms_d * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers: H2D of the state, one step, D2H of state + diagnostics ----
+    bufs = [plan.pinned((Bl, W)), plan.pinned((Bl, W))]
+    dgh = plan.pinned((Bl, 6))
+    bufs[0][...] = A.cpu().numpy()
+    Ra_h, Ras_h = Ra.cpu().numpy(), Ras.cpu().numpy()
+    ne = max(3, a.e2e_steps)
+    cur = 0
+    for _ in range(2):
+        plan.step_host(bufs[cur], Ra_h, Ras_h, nsteps=1, want_diag=True, out=bufs[1 - cur], diag_out=dgh)
+        cur = 1 - cur
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        plan.step_host(bufs[cur], Ra_h, Ras_h, nsteps=1, want_diag=True, out=bufs[1 - cur], diag_out=dgh)
+        cur = 1 - cur
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e = {"value": Btot * ne / (e2e_ms * 1e-3), "unit": "member-steps/s",
+           "h2d_bytes_per_step": int(Bl * W * 8 + 2 * Bl * 8) * world, "d2h_bytes_per_step": int(Bl * W * 8 + Bl * 6 * 8) * world,
+           "steps": ne, "timer": "host wall clock around the blocking sddc_step_host calls, max over ranks",
+           "call": "sddc_step_host(X_host -> X_host, nsteps=1, diagnostics) per step, pinned host buffers"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline_single(a.N_fm, a.N_r, a.cpu_seconds)
+
+    if rank == 0:
+        line = {"metric": "member-steps/sec at N_r=%d,N_theta=%d" % (a.N_r, a.N_fm), "value": value,
+                "unit": "member-steps/s", "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[2] shard: Ra_T sweep (Ra=linspace(2000,6000)), %d members/GPU at "
+                                       "N_r=%d N_theta=%d, random ICs of norm 1e-3" % (Bl, a.N_r, a.N_fm),
+                           "members_total": Btot, "members_per_gpu": Bl, "N_r": a.N_r, "N_theta": a.N_fm,
+                           "parallelism": "ensemble members sharded over %d GPU(s), no data-path collective" % world,
+                           "l2": "state + scratch working set (~%.1f GB/GPU) exceeds the 126 MB L2" %
+                                 (Bl * (W * 5 + 9 * 2 * 32 * 256 + 3 * 2 * 32 * 192) * 8 / 1e9), **PHYS},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "roofline_hbm_step": hbm_view,
+                "stage_ms": stage_ms, "with_diagnostics": {"value": with_diag, "unit": "member-steps/s", "steps": nd,
+                                                           "collective": "all_gather [B,6] f64 per step" if world > 1 else None}}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -122,6 +122,16 @@ int sddc_diagnostics(sddc_plan* plan, const double* X, double* out, int B, void*
  * Synthesis kinds zero-pad / truncate to n_out like scipy's n= argument; analysis kinds truncate. */
 int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, int n_out, void* stream);
 
+/* Per-stage device timing with CUDA events recorded on the caller's stream around each kernel launch.
+ * sddc_profile_begin switches recording on; sddc_profile_end synchronises the device, switches it off and
+ * returns the summed milliseconds and launch counts per stage (arrays of SDDC_STAGE_COUNT). */
+enum sddc_stage {
+    SDDC_STAGE_SCAN = 0, SDDC_STAGE_PREP = 1, SDDC_STAGE_SYNTH = 2, SDDC_STAGE_ANALYSIS = 3, SDDC_STAGE_SOLVE = 4,
+    SDDC_STAGE_KE_PREP = 5, SDDC_STAGE_KE_SYNTH = 6, SDDC_STAGE_DIAG = 7, SDDC_STAGE_COUNT = 8
+};
+int sddc_profile_begin(sddc_plan* plan);
+int sddc_profile_end(sddc_plan* plan, double* ms, int* counts);
+
 /* Host-buffer variants (blocking; copies included): what a ctypes / NumPy caller binds. */
 int sddc_step_host(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
                    int nsteps, int linear, double* diag_out /* [B][6] or NULL */);

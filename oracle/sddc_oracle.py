@@ -27,6 +27,20 @@ from __future__ import annotations
 
 import numpy as np
 
+# Transform back-end.  "dense": closed-form cosine/sine sums (independent restatement, default).
+# "fft": scipy.fft dct/dst (pocketfft, the same engine behind the reference's scipy.fftpack calls) with the
+# scalings of Transforms.py:16-70 -- used when the oracle is *timed* as the CPU baseline so that the baseline
+# is not handicapped by O(K*M) transforms.  tests/test_oracle_golden.py checks both against the golden vectors.
+_BACKEND = "dense"
+
+
+def set_transform_backend(name: str) -> None:
+    global _BACKEND
+    if name not in ("dense", "fft"):
+        raise ValueError(name)
+    _BACKEND = name
+
+
 # --------------------------------------------------------------------------------------
 # Latitudinal grid and transforms (reference Transforms.py)
 # --------------------------------------------------------------------------------------
@@ -51,6 +65,11 @@ def IDCT(f_hat: np.ndarray, n: int | None = None) -> np.ndarray:
     (Transforms.py:16-26,116-129: scaled DCT-III, zero padded / truncated to n)."""
     K = f_hat.shape[-1]
     M = K if n is None else n
+    if _BACKEND == "fft":
+        from scipy.fft import dct
+        a = np.array(f_hat, dtype=np.float64, copy=True)
+        a[..., 1:] *= 0.5
+        return dct(a, type=3, n=M, axis=-1)
     Ku = min(K, M)
     C, _ = _trig_tables(Ku, M)
     return f_hat[..., :Ku] @ C
@@ -61,6 +80,11 @@ def IDST(g_hat: np.ndarray, n: int | None = None) -> np.ndarray:
     (Transforms.py:41-54,87-100: shift-left + DST-III; Nyquist dropped)."""
     K = g_hat.shape[-1]
     M = K if n is None else n
+    if _BACKEND == "fft":
+        from scipy.fft import dst
+        a = np.zeros_like(g_hat, dtype=np.float64)
+        a[..., :-1] = 0.5 * g_hat[..., 1:]
+        return dst(a, type=3, n=M, axis=-1)
     # after the shift the scaled array holds modes 1..K-1 in slots 0..K-2; truncation to n keeps slots < n
     Ku = min(K, M + 1)
     _, S = _trig_tables(Ku, M)
@@ -73,8 +97,12 @@ def DCT(f: np.ndarray, n: int | None = None) -> np.ndarray:
     """f_hat_k = (2/M) sum_j f_j cos(k theta_j), k=0 halved; optionally truncated to n
     (Transforms.py:28-39,102-114)."""
     M = f.shape[-1]
-    C, _ = _trig_tables(M, M)
-    out = (f @ C.T) * (2.0 / M)
+    if _BACKEND == "fft":
+        from scipy.fft import dct
+        out = dct(f, type=2, axis=-1) * (1.0 / M)
+    else:
+        C, _ = _trig_tables(M, M)
+        out = (f @ C.T) * (2.0 / M)
     out[..., 0] *= 0.5
     return out if n is None else out[..., :n]
 
@@ -83,9 +111,15 @@ def DST(g: np.ndarray, n: int | None = None) -> np.ndarray:
     """g_hat_k = (2/M) sum_j g_j sin(k theta_j) for 1<=k<=M-1, g_hat_0 = 0 (the sin(M theta)
     output of the DST-II is shifted out) (Transforms.py:56-70,73-85)."""
     M = g.shape[-1]
-    _, S = _trig_tables(M, M)
-    out = (g @ S.T) * (2.0 / M)
-    out[..., 0] = 0.0
+    if _BACKEND == "fft":
+        from scipy.fft import dst
+        raw = dst(g, type=2, axis=-1) * (1.0 / M)
+        out = np.zeros_like(raw)
+        out[..., 1:] = raw[..., :-1]
+    else:
+        _, S = _trig_tables(M, M)
+        out = (g @ S.T) * (2.0 / M)
+        out[..., 0] = 0.0
     return out if n is None else out[..., :n]
 
 
@@ -215,11 +249,13 @@ def sym_mask(K: int, n: int) -> np.ndarray:
 
 def _parity_suffix_sums(psi: np.ndarray) -> np.ndarray:
     """Ssum[m] = sum_{p=m+2,m+4,..<=K} psi^{(p)} for m = 0..K (psi^{(p)} = block p-1), accumulated
-    from the highest mode downward like the reference's running b / f_e vectors."""
+    from the highest mode downward like the reference's running b / f_e vectors (np.cumsum adds sequentially)."""
     K, n = psi.shape
     S = np.zeros((K + 1, n))
-    for m in range(K - 2, -1, -1):
-        S[m] = S[m + 2] + psi[m + 1]
+    ev = np.cumsum(psi[K - 1::-2], axis=0)      # blocks K-1, K-3, .., 1  -> Ssum[K-2], Ssum[K-4], .., Ssum[0]
+    S[K - 2::-2] = ev
+    od = np.cumsum(psi[K - 2:0:-2], axis=0)     # blocks K-2, K-4, .., 2  -> Ssum[K-3], .., Ssum[1]
+    S[K - 3:0:-2] = od
     return S
 
 
@@ -356,8 +392,77 @@ def NLIN_DFX(dv: np.ndarray, X: np.ndarray, op: Operators, symmetric: bool = Fal
 # --------------------------------------------------------------------------------------
 
 
+_ACCEL = False
+_jit_cache = {}
+
+
+def set_accel(on: bool) -> None:
+    """Compile the two sequential back-substitution loops with numba (no fastmath) -- used only when the oracle
+    is timed as the CPU baseline, to put the port on the same footing as the reference's numba-JIT loops
+    (Matrix_Operators.py:1033,1115).  Same arithmetic, same order."""
+    global _ACCEL
+    _ACCEL = bool(on)
+
+
+def _jit(fn):
+    if fn.__name__ not in _jit_cache:
+        from numba import njit
+        _jit_cache[fn.__name__] = njit(cache=False, fastmath=False)(fn)
+    return _jit_cache[fn.__name__]
+
+
+def _nab2_core(g, Linv, dt, symmetric):
+    K, n = g.shape
+    f = np.zeros_like(g)
+    for c in range(2):
+        if c == 0 and symmetric:
+            continue
+        j0 = K - 1 if c == 0 else K - 2
+        b = np.zeros(n)
+        j = j0
+        while j >= 0:
+            if j < K - 2:
+                b = b + (2.0 * dt * (j + 2.0)) * f[j + 2]
+            if j == 0:
+                rhs = g[j] - 0.5 * b
+            else:
+                rhs = g[j] - b
+            f[j] = Linv[K - 1 - j] @ rhs
+            j -= 2
+    return f
+
+
+def _a4_core(g, Linv, D2, ir2, ir4, dt, symmetric):
+    K, n = g.shape
+    f = np.zeros_like(g)
+    for c in range(2):
+        if c == 1 and symmetric:
+            continue
+        j0 = K - c
+        f_e = np.zeros(n)
+        bf_e = np.zeros(n)
+        j = j0
+        while j >= 1:
+            row = j - 1
+            bj = -1.0 * j * (j + 1)
+            bjt = -2.0 * j
+            if j == j0:
+                f[row] = Linv[K - j] @ g[row]
+                bf_e = bf_e + bj * f[row]
+            else:
+                f_e = f_e + f[row + 2]
+                L1f = D2 @ f_e + bj * (ir4 * f_e)
+                rhs = g[row] + dt * bjt * (L1f + ir4 * bf_e) - bjt * (ir2 * f_e)
+                f[row] = Linv[K - j] @ rhs
+                bf_e = bf_e + bj * f[row] + bjt * f_e
+            j -= 2
+    return f
+
+
 def NAB2_BSub(g: np.ndarray, Linv: np.ndarray, dt: float, symmetric: bool = False) -> np.ndarray:
     """Solve for T or S. g, result: (K, n). dt is dt or Tau*dt."""
+    if _ACCEL:
+        return _jit(_nab2_core)(np.ascontiguousarray(g), Linv, float(dt), bool(symmetric))
     K, n = g.shape
     f = np.zeros_like(g)
     starts = [K - 2] if symmetric else [K - 1, K - 2]
@@ -373,6 +478,9 @@ def NAB2_BSub(g: np.ndarray, Linv: np.ndarray, dt: float, symmetric: bool = Fals
 
 def A4_BSub(g: np.ndarray, Linv: np.ndarray, op: Operators, dt: float, symmetric: bool = False) -> np.ndarray:
     """Solve for psi. g, result: (K, n) with row = sine mode - 1. dt is Pr*dt."""
+    if _ACCEL:
+        return _jit(_a4_core)(np.ascontiguousarray(g), Linv, op.D2, np.ascontiguousarray(np.diag(op.IR2)),
+                              np.ascontiguousarray(np.diag(op.IR4)), float(dt), bool(symmetric))
     K, n = g.shape
     f = np.zeros_like(g)
     ir2 = np.diag(op.IR2)

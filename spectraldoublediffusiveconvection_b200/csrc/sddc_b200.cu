@@ -60,7 +60,26 @@ struct sddc_plan {
     int ana_nt = 0, ana_stage = 0;
     size_t ana_smem = 0;
     size_t solve_smem = 0;
+    // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
+    bool profiling = false;
+    struct Ev { int stage; cudaEvent_t a, b; };
+    std::vector<Ev> events;
 };
+
+namespace {
+struct StageTimer {
+    sddc_plan* pl; cudaStream_t st; int idx = -1;
+    StageTimer(sddc_plan* p, int stage, cudaStream_t s) : pl(p), st(s) {
+        if (!pl->profiling) return;
+        sddc_plan::Ev e{stage, nullptr, nullptr};
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        pl->events.push_back(e);
+        idx = (int)pl->events.size() - 1;
+    }
+    ~StageTimer() { if (idx >= 0) cudaEventRecord(pl->events[idx].b, st); }
+};
+}  // namespace
 
 namespace {
 
@@ -153,6 +172,7 @@ int check_batch(sddc_plan* pl, int B) {
 
 int run_scan(sddc_plan* pl, const double* X, long long stride, int B, cudaStream_t st) {
     const long long tot = (long long)B * 2 * pl->g.n;
+    StageTimer tm(pl, SDDC_STAGE_SCAN, st);
     scan_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(X, stride, pl->JJ, pl->g, B);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -173,6 +193,7 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     pp.ir2 = pl->ir2; pp.ir4 = pl->ir4; pp.r2 = pl->r2; pp.dT0 = pl->dT0; pp.gb = pl->gb;
     pp.g = pl->g; pp.B = B;
     dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
+    StageTimer tm(pl, SDDC_STAGE_PREP, st);
     prep_kernel<<<grid, 256, prep_smem_bytes(pl->g.n, pl->g.n8), st>>>(pp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -188,6 +209,7 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     sp.g = pl->g;
     const int nt = dfx ? pl->synth_nt_dfx : pl->synth_nt_fx;
     const int tiles = pl->g.Mhp / (8 * nt);
+    StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
     if (dfx) return launch_synth<EPI_DFX>(pl, nt, sp, pl->synth_stage_dfx, pl->synth_smem_dfx, tiles, B, st);
     return launch_synth<EPI_FX>(pl, nt, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
 }
@@ -196,6 +218,7 @@ int run_analysis(sddc_plan* pl, const double* lin, double* out, int B, cudaStrea
     AnaParams ap{};
     ap.prd = pl->prd; ap.tab2 = pl->tab2; ap.lin = lin; ap.out = out; ap.g = pl->g; ap.mdt = -pl->g.dt;
     dim3 grid(pl->g.Khp2 / (64 * pl->ana_nt), 2, B);
+    StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
     if (pl->ana_nt == 2) analysis_kernel<2, 15><<<grid, 256, pl->ana_smem, st>>>(ap, pl->ana_stage);
     else analysis_kernel<1, 24><<<grid, 256, pl->ana_smem, st>>>(ap, pl->ana_stage);
     pl->launches++;
@@ -213,6 +236,7 @@ int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double
     sp.dt_psi = pl->g.Pr * pl->g.dt; sp.dt_T = pl->g.dt; sp.dt_S = pl->g.Tau * pl->g.dt;
     // single-field calls pass field offsets of 0; the operator stack follows field_base
     dim3 grid((B + 15) / 16, 2, nfields);
+    StageTimer tm(pl, SDDC_STAGE_SOLVE, st);
     solve_kernel<2><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -540,13 +564,20 @@ int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* s
     kp.X = X; kp.x_stride = 3LL * g.N; kp.JJ = pl->JJ; kp.coef = pl->coef; kp.coef_stride = pl->coef_member_stride;
     kp.DrT = pl->DrT; kp.ir = pl->ir; kp.g = g;
     dim3 grid((g.K + 31) / 32, B);
-    ke_prep_kernel<<<grid, 256, sizeof(double) * ((size_t)32 * g.n + (size_t)g.n * g.n8), st>>>(kp);
+    {
+        StageTimer tm(pl, SDDC_STAGE_KE_PREP, st);
+        ke_prep_kernel<<<grid, 256, sizeof(double) * ((size_t)32 * g.n + (size_t)g.n * g.n8), st>>>(kp);
+    }
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     SynthParams sp{};
     sp.coef = pl->coef; sp.coef_stride = pl->coef_member_stride; sp.tab = pl->tab3; sp.tab_Mhp = pl->Mh3p;
     sp.wr = pl->wr; sp.wth = pl->wth; sp.kepart = pl->kepart; sp.rows = 2 * g.n8; sp.type_mask = 0x2u; sp.g = g;
-    if ((rc = launch_synth<EPI_KE>(pl, 4, sp, pl->synth_stage_ke, pl->synth_smem_ke, pl->Mh3p / 32, B, st))) return rc;
+    {
+        StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
+        if ((rc = launch_synth<EPI_KE>(pl, 4, sp, pl->synth_stage_ke, pl->synth_smem_ke, pl->Mh3p / 32, B, st))) return rc;
+    }
+    StageTimer tm2(pl, SDDC_STAGE_DIAG, st);
     diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, pl->nke, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -559,6 +590,27 @@ int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, 
     const long long tot = (long long)rows * n_out;
     transform_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, in, out, rows, n_in, n_out);
     return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
+int sddc_profile_begin(sddc_plan* pl) {
+    if (!pl) return SDDC_ERR_INVALID;
+    pl->profiling = true;
+    return SDDC_OK;
+}
+
+int sddc_profile_end(sddc_plan* pl, double* ms, int* counts) {
+    if (!pl || !ms || !counts) return SDDC_ERR_INVALID;
+    pl->profiling = false;
+    for (int i = 0; i < SDDC_STAGE_COUNT; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    PLAN_CUDA(pl, cudaSetDevice(pl->device));
+    PLAN_CUDA(pl, cudaDeviceSynchronize());
+    for (auto& e : pl->events) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) { ms[e.stage] += t; counts[e.stage]++; }
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    pl->events.clear();
+    return SDDC_OK;
 }
 
 int sddc_step_host(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B,

@@ -14,6 +14,8 @@ import torch
 from . import _lib
 from .operators import RadialOperators
 
+_PINNED_KEEPALIVE = {}
+
 OP_J_THETA, OP_DT0_THETA, OP_A2_SINE, OP_A2_SINE_R2, OP_KGR, OP_R2 = range(6)
 T_IDCT, T_IDST, T_DCT, T_DST = range(4)
 
@@ -103,6 +105,18 @@ class EnsemblePlan:
     def launch_count(self):
         return int(self.lib.sddc_launch_count(self._h))
 
+    STAGES = ("scan", "prep", "synth", "analysis", "solve", "ke_prep", "ke_synth", "diag")
+
+    def profile_begin(self):
+        self._check(self.lib.sddc_profile_begin(self._h))
+
+    def profile_end(self):
+        """{stage: (total_ms, launches)} measured with CUDA events around each kernel since profile_begin()."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int * 8)()
+        self._check(self.lib.sddc_profile_end(self._h, ms, cnt))
+        return {s: (ms[i], cnt[i]) for i, s in enumerate(self.STAGES)}
+
     def new_state(self, B):
         return torch.empty((B, 3 * self.N), dtype=torch.float64, device=self.device)
 
@@ -178,13 +192,24 @@ class EnsemblePlan:
         return out
 
     # ------------------------------------------------------------------ host-buffer entry points (NumPy in / out)
-    def step_host(self, X, Ra, Ra_s, nsteps=1, linear=False, want_diag=False):
+    @staticmethod
+    def pinned(shape):
+        """Page-locked float64 host array (NumPy view of a pinned torch tensor) for the *_host entry points."""
+        t = torch.empty(tuple(shape), dtype=torch.float64).pin_memory()
+        a = t.numpy()
+        _PINNED_KEEPALIVE[id(a)] = t
+        return a
+
+    def step_host(self, X, Ra, Ra_s, nsteps=1, linear=False, want_diag=False, out=None, diag_out=None):
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
         B = X.shape[0]
         Ra = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra, dtype=np.float64), (B,)))
         Ra_s = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra_s, dtype=np.float64), (B,)))
-        out = np.empty_like(X)
-        diag = np.empty((B, 6)) if want_diag else None
+        if out is None:
+            out = np.empty_like(X)
+        elif out.shape != X.shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %s" % (X.shape,))
+        diag = (np.empty((B, 6)) if diag_out is None else diag_out) if want_diag else None
         self._check(self.lib.sddc_step_host(self._h, X.ctypes.data, out.ctypes.data, Ra.ctypes.data, Ra_s.ctypes.data,
                                             B, int(nsteps), int(bool(linear)), diag.ctypes.data if want_diag else None))
         return (out, diag) if want_diag else out

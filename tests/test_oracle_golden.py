@@ -22,7 +22,22 @@ def case(request):
     return g, _ops(g)
 
 
-def test_transforms_match_reference():
+@pytest.fixture(params=["dense", "fft"])
+def backend(request):
+    orc.set_transform_backend(request.param)
+    yield request.param
+    orc.set_transform_backend("dense")
+
+
+def test_fft_backend_step_matches_golden(backend):
+    g = load_golden("cfg1_nosym")
+    op = _ops(g)
+    assert rel_l2(orc.NLIN_FX(g["Xb"], op, False), g["NLIN_FX"]) < TOL_CALL
+    assert rel_l2(orc.step(g["Xb"], op, float(g["Ra"]), float(g["Ra_s"]), False), g["step_Xb"]) < 1e-10
+    assert abs(orc.kinetic_energy(g["Xb"], op, False) / float(g["KE_Xb"]) - 1) < 1e-12
+
+
+def test_transforms_match_reference(backend):
     g = load_golden("transforms")
     for K in (16, 48):
         M = 3 * K // 2
@@ -155,3 +170,21 @@ def test_time_stepping_parity(case):
     assert rel_l2(Xn, g["X_step%d" % n_steps]) < TOL_STEPS
     for it, dg in hist:
         assert np.allclose(dg, g["diag_hist"][it], rtol=1e-9, atol=0)
+
+
+def test_accelerated_solves_equal_plain_loops():
+    """The numba-compiled loops used for baseline timing do the same arithmetic as the plain NumPy loops."""
+    pytest.importorskip("numba")
+    g = load_golden("small_nosym")
+    op = _ops(g)
+    Xb = g["Xb"].reshape(3, op.K, op.n)
+    for sym in (False, True):
+        a = orc.A4_BSub(Xb[0], op.Linv_A4, op, op.Pr * op.dt, sym)
+        b = orc.NAB2_BSub(Xb[1], op.Linv_T, op.dt, sym)
+        orc.set_accel(True)
+        try:
+            a2 = orc.A4_BSub(Xb[0], op.Linv_A4, op, op.Pr * op.dt, sym)
+            b2 = orc.NAB2_BSub(Xb[1], op.Linv_T, op.dt, sym)
+        finally:
+            orc.set_accel(False)
+        assert rel_l2(a2, a) < 1e-13 and rel_l2(b2, b) < 1e-14
