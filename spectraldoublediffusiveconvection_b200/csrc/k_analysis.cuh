@@ -4,14 +4,17 @@
 //
 // Reference semantics: NLIN_FX step 4-5 (Matrix_Operators.py:797-804), Step_Python (Main.py:262,271,276,280).
 //     F_hat[(f,i), k=2k'+p] = sum_{j'} PRD[f][p][i][j'] * TAB2[type(f)][p][k'][j']
+// Both operands are tile-major in global memory (one contiguous block per pipeline stage, fetched by one TMA
+// bulk copy each):   PRD  : [b][par][chunk][ks][row = f*n8+i][4]      (written by the synthesis epilogue)
+//                    TAB2 : [par][column tile][chunk][ks][type][col][4]  with the 2/M (1/M) scaling folded in
 #pragma once
 #include "common.cuh"
 
 namespace sddc {
 
 struct AnaParams {
-    const double* prd;   // [B][3][2][n8][Mhp]
-    const double* tab2;  // [2 types][2 par][Khp2][Mhp], scale factors folded in
+    const double* prd;
+    const double* tab2;
     const double* lin;   // [B][3N] linear right-hand side (mode RHS) or null (mode F only)
     double* out;         // [B][3N]
     Geo g;
@@ -19,29 +22,36 @@ struct AnaParams {
 };
 
 constexpr int ANA_KC = 8;
+constexpr int ANA_KS = ANA_KC / 4;
+constexpr int ANA_MAX_STAGES = 4;
 
-template <int NT3>
-__host__ __device__ inline size_t ana_stage_doubles(int rows3) {
-    return (size_t)(ANA_KC / 4) * rows3 * 4 + (size_t)(ANA_KC / 4) * 2 * (NT3 * 64) * 4;
+__host__ __device__ constexpr int ana_nt_for(int nt8) { return nt8 <= 5 ? 4 : 2; }  // column tiles per warp
+
+__host__ __device__ inline size_t ana_stage_doubles(int nt8) {
+    return (size_t)ANA_KS * (3 * nt8 * 8) * 4 + (size_t)ANA_KS * 2 * (ana_nt_for(nt8) * 32) * 4;
 }
 
-// grid = (Khp2 / (64*NT3), 2 parities, B), block = 256; warp w owns column tiles [w*NT3, (w+1)*NT3) and all
-// 3*nt8 row tiles (psi rows use the sine table, T and S rows the cosine table).
-template <int NT3, int MT3>
-__global__ void __launch_bounds__(256) analysis_kernel(AnaParams p, int nstage) {
-    constexpr int KT3 = NT3 * 64, KS = ANA_KC / 4;
-    extern __shared__ __align__(16) double smem[];
+// grid = (Khp2 / KT3, 2 parities, B), block = 13 warps: consumer warp = (field f, column group cg) owns the NT8 row
+// tiles of its field (psi rows use the sine table, T and S rows the cosine table) and NT3 column tiles; the last
+// warp is the TMA producer.
+template <int NT8>
+__global__ void __launch_bounds__(416, 1) analysis_kernel(AnaParams p, int nstage) {
+    constexpr int NT3 = ana_nt_for(NT8), KT3 = NT3 * 32, KS = ANA_KS, NCW = 12, NTHR = 416;
+    constexpr int ROWS3 = 3 * NT8 * 8;
+    constexpr int A_ST = KS * ROWS3 * 4, B_ST = KS * 2 * KT3 * 4, STAGE = A_ST + B_ST;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t bar_full[ANA_MAX_STAGES], bar_empty[ANA_MAX_STAGES];
     const Geo& g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int wf = warp >> 2, cg = warp & 3;
     const int kt = blockIdx.x, par = blockIdx.y, b = blockIdx.z;
-    const int n = g.n, n8 = g.n8, K = g.K, N = g.N, Mhp = g.Mhp;
-    const int rows3 = 3 * n8, TM3 = rows3 >> 3;
+    const int n = g.n, K = g.K, N = g.N, Mhp = g.Mhp;
     double* outb = p.out + (long long)b * 3 * N;
     const double* linb = p.lin ? p.lin + (long long)b * 3 * N : nullptr;
 
     if (g.symmetric && par == 1) {
         // every odd-k output block is masked (Vecs_to_X symmetric branch, Matrix_Operators.py:536-556)
-        for (int idx = tid; idx < KT3 * n; idx += 256) {
+        for (int idx = tid; idx < KT3 * n; idx += NTHR) {
             const int kp = kt * KT3 + idx / n, i = idx % n;
             if (kp >= g.Kh) continue;
             const int k = 2 * kp + 1;
@@ -52,105 +62,90 @@ __global__ void __launch_bounds__(256) analysis_kernel(AnaParams p, int nstage) 
         return;
     }
 
-    const double* A = p.prd + (long long)b * 3 * 2 * n8 * Mhp;
-    const long long fps = (long long)n8 * Mhp;  // parity stride; field stride = 2*fps
-    const long long t2s = (long long)g.Khp2 * Mhp;
-    const int A_ST = KS * rows3 * 4;
-    const int STAGE = A_ST + KS * 2 * KT3 * 4;
     const int nchunk = Mhp / ANA_KC;
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NCW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
 
-    double acc[MT3][NT3][2];
+    double acc[NT8][NT3][2];
 #pragma unroll
-    for (int mt = 0; mt < MT3; ++mt)
+    for (int mt = 0; mt < NT8; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    auto load_stage = [&](int st, int chunk) {
-        double* sA = smem + (size_t)st * STAGE;
-        double* sB = sA + A_ST;
-        const int j0 = chunk * ANA_KC;
-        for (int idx = tid; idx < rows3 * 4; idx += 256) {
-            const int piece = idx & 3, row = idx >> 2;
-            const int f = row / n8, i = row - f * n8;
-            const double* src = A + (long long)(f * 2 + par) * fps + (long long)i * Mhp + j0 + piece * 2;
-            cp_async16(sA + ((piece >> 1) * rows3 + row) * 4 + (piece & 1) * 2, src);
-        }
-        for (int idx = tid; idx < 2 * KT3 * 4; idx += 256) {
-            const int piece = idx & 3, r = idx >> 2;
-            const int col = r % KT3, ty = r / KT3;
-            const double* src = p.tab2 + (long long)(ty * 2 + par) * t2s + (long long)(kt * KT3 + col) * Mhp + j0 + piece * 2;
-            cp_async16(sB + (((piece >> 1) * 2 + ty) * KT3 + col) * 4 + (piece & 1) * 2, src);
-        }
-    };
-
-    for (int s = 0; s < nstage - 1; ++s) {
-        if (s < nchunk) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int c = 0; c < nchunk; ++c) {
-        cp_async_wait_dyn(nstage - 2);
-        __syncthreads();
-        {
-            const int cn = c + nstage - 1;
-            if (cn < nchunk) load_stage(cn % nstage, cn);
-            cp_async_commit();
-        }
-        const double* sA = smem + (size_t)(c % nstage) * STAGE;
-        const double* sB = sA + A_ST;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            double bf[2][NT3];
-#pragma unroll
-            for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-                for (int nt = 0; nt < NT3; ++nt)
-                    bf[ty][nt] = sB[((ks * 2 + ty) * KT3 + (warp * NT3 + nt) * 8 + gq) * 4 + tq];
-            const double* sAk = sA + (ks * rows3 + gq) * 4 + tq;
-#pragma unroll
-            for (int mt = 0; mt < MT3; ++mt) {
-                if (mt < TM3) {
-                    const double a = sAk[mt * 32];
-                    const bool sn = mt < g.nt8;  // psi rows: sine table
-#pragma unroll
-                    for (int nt = 0; nt < NT3; ++nt)
-                        mma884(acc[mt][nt][0], acc[mt][nt][1], a, sn ? bf[1][nt] : bf[0][nt]);
-                }
+    if (warp == NCW) {
+        if (lane == 0) {
+            const double* gA = p.prd + ((long long)b * 2 + par) * Mhp * ROWS3;
+            const double* gB = p.tab2 + ((long long)par * gridDim.x + kt) * nchunk * B_ST;
+            int st = 0, ph = 0;
+            for (int c = 0; c < nchunk; ++c) {
+                if (c >= nstage) mbar_wait(&bar_empty[st], ph ^ 1);
+                double* sA = smem + (size_t)st * STAGE;
+                mbar_expect_tx(&bar_full[st], (unsigned)(STAGE * sizeof(double)));
+                bulk_g2s(sA, gA + (long long)c * A_ST, A_ST * sizeof(double), &bar_full[st]);
+                bulk_g2s(sA + A_ST, gB + (long long)c * B_ST, B_ST * sizeof(double), &bar_full[st]);
+                if (++st == nstage) { st = 0; ph ^= 1; }
             }
         }
+        __syncwarp();
+    } else {
+        const int ty = (wf == 0) ? 1 : 0;
+        const int a_off = (wf * NT8 * 8 + gq) * 4 + tq;                       // + ks*ROWS3*4 + mt*32
+        const int b_off = A_ST + (ty * KT3 + cg * NT3 * 8 + gq) * 4 + tq;     // + ks*2*KT3*4 + nt*32
+        int st = 0, ph = 0;
+        for (int c = 0; c < nchunk; ++c) {
+            mbar_wait(&bar_full[st], ph);
+            const double* sS = smem + (size_t)st * STAGE;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double bf[NT3], af[NT8];
+#pragma unroll
+                for (int nt = 0; nt < NT3; ++nt) bf[nt] = sS[b_off + ks * 2 * KT3 * 4 + nt * 32];
+#pragma unroll
+                for (int mt = 0; mt < NT8; ++mt) af[mt] = sS[a_off + ks * ROWS3 * 4 + mt * 32];
+#pragma unroll
+                for (int mt = 0; mt < NT8; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT3; ++nt) mma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[st]);
+            if (++st == nstage) { st = 0; ph ^= 1; }
+        }
     }
-    cp_async_wait<0>();
+    if (warp >= NCW) return;
 
     // ---- epilogue: C fragment (row = (f,i), col = k') -> state layout [f][block][i] ----
+    const int f = wf;
 #pragma unroll
-    for (int mt = 0; mt < MT3; ++mt) {
-        if (mt < TM3) {
-            const int row = mt * 8 + gq;
-            const int f = row / n8, i = row - f * n8;
-            if (i < n) {
+    for (int mt = 0; mt < NT8; ++mt) {
+        const int i = mt * 8 + gq;
+        if (i < n) {
 #pragma unroll
-                for (int nt = 0; nt < NT3; ++nt) {
+            for (int nt = 0; nt < NT3; ++nt) {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int kp = kt * KT3 + (warp * NT3 + nt) * 8 + 2 * tq + e;
-                        if (kp >= g.Kh) continue;
-                        const int k = 2 * kp + par;
-                        const double v = acc[mt][nt][e];
-                        if (f == 0) {
-                            // sinusoid index k -> code block k-1; k = 0 is dropped and block K-1 gets no
-                            // nonlinear contribution (Matrix_Operators.py:802)
-                            const int blk = (k >= 1) ? k - 1 : K - 1;
-                            const double fv = (k >= 1) ? v : 0.0;
-                            const long long o = (long long)blk * n + i;
-                            const bool keep = !(g.symmetric && (blk & 1) == 0);
-                            double r = keep ? fv : 0.0;
-                            if (linb) r = keep ? fma(p.mdt, fv, linb[o]) : 0.0;
-                            outb[o] = r;
-                        } else {
-                            const long long o = (long long)f * N + (long long)k * n + i;
-                            double r = v;
-                            if (linb) r = fma(p.mdt, v, linb[o]);
-                            outb[o] = r;  // odd k never reaches here when symmetric
-                        }
+                for (int e = 0; e < 2; ++e) {
+                    const int kp = kt * KT3 + (cg * NT3 + nt) * 8 + 2 * tq + e;
+                    if (kp >= g.Kh) continue;
+                    const int k = 2 * kp + par;
+                    const double v = acc[mt][nt][e];
+                    if (f == 0) {
+                        // sinusoid index k -> code block k-1; k = 0 is dropped and block K-1 gets no
+                        // nonlinear contribution (Matrix_Operators.py:802)
+                        const int blk = (k >= 1) ? k - 1 : K - 1;
+                        const double fv = (k >= 1) ? v : 0.0;
+                        const long long o = (long long)blk * n + i;
+                        const bool keep = !(g.symmetric && (blk & 1) == 0);
+                        double r = keep ? fv : 0.0;
+                        if (linb) r = keep ? fma(p.mdt, fv, linb[o]) : 0.0;
+                        outb[o] = r;
+                    } else {
+                        const long long o = (long long)f * N + (long long)k * n + i;
+                        double r = v;
+                        if (linb) r = fma(p.mdt, v, linb[o]);
+                        outb[o] = r;  // odd k never reaches here when symmetric
                     }
                 }
             }

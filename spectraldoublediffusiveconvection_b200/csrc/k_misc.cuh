@@ -10,18 +10,30 @@ __device__ __forceinline__ void trig_kj(long long k, long long j, long long M, d
     sincospi((double)q / (double)(2 * M), &s, &c);
 }
 
-// mode 0: synthesis table  tab[type][par][j' (Jp)][k' (Kp)]            = trig((2k'+par) theta_j')
-// mode 1: analysis table   tab[type][par][k' (Kp)][j' (Jp)]  = scale_k * trig((2k'+par) theta_j')
-// entries with k' >= Kh or j' >= Mh are zero.  scale: 2/M (1/M for the cosine k = 0 row); sine k = 0 row is 0.
-__global__ void fill_table_kernel(double* tab, int mode, int M, int Kh, int Mh, int Kp, int Jp) {
-    const long long total = 4LL * Kp * Jp;
+// Tile-major trigonometric tables (one contiguous block per GEMM pipeline stage):
+// mode 0 (synthesis):  tab[jt][chunk][ks][type][par][col (W)][kk]   k' = 8 chunk + 4 ks + kk,  j' = jt W + col
+//                      value = trig((2k'+par) theta_j')
+// mode 1 (analysis):   tab[par][kt][chunk][ks][type][col (W)][kk]   j' = 8 chunk + 4 ks + kk,  k' = kt W + col
+//                      value = scale_k * trig((2k'+par) theta_j'),  scale 2/M (1/M for the cosine k = 0 row)
+// entries with k' >= Kh or j' >= Mh are zero; the sine k = 0 row is zero.  nA = number of tiles of the tiled
+// index (jt or kt), nchunk = chunks of the contraction index.
+__global__ void fill_table_kernel(double* tab, int mode, int M, int Kh, int Mh, int W, int nA, int nchunk) {
+    const long long total = 16LL * nA * nchunk * W * 4;  // 2 ks * 2 types * 2 par * ...
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const long long tp = idx / ((long long)Kp * Jp), rem = idx - tp * (long long)Kp * Jp;
-        const int type = (int)(tp >> 1), par = (int)(tp & 1);
-        int kp, jp;
-        if (mode == 0) { jp = (int)(rem / Kp); kp = (int)(rem - (long long)jp * Kp); }
-        else { kp = (int)(rem / Jp); jp = (int)(rem - (long long)kp * Jp); }
+        long long r = idx;
+        const int kk = (int)(r & 3); r >>= 2;
+        const int col = (int)(r % W); r /= W;
+        int type, par, ks, chunk, tile;
+        if (mode == 0) {
+            par = (int)(r & 1); r >>= 1; type = (int)(r & 1); r >>= 1; ks = (int)(r & 1); r >>= 1;
+            chunk = (int)(r % nchunk); tile = (int)(r / nchunk);
+        } else {
+            type = (int)(r & 1); r >>= 1; ks = (int)(r & 1); r >>= 1;
+            chunk = (int)(r % nchunk); r /= nchunk; tile = (int)(r % nA); par = (int)(r / nA);
+        }
+        const int inner = 8 * chunk + 4 * ks + kk, outer = tile * W + col;
+        const int kp = (mode == 0) ? inner : outer, jp = (mode == 0) ? outer : inner;
         double v = 0.0;
         if (kp < Kh && jp < Mh) {
             const int k = 2 * kp + par;
@@ -50,7 +62,7 @@ __global__ void fill_ke_weights_kernel(double* w, int M3, int Jp) {
 }
 
 // Coefficient rows for the kinetic-energy synthesis: field 0 = J_theta(psi)/r (cosine), field 1 = Dr psi in
-// sinusoid indexing (sine).  Layout [B][2][n8][2][Khp].  (Main.py:104-115)
+// sinusoid indexing (sine).  Tile-major layout [B][Khp/8][2 ks][2 par][2*n8][4].  (Main.py:104-115)
 struct KEPrepParams {
     const double* X; long long x_stride;
     const double* JJ;
@@ -86,9 +98,9 @@ __global__ void __launch_bounds__(256) ke_prep_kernel(KEPrepParams p) {
     for (int i = warp; i < n; i += 8) {
         double d = 0.0;
         for (int ip = 0; ip < n; ++ip) d = fma(mDr[ip * n8 + i], sP[lane * n + ip], d);
-        const long long o = ((long long)i * 2 + par) * g.Khp + kp;
+        const long long o = (((long long)((kp >> 2) * 2 + par) * (2 * n8)) + i) * 4 + (kp & 3);
         cf[o] = p.ir[i] * Jb[(long long)c * n + i];
-        cf[(long long)n8 * 2 * g.Khp + o] = (c >= 1) ? d : 0.0;
+        cf[o + (long long)n8 * 4] = (c >= 1) ? d : 0.0;
     }
 }
 

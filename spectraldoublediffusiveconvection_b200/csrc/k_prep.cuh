@@ -38,7 +38,7 @@ struct PrepParams {
     const double* X;        // [B][3N] state (or perturbation)
     long long x_stride;
     const double* JJ;       // [B][K+1][n] from scan_kernel on the same X
-    double* coef;           // [B][9][n8][2][Khp] coefficient set (already offset to the set), or null
+    double* coef;           // coefficient set, tile-major [B][Khp/8][2 ks][2 par][9*n8][4] (see k_synth.cuh), or null
     long long coef_stride;  // member stride of coef in doubles
     double* lin;            // [B][3N] linear right-hand side, or null
     const double* Ra;       // [B]
@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
         const int c = c0 + lane;
         const int par = c & 1, kp = c >> 1;
         double* cf = p.coef + (long long)b * p.coef_stride;
-        const long long fs = (long long)n8 * 2 * g.Khp;  // field stride
+        const int R9 = 9 * n8;
+        // element (field a, row i, parity, k') -> tile-major offset; fs = field stride inside one [row][4] plane
+        const long long fs = (long long)n8 * 4;
+        const long long cbase = ((long long)((kp >> 2) * 2 + par) * R9) * 4 + (kp & 3);
         for (int it = warp; it < 3 * nq; it += 8) {
             const int grp = it / nq, i0 = (it - grp * nq) * 4;
             const double* sx = (grp == 0) ? sP : (grp == 1 ? sT : sS);
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
                 for (int r = 0; r < 4; ++r) {
                     const int i = i0 + r;
                     if (i >= n) break;
-                    const long long o = ((long long)i * 2 + par) * g.Khp + kp;
+                    const long long o = cbase + (long long)i * 4;
                     if (grp == 0) {
                         const double jj = sJ[lane * n + i];
                         double om = 0.0, dps = 0.0;

@@ -9,6 +9,13 @@
 //     EO_p[row, j'] = sum_{k'} COEF[row][p][k'] * TAB[type(row)][p][j'][k'],   j' < M/2
 // and with theta_{M-1-j'} = pi - theta_{j'}:
 //     cosine-type rows: f(j') = E+O, f(M-1-j') = E-O ;  sine-type rows: f(j') = O+E, f(M-1-j') = O-E.
+//
+// Operand staging: both operands live in global memory in *tile-major* order, so that everything one pipeline
+// stage needs is one contiguous block per operand and is fetched by a single TMA bulk copy
+// (cp.async.bulk ... mbarrier::complete_tx) issued by a dedicated producer warp:
+//     COEF set : [b][chunk][ks][parity][row][4]      chunk = 8 consecutive k', ks = MMA k-step, 4 = MMA k
+//     TAB      : [column tile][chunk][ks][type][parity][col][4]
+// The [row][4] / [col][4] inner layout is exactly the m8n8k4 fragment order (bank-conflict free LDS.64).
 #pragma once
 #include "common.cuh"
 
@@ -17,163 +24,146 @@ namespace sddc {
 enum { EPI_FX = 0, EPI_DFX = 1, EPI_KE = 2 };
 
 struct SynthParams {
-    const double* coef;      // [B][rows][2][Khp]
+    const double* coef0;     // coefficient set of X      [B][Khp/8][2][2][RS][4]
+    const double* coef1;     // coefficient set of dv (EPI_DFX)
     long long coef_stride;   // member stride (doubles)
-    const double* tab;       // [2 types][2 par][Mhp_tab][Khp]
-    int tab_Mhp;             // j' extent of the table
+    const double* tab;       // [Mhp_tab/W][Khp/8][2][2 types][2 par][W][4]
     const double* Dr;        // [n][n] row-major (EPI_FX / EPI_DFX)
-    double* prd;             // [B][3][2][n8][Mhp]            (EPI_FX / EPI_DFX)
+    double* prd;             // [B][2 par][Mhp/8][2][3*n8][4]   (EPI_FX / EPI_DFX), tile-major for the analysis GEMM
     const double* wr;        // [n] radial trapezoid weights     (EPI_KE)
-    const double* wth;       // [tab_Mhp] w_theta(j') sin(theta_j') (EPI_KE), zero padded
+    const double* wth;       // [Mhp_tab] w_theta(j') sin(theta_j') (EPI_KE), zero padded
     double* kepart;          // [B][gridDim.x] partial sums      (EPI_KE)
-    int rows;                // nfields * n8
-    unsigned type_mask;      // bit f set: field f is sine-type
     Geo g;
 };
 
-template <int NT>
-struct SynthCfg {
-    static constexpr int W = NT * 8;   // mirror pairs (columns) per CTA
-    static constexpr int KC = 8;       // k' per pipeline stage
-    static constexpr int KS = KC / 4;  // MMA k-steps per stage
-    static constexpr int LDE = (NT == 4) ? W + 8 : W;  // row stride of the E/O exchange buffer
-};
+constexpr int SYNTH_KC = 8;            // k' per pipeline stage
+constexpr int SYNTH_KS = SYNTH_KC / 4; // MMA k-steps per stage
+constexpr int SYNTH_MAX_STAGES = 4;
 
-template <int NT>
-__host__ __device__ inline size_t synth_stage_doubles(int rows) {
-    return (size_t)SynthCfg<NT>::KS * 2 * rows * 4 + (size_t)SynthCfg<NT>::KS * 4 * SynthCfg<NT>::W * 4;
+// column tiles per CTA for a warp that owns `mtw` 8-row tiles (accumulators: mtw*NT*2 doubles per thread)
+__host__ __device__ constexpr int synth_nt_for(int mtw) { return mtw <= 4 ? 4 : (mtw <= 8 ? 2 : 1); }
+__host__ __device__ constexpr int synth_lde(int nt) { return nt == 4 ? 40 : nt * 8; }  // E/O exchange row stride
+
+// doubles per pipeline stage / for the epilogue, for `nset` coefficient sets of `rs` rows and NT column tiles
+__host__ __device__ inline size_t synth_stage_doubles(int nset, int rs, int nt) {
+    return (size_t)nset * SYNTH_KS * 2 * rs * 4 + (size_t)SYNTH_KS * 4 * (nt * 8) * 4;
 }
-template <int NT>
-__host__ __device__ inline size_t synth_epi_doubles(int rows, int n) {
-    return (size_t)2 * rows * SynthCfg<NT>::LDE + (size_t)2 * n * SynthCfg<NT>::W + (size_t)n * n + 32;
+__host__ __device__ inline size_t synth_epi_doubles(int nset, int rs, int n, int nt) {
+    return (size_t)2 * nset * rs * synth_lde(nt) + (size_t)2 * n * (nt * 8) + (size_t)n * n + 32;
 }
 
-// grid = (Mhp/W, B), block = 256 (8 warps: warps 0-3 even-k GEMM, warps 4-7 odd-k GEMM; each warp owns a
-// contiguous range of 8-row tiles and all NT column tiles).
-template <int NT, int MTW, int EPI>
-__global__ void __launch_bounds__(256, 1) synth_kernel(SynthParams p, int nstage) {
-    using C = SynthCfg<NT>;
-    constexpr int W = C::W, KS = C::KS, KC = C::KC, LDE = C::LDE;
-    extern __shared__ __align__(16) double smem[];
+// grid = (Mhp/W, B).  Warps 0 .. 2*NF-1 are MMA consumers, one per (parity, field): the warp owns the NT8 8-row
+// tiles of its field (in both coefficient sets for EPI_DFX) and all NT column tiles, so table type, tile count and
+// loop bounds are compile-time.  The last warp is the TMA producer.
+template <int NT8, int EPI>
+__global__ void __launch_bounds__(32 * (2 * (EPI == EPI_KE ? 2 : 9) + 1), 1) synth_kernel(SynthParams p, int nstage) {
+    constexpr int NSET = (EPI == EPI_DFX) ? 2 : 1;
+    constexpr int NF = (EPI == EPI_KE) ? 2 : 9;  // fields per set = consumer warps per parity
+    constexpr int RS = NF * NT8 * 8;             // rows per set
+    constexpr int MTW = NT8 * NSET;
+    constexpr int NT = synth_nt_for(MTW);
+    constexpr int W = NT * 8, KS = SYNTH_KS, LDE = synth_lde(NT);
+    constexpr int NCW = 2 * NF, NTHR = 32 * (NCW + 1);
+    constexpr int A_SET = KS * 2 * RS * 4, A_ST = NSET * A_SET, B_ST = KS * 4 * W * 4, STAGE = A_ST + B_ST;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t bar_full[SYNTH_MAX_STAGES], bar_empty[SYNTH_MAX_STAGES];
     const Geo& g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const int par = warp >> 2, q = warp & 3;
-    const int rows = p.rows, TM = rows >> 3, tpw = (TM + 3) >> 2;
-    const int tile0 = q * tpw;
-    const int ntiles = max(0, min(tpw, TM - tile0));
     const int b = blockIdx.y, jt = blockIdx.x;
-    const int Khp = g.Khp;
-    const double* A = p.coef + (long long)b * p.coef_stride;
-    const double* Bt = p.tab + (long long)jt * W * Khp;
-    const long long tab_ps = (long long)p.tab_Mhp * Khp;  // parity stride; type stride = 2*tab_ps
+    const int nchunk = g.Khp / SYNTH_KC;
 
-    const int A_ST = KS * 2 * rows * 4;
-    const int STAGE = A_ST + KS * 4 * W * 4;
-    const int nchunk = Khp / KC;
-
-    // per-warp tile types (bit mt set: sine-type table)
-    unsigned long long my_types = 0;  // up to MTW = 36 tiles
-#pragma unroll
-    for (int mt = 0; mt < MTW; ++mt) {
-        const int fld = (tile0 + mt) / g.nt8;
-        if (fld < 32) my_types |= (unsigned long long)((p.type_mask >> fld) & 1u) << mt;
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NCW); }
+        mbar_fence_init();
     }
+    __syncthreads();
 
     double acc[MTW][NT][2];
 #pragma unroll
     for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    const int par = warp / NF, fw = warp - par * NF;  // consumer identity (garbage for the producer warp)
 
-    auto load_stage = [&](int st, int chunk) {
-        double* sA = smem + (size_t)st * STAGE;
-        double* sB = sA + A_ST;
-        const int k0 = chunk * KC;
-        // A: (row, parity) segments of KC doubles = 4 pieces of 16 B
-        for (int idx = tid; idx < rows * 2 * 4; idx += 256) {
-            const int piece = idx & 3, rp = idx >> 2;
-            const int pr = rp & 1, row = rp >> 1;
-            const double* src = A + ((long long)row * 2 + pr) * Khp + k0 + piece * 2;
-            double* dst = sA + (((piece >> 1) * 2 + pr) * rows + row) * 4 + (piece & 1) * 2;
-            cp_async16(dst, src);
-        }
-        for (int idx = tid; idx < 4 * W * 4; idx += 256) {
-            const int piece = idx & 3, r = idx >> 2;
-            const int col = r % W, tp = r / W;  // tp = type*2 + par
-            const double* src = Bt + (long long)tp * tab_ps + (long long)col * Khp + k0 + piece * 2;
-            double* dst = sB + (((piece >> 1) * 4 + tp) * W + col) * 4 + (piece & 1) * 2;
-            cp_async16(dst, src);
-        }
-    };
-
-    for (int s = 0; s < nstage - 1; ++s) {
-        if (s < nchunk) load_stage(s, s);
-        cp_async_commit();
-    }
-    for (int c = 0; c < nchunk; ++c) {
-        cp_async_wait_dyn(nstage - 2);
-        __syncthreads();
-        {
-            const int cn = c + nstage - 1;
-            if (cn < nchunk) load_stage(cn % nstage, cn);
-            cp_async_commit();
-        }
-        const double* sA = smem + (size_t)(c % nstage) * STAGE;
-        const double* sB = sA + A_ST;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            double bf[2][NT];
-#pragma unroll
-            for (int ty = 0; ty < 2; ++ty)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-                    bf[ty][nt] = sB[(((ks * 2 + ty) * 2 + par) * W + nt * 8 + gq) * 4 + tq];
-            const double* sAk = sA + ((ks * 2 + par) * rows + tile0 * 8 + gq) * 4 + tq;
-#pragma unroll
-            for (int mt = 0; mt < MTW; ++mt) {
-                if (mt < ntiles) {
-                    const double a = sAk[mt * 32];
-                    const bool sn = (my_types >> mt) & 1ull;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        mma884(acc[mt][nt][0], acc[mt][nt][1], a, sn ? bf[1][nt] : bf[0][nt]);
-                }
+    if (warp == NCW) {
+        // ---------------- producer: one lane streams the stages ----------------
+        if (lane == 0) {
+            const double* gA0 = p.coef0 + (long long)b * p.coef_stride;
+            const double* gA1 = (NSET == 2) ? p.coef1 + (long long)b * p.coef_stride : nullptr;
+            const double* gB = p.tab + (long long)jt * nchunk * B_ST;
+            int st = 0, ph = 0;
+            for (int c = 0; c < nchunk; ++c) {
+                if (c >= nstage) mbar_wait(&bar_empty[st], ph ^ 1);
+                double* sA = smem + (size_t)st * STAGE;
+                mbar_expect_tx(&bar_full[st], (unsigned)(STAGE * sizeof(double)));
+                bulk_g2s(sA, gA0 + (long long)c * A_SET, A_SET * sizeof(double), &bar_full[st]);
+                if (NSET == 2) bulk_g2s(sA + A_SET, gA1 + (long long)c * A_SET, A_SET * sizeof(double), &bar_full[st]);
+                bulk_g2s(sA + A_ST, gB + (long long)c * B_ST, B_ST * sizeof(double), &bar_full[st]);
+                if (++st == nstage) { st = 0; ph ^= 1; }
             }
         }
+        __syncwarp();
+    } else {
+        // ---------------- consumers: DMMA main loop ----------------
+        const int ty = (EPI == EPI_KE) ? fw : (fw >= 5 ? 1 : 0);  // 0: cosine table, 1: sine table
+        const int a_off = ((par * RS) + fw * NT8 * 8 + gq) * 4 + tq;          // + set*A_SET + ks*2*RS*4 + mt*32
+        const int b_off = A_ST + ((ty * 2 + par) * W + gq) * 4 + tq;         // + ks*4*W*4 + nt*32
+        int st = 0, ph = 0;
+        for (int c = 0; c < nchunk; ++c) {
+            mbar_wait(&bar_full[st], ph);
+            const double* sS = smem + (size_t)st * STAGE;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                double bf[NT], af[MTW];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) bf[nt] = sS[b_off + ks * 4 * W * 4 + nt * 32];
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt)
+                    af[mt] = sS[a_off + (mt / NT8) * A_SET + ks * 2 * RS * 4 + (mt % NT8) * 32];
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[st]);
+            if (++st == nstage) { st = 0; ph ^= 1; }
+        }
     }
-    cp_async_wait<0>();
-    __syncthreads();
+    __syncthreads();  // every stage has been consumed; the staging area is reused below
 
     // ---- epilogue: exchange E/O through shared memory ----
-    double* sEO = smem;                         // [2][rows][LDE]
-    double* sA1 = sEO + (size_t)2 * rows * LDE; // [2 mirror][n][W]
-    double* sDr = sA1 + (size_t)2 * g.n * W;    // [n][n]
-    double* red = sDr + (size_t)g.n * g.n;      // [32]
+    constexpr int ROWS = NSET * RS;
+    double* sEO = smem;                          // [2 par][ROWS][LDE]
+    double* sA1 = sEO + (size_t)2 * ROWS * LDE;  // [2 mirror][n][W]
+    double* sDr = sA1 + (size_t)2 * g.n * W;     // [n][n]
+    double* red = sDr + (size_t)g.n * g.n;       // [32]
+    if (warp < NCW) {
 #pragma unroll
-    for (int mt = 0; mt < MTW; ++mt) {
-        if (mt < ntiles) {
-            const int row = (tile0 + mt) * 8 + gq;
+        for (int mt = 0; mt < MTW; ++mt) {
+            const int row = (mt / NT8) * RS + (fw * NT8 + (mt % NT8)) * 8 + gq;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 double2 v = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-                *reinterpret_cast<double2*>(&sEO[((size_t)par * rows + row) * LDE + nt * 8 + 2 * tq]) = v;
+                *reinterpret_cast<double2*>(&sEO[((size_t)par * ROWS + row) * LDE + nt * 8 + 2 * tq]) = v;
             }
         }
     }
-    const int n = g.n, n8 = g.n8;
+    const int n = g.n;
+    constexpr int n8 = NT8 * 8;
     if (EPI != EPI_KE) {
-        for (int idx = tid; idx < n * n; idx += 256) sDr[idx] = p.Dr[idx];
+        for (int idx = tid; idx < n * n; idx += NTHR) sDr[idx] = p.Dr[idx];
     }
     __syncthreads();
 
     const double* E = sEO;
-    const double* O = sEO + (size_t)rows * LDE;
+    const double* O = sEO + (size_t)ROWS * LDE;
     const int npts = n * W;
 
     if (EPI == EPI_KE) {
         // rows: field 0 = J_theta(psi)/r (cosine), field 1 = Dr psi (sine).  Main.py:117-130.
         double part = 0.0;
-        for (int pt = tid; pt < npts; pt += 256) {
+        for (int pt = tid; pt < npts; pt += NTHR) {
             const int i = pt / W, c = pt - i * W;
             const double e0 = E[(size_t)i * LDE + c], o0 = O[(size_t)i * LDE + c];
             const double e1 = E[(size_t)(n8 + i) * LDE + c], o1 = O[(size_t)(n8 + i) * LDE + c];
@@ -186,13 +176,19 @@ __global__ void __launch_bounds__(256, 1) synth_kernel(SynthParams p, int nstage
     }
 
     // field order (Derivatives): 0 JT, 1 kDpsi, 2 komega, 3 DT, 4 DS | 5 omega, 6 Dpsi, 7 kT, 8 kS
-    constexpr int PTS = 4;
+    constexpr int PTS = (n8 * W + NTHR - 1) / NTHR;
+    constexpr int ROWS3 = 3 * n8;
     double qv[PTS][2];
-    double* prd = p.prd + (long long)b * 3 * 2 * n8 * g.Mhp;
-    const long long pps = (long long)n8 * g.Mhp;  // parity stride in prd; field stride = 2*pps
+    // prd[b][par][chunk][ks][f*n8 + i][4]: the analysis GEMM's A operand, contraction index j' = 8 chunk + 4 ks + kk
+    double* prd = p.prd + (long long)b * 2 * g.Mhp * ROWS3;
+    const long long pps = (long long)g.Mhp * ROWS3;  // parity stride
+    auto prd_off = [&](int f, int i, int c) {
+        const int jp = jt * W + c;
+        return ((long long)(jp >> 2) * ROWS3 + f * n8 + i) * 4 + (jp & 3);
+    };
 #pragma unroll
     for (int s = 0; s < PTS; ++s) {
-        const int pt = tid + s * 256;
+        const int pt = tid + s * NTHR;
         qv[s][0] = qv[s][1] = 0.0;
         if (pt < npts) {
             const int i = pt / W, c = pt - i * W;
@@ -212,7 +208,7 @@ __global__ void __launch_bounds__(256, 1) synth_kernel(SynthParams p, int nstage
                 double h0[9], h1[9];  // perturbation fields (second coefficient set)
 #pragma unroll
                 for (int a = 0; a < 9; ++a) {
-                    const double e = E[(size_t)((9 + a) * n8 + i) * LDE + c], o = O[(size_t)((9 + a) * n8 + i) * LDE + c];
+                    const double e = E[(size_t)(RS + a * n8 + i) * LDE + c], o = O[(size_t)(RS + a * n8 + i) * LDE + c];
                     if (a < 5) { h0[a] = e + o; h1[a] = e - o; } else { h0[a] = o + e; h1[a] = o - e; }
                 }
                 a1_0 = f0[0] * h0[5] + h0[0] * f0[5];
@@ -227,18 +223,18 @@ __global__ void __launch_bounds__(256, 1) synth_kernel(SynthParams p, int nstage
             sA1[(size_t)i * W + c] = a1_0;
             sA1[(size_t)(n + i) * W + c] = a1_1;
             // cosine-type analysis (T, S): even k uses f(j')+f(mirror), odd k uses the difference
-            const long long o = (long long)i * g.Mhp + jt * W + c;
-            prd[(1 * 2 + 0) * pps + o] = nt0 + nt1;
-            prd[(1 * 2 + 1) * pps + o] = nt0 - nt1;
-            prd[(2 * 2 + 0) * pps + o] = ns0 + ns1;
-            prd[(2 * 2 + 1) * pps + o] = ns0 - ns1;
+            const long long oT = prd_off(1, i, c), oS = prd_off(2, i, c);
+            prd[oT] = nt0 + nt1;
+            prd[pps + oT] = nt0 - nt1;
+            prd[oS] = ns0 + ns1;
+            prd[pps + oS] = ns0 - ns1;
         }
     }
     __syncthreads();
     // N_psi = Dr @ (JT*omega) - (kDpsi*omega + Dpsi*komega)   (Matrix_Operators.py:791)
 #pragma unroll
     for (int s = 0; s < PTS; ++s) {
-        const int pt = tid + s * 256;
+        const int pt = tid + s * NTHR;
         if (pt < npts) {
             const int i = pt / W, c = pt - i * W;
             double v0 = 0.0, v1 = 0.0;
@@ -250,9 +246,9 @@ __global__ void __launch_bounds__(256, 1) synth_kernel(SynthParams p, int nstage
             v0 -= qv[s][0];
             v1 -= qv[s][1];
             // sine-type analysis: odd k uses the sum, even k the difference
-            const long long o = (long long)i * g.Mhp + jt * W + c;
-            prd[(0 * 2 + 1) * pps + o] = v0 + v1;
-            prd[(0 * 2 + 0) * pps + o] = v0 - v1;
+            const long long o = prd_off(0, i, c);
+            prd[pps + o] = v0 + v1;
+            prd[o] = v0 - v1;
         }
     }
 }

@@ -46,16 +46,17 @@ struct sddc_plan {
     double *LA4 = nullptr, *LT = nullptr, *LS = nullptr;
     double *ir2 = nullptr, *ir4 = nullptr, *r2 = nullptr, *dT0 = nullptr, *gb = nullptr, *a4_ir2 = nullptr,
            *a4_ir4 = nullptr, *ir = nullptr, *nu_in = nullptr, *nu_out = nullptr, *wr = nullptr;
-    double *tab1 = nullptr, *tab2 = nullptr, *tab3 = nullptr, *wth = nullptr;
+    double *tab1 = nullptr, *tab1d = nullptr, *tab2 = nullptr, *tab3 = nullptr, *wth = nullptr;
     // scratch
     double *JJ = nullptr, *coef = nullptr, *prd = nullptr, *lin = nullptr, *rhs = nullptr, *xtmp = nullptr,
            *kepart = nullptr, *zeroRa = nullptr;
-    long long coef_set_stride = 0, coef_member_stride = 0;
+    double* coef1 = nullptr;
+    long long coef_member_stride = 0;
     // host-API staging
     double *hX0 = nullptr, *hX1 = nullptr, *hX2 = nullptr, *hRa = nullptr, *hRas = nullptr, *hDiag = nullptr;
     cudaStream_t own_stream = nullptr;
     // kernel configuration
-    int synth_nt_fx = 0, synth_nt_dfx = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
+    int synth_nt_fx = 0, synth_nt_dfx = 0, synth_nt_ke = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
     size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
     int ana_nt = 0, ana_stage = 0;
     size_t ana_smem = 0;
@@ -131,16 +132,15 @@ int set_smem(sddc_plan* pl, Kern kern, size_t bytes) {
     return SDDC_OK;
 }
 
-// choose (NT, stages, smem) of the synthesis kernel for `nfields` coefficient rows per radial point
-int pick_synth(const Geo& g, int nfields, int* nt, int* nstage, size_t* smem) {
-    const int rows = nfields * g.n8, TM = rows / 8, tpw = (TM + 3) / 4;
-    size_t st, ep;
-    if (tpw <= 9 && g.n * 32 <= 1024) { *nt = 4; st = synth_stage_doubles<4>(rows); ep = synth_epi_doubles<4>(rows, g.n); }
-    else if (tpw <= 18 && g.n * 16 <= 1024) { *nt = 2; st = synth_stage_doubles<2>(rows); ep = synth_epi_doubles<2>(rows, g.n); }
-    else if (tpw <= 36 && g.n * 8 <= 1024) { *nt = 1; st = synth_stage_doubles<1>(rows); ep = synth_epi_doubles<1>(rows, g.n); }
-    else return SDDC_ERR_UNSUPPORTED;
-    st *= sizeof(double); ep *= sizeof(double);
-    int ns = 4;
+// stages and dynamic shared memory of the synthesis kernel for `nset` coefficient sets of `nf` fields
+int pick_synth(const Geo& g, int nset, int nf, int* nt, int* nstage, size_t* smem) {
+    const int rs = nf * g.n8, mtw = g.nt8 * nset;
+    if (mtw > 16) return SDDC_ERR_UNSUPPORTED;
+    *nt = synth_nt_for(mtw);
+    if (g.n8 * (*nt) * 8 > 4 * 32 * (2 * nf + 1) && nf == 9) return SDDC_ERR_UNSUPPORTED;
+    const size_t st = synth_stage_doubles(nset, rs, *nt) * sizeof(double);
+    const size_t ep = synth_epi_doubles(nset, rs, g.n, *nt) * sizeof(double);
+    int ns = SYNTH_MAX_STAGES;
     while (ns > 2 && ns * st > SMEM_LIMIT) --ns;
     if (ns * st > SMEM_LIMIT || ep > SMEM_LIMIT) return SDDC_ERR_UNSUPPORTED;
     *nstage = ns;
@@ -148,14 +148,56 @@ int pick_synth(const Geo& g, int nfields, int* nt, int* nstage, size_t* smem) {
     return SDDC_OK;
 }
 
+template <int NT8, int EPI>
+void launch_synth_inst(const SynthParams& sp, int nstage, size_t smem, dim3 grid, cudaStream_t st, bool set_attr) {
+    constexpr int NF = (EPI == EPI_KE) ? 2 : 9;
+    if (set_attr) {
+        cudaFuncSetAttribute(synth_kernel<NT8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return;
+    }
+    synth_kernel<NT8, EPI><<<grid, 32 * (2 * NF + 1), smem, st>>>(sp, nstage);
+}
+
 template <int EPI>
-int launch_synth(sddc_plan* pl, int nt, const SynthParams& sp, int nstage, size_t smem, int ncol_tiles, int B,
-                 cudaStream_t st) {
+int launch_synth(sddc_plan* pl, const SynthParams& sp, int nstage, size_t smem, int ncol_tiles, int B,
+                 cudaStream_t st, bool set_attr = false) {
     dim3 grid(ncol_tiles, B);
-    if (nt == 4) synth_kernel<4, 9, EPI><<<grid, 256, smem, st>>>(sp, nstage);
-    else if (nt == 2) synth_kernel<2, 18, EPI><<<grid, 256, smem, st>>>(sp, nstage);
-    else synth_kernel<1, 36, EPI><<<grid, 256, smem, st>>>(sp, nstage);
-    pl->launches++;
+    switch (pl->g.nt8) {
+        case 3: launch_synth_inst<3, EPI>(sp, nstage, smem, grid, st, set_attr); break;
+        case 4: launch_synth_inst<4, EPI>(sp, nstage, smem, grid, st, set_attr); break;
+        case 5: launch_synth_inst<5, EPI>(sp, nstage, smem, grid, st, set_attr); break;
+        case 6: launch_synth_inst<6, EPI>(sp, nstage, smem, grid, st, set_attr); break;
+        case 7: launch_synth_inst<7, EPI>(sp, nstage, smem, grid, st, set_attr); break;
+        case 8: launch_synth_inst<8, EPI>(sp, nstage, smem, grid, st, set_attr); break;
+        default: pl->err = "unsupported radial tile count"; return SDDC_ERR_UNSUPPORTED;
+    }
+    if (!set_attr) pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+template <int NT8>
+void launch_ana_inst(const AnaParams& ap, int nstage, size_t smem, dim3 grid, cudaStream_t st, bool set_attr) {
+    if (set_attr) {
+        cudaFuncSetAttribute(analysis_kernel<NT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return;
+    }
+    analysis_kernel<NT8><<<grid, 416, smem, st>>>(ap, nstage);
+}
+
+int launch_analysis(sddc_plan* pl, const AnaParams& ap, int B, cudaStream_t st, bool set_attr = false) {
+    const int KT3 = 32 * ana_nt_for(pl->g.nt8);
+    dim3 grid(pl->g.Khp2 / KT3, 2, B);
+    switch (pl->g.nt8) {
+        case 3: launch_ana_inst<3>(ap, pl->ana_stage, pl->ana_smem, grid, st, set_attr); break;
+        case 4: launch_ana_inst<4>(ap, pl->ana_stage, pl->ana_smem, grid, st, set_attr); break;
+        case 5: launch_ana_inst<5>(ap, pl->ana_stage, pl->ana_smem, grid, st, set_attr); break;
+        case 6: launch_ana_inst<6>(ap, pl->ana_stage, pl->ana_smem, grid, st, set_attr); break;
+        case 7: launch_ana_inst<7>(ap, pl->ana_stage, pl->ana_smem, grid, st, set_attr); break;
+        case 8: launch_ana_inst<8>(ap, pl->ana_stage, pl->ana_smem, grid, st, set_attr); break;
+        default: pl->err = "unsupported radial tile count"; return SDDC_ERR_UNSUPPORTED;
+    }
+    if (!set_attr) pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
 }
@@ -186,7 +228,7 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     if (rc) return rc;
     PrepParams pp{};
     pp.X = X; pp.x_stride = 3LL * pl->g.N; pp.JJ = pl->JJ;
-    pp.coef = want_coef ? pl->coef + set * pl->coef_set_stride : nullptr;
+    pp.coef = want_coef ? (set == 0 ? pl->coef : pl->coef1) : nullptr;
     pp.coef_stride = pl->coef_member_stride;
     pp.lin = lin; pp.Ra = Ra; pp.Ras = Ras;
     pp.DrT = pl->DrT; pp.D2rT = pl->D2rT; pp.DsqT = pl->DsqT;
@@ -202,28 +244,21 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
 
 int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     SynthParams sp{};
-    sp.coef = pl->coef; sp.coef_stride = pl->coef_member_stride;
-    sp.tab = pl->tab1; sp.tab_Mhp = pl->g.Mhp; sp.Dr = pl->Dr; sp.prd = pl->prd;
-    sp.rows = (dfx ? 18 : 9) * pl->g.n8;
-    sp.type_mask = dfx ? (0x1E0u | (0x1E0u << 9)) : 0x1E0u;
+    sp.coef0 = pl->coef; sp.coef1 = pl->coef1; sp.coef_stride = pl->coef_member_stride;
+    sp.tab = dfx ? pl->tab1d : pl->tab1; sp.Dr = pl->Dr; sp.prd = pl->prd;
     sp.g = pl->g;
     const int nt = dfx ? pl->synth_nt_dfx : pl->synth_nt_fx;
     const int tiles = pl->g.Mhp / (8 * nt);
     StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-    if (dfx) return launch_synth<EPI_DFX>(pl, nt, sp, pl->synth_stage_dfx, pl->synth_smem_dfx, tiles, B, st);
-    return launch_synth<EPI_FX>(pl, nt, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
+    if (dfx) return launch_synth<EPI_DFX>(pl, sp, pl->synth_stage_dfx, pl->synth_smem_dfx, tiles, B, st);
+    return launch_synth<EPI_FX>(pl, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
 }
 
 int run_analysis(sddc_plan* pl, const double* lin, double* out, int B, cudaStream_t st) {
     AnaParams ap{};
     ap.prd = pl->prd; ap.tab2 = pl->tab2; ap.lin = lin; ap.out = out; ap.g = pl->g; ap.mdt = -pl->g.dt;
-    dim3 grid(pl->g.Khp2 / (64 * pl->ana_nt), 2, B);
     StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
-    if (pl->ana_nt == 2) analysis_kernel<2, 15><<<grid, 256, pl->ana_smem, st>>>(ap, pl->ana_stage);
-    else analysis_kernel<1, 24><<<grid, 256, pl->ana_smem, st>>>(ap, pl->ana_stage);
-    pl->launches++;
-    PLAN_CUDA(pl, cudaGetLastError());
-    return SDDC_OK;
+    return launch_analysis(pl, ap, B, st);
 }
 
 int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double* out, long long os, long long of,
@@ -319,7 +354,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->cfg = *cfg;
     pl->device = cfg->device;
     Geo& g = pl->g;
-    g.n = cfg->N_r - 1; g.n8 = round_up(g.n, 8); g.nt8 = g.n8 / 8;
+    g.n = cfg->N_r - 1; g.n8 = std::max(24, round_up(g.n, 8)); g.nt8 = g.n8 / 8;  // kernels are instantiated for nt8 = 3..8
     g.K = cfg->N_fm; g.Kh = g.K / 2; g.Khp = round_up(g.Kh, 8); g.Khp2 = round_up(g.Kh, 128);
     g.M = 3 * g.K / 2; g.Mh = g.M / 2; g.Mhp = round_up(g.Mh, 32);
     g.N = g.n * g.K; g.symmetric = cfg->symmetric ? 1 : 0;
@@ -369,24 +404,38 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         const double V = (2.0 / 3.0) * (ops->R_out * ops->R_out * ops->R_out - ops->R_in * ops->R_in * ops->R_in);
         pl->ke_scale = 0.5 / V;
     }
-    // ---- trigonometric tables (L2-resident) ----
-    const size_t t1 = 4ull * g.Mhp * g.Khp, t2 = 4ull * g.Khp2 * g.Mhp, t3 = 4ull * pl->Mh3p * g.Khp;
-    TRY(dev_alloc(pl, &pl->tab1, t1, false));
-    TRY(dev_alloc(pl, &pl->tab2, t2, false));
-    TRY(dev_alloc(pl, &pl->tab3, t3, false));
-    TRY(dev_alloc(pl, &pl->wth, pl->Mh3p, false));
-    fill_table_kernel<<<296, 256>>>(pl->tab1, 0, g.M, g.Kh, g.Mh, g.Khp, g.Mhp);
-    fill_table_kernel<<<296, 256>>>(pl->tab2, 1, g.M, g.Kh, g.Mh, g.Khp2, g.Mhp);
-    fill_table_kernel<<<296, 256>>>(pl->tab3, 0, M3, g.Kh, M3 / 2, g.Khp, pl->Mh3p);
-    fill_ke_weights_kernel<<<(pl->Mh3p + 127) / 128, 128>>>(pl->wth, M3, pl->Mh3p);
-    pl->launches += 4;
-    TRYC(cudaGetLastError());
+    // ---- kernel configuration (tile shapes decide the table layouts) ----
+    if (pick_synth(g, 1, 9, &pl->synth_nt_fx, &pl->synth_stage_fx, &pl->synth_smem_fx) ||
+        pick_synth(g, 2, 9, &pl->synth_nt_dfx, &pl->synth_stage_dfx, &pl->synth_smem_dfx) ||
+        pick_synth(g, 1, 2, &pl->synth_nt_ke, &pl->synth_stage_ke, &pl->synth_smem_ke)) {
+        pl->err = "N_r too large for the instantiated synthesis tiles";
+        return fail(SDDC_ERR_UNSUPPORTED);
+    }
+    pl->ana_nt = ana_nt_for(g.nt8);
+    // ---- trigonometric tables (tile-major, L2-resident) ----
+    {
+        const int nch = g.Khp / 8, Wfx = 8 * pl->synth_nt_fx, Wd = 8 * pl->synth_nt_dfx, Wke = 8 * pl->synth_nt_ke;
+        const int KT3 = 32 * pl->ana_nt;
+        const size_t t1 = 4ull * g.Mhp * g.Khp, t2 = 4ull * g.Khp2 * g.Mhp, t3 = 4ull * pl->Mh3p * g.Khp;
+        TRY(dev_alloc(pl, &pl->tab1, t1, false));
+        TRY(dev_alloc(pl, &pl->tab1d, t1, false));
+        TRY(dev_alloc(pl, &pl->tab2, t2, false));
+        TRY(dev_alloc(pl, &pl->tab3, t3, false));
+        TRY(dev_alloc(pl, &pl->wth, pl->Mh3p, false));
+        fill_table_kernel<<<296, 256>>>(pl->tab1, 0, g.M, g.Kh, g.Mh, Wfx, g.Mhp / Wfx, nch);
+        fill_table_kernel<<<296, 256>>>(pl->tab1d, 0, g.M, g.Kh, g.Mh, Wd, g.Mhp / Wd, nch);
+        fill_table_kernel<<<296, 256>>>(pl->tab2, 1, g.M, g.Kh, g.Mh, KT3, g.Khp2 / KT3, g.Mhp / 8);
+        fill_table_kernel<<<296, 256>>>(pl->tab3, 0, M3, g.Kh, M3 / 2, Wke, pl->Mh3p / Wke, nch);
+        fill_ke_weights_kernel<<<(pl->Mh3p + 127) / 128, 128>>>(pl->wth, M3, pl->Mh3p);
+        pl->launches += 5;
+        TRYC(cudaGetLastError());
+    }
     // ---- scratch ----
     const size_t Bm = (size_t)cfg->max_batch;
-    pl->coef_set_stride = 9LL * n8 * 2 * g.Khp;
-    pl->coef_member_stride = 2 * pl->coef_set_stride;
+    pl->coef_member_stride = 9LL * n8 * 2 * g.Khp;
     TRY(dev_alloc(pl, &pl->JJ, Bm * (K + 1) * n, false));
-    TRY(dev_alloc(pl, &pl->coef, Bm * pl->coef_member_stride, true));  // padded rows / columns stay zero
+    TRY(dev_alloc(pl, &pl->coef, Bm * pl->coef_member_stride, true));   // padded rows / columns stay zero
+    TRY(dev_alloc(pl, &pl->coef1, Bm * pl->coef_member_stride, true));  // second set: dv (JVP) or KE rows
     TRY(dev_alloc(pl, &pl->prd, Bm * 3 * 2 * n8 * g.Mhp, true));
     TRY(dev_alloc(pl, &pl->lin, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->rhs, Bm * 3 * g.N, false));
@@ -394,33 +443,16 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->nke = pl->Mh3p / 32;
     TRY(dev_alloc(pl, &pl->kepart, Bm * pl->nke, true));
     TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
-    // ---- kernel configuration ----
-    if (pick_synth(g, 9, &pl->synth_nt_fx, &pl->synth_stage_fx, &pl->synth_smem_fx) ||
-        pick_synth(g, 18, &pl->synth_nt_dfx, &pl->synth_stage_dfx, &pl->synth_smem_dfx)) {
-        pl->err = "N_r too large for the instantiated synthesis tiles";
-        return fail(SDDC_ERR_UNSUPPORTED);
-    }
+    // ---- opt in to large dynamic shared memory ----
     {
-        const size_t st = synth_stage_doubles<4>(2 * n8) * sizeof(double), ep = synth_epi_doubles<4>(2 * n8, n) * sizeof(double);
-        pl->synth_stage_ke = 4;
-        pl->synth_smem_ke = std::max(4 * st, ep);
-    }
-    const size_t smax = std::max(std::max(pl->synth_smem_fx, pl->synth_smem_dfx), pl->synth_smem_ke);
-    TRY(set_smem(pl, synth_kernel<4, 9, EPI_FX>, smax));
-    TRY(set_smem(pl, synth_kernel<2, 18, EPI_FX>, smax));
-    TRY(set_smem(pl, synth_kernel<1, 36, EPI_FX>, smax));
-    TRY(set_smem(pl, synth_kernel<4, 9, EPI_DFX>, smax));
-    TRY(set_smem(pl, synth_kernel<2, 18, EPI_DFX>, smax));
-    TRY(set_smem(pl, synth_kernel<1, 36, EPI_DFX>, smax));
-    TRY(set_smem(pl, synth_kernel<4, 9, EPI_KE>, smax));
-    {
-        const int TM3 = 3 * g.nt8;
-        pl->ana_nt = (TM3 <= 15) ? 2 : 1;
-        const size_t st = (pl->ana_nt == 2 ? ana_stage_doubles<2>(3 * n8) : ana_stage_doubles<1>(3 * n8)) * sizeof(double);
-        pl->ana_stage = 4;
-        pl->ana_smem = 4 * st;
-        TRY(set_smem(pl, analysis_kernel<2, 15>, pl->ana_smem));
-        TRY(set_smem(pl, analysis_kernel<1, 24>, pl->ana_smem));
+        SynthParams sp{};
+        TRY(launch_synth<EPI_FX>(pl, sp, 0, pl->synth_smem_fx, 1, 1, nullptr, true));
+        TRY(launch_synth<EPI_DFX>(pl, sp, 0, pl->synth_smem_dfx, 1, 1, nullptr, true));
+        TRY(launch_synth<EPI_KE>(pl, sp, 0, pl->synth_smem_ke, 1, 1, nullptr, true));
+        pl->ana_stage = ANA_MAX_STAGES;
+        pl->ana_smem = ANA_MAX_STAGES * ana_stage_doubles(g.nt8) * sizeof(double);
+        AnaParams ap{};
+        TRY(launch_analysis(pl, ap, 1, nullptr, true));
     }
     pl->solve_smem = solve_smem_doubles<2>(n8) * sizeof(double);
     TRY(set_smem(pl, solve_kernel<2>, pl->solve_smem));
@@ -561,7 +593,7 @@ int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* s
     const Geo& g = pl->g;
     if ((rc = run_scan(pl, X, 3LL * g.N, B, st))) return rc;
     KEPrepParams kp{};
-    kp.X = X; kp.x_stride = 3LL * g.N; kp.JJ = pl->JJ; kp.coef = pl->coef; kp.coef_stride = pl->coef_member_stride;
+    kp.X = X; kp.x_stride = 3LL * g.N; kp.JJ = pl->JJ; kp.coef = pl->coef1; kp.coef_stride = pl->coef_member_stride;
     kp.DrT = pl->DrT; kp.ir = pl->ir; kp.g = g;
     dim3 grid((g.K + 31) / 32, B);
     {
@@ -571,11 +603,11 @@ int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* s
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     SynthParams sp{};
-    sp.coef = pl->coef; sp.coef_stride = pl->coef_member_stride; sp.tab = pl->tab3; sp.tab_Mhp = pl->Mh3p;
-    sp.wr = pl->wr; sp.wth = pl->wth; sp.kepart = pl->kepart; sp.rows = 2 * g.n8; sp.type_mask = 0x2u; sp.g = g;
+    sp.coef0 = pl->coef1; sp.coef_stride = pl->coef_member_stride; sp.tab = pl->tab3;
+    sp.wr = pl->wr; sp.wth = pl->wth; sp.kepart = pl->kepart; sp.g = g;
     {
         StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
-        if ((rc = launch_synth<EPI_KE>(pl, 4, sp, pl->synth_stage_ke, pl->synth_smem_ke, pl->Mh3p / 32, B, st))) return rc;
+        if ((rc = launch_synth<EPI_KE>(pl, sp, pl->synth_stage_ke, pl->synth_smem_ke, pl->Mh3p / (8 * pl->synth_nt_ke), B, st))) return rc;
     }
     StageTimer tm2(pl, SDDC_STAGE_DIAG, st);
     diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, pl->nke, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
