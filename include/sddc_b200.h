@@ -90,6 +90,15 @@ const char* sddc_last_error(const sddc_plan* plan); /* plan may be NULL: error o
 /* number of this library's kernel launches issued through the plan so far */
 long long sddc_launch_count(const sddc_plan* plan);
 
+/* Replace one pre-inverted operator stack (which: 0 = A4 / psi, 1 = NAB2 / T, 2 = NAB2 / S) and the effective
+ * time step the matching back-substitution uses (the `dt` argument of A4_BSub_TSTEP_V2 / NAB2_BSub_TSTEP_V2).
+ * Blocking; used by the drop-in Matrix_Operators module when the caller supplies its own L_inv lists. */
+int sddc_plan_set_linv(sddc_plan* plan, int which, const double* Linv /* [K*n*n] host */, double dt_eff);
+
+/* Replace the auxiliary arrays of the A4 back-substitution: D2 [n*n], diag(IR2) [n], diag(IR4) [n] -- the
+ * positional arguments args_A4 of A4_BSub_TSTEP_V2 (Main.py:222, Matrix_Operators.py:1116). Blocking. */
+int sddc_plan_set_a4_aux(sddc_plan* plan, const double* D2, const double* ir2, const double* ir4);
+
 /* F(X) for B members: Matrix_Operators.NLIN_FX (743-804). X, F: [B][3Kn] */
 int sddc_nlin_fx(sddc_plan* plan, const double* X, double* F, int B, void* stream);
 /* DF(X) dv: Matrix_Operators.NLIN_DFX (807-898) */

@@ -61,6 +61,7 @@ struct sddc_plan {
     int ana_nt = 0, ana_stage = 0;
     size_t ana_smem = 0;
     size_t solve_smem = 0;
+    double dt_psi = 0, dt_T = 0, dt_S = 0;  // effective time steps of the three operator stacks
     // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
     bool profiling = false;
     struct Ev { int stage; cudaEvent_t a, b; };
@@ -268,7 +269,7 @@ int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double
     sp.sub = sub; sp.LinvA4 = pl->LA4; sp.LinvT = pl->LT; sp.LinvS = pl->LS; sp.D2 = pl->D2p;
     sp.ir2 = pl->a4_ir2; sp.ir4 = pl->a4_ir4; sp.geo = pl->g; sp.B = B;
     sp.field_mask = 7; sp.field_base = field_base;
-    sp.dt_psi = pl->g.Pr * pl->g.dt; sp.dt_T = pl->g.dt; sp.dt_S = pl->g.Tau * pl->g.dt;
+    sp.dt_psi = pl->dt_psi; sp.dt_T = pl->dt_T; sp.dt_S = pl->dt_S;
     // single-field calls pass field offsets of 0; the operator stack follows field_base
     dim3 grid((B + 15) / 16, 2, nfields);
     StageTimer tm(pl, SDDC_STAGE_SOLVE, st);
@@ -360,6 +361,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     g.N = g.n * g.K; g.symmetric = cfg->symmetric ? 1 : 0;
     g.dt = cfg->dt; g.Pr = cfg->Pr; g.Tau = cfg->Tau;
     pl->LDL = g.n8 + 4;
+    pl->dt_psi = g.Pr * g.dt; pl->dt_T = g.dt; pl->dt_S = g.Tau * g.dt;
     const int n = g.n, n8 = g.n8, K = g.K;
     const int M3 = 3 * K;
     pl->Mh3p = round_up(M3 / 2, 32);
@@ -463,6 +465,30 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
 #undef TRY
 #undef TRYC
     *out = pl;
+    return SDDC_OK;
+}
+
+int sddc_plan_set_linv(sddc_plan* pl, int which, const double* Linv, double dt_eff) {
+    if (!pl || !Linv || which < 0 || which > 2) return SDDC_ERR_INVALID;
+    PLAN_CUDA(pl, cudaSetDevice(pl->device));
+    const Geo& g = pl->g;
+    std::vector<double> h = pad_stack(Linv, g.K, g.n, g.n8, pl->LDL);
+    double* dst = which == 0 ? pl->LA4 : (which == 1 ? pl->LT : pl->LS);
+    PLAN_CUDA(pl, cudaDeviceSynchronize());
+    PLAN_CUDA(pl, cudaMemcpy(dst, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    (which == 0 ? pl->dt_psi : (which == 1 ? pl->dt_T : pl->dt_S)) = dt_eff;
+    return SDDC_OK;
+}
+
+int sddc_plan_set_a4_aux(sddc_plan* pl, const double* D2, const double* ir2, const double* ir4) {
+    if (!pl || !D2 || !ir2 || !ir4) return SDDC_ERR_INVALID;
+    PLAN_CUDA(pl, cudaSetDevice(pl->device));
+    const Geo& g = pl->g;
+    std::vector<double> h = pad_stack(D2, 1, g.n, g.n8, pl->LDL);
+    PLAN_CUDA(pl, cudaDeviceSynchronize());
+    PLAN_CUDA(pl, cudaMemcpy(pl->D2p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PLAN_CUDA(pl, cudaMemcpy(pl->a4_ir2, ir2, g.n * sizeof(double), cudaMemcpyHostToDevice));
+    PLAN_CUDA(pl, cudaMemcpy(pl->a4_ir4, ir4, g.n * sizeof(double), cudaMemcpyHostToDevice));
     return SDDC_OK;
 }
 

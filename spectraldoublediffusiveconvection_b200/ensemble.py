@@ -1,0 +1,95 @@
+"""Ensemble driver: many independent members (random initial conditions, Ra_T / Ra_S sweeps) advanced in lock
+step, sharded by member over the GPUs of one node.
+
+Members never exchange state, so there is no data-path collective; the only communication is the all-gather of
+the per-step diagnostics [B_local, 4] -> [B, 4] (Norm, KE, Nu_T, Nu_S: the four scalars Main._Time_Step appends
+per step, Main.py:292-295) and, on request, of the final states.  One process per GPU (torchrun); with a single
+process everything degenerates to the local plan.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def partition(n_members: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of rank `rank`: the first n % world ranks own one extra member."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad world/rank")
+    base, extra = divmod(n_members, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_members: int, world: int):
+    return [partition(n_members, world, r)[1] - partition(n_members, world, r)[0] for r in range(world)]
+
+
+def gather_rows(local: torch.Tensor, n_members: int, group=None) -> torch.Tensor:
+    """All-gather row-sharded [B_local, C] tensors (possibly ragged over ranks) into [n_members, C] on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(n_members, world)
+    if len(set(sizes)) == 1:
+        out = torch.empty((n_members,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    # ragged shards: pad every shard to the largest one (collectives need equal sizes), gather, strip the padding
+    smax = max(sizes)
+    padded = torch.zeros((smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty((world * smax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * smax:r * smax + sizes[r]] for r in range(world)], dim=0)
+
+
+class Ensemble:
+    """B members of one (N_fm, N_r, d, dt, Pr, Tau, symmetric) with per-member Ra, Ra_s, sharded over ranks."""
+
+    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, Ra, Ra_s, symmetric=False, device=None, group=None):
+        from .plan import EnsemblePlan
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        Ra = np.atleast_1d(np.asarray(Ra, dtype=np.float64))
+        Ra_s = np.broadcast_to(np.atleast_1d(np.asarray(Ra_s, dtype=np.float64)), Ra.shape)
+        self.n_members = int(Ra.shape[0])
+        self.lo, self.hi = partition(self.n_members, self.world, self.rank)
+        self.n_local = self.hi - self.lo
+        self.plan = EnsemblePlan(N_fm, N_r, d, dt, Pr, Tau, symmetric=symmetric, max_batch=max(1, self.n_local),
+                                 device=device)
+        dev = self.plan.device
+        self.Ra = torch.as_tensor(np.ascontiguousarray(Ra[self.lo:self.hi])).to(dev)
+        self.Ra_s = torch.as_tensor(np.ascontiguousarray(Ra_s[self.lo:self.hi])).to(dev)
+        self.dt = float(dt)
+
+    def shard(self, X_all):
+        """Local rows of a global [B, 3N] host array, uploaded to this rank's GPU."""
+        X_all = np.asarray(X_all, dtype=np.float64).reshape(self.n_members, -1)
+        return torch.as_tensor(np.ascontiguousarray(X_all[self.lo:self.hi])).to(self.plan.device)
+
+    def time_step(self, X, n_steps, diag_every=1, linear=False):
+        """Advance the local members n_steps; every `diag_every` steps (0 = never) compute the diagnostics of all
+        local members and all-gather them.  Returns (X_new, history) with history [n_records, B, 4] on every rank
+        (the ensemble analogue of Scalar_Data/{Norm,KE,Nu_T,Nu_S}, Main.py:310-315)."""
+        hist = []
+        cur = X
+        done = 0
+        while done < n_steps:
+            k = n_steps - done if not diag_every else min(diag_every, n_steps - done)
+            cur = self.plan.step(cur, self.Ra, self.Ra_s, nsteps=k, linear=linear)
+            done += k
+            if diag_every:
+                d = self.plan.diagnostics(cur)[:, :4]
+                hist.append(gather_rows(d, self.n_members, self.group))
+        history = torch.stack(hist) if hist else torch.empty((0, self.n_members, 4), dtype=torch.float64,
+                                                             device=self.plan.device)
+        return cur, history
+
+    def gather_states(self, X):
+        return gather_rows(X, self.n_members, self.group)
+
+    def close(self):
+        self.plan.close()

@@ -117,6 +117,22 @@ class EnsemblePlan:
         self._check(self.lib.sddc_profile_end(self._h, ms, cnt))
         return {s: (ms[i], cnt[i]) for i, s in enumerate(self.STAGES)}
 
+    def set_linv(self, which, stack, dt_eff):
+        """Upload another pre-inverted operator stack [N_fm, nr, nr] (0: A4, 1: NAB2-T, 2: NAB2-S) and the
+        effective dt its back-substitution uses."""
+        stack = np.ascontiguousarray(stack, dtype=np.float64)
+        if stack.shape != (self.N_fm, self.nr, self.nr):
+            raise ValueError("operator stack has shape %s, expected %s" % (stack.shape, (self.N_fm, self.nr, self.nr)))
+        self._check(self.lib.sddc_plan_set_linv(self._h, int(which), stack.ctypes.data, float(dt_eff)))
+
+    def set_a4_aux(self, D2, ir2_diag, ir4_diag):
+        D2 = np.ascontiguousarray(D2, dtype=np.float64)
+        a = np.ascontiguousarray(ir2_diag, dtype=np.float64)
+        b = np.ascontiguousarray(ir4_diag, dtype=np.float64)
+        if D2.shape != (self.nr, self.nr) or a.shape != (self.nr,) or b.shape != (self.nr,):
+            raise ValueError("A4 auxiliary arrays have the wrong shape")
+        self._check(self.lib.sddc_plan_set_a4_aux(self._h, D2.ctypes.data, a.ctypes.data, b.ctypes.data))
+
     def new_state(self, B):
         return torch.empty((B, 3 * self.N), dtype=torch.float64, device=self.device)
 

@@ -1,0 +1,83 @@
+"""Call sequences of the reference's drivers, written against whatever modules are registered as
+`Matrix_Operators` / `Transforms` in sys.modules (the compat drop-ins in these tests).  They mirror, call for
+call, what Main.Build_Matrix_Operators (Main.py:179-225), Step_Python (255-283), PFX / PDFX (473-521) and PDFmu
+(829-837) ask of the operator layer -- same function names, positional arguments and return conventions -- so a
+pass here means Main.py itself can run on the drop-ins unchanged."""
+import numpy as np
+
+
+def build_matrix_operators(MO, N_fm, N_r, d, dt, Pr, Tau):
+    D, R = MO.cheb_radial(N_r, d)
+    Rsq = MO.R2(R, N_fm)
+    gr_K = MO.kGR_RT(R, N_fm, d)
+    R_1, R_2 = 1.0 / d, (1.0 + d) / d
+    A_T = (R_1 * R_2) / (R_1 - R_2)
+    DT0 = A_T / (R[1:-1] ** 2)
+    nr = len(R[1:-1])
+    L4 = MO.A4_TSTEP_MATS(Pr * dt, N_fm, nr, D, R)
+    LT = MO.NAB2_TSTEP_MATS(dt, N_fm, nr, D, R)
+    LS = MO.NAB2_TSTEP_MATS(Tau * dt, N_fm, nr, D, R)
+    IR = np.diag(1.0 / R)
+    IR2 = IR @ IR
+    D2 = np.ascontiguousarray(np.matmul(IR2, 2 * (D @ D) - 4 * (IR @ D) + 6 * IR2)[1:-1, 1:-1])
+    IR2 = np.ascontiguousarray(IR2[1:-1, 1:-1])
+    IR4 = np.ascontiguousarray(IR2 @ IR2)
+    return np.ascontiguousarray(D), R, Rsq, DT0, gr_K, L4, LT, LS, (D2, IR4, IR2, N_fm, nr), (D, R, N_fm, nr)
+
+
+def make_closures(MO, ops, Ra, Ra_s, dt, Pr, Tau, symmetric):
+    D, R, Rsq, DT0, gr_k, L4, LT, LS, args_A4, args_FX = ops
+    N_fm, nr = args_FX[2], args_FX[3]
+    N = N_fm * nr
+
+    def advance(NX, Y, sub):
+        y0, y1, y2 = Y[0:N], Y[N:2 * N], Y[2 * N:3 * N]
+        y_T0 = MO.DT0_theta(y0, DT0, N_fm, nr, symmetric)
+        Om = MO.A2_SINE(y0, D, R, N_fm, nr, symmetric)
+        NX[0:N] += Om + dt * Pr * gr_k.dot(Ra * y1 - Ra_s * y2)
+        a = MO.A4_BSub_TSTEP_V2(NX[0:N], L4, *args_A4, Pr * dt, symmetric)
+        NX[N:2 * N] += Rsq.dot(y1) - dt * y_T0
+        b = MO.NAB2_BSub_TSTEP_V2(NX[N:2 * N], LT, N_fm, nr, dt, symmetric)
+        NX[2 * N:3 * N] += Rsq.dot(y2) - dt * y_T0
+        c = MO.NAB2_BSub_TSTEP_V2(NX[2 * N:3 * N], LS, N_fm, nr, Tau * dt, symmetric)
+        out = np.hstack((a, b, c))
+        return out - Y if sub else out
+
+    def step(Xn):
+        return advance(-1 * dt * MO.NLIN_FX(Xn, *args_FX, symmetric), Xn, False)
+
+    def residual(Xn):
+        return advance(-1.0 * dt * MO.NLIN_FX(Xn, *args_FX, symmetric), Xn, True)
+
+    def jvp(dv, Xn):
+        return advance(-1.0 * dt * MO.NLIN_DFX(dv, Xn, *args_FX, symmetric), dv, True)
+
+    def dmu(Xn):
+        out = 0.0 * Xn
+        out[0:N] = MO.A4_BSub_TSTEP_V2(dt * Pr * gr_k.dot(Xn[N:2 * N]), L4, *args_A4, Pr * dt, symmetric)
+        return out
+
+    return step, residual, jvp, dmu
+
+
+def kinetic_energy(MO, TR, X_hat, R, D, N_fm, nr, symmetric):
+    """Main.Kinetic_Energy (Main.py:71-134) on the drop-in J_theta_RT / IDCT / IDST / grid."""
+    N = N_fm * nr
+    Dr = D[1:-1, 1:-1]
+    IR = np.diag(1.0 / R[1:-1])
+    psi = X_hat[0:N]
+    JPSI = MO.J_theta_RT(psi, nr, N_fm, symmetric)
+    Jh = np.zeros((nr, N_fm))
+    Dh = np.zeros((nr, N_fm))
+    for k in range(N_fm):
+        Dh[:, k] = Dr @ psi[k * nr:(1 + k) * nr]
+        Jh[:, k] = IR @ JPSI[k * nr:(1 + k) * nr]
+    Dh[:, 1:] = Dh[:, 0:-1]
+    Dh[:, 0] = 0.0
+    th = TR.grid(3 * N_fm)
+    KE_rt = TR.IDCT(Jh, n=3 * N_fm) ** 2 + TR.IDST(Dh, n=3 * N_fm) ** 2
+    KE_t = np.trapz(KE_rt, x=R[1:-1], axis=0) if hasattr(np, "trapz") else np.trapezoid(KE_rt, x=R[1:-1], axis=0)
+    trap = np.trapz if hasattr(np, "trapz") else np.trapezoid
+    KE = trap(KE_t * np.sin(th), x=th, axis=-1)
+    V = (2.0 / 3.0) * (R[-1] ** 3 - R[0] ** 3)
+    return (0.5 / V) * KE
