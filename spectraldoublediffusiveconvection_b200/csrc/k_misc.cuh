@@ -18,7 +18,7 @@ __device__ __forceinline__ void trig_kj(long long k, long long j, long long M, d
 // entries with k' >= Kh or j' >= Mh are zero; the sine k = 0 row is zero.  nA = number of tiles of the tiled
 // index (jt or kt), nchunk = chunks of the contraction index.
 __global__ void fill_table_kernel(double* tab, int mode, int M, int Kh, int Mh, int W, int nA, int nchunk) {
-    const long long total = 16LL * nA * nchunk * W * 4;  // 2 ks * 2 types * 2 par * ...
+    const long long total = 8LL * nA * nchunk * W * 4;  // (2 ks * 2 types * 2 par) * tiles * chunks * W * 4
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         long long r = idx;
@@ -73,7 +73,7 @@ struct KEPrepParams {
 };
 
 __global__ void __launch_bounds__(256) ke_prep_kernel(KEPrepParams p) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K;
     const int b = blockIdx.y, c0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

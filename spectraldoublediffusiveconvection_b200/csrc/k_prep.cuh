@@ -58,7 +58,7 @@ __host__ __device__ inline size_t prep_smem_bytes(int n, int n8) {
 // One CTA per (member, tile of 32 sinusoid columns).  Phase A writes the coefficient arrays (k fastest),
 // phase B the linear right-hand sides (radial index fastest, the state layout).
 __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K, N = g.N;
     const int b = blockIdx.y, c0 = blockIdx.x * PREP_TC;
@@ -194,7 +194,7 @@ struct LinopParams {
 };
 
 __global__ void __launch_bounds__(256) linop_kernel(LinopParams p) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K;
     const int b = blockIdx.y, c0 = blockIdx.x * PREP_TC, tid = threadIdx.x;

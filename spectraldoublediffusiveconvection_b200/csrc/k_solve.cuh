@@ -43,7 +43,7 @@ __host__ __device__ inline size_t solve_smem_doubles(int n8) {
 template <int NTB>
 __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     constexpr int BT = 8 * NTB, NE = 2 * NTB;
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     const Geo& G = p.geo;
     const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;

@@ -76,8 +76,8 @@ def kinetic_energy(MO, TR, X_hat, R, D, N_fm, nr, symmetric):
     Dh[:, 0] = 0.0
     th = TR.grid(3 * N_fm)
     KE_rt = TR.IDCT(Jh, n=3 * N_fm) ** 2 + TR.IDST(Dh, n=3 * N_fm) ** 2
-    KE_t = np.trapz(KE_rt, x=R[1:-1], axis=0) if hasattr(np, "trapz") else np.trapezoid(KE_rt, x=R[1:-1], axis=0)
-    trap = np.trapz if hasattr(np, "trapz") else np.trapezoid
+    trap = np.trapezoid if hasattr(np, "trapezoid") else np.trapz
+    KE_t = trap(KE_rt, x=R[1:-1], axis=0)
     KE = trap(KE_t * np.sin(th), x=th, axis=-1)
     V = (2.0 / 3.0) * (R[-1] ** 3 - R[0] ** 3)
     return (0.5 / V) * KE

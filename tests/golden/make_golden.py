@@ -185,9 +185,27 @@ def make_transforms(TR):
     print("wrote transforms")
 
 
+def make_interp(MO):
+    """Resolution-transfer helpers the drivers call right before the hot path (Main.py:414-416)."""
+    import contextlib, io
+    rng = np.random.default_rng(11)
+    N_fm, N_r, d = 16, 10, 0.4
+    X = rng.random(3 * (N_r - 1) * N_fm)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = dict(X=X, N_fm=N_fm, N_r=N_r, d=d,
+                   theta_up=MO.INTERP_THETAS(32, N_fm, X), theta_down=MO.INTERP_THETAS(8, N_fm, X),
+                   radial_up=MO.INTERP_RADIAL(14, N_r, X, d))
+    np.savez_compressed(os.path.join(HERE, "interp.npz"), **out)
+    print("wrote interp")
+
+
 if __name__ == "__main__":
     Main, MO, TR = import_reference()
+    if "--only-interp" in sys.argv:
+        make_interp(MO)
+        sys.exit(0)
     make_transforms(TR)
+    make_interp(MO)
     common = dict(d=0.4, dt=1e-2, Pr=0.7, Tau=1.0 / 15.0, Ra=3000.0, Ra_s=400.0)
     make_case(Main, MO, "small_nosym", 16, 10, symmetric=False, seed=1, n_steps=20, store_ops=True, **common)
     make_case(Main, MO, "small_sym", 16, 10, symmetric=True, seed=2, n_steps=20, **common)

@@ -81,6 +81,10 @@ def test_single_function_signatures(modules):
     assert rel_l2(TR.grid(24), gt["grid_16"]) < 1e-15
     # resolution transfer helpers keep a state unchanged when the resolution is unchanged, and theta-interpolation
     # to more modes zero-pads the spectrum
-    assert MO.INTERP_RADIAL(N_r, N_r, Xb, d) is Xb
-    X2 = MO.INTERP_THETAS(2 * N_fm, N_fm, Xb).reshape(3, 2 * N_fm, nr)
-    assert rel_l2(X2[:, :N_fm - 1], Xb.reshape(3, N_fm, nr)[:, :N_fm - 1]) < 1e-12
+    # resolution transfer (Matrix_Operators.py:901-1011) against outputs of the reference's own functions
+    gi = load_golden("interp")
+    Xi, di = gi["X"], float(gi["d"])
+    assert MO.INTERP_RADIAL(10, 10, Xi, di) is Xi
+    assert rel_l2(MO.INTERP_THETAS(32, 16, Xi), gi["theta_up"]) < 1e-12
+    assert rel_l2(MO.INTERP_THETAS(8, 16, Xi), gi["theta_down"]) < 1e-12
+    assert rel_l2(MO.INTERP_RADIAL(14, 10, Xi, di), gi["radial_up"]) < 1e-9
