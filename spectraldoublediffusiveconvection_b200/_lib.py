@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsddc_b200.so")
+LIB_PATH = os.environ.get("SDDC_B200_LIB", os.path.join(_HERE, "libsddc_b200.so"))  # override: A/B builds
 
 c_double_p = C.POINTER(C.c_double)
 

@@ -15,10 +15,10 @@ namespace sddc {
 struct AnaParams {
     const double* prd;
     const double* tab2;
-    const double* lin;   // [B][3N] linear right-hand side (mode RHS) or null (mode F only)
-    double* out;         // [B][3N]
+    double* out;         // F(X): state layout [B][3N] (bstride == 0) or solve-major [3][K][bstride][n8+2] (k_solve.cuh);
+                         // the -dt factor and the linear terms are applied by the solve kernel
+    long long bstride;
     Geo g;
-    double mdt;          // -dt (RHS mode)
 };
 
 constexpr int ANA_KC = 8;
@@ -46,8 +46,13 @@ __global__ void __launch_bounds__(416, 1) analysis_kernel(AnaParams p, int nstag
     const int wf = warp >> 2, cg = warp & 3;
     const int kt = blockIdx.x, par = blockIdx.y, b = blockIdx.z;
     const int n = g.n, K = g.K, N = g.N, Mhp = g.Mhp;
-    double* outb = p.out + (long long)b * 3 * N;
-    const double* linb = p.lin ? p.lin + (long long)b * 3 * N : nullptr;
+    const bool sm = p.bstride != 0;
+    const int LDG = NT8 * 8 + 2;
+    // element (field f, block blk, radial i) of member b
+    auto out_at = [&](int f, int blk, int i) -> double& {
+        return sm ? p.out[(((long long)f * K + blk) * p.bstride + b) * LDG + i]
+                  : p.out[(long long)b * 3 * N + (long long)f * N + (long long)blk * n + i];
+    };
 
     if (g.symmetric && par == 1) {
         // every odd-k output block is masked (Vecs_to_X symmetric branch, Matrix_Operators.py:536-556)
@@ -55,9 +60,9 @@ __global__ void __launch_bounds__(416, 1) analysis_kernel(AnaParams p, int nstag
             const int kp = kt * KT3 + idx / n, i = idx % n;
             if (kp >= g.Kh) continue;
             const int k = 2 * kp + 1;
-            outb[(long long)(k - 1) * n + i] = 0.0;
-            outb[(long long)N + (long long)k * n + i] = 0.0;
-            outb[2LL * N + (long long)k * n + i] = 0.0;
+            out_at(0, k - 1, i) = 0.0;
+            out_at(1, k, i) = 0.0;
+            out_at(2, k, i) = 0.0;
         }
         return;
     }
@@ -136,16 +141,10 @@ __global__ void __launch_bounds__(416, 1) analysis_kernel(AnaParams p, int nstag
                         // nonlinear contribution (Matrix_Operators.py:802)
                         const int blk = (k >= 1) ? k - 1 : K - 1;
                         const double fv = (k >= 1) ? v : 0.0;
-                        const long long o = (long long)blk * n + i;
                         const bool keep = !(g.symmetric && (blk & 1) == 0);
-                        double r = keep ? fv : 0.0;
-                        if (linb) r = keep ? fma(p.mdt, fv, linb[o]) : 0.0;
-                        outb[o] = r;
+                        out_at(0, blk, i) = keep ? fv : 0.0;
                     } else {
-                        const long long o = (long long)f * N + (long long)k * n + i;
-                        double r = v;
-                        if (linb) r = fma(p.mdt, v, linb[o]);
-                        outb[o] = r;  // odd k never reaches here when symmetric
+                        out_at(f, k, i) = v;  // odd k never reaches here when symmetric
                     }
                 }
             }

@@ -22,15 +22,27 @@ __global__ void __launch_bounds__(128) scan_kernel(const double* __restrict__ X,
     const double* psi = X + (long long)b * x_stride;  // block m-1 holds sine mode m
     double* out = JJ + (long long)b * (K + 1) * n;
     const bool zero_chain = g.symmetric && ch == 1;   // odd sine modes are masked out (Main.py:157-164)
-    int m = K - ch;
-    double S = 0.0;
-    double pm = zero_chain ? 0.0 : psi[(long long)(m - 1) * n + i];
-    out[(long long)m * n + i] = (m + 1.0) * pm;
-#pragma unroll 8
-    for (m -= 2; m >= 0; m -= 2) {
-        S += pm;  // += psi^(m+2)
-        pm = (m >= 1 && !zero_chain) ? psi[(long long)(m - 1) * n + i] : 0.0;
-        out[(long long)m * n + i] = (m >= 1) ? ((m + 1.0) * pm + 2.0 * S) : S;
+    // chain of sine modes m = K-ch, K-ch-2, ... ; loads are issued in batches of U so that the memory latency is
+    // paid once per batch, the additions stay strictly sequential (same order as the reference)
+    constexpr int U = 16;
+    double S = 0.0, prev = 0.0;  // prev = psi^(m+2)
+    bool first = true;
+    for (int m0 = K - ch; m0 >= 0; m0 -= 2 * U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 - 2 * u;
+            v[u] = (m >= 1 && !zero_chain) ? psi[(long long)(m - 1) * n + i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 - 2 * u;
+            if (m < 0) break;
+            if (!first) S += prev;
+            first = false;
+            prev = v[u];
+            out[(long long)m * n + i] = (m >= 1) ? ((m + 1.0) * v[u] + 2.0 * S) : S;
+        }
     }
 }
 
@@ -40,10 +52,11 @@ struct PrepParams {
     const double* JJ;       // [B][K+1][n] from scan_kernel on the same X
     double* coef;           // coefficient set, tile-major [B][Khp/8][2 ks][2 par][9*n8][4] (see k_synth.cuh), or null
     long long coef_stride;  // member stride of coef in doubles
-    double* lin;            // [B][3N] linear right-hand side, or null
+    double* lin;            // linear right-hand side in solve-major order [3][K][bstride][n8+2] (k_solve.cuh), or null
+    long long bstride;      // members per (field, mode) slab of lin
     const double* Ra;       // [B]
     const double* Ras;      // [B]
-    const double *DrT, *D2rT, *DsqT;  // transposed, row-padded operators [n][n8]: M^T[i'][i]
+    const double *DrP, *D2rP, *DsqP;  // row-major operators zero-padded to [n8][n8+4]
     const double *ir2, *ir4, *r2, *dT0, *gb;  // [n]
     Geo g;
     int B;
@@ -51,133 +64,124 @@ struct PrepParams {
 
 constexpr int PREP_TC = 32;  // sinusoid columns per CTA
 
-__host__ __device__ inline size_t prep_smem_bytes(int n, int n8) {
-    return sizeof(double) * (size_t)(4 * (PREP_TC + 1) * n + 3 * n * n8);
+__host__ __device__ inline size_t prep_smem_bytes(int n8) {
+    return sizeof(double) * (size_t)(4 * (PREP_TC + 1) + 3 * n8) * (n8 + 4);
 }
 
-// One CTA per (member, tile of 32 sinusoid columns).  Phase A writes the coefficient arrays (k fastest),
-// phase B the linear right-hand sides (radial index fastest, the state layout).
-__global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
+// One CTA per (member, tile of 32 sinusoid columns), 2*nt8 warps: warp = (8-row radial tile mt, half of the
+// columns).  The radial derivatives Dr psi, D2r psi, Dsq psi, Dr T, Dr S are DMMA GEMMs
+//     OUT[i, c] = sum_i' Mat[i, i'] * X[c][i']      (A = operator, B = 32 mode blocks of the state tile)
+// whose accumulator fragments are written straight into (a) the tile-major coefficient arrays of the synthesis
+// GEMM -- one accumulator tile is one contiguous 256-byte A-fragment block there -- and (b) the linear
+// right-hand sides of Step_Python (Main.py:266-280) in the state layout.
+__global__ void __launch_bounds__(512) prep_kernel(PrepParams p) {
     extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
-    const int n = g.n, n8 = g.n8, K = g.K, N = g.N;
+    const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDX = n8 + 4;
     const int b = blockIdx.y, c0 = blockIdx.x * PREP_TC;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int TQ = PREP_TC + 1;
-    double* sP = smem;              // psi blocks c0-1 .. c0+31   (q = 0..32)
-    double* sT = sP + TQ * n;       // T   blocks c0   .. c0+32
-    double* sS = sT + TQ * n;       // S   blocks c0   .. c0+32
-    double* sJ = sS + TQ * n;       // JJ  modes  c0   .. c0+32
-    double* mDr = sJ + TQ * n;      // [n][n8]
-    double* mD2r = mDr + n * n8;
-    double* mDsq = mD2r + n * n8;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
+    constexpr int TQ = PREP_TC + 1;
+    double* sP = smem;               // psi blocks c0-1 .. c0+31   (q = 0..32), row stride LDX, padded entries zero
+    double* sT = sP + TQ * LDX;      // T   blocks c0   .. c0+32
+    double* sS = sT + TQ * LDX;      // S   blocks c0   .. c0+32
+    double* sJ = sS + TQ * LDX;      // JJ  modes  c0   .. c0+32
+    double* mDr = sJ + TQ * LDX;     // [n8][LDX]
+    double* mD2r = mDr + n8 * LDX;
+    double* mDsq = mD2r + n8 * LDX;
 
     const double* Xb = p.X + (long long)b * p.x_stride;
     const double* Jb = p.JJ + (long long)b * (K + 1) * n;
-    for (int idx = tid; idx < TQ * n; idx += 256) {
-        const int q = idx / n, i = idx - q * n;
+    for (int idx = tid; idx < TQ * LDX; idx += nthr) {
+        const int q = idx / LDX, i = idx - q * LDX;
         const int bp = c0 - 1 + q, bt = c0 + q;
         double vp = 0.0, vt = 0.0, vs = 0.0, vj = 0.0;
-        if (bp >= 0 && bp < K && !(g.symmetric && (bp & 1) == 0)) vp = Xb[(long long)bp * n + i];
-        if (bt < K && !(g.symmetric && (bt & 1) == 1)) {
-            vt = Xb[(long long)N + (long long)bt * n + i];
-            vs = Xb[2LL * N + (long long)bt * n + i];
+        if (i < n) {
+            if (bp >= 0 && bp < K && !(g.symmetric && (bp & 1) == 0)) vp = Xb[(long long)bp * n + i];
+            if (bt < K && !(g.symmetric && (bt & 1) == 1)) {
+                vt = Xb[(long long)N + (long long)bt * n + i];
+                vs = Xb[2LL * N + (long long)bt * n + i];
+            }
+            if (bt <= K) vj = Jb[(long long)bt * n + i];
         }
-        if (bt <= K) vj = Jb[(long long)bt * n + i];
         sP[idx] = vp; sT[idx] = vt; sS[idx] = vs; sJ[idx] = vj;
     }
-    for (int idx = tid; idx < n * n8; idx += 256) {
-        mDr[idx] = p.DrT[idx]; mD2r[idx] = p.D2rT[idx]; mDsq[idx] = p.DsqT[idx];
+    for (int idx = tid; idx < n8 * LDX; idx += nthr) {
+        mDr[idx] = p.DrP[idx]; mD2r[idx] = p.D2rP[idx]; mDsq[idx] = p.DsqP[idx];
     }
     __syncthreads();
 
-    // ---- phase A: coefficient arrays; warp item = (field group, quad of radial rows); lane = column ----
-    if (p.coef != nullptr) {
-        const int nq = n8 / 4;
-        const int c = c0 + lane;
-        const int par = c & 1, kp = c >> 1;
-        double* cf = p.coef + (long long)b * p.coef_stride;
-        const int R9 = 9 * n8;
-        // element (field a, row i, parity, k') -> tile-major offset; fs = field stride inside one [row][4] plane
-        const long long fs = (long long)n8 * 4;
-        const long long cbase = ((long long)((kp >> 2) * 2 + par) * R9) * 4 + (kp & 3);
-        for (int it = warp; it < 3 * nq; it += 8) {
-            const int grp = it / nq, i0 = (it - grp * nq) * 4;
-            const double* sx = (grp == 0) ? sP : (grp == 1 ? sT : sS);
-            double d[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
-            if (grp == 0) {
-                for (int ip = 0; ip < n; ++ip) {
-                    const double x = sx[lane * n + ip];
-                    const double2 a0 = *reinterpret_cast<const double2*>(&mDr[ip * n8 + i0]);
-                    const double2 a1 = *reinterpret_cast<const double2*>(&mDr[ip * n8 + i0 + 2]);
-                    const double2 b0 = *reinterpret_cast<const double2*>(&mD2r[ip * n8 + i0]);
-                    const double2 b1 = *reinterpret_cast<const double2*>(&mD2r[ip * n8 + i0 + 2]);
-                    d[0] = fma(a0.x, x, d[0]); d[1] = fma(a0.y, x, d[1]);
-                    d[2] = fma(a1.x, x, d[2]); d[3] = fma(a1.y, x, d[3]);
-                    e[0] = fma(b0.x, x, e[0]); e[1] = fma(b0.y, x, e[1]);
-                    e[2] = fma(b1.x, x, e[2]); e[3] = fma(b1.y, x, e[3]);
-                }
-            } else {
-                for (int ip = 0; ip < n; ++ip) {
-                    const double x = sx[lane * n + ip];
-                    const double2 a0 = *reinterpret_cast<const double2*>(&mDr[ip * n8 + i0]);
-                    const double2 a1 = *reinterpret_cast<const double2*>(&mDr[ip * n8 + i0 + 2]);
-                    d[0] = fma(a0.x, x, d[0]); d[1] = fma(a0.y, x, d[1]);
-                    d[2] = fma(a1.x, x, d[2]); d[3] = fma(a1.y, x, d[3]);
-                }
-            }
-            if (c < K) {
+    const int mt = warp >> 1, nh = warp & 1;
+    const bool want_lin = p.lin != nullptr;
+    double dps[2][2] = {}, d2r[2][2] = {}, dsq[2][2] = {}, dT[2][2] = {}, dS[2][2] = {};
+    {
+        const int arow = (mt * 8 + gq) * LDX + tq;
+        const int bcol = (nh * 16 + gq) * LDX + tq;
+        for (int ks = 0; ks < n8 / 4; ++ks) {
+            const double aDr = mDr[arow + ks * 4], aD2r = mD2r[arow + ks * 4], aDsq = mDsq[arow + ks * 4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int i = i0 + r;
-                    if (i >= n) break;
-                    const long long o = cbase + (long long)i * 4;
-                    if (grp == 0) {
-                        const double jj = sJ[lane * n + i];
-                        double om = 0.0, dps = 0.0;
-                        if (c >= 1) {
-                            om = e[r] - (double)c * (p.ir4[i] * jj);
-                            dps = d[r];
-                        }
-                        cf[0 * fs + o] = jj;                 // JT
-                        cf[1 * fs + o] = (double)c * dps;    // k Dpsi
-                        cf[2 * fs + o] = (double)c * om;     // k omega
-                        cf[5 * fs + o] = om;                 // omega
-                        cf[6 * fs + o] = dps;                // Dpsi
-                    } else {
-                        const double x = sx[lane * n + i];
-                        cf[(grp == 1 ? 3 : 4) * fs + o] = d[r];               // DT / DS
-                        cf[(grp == 1 ? 7 : 8) * fs + o] = -(double)c * x;     // -k T / -k S
-                    }
-                }
+            for (int nl = 0; nl < 2; ++nl) {
+                const int o = bcol + nl * 8 * LDX + ks * 4;
+                const double bP = sP[o], bT = sT[o], bS = sS[o];
+                mma884(dps[nl][0], dps[nl][1], aDr, bP);
+                mma884(d2r[nl][0], d2r[nl][1], aD2r, bP);
+                mma884(dT[nl][0], dT[nl][1], aDr, bT);
+                mma884(dS[nl][0], dS[nl][1], aDr, bS);
+                if (want_lin) mma884(dsq[nl][0], dsq[nl][1], aDsq, sP[o + LDX]);  // psi block c (sine mode c+1)
             }
         }
     }
-
-    // ---- phase B: linear right-hand sides, state layout (radial index fastest) ----
-    if (p.lin != nullptr) {
-        double* lb = p.lin + (long long)b * 3 * N;
-        const double Ra = p.Ra[b], Ras = p.Ras[b];
-        const double dtPr = g.dt * g.Pr;
-        for (int idx = tid; idx < PREP_TC * n; idx += 256) {
-            const int ql = idx / n, i = idx - ql * n;
-            const int blk = c0 + ql;
-            if (blk >= K) continue;
-            // psi equation: A2_SINE(psi) + dt Pr G(Ra T - Ra_s S), sine mode m = blk + 1
-            const int m = blk + 1;
-            const double* xp = &sP[(ql + 1) * n];
-            double mv = 0.0;
-            for (int ip = 0; ip < n; ++ip) mv = fma(mDsq[ip * n8 + i], xp[ip], mv);
-            double a2 = mv - (double)m * (p.ir2[i] * sJ[(ql + 1) * n + i]);
-            if (m <= K - 1) {
-                const double w = Ra * sT[(ql + 1) * n + i] - Ras * sS[(ql + 1) * n + i];
-                a2 += dtPr * ((-(double)m * p.gb[i]) * w);
+    const int i = mt * 8 + gq;
+    if (i >= n) return;
+    const double ir2 = p.ir2[i], ir4 = p.ir4[i], r2 = p.r2[i], dT0 = p.dT0[i], gb = p.gb[i];
+    const int R9 = 9 * n8;
+    double* cf = p.coef ? p.coef + (long long)b * p.coef_stride : nullptr;
+    double* lb = p.lin;
+    const int LDG = n8 + 2;
+    auto lin_off = [&](int f, int blk) { return (((long long)f * K + blk) * p.bstride + b) * LDG + i; };
+    const double Ra = want_lin ? p.Ra[b] : 0.0, Ras = want_lin ? p.Ras[b] : 0.0;
+    const double dtPr = g.dt * g.Pr;
+#pragma unroll
+    for (int nl = 0; nl < 2; ++nl) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int col = nh * 16 + nl * 8 + 2 * tq + e;
+            const int c = c0 + col;
+            if (c >= K) continue;
+            const double jj = sJ[col * LDX + i];
+            const double tv = sT[col * LDX + i], sv = sS[col * LDX + i];
+            if (cf) {
+                const int kp = c >> 1;  // parity of c is e (c0 is a multiple of 32)
+                const long long o = (((long long)((kp >> 2) * 2 + e) * R9) + i) * 4 + (kp & 3);
+                const long long fs = (long long)n8 * 4;
+                double om = 0.0, dp = 0.0;
+                if (c >= 1) {
+                    om = d2r[nl][e] - (double)c * (ir4 * jj);
+                    dp = dps[nl][e];
+                }
+                cf[0 * fs + o] = jj;                  // JT
+                cf[1 * fs + o] = (double)c * dp;      // k Dpsi
+                cf[2 * fs + o] = (double)c * om;      // k omega
+                cf[3 * fs + o] = dT[nl][e];           // DT
+                cf[4 * fs + o] = dS[nl][e];           // DS
+                cf[5 * fs + o] = om;                  // omega
+                cf[6 * fs + o] = dp;                  // Dpsi
+                cf[7 * fs + o] = -(double)c * tv;     // -k T
+                cf[8 * fs + o] = -(double)c * sv;     // -k S
             }
-            lb[(long long)blk * n + i] = a2;
-            // T, S equations: r^2 T - dt * dT0 * J_theta(psi), cosine mode k = blk
-            const double pT0 = p.dT0[i] * sJ[ql * n + i];
-            lb[(long long)N + (long long)blk * n + i] = p.r2[i] * sT[ql * n + i] - g.dt * pT0;
-            lb[2LL * N + (long long)blk * n + i] = p.r2[i] * sS[ql * n + i] - g.dt * pT0;
+            if (lb) {
+                // psi equation, block c <-> sine mode m = c+1: A2_SINE(psi) + dt Pr G(Ra T - Ra_s S)
+                const int m = c + 1;
+                double a2 = dsq[nl][e] - (double)m * (ir2 * sJ[(col + 1) * LDX + i]);
+                if (m <= K - 1) {
+                    const double w = Ra * sT[(col + 1) * LDX + i] - Ras * sS[(col + 1) * LDX + i];
+                    a2 += dtPr * ((-(double)m * gb) * w);
+                }
+                lb[lin_off(0, c)] = a2;
+                // T, S equations, cosine mode c: r^2 T - dt * dT0 * J_theta(psi)
+                const double pT0 = dT0 * jj;
+                lb[lin_off(1, c)] = r2 * tv - g.dt * pT0;
+                lb[lin_off(2, c)] = r2 * sv - g.dt * pT0;
+            }
         }
     }
 }

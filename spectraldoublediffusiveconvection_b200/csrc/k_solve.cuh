@@ -9,9 +9,17 @@
 namespace sddc {
 
 struct SolveParams {
-    const double* g;        // right-hand sides
-    long long g_stride;     // member stride (doubles); field offset added via g_field_off
-    long long g_field_off;  // offset between fields inside a member (N for a full state, 0 for single field)
+    // right-hand sides, one of two layouts:
+    //  * state layout (SM = false): g[member*g_stride + fld*g_field_off + row*n + i]   (stand-alone solves)
+    //  * solve-major (SM = true):   g[((fld*K + row)*bstride + member)*LDG + i], LDG = n8+2: the 16 members a CTA
+    //    owns are one contiguous tile per chain step, fetched by one TMA bulk copy (hot path; written in this
+    //    order by prep_kernel / analysis_kernel)
+    const double* g;
+    const double* fnl;      // optional nonlinear term F(X), same layout as g: rhs = g + mdt * fnl  (Main.py:262,271)
+    double mdt;             // -dt
+    long long g_stride;     // state layout: member stride (doubles)
+    long long g_field_off;  // state layout: offset between fields inside a member (N, or 0 for single-field calls)
+    long long bstride;      // solve-major: members per (field, row) slab (max_batch rounded up to 16)
     double* out;
     long long out_stride;
     long long out_field_off;
@@ -29,23 +37,25 @@ struct SolveParams {
     double dt_psi, dt_T, dt_S;  // Pr*dt, dt, Tau*dt
 };
 
-constexpr int SOLVE_NSL = 3;  // operator pipeline stages
+constexpr int SOLVE_NSL = 3;  // pipeline stages (operator + right-hand-side tiles)
 
 template <int NTB>
 __host__ __device__ inline size_t solve_smem_doubles(int n8) {
-    const int LDL = n8 + 4;
-    return (size_t)(SOLVE_NSL + 1) * n8 * LDL + (size_t)2 * (8 * NTB) * LDL;
+    const int LDL = n8 + 4, LDG = n8 + 2;
+    return (size_t)(SOLVE_NSL + 1) * n8 * LDL + (size_t)2 * (8 * NTB) * LDL + (size_t)SOLVE_NSL * 2 * (8 * NTB) * LDG;
 }
 
 // grid = (ceil(B / (8*NTB)), 2 chains, nfields), block = 32 * nt8 (warp w owns radial rows 8w..8w+7).
 // Every thread owns the elements (i = 8w + g, member = nt*8 + 2t + e) in MMA accumulator layout, so the
-// running vectors b / f_e / bf_e of the reference live in registers.
-template <int NTB>
+// running vectors b / f_e / bf_e of the reference live in registers.  Per chain step one thread issues TMA bulk
+// copies (pre-inverted operator of the mode, right-hand-side tiles) two steps ahead into a 3-stage ring.
+template <int NTB, bool SM>
 __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     constexpr int BT = 8 * NTB, NE = 2 * NTB;
     extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t bar_full[SOLVE_NSL];
     const Geo& G = p.geo;
-    const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL;
+    const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, GT = BT * LDG;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const int nthr = blockDim.x;
     const int b0 = blockIdx.x * BT, which = blockIdx.y, fld = p.field_base + blockIdx.z;
@@ -53,6 +63,7 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     double* sL = smem;                          // [NSL][n8][LDL]
     double* sD2 = sL + (size_t)SOLVE_NSL * MAT; // [n8][LDL]
     double* sR = sD2 + MAT;                     // [2][BT][LDL]
+    double* sG = sR + (size_t)2 * BT * LDL;     // [NSL][2][BT][LDG]  (solve-major right-hand-side tiles: lin, F)
 
     const int i = warp * 8 + gq;
     const bool row_ok = i < n;
@@ -65,6 +76,26 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
         goff[e] = (long long)(b0 + m) * p.g_stride + (long long)fld * p.g_field_off + i;
         ooff[e] = (long long)(b0 + m) * p.out_stride + (long long)fld * p.out_field_off + i;
     }
+    // right-hand side of chain row `row` (pipeline stage st) -> registers
+    auto load_g = [&](int row, int st, double* v) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            double x = 0.0;
+            if (ok[e]) {
+                if (SM) {
+                    const int m = (e >> 1) * 8 + 2 * tq + (e & 1);
+                    const double* t = sG + (size_t)st * 2 * GT + m * LDG + i;
+                    x = t[0];
+                    if (p.fnl) x = fma(p.mdt, t[GT], x);
+                } else {
+                    const long long o = goff[e] + (long long)row * n;
+                    x = p.g[o];
+                    if (p.fnl) x = fma(p.mdt, p.fnl[o], x);
+                }
+            }
+            v[e] = x;
+        }
+    };
     auto store_out = [&](int row, const double* f) {
 #pragma unroll
         for (int e = 0; e < NE; ++e)
@@ -77,17 +108,25 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
 #pragma unroll
         for (int e = 0; e < NE; ++e) buf[((e >> 1) * 8 + 2 * tq + (e & 1)) * LDL + i] = v[e];
     };
-    // C = Mat(n8 x n8, smem, row stride LDL) @ V (smem [member][i'])
+    // C = Mat(n8 x n8, smem, row stride LDL) @ V (smem [member][i']); two independent accumulator chains
+    // (even / odd k-steps) halve the dependent-MMA latency
     auto gemm = [&](const double* mat, const double* vec, double* c) {
+        double c1[NE];
 #pragma unroll
-        for (int e = 0; e < NE; ++e) c[e] = 0.0;
+        for (int e = 0; e < NE; ++e) c[e] = c1[e] = 0.0;
         const double* ar = mat + (warp * 8 + gq) * LDL + tq;
         const double* br = vec + gq * LDL + tq;
-        for (int ks = 0; ks < n8 / 4; ++ks) {
-            const double a = ar[ks * 4];
+#pragma unroll 2
+        for (int ks = 0; ks < n8 / 4; ks += 2) {
+            const double a0 = ar[ks * 4], a1 = ar[ks * 4 + 4];
 #pragma unroll
-            for (int nt = 0; nt < NTB; ++nt) mma884(c[2 * nt], c[2 * nt + 1], a, br[nt * 8 * LDL + ks * 4]);
+            for (int nt = 0; nt < NTB; ++nt) {
+                mma884(c[2 * nt], c[2 * nt + 1], a0, br[nt * 8 * LDL + ks * 4]);
+                mma884(c1[2 * nt], c1[2 * nt + 1], a1, br[nt * 8 * LDL + ks * 4 + 4]);
+            }
         }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) c[e] += c1[e];
     };
 
     const bool is_psi = (fld == 0);
@@ -104,22 +143,33 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     }
     const double* Lg = is_psi ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
     const int nsteps = (j0 - jend) / 2 + 1;
-    auto load_op = [&](int step) {  // operator of chain step `step` (mode j0 - 2*step) -> stage step % NSL
-        if (step < nsteps) {
-            const int j = j0 - 2 * step;
-            const int jj = is_psi ? (K - j) : (K - 1 - j);
-            const double* src = Lg + (long long)jj * MAT;
-            double* dst = sL + (size_t)(step % SOLVE_NSL) * MAT;
-            for (int idx = tid; idx < MAT / 2; idx += nthr) cp_async16(dst + idx * 2, src + idx * 2);
+    if (tid == 0) {
+        for (int s = 0; s < SOLVE_NSL; ++s) mbar_init(&bar_full[s], 1);
+        mbar_fence_init();
+    }
+    // chain step `step` handles mode j = j0 - 2*step, state row (j-1 for psi, j otherwise)
+    auto issue = [&](int step) {
+        if (tid == 0 && step < nsteps) {
+            const int j = j0 - 2 * step, st = step % SOLVE_NSL;
+            const int jj = is_psi ? (K - j) : (K - 1 - j), row = is_psi ? j - 1 : j;
+            const unsigned tile_bytes = (unsigned)(GT * sizeof(double));
+            unsigned bytes = (unsigned)(MAT * sizeof(double));
+            if (SM) bytes += tile_bytes * (p.fnl ? 2u : 1u);
+            mbar_expect_tx(&bar_full[st], bytes);
+            bulk_g2s(sL + (size_t)st * MAT, Lg + (long long)jj * MAT, (unsigned)(MAT * sizeof(double)), &bar_full[st]);
+            if (SM) {
+                const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
+                bulk_g2s(sG + (size_t)st * 2 * GT, p.g + o, tile_bytes, &bar_full[st]);
+                if (p.fnl) bulk_g2s(sG + (size_t)st * 2 * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
+            }
         }
-        cp_async_commit();
     };
-    load_op(0);
-    load_op(1);
     if (is_psi)
         for (int idx = tid; idx < MAT; idx += nthr) sD2[idx] = p.D2[idx];
     for (int idx = tid; idx < 2 * BT * LDL; idx += nthr) sR[idx] = 0.0;  // padded rows stay zero
     __syncthreads();
+    issue(0);
+    issue(1);
 
     double f[NE], gv[NE];
     if (!is_psi) {
@@ -128,9 +178,9 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
 #pragma unroll
         for (int e = 0; e < NE; ++e) { bsum[e] = 0.0; f[e] = 0.0; }
         for (int step = 0; step < nsteps; ++step) {
-            const int j = j0 - 2 * step;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) gv[e] = ok[e] ? p.g[goff[e] + (long long)j * n] : 0.0;
+            const int j = j0 - 2 * step, st = step % SOLVE_NSL;
+            mbar_wait(&bar_full[st], (step / SOLVE_NSL) & 1);
+            load_g(j, st, gv);
             double rhs[NE];
             const double beta = 2.0 * dt * (j + 2.0);
 #pragma unroll
@@ -140,10 +190,9 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
             }
             double* buf = sR + (size_t)(step & 1) * BT * LDL;
             put_rhs(buf, rhs);
-            cp_async_wait<1>();
             __syncthreads();
-            load_op(step + 2);
-            gemm(sL + (size_t)(step % SOLVE_NSL) * MAT, buf, f);
+            issue(step + 2);  // its stage was last read in step-1, which every warp has left
+            gemm(sL + (size_t)st * MAT, buf, f);
             store_out(j, f);
         }
     } else {
@@ -155,12 +204,12 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
         double* bufA = sR;
         double* bufB = sR + (size_t)BT * LDL;
         for (int step = 0; step < nsteps; ++step) {
-            const int j = j0 - 2 * step;
+            const int j = j0 - 2 * step, st = step % SOLVE_NSL;
             const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
-#pragma unroll
-            for (int e = 0; e < NE; ++e) gv[e] = ok[e] ? p.g[goff[e] + (long long)(j - 1) * n] : 0.0;
             double rhs[NE];
             if (step == 0) {
+                mbar_wait(&bar_full[st], 0);
+                load_g(j - 1, st, gv);
 #pragma unroll
                 for (int e = 0; e < NE; ++e) rhs[e] = gv[e];
             } else {
@@ -169,6 +218,8 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
                 put_rhs(bufA, fe);
                 __syncthreads();
                 gemm(sD2, bufA, u);  // D2 @ f_e ; L1 = D2 + b_j IR4
+                mbar_wait(&bar_full[st], (step / SOLVE_NSL) & 1);
+                load_g(j - 1, st, gv);
 #pragma unroll
                 for (int e = 0; e < NE; ++e) {
                     const double l1 = u[e] + bj * (ir4 * fe[e]);
@@ -176,10 +227,9 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
                 }
             }
             put_rhs(bufB, rhs);
-            cp_async_wait<1>();
             __syncthreads();
-            load_op(step + 2);
-            gemm(sL + (size_t)(step % SOLVE_NSL) * MAT, bufB, f);
+            issue(step + 2);
+            gemm(sL + (size_t)st * MAT, bufB, f);
             store_out(j - 1, f);
 #pragma unroll
             for (int e = 0; e < NE; ++e) bfe[e] += (step == 0) ? bj * f[e] : (bj * f[e] + bjt * fe[e]);

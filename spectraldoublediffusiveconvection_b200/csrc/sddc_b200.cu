@@ -43,6 +43,7 @@ struct sddc_plan {
     std::vector<void*> allocs;
     // operators
     double *DrT = nullptr, *D2rT = nullptr, *DsqT = nullptr, *Dr = nullptr, *D2p = nullptr;
+    double *DrP = nullptr, *D2rP = nullptr, *DsqP = nullptr;  // [n8][n8+4] zero-padded row-major
     double *LA4 = nullptr, *LT = nullptr, *LS = nullptr;
     double *ir2 = nullptr, *ir4 = nullptr, *r2 = nullptr, *dT0 = nullptr, *gb = nullptr, *a4_ir2 = nullptr,
            *a4_ir4 = nullptr, *ir = nullptr, *nu_in = nullptr, *nu_out = nullptr, *wr = nullptr;
@@ -52,9 +53,12 @@ struct sddc_plan {
            *kepart = nullptr, *zeroRa = nullptr;
     double* coef1 = nullptr;
     long long coef_member_stride = 0;
+    double *lin_sm = nullptr, *f_sm = nullptr;  // solve-major [3][K][bstride][n8+2]
+    long long bstride = 0;
     // host-API staging
     double *hX0 = nullptr, *hX1 = nullptr, *hX2 = nullptr, *hRa = nullptr, *hRas = nullptr, *hDiag = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
     int synth_nt_fx = 0, synth_nt_dfx = 0, synth_nt_ke = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
     size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
@@ -231,13 +235,13 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     pp.X = X; pp.x_stride = 3LL * pl->g.N; pp.JJ = pl->JJ;
     pp.coef = want_coef ? (set == 0 ? pl->coef : pl->coef1) : nullptr;
     pp.coef_stride = pl->coef_member_stride;
-    pp.lin = lin; pp.Ra = Ra; pp.Ras = Ras;
-    pp.DrT = pl->DrT; pp.D2rT = pl->D2rT; pp.DsqT = pl->DsqT;
+    pp.lin = lin; pp.bstride = pl->bstride; pp.Ra = Ra; pp.Ras = Ras;
+    pp.DrP = pl->DrP; pp.D2rP = pl->D2rP; pp.DsqP = pl->DsqP;
     pp.ir2 = pl->ir2; pp.ir4 = pl->ir4; pp.r2 = pl->r2; pp.dT0 = pl->dT0; pp.gb = pl->gb;
     pp.g = pl->g; pp.B = B;
     dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
     StageTimer tm(pl, SDDC_STAGE_PREP, st);
-    prep_kernel<<<grid, 256, prep_smem_bytes(pl->g.n, pl->g.n8), st>>>(pp);
+    prep_kernel<<<grid, 64 * pl->g.nt8, prep_smem_bytes(pl->g.n8), st>>>(pp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
@@ -255,17 +259,20 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     return launch_synth<EPI_FX>(pl, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
 }
 
-int run_analysis(sddc_plan* pl, const double* lin, double* out, int B, cudaStream_t st) {
+int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream_t st) {
     AnaParams ap{};
-    ap.prd = pl->prd; ap.tab2 = pl->tab2; ap.lin = lin; ap.out = out; ap.g = pl->g; ap.mdt = -pl->g.dt;
+    ap.prd = pl->prd; ap.tab2 = pl->tab2; ap.out = out; ap.bstride = solve_major ? pl->bstride : 0; ap.g = pl->g;
     StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
     return launch_analysis(pl, ap, B, st);
 }
 
-int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double* out, long long os, long long of,
-              const double* sub, int field_base, int nfields, int B, cudaStream_t st) {
+// gs < 0 selects the solve-major layout for g / fnl
+int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, long long gf, double* out, long long os,
+              long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st) {
     SolveParams sp{};
-    sp.g = g; sp.g_stride = gs; sp.g_field_off = gf; sp.out = out; sp.out_stride = os; sp.out_field_off = of;
+    const bool sm = gs < 0;
+    sp.bstride = pl->bstride;
+    sp.g = g; sp.fnl = fnl; sp.mdt = -pl->g.dt; sp.g_stride = gs; sp.g_field_off = gf; sp.out = out; sp.out_stride = os; sp.out_field_off = of;
     sp.sub = sub; sp.LinvA4 = pl->LA4; sp.LinvT = pl->LT; sp.LinvS = pl->LS; sp.D2 = pl->D2p;
     sp.ir2 = pl->a4_ir2; sp.ir4 = pl->a4_ir4; sp.geo = pl->g; sp.B = B;
     sp.field_mask = 7; sp.field_base = field_base;
@@ -273,7 +280,8 @@ int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double
     // single-field calls pass field offsets of 0; the operator stack follows field_base
     dim3 grid((B + 15) / 16, 2, nfields);
     StageTimer tm(pl, SDDC_STAGE_SOLVE, st);
-    solve_kernel<2><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
+    if (sm) solve_kernel<2, true><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
+    else solve_kernel<2, false><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
@@ -283,15 +291,15 @@ int run_solve(sddc_plan* pl, const double* g, long long gs, long long gf, double
 int run_member_step(sddc_plan* pl, const double* X, double* out, const double* sub, const double* Ra,
                     const double* Ras, int B, bool linear, cudaStream_t st) {
     const long long N3 = 3LL * pl->g.N;
-    int rc = run_prep(pl, X, 0, !linear, pl->lin, Ra, Ras, B, st);
+    int rc = run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st);
     if (rc) return rc;
-    const double* rhs = pl->lin;
+    const double* fnl = nullptr;
     if (!linear) {
         if ((rc = run_synth_nl(pl, false, B, st))) return rc;
-        if ((rc = run_analysis(pl, pl->lin, pl->rhs, B, st))) return rc;
-        rhs = pl->rhs;
+        if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
+        fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
     }
-    return run_solve(pl, rhs, N3, pl->g.N, out, N3, pl->g.N, sub, 0, 3, B, st);
+    return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
 }
 
 int ensure_host_staging(sddc_plan* pl) {
@@ -305,6 +313,8 @@ int ensure_host_staging(sddc_plan* pl) {
     if ((rc = dev_alloc(pl, &pl->hRas, pl->cfg.max_batch, false))) return rc;
     if ((rc = dev_alloc(pl, &pl->hDiag, (size_t)pl->cfg.max_batch * 6, false))) return rc;
     PLAN_CUDA(pl, cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+    PLAN_CUDA(pl, cudaStreamCreateWithFlags(&pl->in_stream, cudaStreamNonBlocking));
+    PLAN_CUDA(pl, cudaStreamCreateWithFlags(&pl->out_stream, cudaStreamNonBlocking));
     return SDDC_OK;
 }
 
@@ -329,6 +339,10 @@ void sddc_plan_destroy(sddc_plan* plan) {
     cudaSetDevice(plan->device);
     for (void* p : plan->allocs) cudaFree(p);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
+    if (plan->in_stream) cudaStreamDestroy(plan->in_stream);
+    if (plan->out_stream) cudaStreamDestroy(plan->out_stream);
+    for (auto e : plan->ev_in) cudaEventDestroy(e);
+    for (auto e : plan->ev_done) cudaEventDestroy(e);
     delete plan;
 }
 
@@ -381,6 +395,9 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(upload(pl, &pl->DsqT, transpose_pad(ops->Dsq, n, n8)));
     TRY(upload(pl, &pl->Dr, std::vector<double>(ops->Dr, ops->Dr + (size_t)n * n)));
     TRY(upload(pl, &pl->D2p, pad_stack(ops->D2, 1, n, n8, pl->LDL)));
+    TRY(upload(pl, &pl->DrP, pad_stack(ops->Dr, 1, n, n8, pl->LDL)));
+    TRY(upload(pl, &pl->D2rP, pad_stack(ops->D2r, 1, n, n8, pl->LDL)));
+    TRY(upload(pl, &pl->DsqP, pad_stack(ops->Dsq, 1, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->LA4, pad_stack(ops->Linv_A4, K, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->LT, pad_stack(ops->Linv_T, K, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->LS, pad_stack(ops->Linv_S, K, n, n8, pl->LDL)));
@@ -439,6 +456,9 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(dev_alloc(pl, &pl->coef, Bm * pl->coef_member_stride, true));   // padded rows / columns stay zero
     TRY(dev_alloc(pl, &pl->coef1, Bm * pl->coef_member_stride, true));  // second set: dv (JVP) or KE rows
     TRY(dev_alloc(pl, &pl->prd, Bm * 3 * 2 * n8 * g.Mhp, true));
+    pl->bstride = (long long)round_up(cfg->max_batch, 16);
+    TRY(dev_alloc(pl, &pl->lin_sm, (size_t)3 * K * pl->bstride * (n8 + 2), true));
+    TRY(dev_alloc(pl, &pl->f_sm, (size_t)3 * K * pl->bstride * (n8 + 2), true));
     TRY(dev_alloc(pl, &pl->lin, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->rhs, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->xtmp, Bm * 3 * g.N, false));
@@ -457,8 +477,9 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         TRY(launch_analysis(pl, ap, 1, nullptr, true));
     }
     pl->solve_smem = solve_smem_doubles<2>(n8) * sizeof(double);
-    TRY(set_smem(pl, solve_kernel<2>, pl->solve_smem));
-    TRY(set_smem(pl, prep_kernel, prep_smem_bytes(n, n8)));
+    TRY(set_smem(pl, solve_kernel<2, true>, pl->solve_smem));
+    TRY(set_smem(pl, solve_kernel<2, false>, pl->solve_smem));
+    TRY(set_smem(pl, prep_kernel, prep_smem_bytes(n8)));
     TRY(set_smem(pl, linop_kernel, sizeof(double) * ((size_t)PREP_TC * n + (size_t)n * n8)));
     TRY(set_smem(pl, ke_prep_kernel, sizeof(double) * ((size_t)32 * n + (size_t)n * n8)));
     TRYC(cudaDeviceSynchronize());
@@ -498,7 +519,7 @@ int sddc_nlin_fx(sddc_plan* pl, const double* X, double* F, int B, void* stream)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, false, B, st))) return rc;
-    return run_analysis(pl, nullptr, F, B, st);
+    return run_analysis(pl, F, false, B, st);
 }
 
 int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, int B, void* stream) {
@@ -508,7 +529,7 @@ int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, i
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
-    return run_analysis(pl, nullptr, F, B, st);
+    return run_analysis(pl, F, false, B, st);
 }
 
 int sddc_linear_op(sddc_plan* pl, int op, const double* in, double* out, int B, void* stream) {
@@ -541,14 +562,14 @@ int sddc_linear_op(sddc_plan* pl, int op, const double* in, double* out, int B, 
 int sddc_solve_a4(sddc_plan* pl, const double* g, double* f, int B, void* stream) {
     int rc = check_batch(pl, B);
     if (rc) return rc;
-    return run_solve(pl, g, pl->g.N, 0, f, pl->g.N, 0, nullptr, 0, 1, B, static_cast<cudaStream_t>(stream));
+    return run_solve(pl, g, nullptr, pl->g.N, 0, f, pl->g.N, 0, nullptr, 0, 1, B, static_cast<cudaStream_t>(stream));
 }
 
 int sddc_solve_nab2(sddc_plan* pl, int which, const double* g, double* f, int B, void* stream) {
     int rc = check_batch(pl, B);
     if (rc) return rc;
     if (which != 0 && which != 1) { pl->err = "which must be 0 (T) or 1 (S)"; return SDDC_ERR_INVALID; }
-    return run_solve(pl, g, pl->g.N, 0, f, pl->g.N, 0, nullptr, 1 + which, 1, B, static_cast<cudaStream_t>(stream));
+    return run_solve(pl, g, nullptr, pl->g.N, 0, f, pl->g.N, 0, nullptr, 1 + which, 1, B, static_cast<cudaStream_t>(stream));
 }
 
 int sddc_step(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B, int nsteps,
@@ -581,10 +602,10 @@ int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long N3 = 3LL * pl->g.N;
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
-    if ((rc = run_prep(pl, dv, 1, true, pl->lin, Ra, Ras, B, st))) return rc;
+    if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
-    if ((rc = run_analysis(pl, pl->lin, pl->rhs, B, st))) return rc;
-    return run_solve(pl, pl->rhs, N3, pl->g.N, out, N3, pl->g.N, dv, 0, 3, B, st);
+    if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
+    return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
 }
 
 int sddc_dF_dRa(sddc_plan* pl, const double* X, double* out, int B, void* stream) {
@@ -609,7 +630,7 @@ int sddc_dF_dRa(sddc_plan* pl, const double* X, double* out, int B, void* stream
     axpby_kernel<<<296, 256, 0, st>>>(pl->rhs, pl->rhs, pl->rhs, s, 0.0, (long long)B * N);
     pl->launches++;
     PLAN_CUDA(pl, cudaMemsetAsync(out, 0, sizeof(double) * B * N3, st));
-    return run_solve(pl, pl->rhs, N, 0, out, N3, N, nullptr, 0, 1, B, st);
+    return run_solve(pl, pl->rhs, nullptr, N, 0, out, N3, N, nullptr, 0, 1, B, st);
 }
 
 int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* stream) {
@@ -671,23 +692,45 @@ int sddc_profile_end(sddc_plan* pl, double* ms, int* counts) {
     return SDDC_OK;
 }
 
+// Host-buffer member-steps.  The batch is cut into chunks of members that flow through a three-stream pipeline
+// (H2D copy | kernels | D2H copy), so PCIe transfers in both directions overlap each other and the compute.
 int sddc_step_host(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B,
                    int nsteps, int linear, double* diag_out) {
     int rc = check_batch(pl, B);
     if (rc) return rc;
     if ((rc = ensure_host_staging(pl))) return rc;
-    cudaStream_t st = pl->own_stream;
-    const size_t bytes = sizeof(double) * (size_t)B * 3 * pl->g.N;
-    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX0, Xin, bytes, cudaMemcpyHostToDevice, st));
-    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRa, Ra, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRas, Ras, sizeof(double) * B, cudaMemcpyHostToDevice, st));
-    if ((rc = sddc_step(pl, pl->hX0, pl->hX1, pl->hRa, pl->hRas, B, nsteps, linear, st))) return rc;
-    if (diag_out) {
-        if ((rc = sddc_diagnostics(pl, pl->hX1, pl->hDiag, B, st))) return rc;
-        PLAN_CUDA(pl, cudaMemcpyAsync(diag_out, pl->hDiag, sizeof(double) * B * 6, cudaMemcpyDeviceToHost, st));
+    const size_t W = 3 * (size_t)pl->g.N;
+    const int chunk = std::min(B, std::max(16, (B + 7) / 8));
+    const int nchunks = (B + chunk - 1) / chunk;
+    while ((int)pl->ev_in.size() < nchunks) {
+        cudaEvent_t a, b2;
+        PLAN_CUDA(pl, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        PLAN_CUDA(pl, cudaEventCreateWithFlags(&b2, cudaEventDisableTiming));
+        pl->ev_in.push_back(a); pl->ev_done.push_back(b2);
     }
-    PLAN_CUDA(pl, cudaMemcpyAsync(Xout, pl->hX1, bytes, cudaMemcpyDeviceToHost, st));
-    PLAN_CUDA(pl, cudaStreamSynchronize(st));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRa, Ra, sizeof(double) * B, cudaMemcpyHostToDevice, pl->in_stream));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRas, Ras, sizeof(double) * B, cudaMemcpyHostToDevice, pl->in_stream));
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * chunk, nb = std::min(chunk, B - b0);
+        const size_t off = (size_t)b0 * W, bytes = sizeof(double) * (size_t)nb * W;
+        PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX0 + off, Xin + off, bytes, cudaMemcpyHostToDevice, pl->in_stream));
+        PLAN_CUDA(pl, cudaEventRecord(pl->ev_in[c], pl->in_stream));
+        PLAN_CUDA(pl, cudaStreamWaitEvent(pl->own_stream, pl->ev_in[c], 0));
+        // xtmp is indexed from member 0 inside sddc_step; chunks run back to back on own_stream, so it is free
+        if ((rc = sddc_step(pl, pl->hX0 + off, pl->hX1 + off, pl->hRa + b0, pl->hRas + b0, nb, nsteps, linear,
+                            pl->own_stream)))
+            return rc;
+        if (diag_out && (rc = sddc_diagnostics(pl, pl->hX1 + off, pl->hDiag + (size_t)b0 * 6, nb, pl->own_stream)))
+            return rc;
+        PLAN_CUDA(pl, cudaEventRecord(pl->ev_done[c], pl->own_stream));
+        PLAN_CUDA(pl, cudaStreamWaitEvent(pl->out_stream, pl->ev_done[c], 0));
+        PLAN_CUDA(pl, cudaMemcpyAsync(Xout + off, pl->hX1 + off, bytes, cudaMemcpyDeviceToHost, pl->out_stream));
+        if (diag_out)
+            PLAN_CUDA(pl, cudaMemcpyAsync(diag_out + (size_t)b0 * 6, pl->hDiag + (size_t)b0 * 6, sizeof(double) * nb * 6,
+                                          cudaMemcpyDeviceToHost, pl->out_stream));
+    }
+    PLAN_CUDA(pl, cudaStreamSynchronize(pl->out_stream));
+    PLAN_CUDA(pl, cudaStreamSynchronize(pl->own_stream));
     return SDDC_OK;
 }
 
