@@ -74,7 +74,8 @@ __host__ __device__ inline size_t prep_smem_bytes(int n8) {
 // whose accumulator fragments are written straight into (a) the tile-major coefficient arrays of the synthesis
 // GEMM -- one accumulator tile is one contiguous 256-byte A-fragment block there -- and (b) the linear
 // right-hand sides of Step_Python (Main.py:266-280) in the state layout.
-__global__ void __launch_bounds__(512) prep_kernel(PrepParams p) {
+template <int NT8>
+__global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(PrepParams p) {
     extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDX = n8 + 4;

@@ -241,7 +241,15 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     pp.g = pl->g; pp.B = B;
     dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
     StageTimer tm(pl, SDDC_STAGE_PREP, st);
-    prep_kernel<<<grid, 64 * pl->g.nt8, prep_smem_bytes(pl->g.n8), st>>>(pp);
+    const size_t smem = prep_smem_bytes(pl->g.n8);
+    switch (pl->g.nt8) {
+        case 3: prep_kernel<3><<<grid, 192, smem, st>>>(pp); break;
+        case 4: prep_kernel<4><<<grid, 256, smem, st>>>(pp); break;
+        case 5: prep_kernel<5><<<grid, 320, smem, st>>>(pp); break;
+        case 6: prep_kernel<6><<<grid, 384, smem, st>>>(pp); break;
+        case 7: prep_kernel<7><<<grid, 448, smem, st>>>(pp); break;
+        default: prep_kernel<8><<<grid, 512, smem, st>>>(pp); break;
+    }
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
@@ -479,7 +487,12 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->solve_smem = solve_smem_doubles<2>(n8) * sizeof(double);
     TRY(set_smem(pl, solve_kernel<2, true>, pl->solve_smem));
     TRY(set_smem(pl, solve_kernel<2, false>, pl->solve_smem));
-    TRY(set_smem(pl, prep_kernel, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<5>, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<6>, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<7>, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<8>, prep_smem_bytes(n8)));
     TRY(set_smem(pl, linop_kernel, sizeof(double) * ((size_t)PREP_TC * n + (size_t)n * n8)));
     TRY(set_smem(pl, ke_prep_kernel, sizeof(double) * ((size_t)32 * n + (size_t)n * n8)));
     TRYC(cudaDeviceSynchronize());

@@ -81,3 +81,84 @@ def kinetic_energy(MO, TR, X_hat, R, D, N_fm, nr, symmetric):
     KE = trap(KE_t * np.sin(th), x=th, axis=-1)
     V = (2.0 / 3.0) * (R[-1] ** 3 - R[0] ** 3)
     return (0.5 / V) * KE
+
+
+def newton(MO, X, Ra, Ra_s, Tau, Pr, d, N_fm, N_r, symmetric, dt=1.0, tol_newton=1e-8, tol_gmres=1e-4,
+           Krylov_Space_Size=300, max_it=5):
+    """The iteration of Main._Newton (Main.py:430-554): X <- X - lgmres(PDFX(.,X), PFX(X)); returns the final X and
+    the printed history error_k = |dv| / |X|.  SciPy's LGMRES stays on the host exactly as in the reference."""
+    import scipy.sparse.linalg as spla
+    ops = build_matrix_operators(MO, N_fm, N_r, d, dt, Pr, Tau)
+    _, residual, jvp, _ = make_closures(MO, ops, Ra, Ra_s, dt, Pr, Tau, symmetric)
+    nr = N_r - 1
+    mask = np.ones(3 * N_fm * nr)
+    if symmetric:
+        m3 = mask.reshape(3, N_fm, nr)
+        m3[0, 0::2] = 0.0
+        m3[1:, 1::2] = 0.0
+    history, n_matvec = [], [0]
+    error, it = 1.0, 0
+    X = X.copy()
+    while error > tol_newton and it < max_it:
+        X = mask * X
+        fx = residual(X)
+
+        def DF(v, X=X):
+            n_matvec[0] += 1
+            return jvp(v, X)
+
+        A = spla.LinearOperator((X.shape[0], X.shape[0]), matvec=DF, dtype="float64")
+        b_norm = np.linalg.norm(fx, 2)
+        dv, info = spla.lgmres(A, fx, maxiter=250, inner_m=Krylov_Space_Size, atol=tol_gmres * b_norm)
+        X = X - dv
+        error = np.linalg.norm(dv, 2) / np.linalg.norm(X, 2)
+        history.append(error)
+        it += 1
+    return X, np.array(history), n_matvec[0]
+
+
+class OracleOperators:
+    """The same operator-layer surface as Matrix_Operators, backed by the NumPy oracle (CPU) -- the comparison arm
+    for driver-level parity tests."""
+
+    def __init__(self, orc, N_fm, N_r, d, dt, Pr, Tau):
+        self.orc = orc
+        self.op = orc.Operators(N_fm, N_r, d, dt, Pr, Tau)
+        self.K, self.n = N_fm, N_r - 1
+
+    def _f(self, v):
+        return np.asarray(v, dtype=np.float64).reshape(self.K, self.n)
+
+    def cheb_radial(self, N, d):
+        return self.orc.cheb_radial(N, d)
+
+    def R2(self, R, N_fm):
+        r2 = (R[1:-1] ** 2)[None, :]
+        return type("Dot", (), {"dot": lambda s, v: (r2 * self._f(v)).reshape(-1)})()
+
+    def kGR_RT(self, R, N_fm, d):
+        return type("Dot", (), {"dot": lambda s, v: self.orc.buoyancy(self._f(v), self.op).reshape(-1)})()
+
+    def A4_TSTEP_MATS(self, dt, N_fm, nr, D, R):
+        return self.orc.a4_tstep_mats(dt, N_fm, nr, D, R)
+
+    def NAB2_TSTEP_MATS(self, dt, N_fm, nr, D, R):
+        return self.orc.nab2_tstep_mats(dt, N_fm, nr, D, R)
+
+    def DT0_theta(self, g, dT0, N_fm, nr, symmetric):
+        return self.orc.DT0_theta(self._f(g), dT0, symmetric).reshape(-1)
+
+    def A2_SINE(self, g, D, R, N_fm, nr, symmetric):
+        return self.orc.A2_SINE(self._f(g), self.op, symmetric).reshape(-1)
+
+    def NLIN_FX(self, X, D, R, N_fm, nr, symmetric):
+        return self.orc.NLIN_FX(X, self.op, symmetric)
+
+    def NLIN_DFX(self, dv, X, D, R, N_fm, nr, symmetric):
+        return self.orc.NLIN_DFX(dv, X, self.op, symmetric)
+
+    def A4_BSub_TSTEP_V2(self, g, L_inv, D2, IR4, IR2, N_fm, nr, dt, symmetric):
+        return self.orc.A4_BSub(self._f(g), L_inv, self.op, dt, symmetric).reshape(-1)
+
+    def NAB2_BSub_TSTEP_V2(self, g, L_inv, N_fm, nr, dt, symmetric):
+        return self.orc.NAB2_BSub(self._f(g), L_inv, dt, symmetric).reshape(-1)

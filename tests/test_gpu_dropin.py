@@ -88,3 +88,33 @@ def test_single_function_signatures(modules):
     assert rel_l2(MO.INTERP_THETAS(32, 16, Xi), gi["theta_up"]) < 1e-12
     assert rel_l2(MO.INTERP_THETAS(8, 16, Xi), gi["theta_down"]) < 1e-12
     assert rel_l2(MO.INTERP_RADIAL(14, 10, Xi, di), gi["radial_up"]) < 1e-9
+
+
+def test_newton_history_matches_cpu_path(modules):
+    """BASELINE config 4 in miniature: the Newton iteration of Main._Newton (host SciPy LGMRES, matrix-free JVPs)
+    produces the same error history on the GPU operators as on the CPU oracle operators, from the same X0."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    MO, _ = modules
+    # wide-gap l=2 case of Tests/Run_Tests.py:140-199 (d=2, Pr=10, N_fm=32, N_r=16, symmetric)
+    N_fm, N_r, d, Pr, Tau, Ra, Ra_s, sym = 32, 16, 2.0, 10.0, 1.0, 6780.0, 0.0, True
+    nr = N_r - 1
+    # a reproducible starting state: time-step a seeded random IC towards the steady branch on the GPU
+    pl = EnsemblePlan(N_fm, N_r, d, 0.075, Pr, Tau, symmetric=sym, max_batch=1)
+    X0 = np.random.default_rng(0).random(3 * nr * N_fm)
+    X0 = 1e-3 * X0 / np.linalg.norm(X0)
+    X0 = torch.as_tensor(X0 * orc.sym_mask(N_fm, nr).reshape(-1)).cuda().reshape(1, -1)
+    Xs = pl.step(X0, Ra, Ra_s, nsteps=13000).cpu().numpy().ravel()   # transient, not yet on the steady branch
+    pl.close()
+    assert np.isfinite(Xs).all() and 0.1 < np.linalg.norm(Xs) < 0.3
+    Xg, hg, ng = drv.newton(MO, Xs, Ra, Ra_s, Tau, Pr, d, N_fm, N_r, sym, max_it=5)
+    Xc, hc, nc = drv.newton(drv.OracleOperators(orc, N_fm, N_r, d, 1.0, Pr, Tau), Xs, Ra, Ra_s, Tau, Pr, d, N_fm, N_r,
+                            sym, max_it=5)
+    print("newton history gpu", hg, "cpu", hc, "matvecs", ng, nc, "rel", np.abs(hg / hc - 1))
+    assert len(hg) == len(hc) == 5 and ng == nc, (hg, hc, ng, nc)
+    # north_star: histories agree to 1e-10 (absolute; the last entries are ~1e-6 and agree to ~1e-13 absolute)
+    assert np.max(np.abs(hg - hc)) < 1e-10 and np.allclose(hg, hc, rtol=1e-6, atol=0), (hg, hc)
+    assert rel_l2(Xg, Xc) < 1e-9
+    # both land on the steady branch of the reference's wide-gap test (KE = 2.57522e-2, SURVEY.md section 4)
+    ke = orc.kinetic_energy(Xg, orc.Operators(N_fm, N_r, d, 1.0, Pr, Tau), sym)
+    assert abs(ke / 2.5752204992e-2 - 1) < 1e-6

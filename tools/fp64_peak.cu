@@ -73,6 +73,18 @@ __global__ void __launch_bounds__(256) dmma16816_kernel(double* out, int iters, 
     if (s == 123.456) out[0] = s;
 }
 
+// dependent-issue latency of DMMA.8x8x4: one warp, one accumulator chain
+__global__ void dmma_latency_kernel(double* out, long long* cycles, int iters, double a, double b) {
+    double c0 = threadIdx.x, c1 = 1.0;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    if (c0 + c1 == 123.456) out[0] = c0;
+}
+
 __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -119,6 +131,12 @@ int main() {
             double fl = 2.0 * 16 * 8 * 16 * 8 * (double)(iters / 8) * 8.0 * grid;
             printf("DMMA 16x8x16 ilp8 blocks/SM=%d : %.3f ms  %.2f TFLOP/s\n", bps, ms, fl / ms * 1e-9);
         }
+    }
+    {
+        long long* cyc; CK(cudaMalloc(&cyc, 8));
+        dmma_latency_kernel<<<1, 32>>>(out, cyc, 4096, 1.0000001, 1e-9);
+        long long h = 0; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+        printf("DMMA 8x8x4 dependent-chain latency: %.1f cycles/instr\n", (double)h / 4096.0);
     }
     // HBM copy
     size_t n = (size_t)1 << 27;  // 128 Mi double2 = 2 GiB
