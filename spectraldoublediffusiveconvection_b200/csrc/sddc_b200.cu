@@ -60,6 +60,7 @@ struct sddc_plan {
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
+    bool dfx_ok = true;
     int synth_nt_fx = 0, synth_nt_dfx = 0, synth_nt_ke = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
     size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
     int ana_nt = 0, ana_stage = 0;
@@ -256,6 +257,10 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
 }
 
 int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
+    if (dfx && !pl->dfx_ok) {
+        pl->err = "NLIN_DFX / JVP is not available for this N_r (two-state synthesis exceeds shared memory; N_r <= 41)";
+        return SDDC_ERR_UNSUPPORTED;
+    }
     SynthParams sp{};
     sp.coef0 = pl->coef; sp.coef1 = pl->coef1; sp.coef_stride = pl->coef_member_stride;
     sp.tab = dfx ? pl->tab1d : pl->tab1; sp.Dr = pl->Dr; sp.prd = pl->prd;
@@ -433,11 +438,13 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     }
     // ---- kernel configuration (tile shapes decide the table layouts) ----
     if (pick_synth(g, 1, 9, &pl->synth_nt_fx, &pl->synth_stage_fx, &pl->synth_smem_fx) ||
-        pick_synth(g, 2, 9, &pl->synth_nt_dfx, &pl->synth_stage_dfx, &pl->synth_smem_dfx) ||
         pick_synth(g, 1, 2, &pl->synth_nt_ke, &pl->synth_stage_ke, &pl->synth_smem_ke)) {
         pl->err = "N_r too large for the instantiated synthesis tiles";
         return fail(SDDC_ERR_UNSUPPORTED);
     }
+    // the two-state (JVP) synthesis needs twice the staging; beyond N_r = 41 it does not fit in shared memory
+    pl->dfx_ok = pick_synth(g, 2, 9, &pl->synth_nt_dfx, &pl->synth_stage_dfx, &pl->synth_smem_dfx) == SDDC_OK;
+    if (!pl->dfx_ok) { pl->synth_nt_dfx = pl->synth_nt_fx; pl->synth_smem_dfx = 0; }
     pl->ana_nt = ana_nt_for(g.nt8);
     // ---- trigonometric tables (tile-major, L2-resident) ----
     {
@@ -470,14 +477,14 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(dev_alloc(pl, &pl->lin, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->rhs, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->xtmp, Bm * 3 * g.N, false));
-    pl->nke = pl->Mh3p / 32;
+    pl->nke = pl->Mh3p / (8 * pl->synth_nt_ke);
     TRY(dev_alloc(pl, &pl->kepart, Bm * pl->nke, true));
     TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
     // ---- opt in to large dynamic shared memory ----
     {
         SynthParams sp{};
         TRY(launch_synth<EPI_FX>(pl, sp, 0, pl->synth_smem_fx, 1, 1, nullptr, true));
-        TRY(launch_synth<EPI_DFX>(pl, sp, 0, pl->synth_smem_dfx, 1, 1, nullptr, true));
+        if (pl->dfx_ok) TRY(launch_synth<EPI_DFX>(pl, sp, 0, pl->synth_smem_dfx, 1, 1, nullptr, true));
         TRY(launch_synth<EPI_KE>(pl, sp, 0, pl->synth_smem_ke, 1, 1, nullptr, true));
         pl->ana_stage = ANA_MAX_STAGES;
         pl->ana_smem = ANA_MAX_STAGES * ana_stage_doubles(g.nt8) * sizeof(double);

@@ -172,3 +172,41 @@ def test_error_behaviour():
     with pytest.raises(ValueError):
         pl.nlin_fx(torch.zeros((3, 3 * pl.N), dtype=torch.float64, device="cuda"))   # B > max_batch
     pl.close()
+
+
+@pytest.mark.parametrize("K,N_r,sym", [(128, 20, False), (512, 40, False), (64, 33, True), (40, 50, False),
+                                        (24, 65, False), (8, 18, True)])
+def test_other_shapes_against_oracle(K, N_r, sym):
+    """Every kernel instantiation (radial tile counts 3..8, BASELINE configs 2 and 5 shapes, ragged mode counts):
+    one step, one JVP, diagnostics and the nonlinear term against the NumPy oracle on seeded inputs."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    d, dt, Pr, Tau = 0.353, 2e-3, 1.0, 1.0 / 15.0
+    pl = EnsemblePlan(K, N_r, d, dt, Pr, Tau, symmetric=sym, max_batch=3)
+    op = orc.Operators(K, N_r, d, dt, Pr, Tau)
+    rng = np.random.default_rng(K + N_r)
+    B = 3
+    X = rng.random((B, 3 * pl.N)) * 1e-2
+    dv = rng.standard_normal((B, 3 * pl.N))
+    Ra, Ra_s = np.array([3000.0, 4000.0, 9000.0]), np.array([0.0, 300.0, 500.0])
+    Xd, dvd = _dev(X), _dev(dv)
+    F = pl.nlin_fx(Xd).cpu().numpy()
+    st = pl.step(Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
+    has_jvp = N_r <= 41           # the two-state synthesis needs 2x the staging shared memory (DESIGN.md section 7)
+    if has_jvp:
+        jv = pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
+    else:
+        from spectraldoublediffusiveconvection_b200.plan import SddcError
+        with pytest.raises(SddcError):
+            pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s))
+    dg = pl.diagnostics(Xd).cpu().numpy()
+    mask = orc.sym_mask(K, N_r - 1).reshape(-1) if sym else 1.0
+    for m in range(B):
+        assert rel_l2(F[m], orc.NLIN_FX(X[m], op, sym)) < 1e-11
+        assert rel_l2(st[m], orc.step(X[m], op, Ra[m], Ra_s[m], sym)) < 1e-9
+        if has_jvp:
+            assert rel_l2(jv[m], orc.jvp(dv[m], X[m], op, Ra[m], Ra_s[m], sym)) < 1e-9
+        ref = orc.diagnostics(X[m] * mask, op, sym) if sym else orc.diagnostics(X[m], op, sym)
+        got = pl.diagnostics(_dev(X[m] * mask)).cpu().numpy()[0] if sym else dg[m]
+        assert np.allclose(got[:4], ref, rtol=1e-10)
+    pl.close()
