@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--members-per-gpu", type=int, default=512)
     ap.add_argument("--N_r", type=int, default=30)
     ap.add_argument("--N_fm", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -312,27 +312,47 @@ def run_ours(a):
     ms_d = max_over_ranks(e0.elapsed_time(e1))
     with_diag = Btot * nd / (ms_d * 1e-3)
 
-    # ---- end to end through the C ABI with HOST buffers: H2D of the state, one step, D2H of state + diagnostics ----
-    bufs = [plan.pinned((Bl, W)), plan.pinned((Bl, W))]
-    dgh = plan.pinned((Bl, 6))
-    bufs[0][...] = A.cpu().numpy()
+    # ---- end to end through the C ABI with HOST buffers (pinned): the ensemble analogue of Main._Time_Step
+    # (Main.py:286-329): state H2D, K_e member-steps, the diagnostics of EVERY step copied back to the host, the
+    # state checkpointed to the host every K_e/10 steps (the reference's N_save cadence) and at the end.
+    ne = max(10, a.e2e_steps)
+    ck = max(1, ne // 10)
+    xin, xout = plan.pinned((Bl, W)), plan.pinned((Bl, W))
+    hist = plan.pinned((ne, Bl, 6))
+    ckp = plan.pinned((ne // ck, Bl, W))
+    xin[...] = A.cpu().numpy()
     Ra_h, Ras_h = Ra.cpu().numpy(), Ras.cpu().numpy()
-    ne = max(3, a.e2e_steps)
+    plan.time_step_host(xin, Ra_h, Ras_h, 3, diag_every=1, ckpt_every=0, out=xout, diag_hist=hist[:3])   # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    plan.time_step_host(xin, Ra_h, Ras_h, ne, diag_every=1, ckpt_every=ck, out=xout, diag_hist=hist, ckpt=ckp)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    state_b = Bl * W * 8
+    e2e = {"value": Btot * ne / (e2e_ms * 1e-3), "unit": "member-steps/s",
+           "h2d_bytes_per_step": int((state_b + 2 * Bl * 8) / ne) * world,
+           "d2h_bytes_per_step": int(Bl * 6 * 8 + state_b * (ne // ck + 1) / ne) * world,
+           "steps": ne, "timer": "host wall clock around the blocking C-ABI call, max over ranks",
+           "call": "sddc_time_step_host(X_host, nsteps=%d, diag_every=1, ckpt_every=%d): state H2D once, per-step "
+                   "diagnostics D2H, state checkpoints D2H, pinned host buffers" % (ne, ck)}
+    # strictest variant: the full state crosses PCIe in both directions on every single step
+    bufs = [xin, xout]
+    dgh = plan.pinned((Bl, 6))
     cur = 0
+    nr_ = 5
     for _ in range(2):
         plan.step_host(bufs[cur], Ra_h, Ras_h, nsteps=1, want_diag=True, out=bufs[1 - cur], diag_out=dgh)
         cur = 1 - cur
     barrier()
     t0 = time.perf_counter()
-    for _ in range(ne):
+    for _ in range(nr_):
         plan.step_host(bufs[cur], Ra_h, Ras_h, nsteps=1, want_diag=True, out=bufs[1 - cur], diag_out=dgh)
         cur = 1 - cur
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    e2e = {"value": Btot * ne / (e2e_ms * 1e-3), "unit": "member-steps/s",
-           "h2d_bytes_per_step": int(Bl * W * 8 + 2 * Bl * 8) * world, "d2h_bytes_per_step": int(Bl * W * 8 + Bl * 6 * 8) * world,
-           "steps": ne, "timer": "host wall clock around the blocking sddc_step_host calls, max over ranks",
-           "call": "sddc_step_host(X_host -> X_host, nsteps=1, diagnostics) per step, pinned host buffers"}
+    rt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_roundtrip = {"value": Btot * nr_ / (rt_ms * 1e-3), "unit": "member-steps/s",
+                     "h2d_bytes_per_step": int(state_b + 2 * Bl * 8) * world, "d2h_bytes_per_step": int(state_b + Bl * 48) * world,
+                     "call": "sddc_step_host(nsteps=1) per step: full state H2D + D2H every step (PCIe-bound)"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -349,7 +369,7 @@ def run_ours(a):
                            "parallelism": "ensemble members sharded over %d GPU(s), no data-path collective" % world,
                            "l2": "state + scratch working set (~%.1f GB/GPU) exceeds the 126 MB L2" %
                                  (Bl * (W * 5 + 9 * 2 * 32 * 256 + 3 * 2 * 32 * 192) * 8 / 1e9), **PHYS},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "clocks": clocks, "e2e": e2e, "e2e_state_roundtrip_every_step": e2e_roundtrip, "gpu_launches": launches,
                 "roofline": roofline, "roofline_hbm_step": hbm_view,
                 "stage_ms": stage_ms, "with_diagnostics": {"value": with_diag, "unit": "member-steps/s", "steps": nd,
                                                            "collective": "all_gather [B,6] f64 per step" if world > 1 else None}}

@@ -144,6 +144,12 @@ int sddc_profile_end(sddc_plan* plan, double* ms, int* counts);
 /* Host-buffer variants (blocking; copies included): what a ctypes / NumPy caller binds. */
 int sddc_step_host(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
                    int nsteps, int linear, double* diag_out /* [B][6] or NULL */);
+/* Main._Time_Step for an ensemble from host buffers (Main.py:286-329): state H2D once, nsteps member-steps, the
+ * diagnostics of every diag_every-th step copied back to diag_hist[nsteps/diag_every][B][6] and the state of every
+ * ckpt_every-th step to ckpt[nsteps/ckpt_every][B][3Kn] while later steps run (0 disables either), final state in
+ * Xout. Blocking. */
+int sddc_time_step_host(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
+                        int nsteps, int linear, int diag_every, double* diag_hist, int ckpt_every, double* ckpt);
 int sddc_jvp_host(sddc_plan* plan, const double* dv, const double* X, double* out, const double* Ra,
                   const double* Ra_s, int B);
 

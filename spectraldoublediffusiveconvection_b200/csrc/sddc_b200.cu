@@ -57,6 +57,9 @@ struct sddc_plan {
     long long bstride = 0;
     // host-API staging
     double *hX0 = nullptr, *hX1 = nullptr, *hX2 = nullptr, *hRa = nullptr, *hRas = nullptr, *hDiag = nullptr;
+    double* hHist = nullptr;  // [hist_cap][max_batch][6] diagnostics history of sddc_time_step_host
+    int hist_cap = 0;
+    cudaEvent_t ev_ckpt = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
@@ -351,9 +354,11 @@ void sddc_plan_destroy(sddc_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
     for (void* p : plan->allocs) cudaFree(p);
+    if (plan->hHist) cudaFree(plan->hHist);
     if (plan->own_stream) cudaStreamDestroy(plan->own_stream);
     if (plan->in_stream) cudaStreamDestroy(plan->in_stream);
     if (plan->out_stream) cudaStreamDestroy(plan->out_stream);
+    if (plan->ev_ckpt) cudaEventDestroy(plan->ev_ckpt);
     for (auto e : plan->ev_in) cudaEventDestroy(e);
     for (auto e : plan->ev_done) cudaEventDestroy(e);
     delete plan;
@@ -751,6 +756,72 @@ int sddc_step_host(sddc_plan* pl, const double* Xin, double* Xout, const double*
     }
     PLAN_CUDA(pl, cudaStreamSynchronize(pl->out_stream));
     PLAN_CUDA(pl, cudaStreamSynchronize(pl->own_stream));
+    return SDDC_OK;
+}
+
+// The loop of Main._Time_Step (Main.py:286-329) for an ensemble, driven from HOST buffers: the state goes to the
+// device once, every `diag_every` steps the diagnostics of all members are computed and copied back to
+// diag_hist[record][B][6] (asynchronously, overlapped with the following steps), every `ckpt_every` steps the state
+// is copied back to ckpt[record][B][3N] (the reference's X_DATA checkpoints), and the final state lands in Xout.
+int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B,
+                        int nsteps, int linear, int diag_every, double* diag_hist, int ckpt_every, double* ckpt) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (nsteps < 1 || diag_every < 0 || ckpt_every < 0 || (diag_every > 0 && !diag_hist) || (ckpt_every > 0 && !ckpt)) {
+        pl->err = "bad arguments to sddc_time_step_host";
+        return SDDC_ERR_INVALID;
+    }
+    if ((rc = ensure_host_staging(pl))) return rc;
+    const size_t W = 3 * (size_t)pl->g.N, bytes = sizeof(double) * (size_t)B * W;
+    const int nrec = diag_every ? nsteps / diag_every : 0;
+    if (nrec > pl->hist_cap) {
+        PLAN_CUDA(pl, cudaDeviceSynchronize());
+        if (pl->hHist) cudaFree(pl->hHist);  // stays registered in allocs only once: allocate fresh, track manually
+        void* q = nullptr;
+        PLAN_CUDA(pl, cudaMalloc(&q, sizeof(double) * (size_t)nrec * pl->cfg.max_batch * 6));
+        pl->hHist = static_cast<double*>(q);
+        pl->hist_cap = nrec;
+    }
+    if (!pl->ev_ckpt) PLAN_CUDA(pl, cudaEventCreateWithFlags(&pl->ev_ckpt, cudaEventDisableTiming));
+    if (pl->ev_in.empty()) {
+        cudaEvent_t a, b2;
+        PLAN_CUDA(pl, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        PLAN_CUDA(pl, cudaEventCreateWithFlags(&b2, cudaEventDisableTiming));
+        pl->ev_in.push_back(a); pl->ev_done.push_back(b2);
+    }
+    cudaStream_t cs = pl->own_stream;
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRa, Ra, sizeof(double) * B, cudaMemcpyHostToDevice, cs));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hRas, Ras, sizeof(double) * B, cudaMemcpyHostToDevice, cs));
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX0, Xin, bytes, cudaMemcpyHostToDevice, cs));
+    double* cur = pl->hX0;
+    double* nxt = pl->hX1;
+    bool ckpt_pending = false;
+    for (int s = 1; s <= nsteps; ++s) {
+        if ((rc = run_member_step(pl, cur, nxt, nullptr, pl->hRa, pl->hRas, B, linear != 0, cs))) return rc;
+        std::swap(cur, nxt);
+        if (diag_every && s % diag_every == 0) {
+            const int r = s / diag_every - 1;
+            double* drec = pl->hHist + (size_t)r * B * 6;
+            if ((rc = sddc_diagnostics(pl, cur, drec, B, cs))) return rc;
+            PLAN_CUDA(pl, cudaEventRecord(pl->ev_done[0], cs));
+            PLAN_CUDA(pl, cudaStreamWaitEvent(pl->out_stream, pl->ev_done[0], 0));
+            PLAN_CUDA(pl, cudaMemcpyAsync(diag_hist + (size_t)r * B * 6, drec, sizeof(double) * B * 6,
+                                          cudaMemcpyDeviceToHost, pl->out_stream));
+        }
+        if (ckpt_every && s % ckpt_every == 0) {
+            const int r = s / ckpt_every - 1;
+            if (ckpt_pending) PLAN_CUDA(pl, cudaStreamWaitEvent(cs, pl->ev_ckpt, 0));  // staging buffer free again
+            PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX2, cur, bytes, cudaMemcpyDeviceToDevice, cs));
+            PLAN_CUDA(pl, cudaEventRecord(pl->ev_in[0], cs));
+            PLAN_CUDA(pl, cudaStreamWaitEvent(pl->out_stream, pl->ev_in[0], 0));
+            PLAN_CUDA(pl, cudaMemcpyAsync(ckpt + (size_t)r * B * W, pl->hX2, bytes, cudaMemcpyDeviceToHost, pl->out_stream));
+            PLAN_CUDA(pl, cudaEventRecord(pl->ev_ckpt, pl->out_stream));
+            ckpt_pending = true;
+        }
+    }
+    PLAN_CUDA(pl, cudaMemcpyAsync(Xout, cur, bytes, cudaMemcpyDeviceToHost, cs));
+    PLAN_CUDA(pl, cudaStreamSynchronize(cs));
+    PLAN_CUDA(pl, cudaStreamSynchronize(pl->out_stream));
     return SDDC_OK;
 }
 

@@ -230,6 +230,29 @@ class EnsemblePlan:
                                             B, int(nsteps), int(bool(linear)), diag.ctypes.data if want_diag else None))
         return (out, diag) if want_diag else out
 
+    def time_step_host(self, X, Ra, Ra_s, nsteps, diag_every=1, ckpt_every=0, linear=False, out=None, diag_hist=None,
+                       ckpt=None):
+        """Ensemble analogue of Main._Time_Step from NumPy buffers: returns (X_final, diag_hist[, checkpoints]) with
+        diag_hist [nsteps // diag_every, B, 6] and checkpoints [nsteps // ckpt_every, B, 3N]."""
+        X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
+        B = X.shape[0]
+        Ra = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra, dtype=np.float64), (B,)))
+        Ra_s = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra_s, dtype=np.float64), (B,)))
+        out = np.empty_like(X) if out is None else out
+        nrec = nsteps // diag_every if diag_every else 0
+        nck = nsteps // ckpt_every if ckpt_every else 0
+        if diag_hist is None:
+            diag_hist = np.empty((nrec, B, 6))
+        if ckpt is None and nck:
+            ckpt = np.empty((nck, B, 3 * self.N))
+        if diag_hist.shape != (nrec, B, 6) or (nck and ckpt.shape != (nck, B, 3 * self.N)):
+            raise ValueError("history / checkpoint buffers have the wrong shape")
+        self._check(self.lib.sddc_time_step_host(
+            self._h, X.ctypes.data, out.ctypes.data, Ra.ctypes.data, Ra_s.ctypes.data, B, int(nsteps),
+            int(bool(linear)), int(diag_every), diag_hist.ctypes.data if nrec else None, int(ckpt_every),
+            ckpt.ctypes.data if nck else None))
+        return (out, diag_hist, ckpt) if nck else (out, diag_hist)
+
     def jvp_host(self, dv, X, Ra, Ra_s):
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
         dv = np.ascontiguousarray(dv, dtype=np.float64).reshape(-1, 3 * self.N)

@@ -210,3 +210,25 @@ def test_other_shapes_against_oracle(K, N_r, sym):
         got = pl.diagnostics(_dev(X[m] * mask)).cpu().numpy()[0] if sym else dg[m]
         assert np.allclose(got[:4], ref, rtol=1e-10)
     pl.close()
+
+
+def test_time_step_host_matches_device_loop():
+    """sddc_time_step_host (host buffers, async diagnostics / checkpoints) == explicit device loop, bit for bit."""
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    K, N_r, d, dt, Pr, Tau = 32, 20, 0.5, 5e-3, 1.0, 0.5
+    B, nsteps = 5, 12
+    pl = EnsemblePlan(K, N_r, d, dt, Pr, Tau, max_batch=B)
+    rng = np.random.default_rng(9)
+    X = rng.random((B, 3 * pl.N)) * 1e-2
+    Ra, Ra_s = np.linspace(2000.0, 4000.0, B), np.linspace(0.0, 200.0, B)
+    out, hist, ck = pl.time_step_host(X, Ra, Ra_s, nsteps, diag_every=2, ckpt_every=4)
+    assert hist.shape == (6, B, 6) and ck.shape == (3, B, 3 * pl.N)
+    cur = _dev(X)
+    for s in range(1, nsteps + 1):
+        cur = pl.step(cur, _dev(Ra), _dev(Ra_s))
+        if s % 2 == 0:
+            assert np.array_equal(hist[s // 2 - 1], pl.diagnostics(cur).cpu().numpy())
+        if s % 4 == 0:
+            assert np.array_equal(ck[s // 4 - 1], cur.cpu().numpy())
+    assert np.array_equal(out, cur.cpu().numpy())
+    pl.close()
