@@ -55,7 +55,8 @@ def main(rep, out):
                 stalls[h.split("stalled_")[1].split("_per")[0]] = float(r[i])
         top = sorted(stalls.items(), key=lambda kv: -kv[1])[:6]
         lines.append("   top warp stalls (per issue): " + ", ".join("%s %.2f" % kv for kv in top))
-        if "synth_kernel" in name and "(int)0" in name.replace(" ", "") and traffic is None:
+        import re
+        if re.search(r"synth_kernel<(\(int\))?\d+, *(\(int\))?0>", name) and traffic is None:
             rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
             wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
             traffic = {"kernel": name, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
