@@ -24,7 +24,7 @@ struct SolveParams {
     long long out_stride;
     long long out_field_off;
     const double* sub;      // optional: out = f - sub (same layout as out) for residual / JVP
-    const double* LinvA4;   // [K][n8][LDL] zero padded, descending-mode order (index K - j)
+    const double* LinvA4;   // [K][2][n8][LDL] zero padded, descending-mode order (index K - j): {L_inv_j, L_inv_j @ D2}
     const double* LinvT;    // [K][n8][LDL] index K-1-j
     const double* LinvS;
     const double* D2;       // [n8][LDL]
@@ -35,14 +35,15 @@ struct SolveParams {
     int field_mask;         // bit f: solve field f (0 psi, 1 T, 2 S)
     int field_base;         // field index of chain group 0 (for single-field calls)
     double dt_psi, dt_T, dt_S;  // Pr*dt, dt, Tau*dt
+    int nsl;                    // pipeline stages in use (2 or 3)
 };
 
-constexpr int SOLVE_NSL = 3;  // pipeline stages (operator + right-hand-side tiles)
+constexpr int SOLVE_NSL = 3;  // maximum pipeline stages (operator + right-hand-side tiles)
 
 template <int NTB>
-__host__ __device__ inline size_t solve_smem_doubles(int n8) {
+__host__ __device__ inline size_t solve_smem_doubles(int n8, int nsl) {
     const int LDL = n8 + 4, LDG = n8 + 2;
-    return (size_t)(SOLVE_NSL + 1) * n8 * LDL + (size_t)2 * (8 * NTB) * LDL + (size_t)SOLVE_NSL * 2 * (8 * NTB) * LDG;
+    return (size_t)(2 * nsl) * n8 * LDL + (size_t)4 * (8 * NTB) * LDL + (size_t)nsl * 2 * (8 * NTB) * LDG;
 }
 
 // grid = (ceil(B / (8*NTB)), 2 chains, nfields), block = 32 * nt8 (warp w owns radial rows 8w..8w+7).
@@ -60,10 +61,10 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     const int nthr = blockDim.x;
     const int b0 = blockIdx.x * BT, which = blockIdx.y, fld = p.field_base + blockIdx.z;
     if (!((p.field_mask >> fld) & 1)) return;
-    double* sL = smem;                          // [NSL][n8][LDL]
-    double* sD2 = sL + (size_t)SOLVE_NSL * MAT; // [n8][LDL]
-    double* sR = sD2 + MAT;                     // [2][BT][LDL]
-    double* sG = sR + (size_t)2 * BT * LDL;     // [NSL][2][BT][LDG]  (solve-major right-hand-side tiles: lin, F)
+    double* sL = smem;                          // [NSL][2][n8][LDL]  (second matrix only used by the psi chains)
+    const int NSL = p.nsl;
+    double* sR = sL + (size_t)NSL * 2 * MAT;  // [2 step parities][2][BT][LDL]
+    double* sG = sR + (size_t)4 * BT * LDL;     // [NSL][2][BT][LDG]  (solve-major right-hand-side tiles: lin, F)
 
     const int i = warp * 8 + gq;
     const bool row_ok = i < n;
@@ -128,6 +129,24 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
 #pragma unroll
         for (int e = 0; e < NE; ++e) c[e] += c1[e];
     };
+    // C = MatA @ VA + MatB @ VB as two interleaved, independent accumulator chains (one per product)
+    auto gemm2 = [&](const double* matA, const double* vecA, const double* matB, const double* vecB, double* c) {
+        double c1[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) c[e] = c1[e] = 0.0;
+        const int ao = (warp * 8 + gq) * LDL + tq, bo = gq * LDL + tq;
+#pragma unroll 2
+        for (int ks = 0; ks < n8 / 4; ++ks) {
+            const double a0 = matA[ao + ks * 4], a1 = matB[ao + ks * 4];
+#pragma unroll
+            for (int nt = 0; nt < NTB; ++nt) {
+                mma884(c[2 * nt], c[2 * nt + 1], a0, vecA[bo + nt * 8 * LDL + ks * 4]);
+                mma884(c1[2 * nt], c1[2 * nt + 1], a1, vecB[bo + nt * 8 * LDL + ks * 4]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) c[e] += c1[e];
+    };
 
     const bool is_psi = (fld == 0);
     // chain start mode: psi: j0 = K (which 0) | K-1 (which 1, skipped if symmetric)
@@ -144,19 +163,20 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     const double* Lg = is_psi ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
     const int nsteps = (j0 - jend) / 2 + 1;
     if (tid == 0) {
-        for (int s = 0; s < SOLVE_NSL; ++s) mbar_init(&bar_full[s], 1);
+        for (int s = 0; s < NSL; ++s) mbar_init(&bar_full[s], 1);
         mbar_fence_init();
     }
     // chain step `step` handles mode j = j0 - 2*step, state row (j-1 for psi, j otherwise)
     auto issue = [&](int step) {
         if (tid == 0 && step < nsteps) {
-            const int j = j0 - 2 * step, st = step % SOLVE_NSL;
+            const int j = j0 - 2 * step, st = step % NSL;
             const int jj = is_psi ? (K - j) : (K - 1 - j), row = is_psi ? j - 1 : j;
             const unsigned tile_bytes = (unsigned)(GT * sizeof(double));
-            unsigned bytes = (unsigned)(MAT * sizeof(double));
+            const unsigned mat_bytes = (unsigned)((is_psi ? 2 : 1) * MAT * sizeof(double));
+            unsigned bytes = mat_bytes;
             if (SM) bytes += tile_bytes * (p.fnl ? 2u : 1u);
             mbar_expect_tx(&bar_full[st], bytes);
-            bulk_g2s(sL + (size_t)st * MAT, Lg + (long long)jj * MAT, (unsigned)(MAT * sizeof(double)), &bar_full[st]);
+            bulk_g2s(sL + (size_t)st * 2 * MAT, Lg + (long long)jj * (is_psi ? 2 : 1) * MAT, mat_bytes, &bar_full[st]);
             if (SM) {
                 const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
                 bulk_g2s(sG + (size_t)st * 2 * GT, p.g + o, tile_bytes, &bar_full[st]);
@@ -164,12 +184,9 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
             }
         }
     };
-    if (is_psi)
-        for (int idx = tid; idx < MAT; idx += nthr) sD2[idx] = p.D2[idx];
-    for (int idx = tid; idx < 2 * BT * LDL; idx += nthr) sR[idx] = 0.0;  // padded rows stay zero
+    for (int idx = tid; idx < 4 * BT * LDL; idx += nthr) sR[idx] = 0.0;  // padded rows stay zero
     __syncthreads();
-    issue(0);
-    issue(1);
+    for (int s0 = 0; s0 < NSL - 1; ++s0) issue(s0);
 
     double f[NE], gv[NE];
     if (!is_psi) {
@@ -178,8 +195,8 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
 #pragma unroll
         for (int e = 0; e < NE; ++e) { bsum[e] = 0.0; f[e] = 0.0; }
         for (int step = 0; step < nsteps; ++step) {
-            const int j = j0 - 2 * step, st = step % SOLVE_NSL;
-            mbar_wait(&bar_full[st], (step / SOLVE_NSL) & 1);
+            const int j = j0 - 2 * step, st = step % NSL;
+            mbar_wait(&bar_full[st], (step / NSL) & 1);
             load_g(j, st, gv);
             double rhs[NE];
             const double beta = 2.0 * dt * (j + 2.0);
@@ -191,45 +208,47 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
             double* buf = sR + (size_t)(step & 1) * BT * LDL;
             put_rhs(buf, rhs);
             __syncthreads();
-            issue(step + 2);  // its stage was last read in step-1, which every warp has left
-            gemm(sL + (size_t)st * MAT, buf, f);
+            issue(step + NSL - 1);  // its stage was last read in step-1, which every warp has left
+            gemm(sL + (size_t)st * 2 * MAT, buf, f);
             store_out(j, f);
         }
     } else {
         const double dt = p.dt_psi;
-        double fe[NE], bfe[NE], u[NE];
+        double fe[NE], bfe[NE];
         const double ir2 = row_ok ? p.ir2[i] : 0.0, ir4 = row_ok ? p.ir4[i] : 0.0;
 #pragma unroll
         for (int e = 0; e < NE; ++e) { fe[e] = 0.0; bfe[e] = 0.0; f[e] = 0.0; }
-        double* bufA = sR;
-        double* bufB = sR + (size_t)BT * LDL;
+        double* bufA = sR;                        // dt*bjt*f_e   (multiplied by L_inv_j @ D2)
+        double* bufB = sR + (size_t)BT * LDL;     // elementwise part of the right-hand side (multiplied by L_inv_j)
+        // With L1_j = D2 + b_j IR4 (Matrix_Operators.py:1149) the reference's update
+        //     f_j = L_inv_j @ ( g_j + dt*bjt*(L1_j @ f_e + IR4 @ bf_e) - bjt*IR2 @ f_e )
+        // is evaluated as  L_inv_j @ rhs_elem + (L_inv_j @ D2) @ (dt*bjt*f_e)  with the product L_inv_j @ D2 formed
+        // once on the host: one barrier and one (double-width) GEMM round per chain step instead of two.
         for (int step = 0; step < nsteps; ++step) {
-            const int j = j0 - 2 * step, st = step % SOLVE_NSL;
+            const int j = j0 - 2 * step, st = step % NSL;
             const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
-            double rhs[NE];
+            double rhs[NE], sfe[NE];
+            mbar_wait(&bar_full[st], (step / NSL) & 1);
+            load_g(j - 1, st, gv);
             if (step == 0) {
-                mbar_wait(&bar_full[st], 0);
-                load_g(j - 1, st, gv);
 #pragma unroll
-                for (int e = 0; e < NE; ++e) rhs[e] = gv[e];
+                for (int e = 0; e < NE; ++e) { rhs[e] = gv[e]; sfe[e] = 0.0; }
             } else {
 #pragma unroll
-                for (int e = 0; e < NE; ++e) fe[e] += f[e];
-                put_rhs(bufA, fe);
-                __syncthreads();
-                gemm(sD2, bufA, u);  // D2 @ f_e ; L1 = D2 + b_j IR4
-                mbar_wait(&bar_full[st], (step / SOLVE_NSL) & 1);
-                load_g(j - 1, st, gv);
-#pragma unroll
                 for (int e = 0; e < NE; ++e) {
-                    const double l1 = u[e] + bj * (ir4 * fe[e]);
-                    rhs[e] = gv[e] + (dt * bjt * (l1 + ir4 * bfe[e]) - bjt * (ir2 * fe[e]));
+                    fe[e] += f[e];
+                    rhs[e] = gv[e] + (dt * bjt * (bj * (ir4 * fe[e]) + ir4 * bfe[e]) - bjt * (ir2 * fe[e]));
+                    sfe[e] = (dt * bjt) * fe[e];
                 }
             }
-            put_rhs(bufB, rhs);
+            double* bA = bufA + (size_t)(step & 1) * 2 * BT * LDL;
+            double* bB = bufB + (size_t)(step & 1) * 2 * BT * LDL;
+            put_rhs(bA, sfe);
+            put_rhs(bB, rhs);
             __syncthreads();
-            issue(step + 2);
-            gemm(sL + (size_t)st * MAT, bufB, f);
+            issue(step + NSL - 1);
+            const double* Lm = sL + (size_t)st * 2 * MAT;
+            gemm2(Lm, bB, Lm + MAT, bA, f);
             store_out(j - 1, f);
 #pragma unroll
             for (int e = 0; e < NE; ++e) bfe[e] += (step == 0) ? bj * f[e] : (bj * f[e] + bjt * fe[e]);

@@ -41,6 +41,7 @@ struct sddc_plan {
     long long launches = 0;
     std::string err;
     std::vector<void*> allocs;
+    std::vector<double> h_LinvA4, h_D2;  // host copies (unpadded) to rebuild the fused A4 stack
     // operators
     double *DrT = nullptr, *D2rT = nullptr, *DsqT = nullptr, *Dr = nullptr, *D2p = nullptr;
     double *DrP = nullptr, *D2rP = nullptr, *DsqP = nullptr;  // [n8][n8+4] zero-padded row-major
@@ -69,6 +70,7 @@ struct sddc_plan {
     int ana_nt = 0, ana_stage = 0;
     size_t ana_smem = 0;
     size_t solve_smem = 0;
+    int solve_nsl = 3;
     double dt_psi = 0, dt_T = 0, dt_S = 0;  // effective time steps of the three operator stacks
     // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
     bool profiling = false;
@@ -132,6 +134,27 @@ std::vector<double> pad_stack(const double* M, int nmat, int n, int n8, int LDL)
     for (int m = 0; m < nmat; ++m)
         for (int i = 0; i < n; ++i)
             std::memcpy(&o[((size_t)m * n8 + i) * LDL], &M[((size_t)m * n + i) * n], sizeof(double) * n);
+    return o;
+}
+
+// A4 operator stack [K][2][n8][LDL]: for every mode the pre-inverted operator L_inv_j and the product L_inv_j @ D2
+// (k_solve.cuh), zero padded
+std::vector<double> build_a4_stack(const double* Linv, const double* D2, int K, int n, int n8, int LDL) {
+    std::vector<double> o((size_t)K * 2 * n8 * LDL, 0.0);
+    std::vector<double> P((size_t)n * n);
+    for (int m = 0; m < K; ++m) {
+        const double* L = Linv + (size_t)m * n * n;
+        for (int i = 0; i < n; ++i)
+            for (int c = 0; c < n; ++c) {
+                double acc = 0.0;
+                for (int k = 0; k < n; ++k) acc = std::fma(L[(size_t)i * n + k], D2[(size_t)k * n + c], acc);
+                P[(size_t)i * n + c] = acc;
+            }
+        for (int i = 0; i < n; ++i) {
+            std::memcpy(&o[(((size_t)m * 2 + 0) * n8 + i) * LDL], &L[(size_t)i * n], sizeof(double) * n);
+            std::memcpy(&o[(((size_t)m * 2 + 1) * n8 + i) * LDL], &P[(size_t)i * n], sizeof(double) * n);
+        }
+    }
     return o;
 }
 
@@ -292,7 +315,7 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     sp.sub = sub; sp.LinvA4 = pl->LA4; sp.LinvT = pl->LT; sp.LinvS = pl->LS; sp.D2 = pl->D2p;
     sp.ir2 = pl->a4_ir2; sp.ir4 = pl->a4_ir4; sp.geo = pl->g; sp.B = B;
     sp.field_mask = 7; sp.field_base = field_base;
-    sp.dt_psi = pl->dt_psi; sp.dt_T = pl->dt_T; sp.dt_S = pl->dt_S;
+    sp.dt_psi = pl->dt_psi; sp.dt_T = pl->dt_T; sp.dt_S = pl->dt_S; sp.nsl = pl->solve_nsl;
     // single-field calls pass field offsets of 0; the operator stack follows field_base
     dim3 grid((B + 15) / 16, 2, nfields);
     StageTimer tm(pl, SDDC_STAGE_SOLVE, st);
@@ -416,7 +439,9 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(upload(pl, &pl->DrP, pad_stack(ops->Dr, 1, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->D2rP, pad_stack(ops->D2r, 1, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->DsqP, pad_stack(ops->Dsq, 1, n, n8, pl->LDL)));
-    TRY(upload(pl, &pl->LA4, pad_stack(ops->Linv_A4, K, n, n8, pl->LDL)));
+    pl->h_LinvA4.assign(ops->Linv_A4, ops->Linv_A4 + (size_t)K * n * n);
+    pl->h_D2.assign(ops->D2, ops->D2 + (size_t)n * n);
+    TRY(upload(pl, &pl->LA4, build_a4_stack(ops->Linv_A4, ops->D2, K, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->LT, pad_stack(ops->Linv_T, K, n, n8, pl->LDL)));
     TRY(upload(pl, &pl->LS, pad_stack(ops->Linv_S, K, n, n8, pl->LDL)));
     auto vec = [&](const double* v) { return std::vector<double>(v, v + n); };
@@ -496,7 +521,8 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         AnaParams ap{};
         TRY(launch_analysis(pl, ap, 1, nullptr, true));
     }
-    pl->solve_smem = solve_smem_doubles<2>(n8) * sizeof(double);
+    pl->solve_nsl = (solve_smem_doubles<2>(n8, 3) * sizeof(double) <= SMEM_LIMIT) ? 3 : 2;
+    pl->solve_smem = solve_smem_doubles<2>(n8, pl->solve_nsl) * sizeof(double);
     TRY(set_smem(pl, solve_kernel<2, true>, pl->solve_smem));
     TRY(set_smem(pl, solve_kernel<2, false>, pl->solve_smem));
     TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8)));
@@ -518,7 +544,13 @@ int sddc_plan_set_linv(sddc_plan* pl, int which, const double* Linv, double dt_e
     if (!pl || !Linv || which < 0 || which > 2) return SDDC_ERR_INVALID;
     PLAN_CUDA(pl, cudaSetDevice(pl->device));
     const Geo& g = pl->g;
-    std::vector<double> h = pad_stack(Linv, g.K, g.n, g.n8, pl->LDL);
+    std::vector<double> h;
+    if (which == 0) {
+        pl->h_LinvA4.assign(Linv, Linv + (size_t)g.K * g.n * g.n);
+        h = build_a4_stack(Linv, pl->h_D2.data(), g.K, g.n, g.n8, pl->LDL);
+    } else {
+        h = pad_stack(Linv, g.K, g.n, g.n8, pl->LDL);
+    }
     double* dst = which == 0 ? pl->LA4 : (which == 1 ? pl->LT : pl->LS);
     PLAN_CUDA(pl, cudaDeviceSynchronize());
     PLAN_CUDA(pl, cudaMemcpy(dst, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -530,9 +562,10 @@ int sddc_plan_set_a4_aux(sddc_plan* pl, const double* D2, const double* ir2, con
     if (!pl || !D2 || !ir2 || !ir4) return SDDC_ERR_INVALID;
     PLAN_CUDA(pl, cudaSetDevice(pl->device));
     const Geo& g = pl->g;
-    std::vector<double> h = pad_stack(D2, 1, g.n, g.n8, pl->LDL);
+    pl->h_D2.assign(D2, D2 + (size_t)g.n * g.n);
+    std::vector<double> h = build_a4_stack(pl->h_LinvA4.data(), D2, g.K, g.n, g.n8, pl->LDL);
     PLAN_CUDA(pl, cudaDeviceSynchronize());
-    PLAN_CUDA(pl, cudaMemcpy(pl->D2p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    PLAN_CUDA(pl, cudaMemcpy(pl->LA4, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
     PLAN_CUDA(pl, cudaMemcpy(pl->a4_ir2, ir2, g.n * sizeof(double), cudaMemcpyHostToDevice));
     PLAN_CUDA(pl, cudaMemcpy(pl->a4_ir4, ir4, g.n * sizeof(double), cudaMemcpyHostToDevice));
     return SDDC_OK;
