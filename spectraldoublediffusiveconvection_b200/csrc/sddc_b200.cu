@@ -1,6 +1,7 @@
 // Host side of the C ABI (include/sddc_b200.h): plan construction, operator upload / padding, kernel dispatch.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -13,6 +14,7 @@
 #include "k_prep.cuh"
 #include "k_solve.cuh"
 #include "k_synth.cuh"
+#include "k_synth_ws.cuh"
 
 using namespace sddc;
 
@@ -65,6 +67,9 @@ struct sddc_plan {
     std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
     bool dfx_ok = true;
+    bool ws_ok = false;       // persistent warp-specialised synthesis available for this shape
+    size_t ws_smem = 0;
+    int num_sms = 148;
     int synth_nt_fx = 0, synth_nt_dfx = 0, synth_nt_ke = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
     size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
     int ana_nt = 0, ana_stage = 0;
@@ -294,6 +299,15 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     const int nt = dfx ? pl->synth_nt_dfx : pl->synth_nt_fx;
     const int tiles = pl->g.Mhp / (8 * nt);
     StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
+    if (!dfx && pl->ws_ok) {
+        sp.tab = pl->tab1d;  // W = 16 table tiling
+        const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
+        const int grid = std::min(nwork, pl->num_sms);
+        synth_ws_kernel<4><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+        return SDDC_OK;
+    }
     if (dfx) return launch_synth<EPI_DFX>(pl, sp, pl->synth_stage_dfx, pl->synth_smem_dfx, tiles, B, st);
     return launch_synth<EPI_FX>(pl, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
 }
@@ -520,6 +534,18 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         pl->ana_smem = ANA_MAX_STAGES * ana_stage_doubles(g.nt8) * sizeof(double);
         AnaParams ap{};
         TRY(launch_analysis(pl, ap, 1, nullptr, true));
+    }
+    {
+        cudaDeviceProp prop;
+        TRYC(cudaGetDeviceProperties(&prop, pl->device));
+        pl->num_sms = prop.multiProcessorCount;
+        pl->ws_smem = synth_ws_smem_doubles(n, n8) * sizeof(double);
+        const char* env = getenv("SDDC_SYNTH_WS");
+        pl->ws_ok = g.nt8 == 4 && pl->synth_nt_dfx == SWS_NT && pl->dfx_ok && pl->ws_smem <= SMEM_LIMIT &&
+                    !(env && env[0] == '0');
+        if (pl->ws_ok) {
+            TRY(set_smem(pl, synth_ws_kernel<4>, pl->ws_smem));
+        }
     }
     pl->solve_nsl = (solve_smem_doubles<2>(n8, 3) * sizeof(double) <= SMEM_LIMIT) ? 3 : 2;
     pl->solve_smem = solve_smem_doubles<2>(n8, pl->solve_nsl) * sizeof(double);

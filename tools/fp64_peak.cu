@@ -85,6 +85,42 @@ __global__ void dmma_latency_kernel(double* out, long long* cycles, int iters, d
     if (c0 + c1 == 123.456) out[0] = c0;
 }
 
+// DMMA fed from shared memory the way the GEMM kernels do it: per k-step MT A-fragments + NT B-fragments (LDS.64,
+// conflict-free [row][4] layout), MT*NT independent accumulator tiles.  No global traffic, no barriers.
+template <int MT, int NT>
+__global__ void __launch_bounds__(640, 1) dmma_smem_kernel(double* out, int iters) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) sm[i] = 1e-3 * (i & 127);
+    __syncthreads();
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+    const double* base = sm + (warp * 128 + g * 4 + t);
+    for (int it = 0; it < iters; ++it) {
+        const double* p = base + (it & 7) * 1024;
+        double af[MT], bf[NT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) af[m] = p[m * 32];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) bf[n] = p[4096 + n * 32];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[m][n][0]), "+d"(acc[m][n][1]) : "d"(af[m]), "d"(bf[n]));
+    }
+    double s = 0;
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) s += acc[m][n][0] + acc[m][n][1];
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void copy_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -137,6 +173,27 @@ int main() {
         dmma_latency_kernel<<<1, 32>>>(out, cyc, 4096, 1.0000001, 1e-9);
         long long h = 0; CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
         printf("DMMA 8x8x4 dependent-chain latency: %.1f cycles/instr\n", (double)h / 4096.0);
+    }
+    {
+        cudaFuncSetAttribute(dmma_smem_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(dmma_smem_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        const int it2 = 20000;
+        float ms = time_ms([&] { dmma_smem_kernel<4, 4><<<sms, 576, 160 * 1024>>>(out, it2); }, 5);
+        printf("DMMA from smem 4x4 tiles/warp, 18 warps/SM: %.3f ms  %.2f TFLOP/s\n", ms, 2.0 * 256 * 16 * it2 * 18.0 * sms / ms * 1e-9);
+        ms = time_ms([&] { dmma_smem_kernel<4, 2><<<sms, 576, 160 * 1024>>>(out, it2); }, 5);
+        printf("DMMA from smem 4x2 tiles/warp, 18 warps/SM: %.3f ms  %.2f TFLOP/s\n", ms, 2.0 * 256 * 8 * it2 * 18.0 * sms / ms * 1e-9);
+        ms = time_ms([&] { dmma_smem_kernel<4, 4><<<sms, 256, 160 * 1024>>>(out, it2); }, 5);
+        printf("DMMA from smem 4x4 tiles/warp, 8 warps/SM: %.3f ms  %.2f TFLOP/s\n", ms, 2.0 * 256 * 16 * it2 * 8.0 * sms / ms * 1e-9);
+        cudaFuncSetAttribute(dmma_smem_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(dmma_smem_kernel<9, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        for (int nw : {4, 8, 12, 16, 20}) {
+            ms = time_ms([&] { dmma_smem_kernel<6, 2><<<sms, 32 * nw, 160 * 1024>>>(out, it2); }, 3);
+            printf("DMMA from smem 6x2 tiles/warp, %2d warps/SM: %.2f TFLOP/s\n", nw, 2.0 * 256 * 12 * it2 * nw * sms / ms * 1e-9);
+            ms = time_ms([&] { dmma_smem_kernel<9, 2><<<sms, 32 * nw, 160 * 1024>>>(out, it2); }, 3);
+            printf("DMMA from smem 9x2 tiles/warp, %2d warps/SM: %.2f TFLOP/s\n", nw, 2.0 * 256 * 18 * it2 * nw * sms / ms * 1e-9);
+            ms = time_ms([&] { dmma_smem_kernel<4, 4><<<sms, 32 * nw, 160 * 1024>>>(out, it2); }, 3);
+            printf("DMMA from smem 4x4 tiles/warp, %2d warps/SM: %.2f TFLOP/s\n", nw, 2.0 * 256 * 16 * it2 * nw * sms / ms * 1e-9);
+        }
     }
     // HBM copy
     size_t n = (size_t)1 << 27;  // 128 Mi double2 = 2 GiB
