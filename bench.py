@@ -312,6 +312,22 @@ def run_ours(a):
     ms_d = max_over_ranks(e0.elapsed_time(e1))
     with_diag = Btot * nd / (ms_d * 1e-3)
 
+    # ---- Jacobian-vector products (PDFX, Main.py:498-521): the unit of work of the Newton / arc-length configs ----
+    dv = torch.randn((Bl, W), dtype=torch.float64, device=dev)
+    jout = torch.empty_like(dv)
+    for _ in range(3):
+        plan.jvp(dv, A, Ra, Ras, out=jout)
+    nj = max(5, a.steps // 10)
+    barrier()
+    e0.record()
+    for _ in range(nj):
+        plan.jvp(dv, A, Ra, Ras, out=jout)
+    e1.record()
+    barrier()
+    ms_j = max_over_ranks(e0.elapsed_time(e1))
+    jvp_rate = {"value": Btot * nj / (ms_j * 1e-3), "unit": "member-JVPs/s", "steps": nj,
+                "algorithmic_bytes_per_member_jvp": 72.0 * nr * K}
+
     # ---- end to end through the C ABI with HOST buffers (pinned): the ensemble analogue of Main._Time_Step
     # (Main.py:286-329): state H2D, K_e member-steps, the diagnostics of EVERY step copied back to the host, the
     # state checkpointed to the host every K_e/10 steps (the reference's N_save cadence) and at the end.
@@ -371,7 +387,7 @@ def run_ours(a):
                                  (Bl * (W * 5 + 9 * 2 * 32 * 256 + 3 * 2 * 32 * 192) * 8 / 1e9), **PHYS},
                 "clocks": clocks, "e2e": e2e, "e2e_state_roundtrip_every_step": e2e_roundtrip, "gpu_launches": launches,
                 "roofline": roofline, "roofline_hbm_step": hbm_view,
-                "stage_ms": stage_ms, "with_diagnostics": {"value": with_diag, "unit": "member-steps/s", "steps": nd,
+                "stage_ms": stage_ms, "jvp": jvp_rate, "with_diagnostics": {"value": with_diag, "unit": "member-steps/s", "steps": nd,
                                                            "collective": "all_gather [B,6] f64 per step" if world > 1 else None}}
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -25,7 +25,12 @@ constexpr int ANA_KC = 8;
 constexpr int ANA_KS = ANA_KC / 4;
 constexpr int ANA_MAX_STAGES = 4;
 
-__host__ __device__ constexpr int ana_nt_for(int nt8) { return nt8 <= 5 ? 4 : 2; }  // column tiles per warp
+#ifndef ANA_NT
+#define ANA_NT 2
+#endif
+// column tiles per warp: 2 keeps the kernel at <= 80 registers so that two CTAs share an SM and one CTA's prologue /
+// scattered-store epilogue overlaps the other's DMMA main loop
+__host__ __device__ constexpr int ana_nt_for(int nt8) { return nt8 <= 5 ? ANA_NT : 2; }
 
 __host__ __device__ inline size_t ana_stage_doubles(int nt8) {
     return (size_t)ANA_KS * (3 * nt8 * 8) * 4 + (size_t)ANA_KS * 2 * (ana_nt_for(nt8) * 32) * 4;
@@ -35,7 +40,7 @@ __host__ __device__ inline size_t ana_stage_doubles(int nt8) {
 // tiles of its field (psi rows use the sine table, T and S rows the cosine table) and NT3 column tiles; the last
 // warp is the TMA producer.
 template <int NT8>
-__global__ void __launch_bounds__(416, 1) analysis_kernel(AnaParams p, int nstage) {
+__global__ void __launch_bounds__(416, (NT8 <= 5 && ANA_NT == 2) ? 2 : 1) analysis_kernel(AnaParams p, int nstage) {
     constexpr int NT3 = ana_nt_for(NT8), KT3 = NT3 * 32, KS = ANA_KS, NCW = 12, NTHR = 416;
     constexpr int ROWS3 = 3 * NT8 * 8;
     constexpr int A_ST = KS * ROWS3 * 4, B_ST = KS * 2 * KT3 * 4, STAGE = A_ST + B_ST;

@@ -38,7 +38,10 @@ struct SolveParams {
     int nsl;                    // pipeline stages in use (2 or 3)
 };
 
-constexpr int SOLVE_NSL = 3;  // maximum pipeline stages (operator + right-hand-side tiles)
+#ifndef SOLVE_NSL_MAX
+#define SOLVE_NSL_MAX 6
+#endif
+constexpr int SOLVE_NSL = SOLVE_NSL_MAX;  // maximum pipeline stages (operator + right-hand-side tiles)
 
 template <int NTB>
 __host__ __device__ inline size_t solve_smem_doubles(int n8, int nsl) {
@@ -46,19 +49,22 @@ __host__ __device__ inline size_t solve_smem_doubles(int n8, int nsl) {
     return (size_t)(2 * nsl) * n8 * LDL + (size_t)4 * (8 * NTB) * LDL + (size_t)nsl * 2 * (8 * NTB) * LDG;
 }
 
-// grid = (ceil(B / (8*NTB)), 2 chains, nfields), block = 32 * nt8 (warp w owns radial rows 8w..8w+7).
+// grid = (ceil(B / (8*NTB)), 2 chains, nfields), block = 32 * (nt8 + 1): compute warp w < nt8 owns radial rows
+// 8w..8w+7, the last warp is the TMA producer.
 // Every thread owns the elements (i = 8w + g, member = nt*8 + 2t + e) in MMA accumulator layout, so the
 // running vectors b / f_e / bf_e of the reference live in registers.  Per chain step one thread issues TMA bulk
 // copies (pre-inverted operator of the mode, right-hand-side tiles) two steps ahead into a 3-stage ring.
 template <int NTB, bool SM>
-__global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
+__global__ void __launch_bounds__(288) solve_kernel(SolveParams p) {
     constexpr int BT = 8 * NTB, NE = 2 * NTB;
     extern __shared__ __align__(128) double smem[];
-    __shared__ __align__(8) uint64_t bar_full[SOLVE_NSL];
+    __shared__ __align__(8) uint64_t bar_full[SOLVE_NSL], bar_empty[SOLVE_NSL];
     const Geo& G = p.geo;
     const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, GT = BT * LDG;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const int nthr = blockDim.x;
+    const int nthr = blockDim.x - 32;          // compute threads (the last warp only streams operands)
+    const int ncw = nthr >> 5;
+    const bool is_producer = warp == ncw;
     const int b0 = blockIdx.x * BT, which = blockIdx.y, fld = p.field_base + blockIdx.z;
     if (!((p.field_mask >> fld) & 1)) return;
     double* sL = smem;                          // [NSL][2][n8][LDL]  (second matrix only used by the psi chains)
@@ -154,6 +160,7 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     const int j0 = is_psi ? (K - which) : (which == 0 ? K - 2 : K - 1);
     const int jend = is_psi ? 1 : 0;
     if (G.symmetric && which == 1) {
+        if (is_producer) return;
         double z[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) z[e] = 0.0;
@@ -163,18 +170,19 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
     const double* Lg = is_psi ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
     const int nsteps = (j0 - jend) / 2 + 1;
     if (tid == 0) {
-        for (int s = 0; s < NSL; ++s) mbar_init(&bar_full[s], 1);
+        for (int s = 0; s < NSL; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], ncw); }
         mbar_fence_init();
     }
     // chain step `step` handles mode j = j0 - 2*step, state row (j-1 for psi, j otherwise)
-    auto issue = [&](int step) {
-        if (tid == 0 && step < nsteps) {
-            const int j = j0 - 2 * step, st = step % NSL;
+    auto producer_loop = [&]() {
+        const unsigned tile_bytes = (unsigned)(GT * sizeof(double));
+        const unsigned mat_bytes = (unsigned)((is_psi ? 2 : 1) * MAT * sizeof(double));
+        const unsigned bytes = mat_bytes + (SM ? tile_bytes * (p.fnl ? 2u : 1u) : 0u);
+        int st = 0, ph = 0;
+        for (int step = 0; step < nsteps; ++step) {
+            const int j = j0 - 2 * step;
             const int jj = is_psi ? (K - j) : (K - 1 - j), row = is_psi ? j - 1 : j;
-            const unsigned tile_bytes = (unsigned)(GT * sizeof(double));
-            const unsigned mat_bytes = (unsigned)((is_psi ? 2 : 1) * MAT * sizeof(double));
-            unsigned bytes = mat_bytes;
-            if (SM) bytes += tile_bytes * (p.fnl ? 2u : 1u);
+            if (step >= NSL) mbar_wait(&bar_empty[st], ph ^ 1);
             mbar_expect_tx(&bar_full[st], bytes);
             bulk_g2s(sL + (size_t)st * 2 * MAT, Lg + (long long)jj * (is_psi ? 2 : 1) * MAT, mat_bytes, &bar_full[st]);
             if (SM) {
@@ -182,11 +190,18 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
                 bulk_g2s(sG + (size_t)st * 2 * GT, p.g + o, tile_bytes, &bar_full[st]);
                 if (p.fnl) bulk_g2s(sG + (size_t)st * 2 * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
             }
+            if (++st == NSL) { st = 0; ph ^= 1; }
         }
     };
     for (int idx = tid; idx < 4 * BT * LDL; idx += nthr) sR[idx] = 0.0;  // padded rows stay zero
+    if (is_producer) {
+        // (no shared-memory initialisation duty: threads >= nthr skip the loop above)
+    }
     __syncthreads();
-    for (int s0 = 0; s0 < NSL - 1; ++s0) issue(s0);
+    if (is_producer) {
+        if (lane == 0) producer_loop();
+        return;
+    }
 
     double f[NE], gv[NE];
     if (!is_psi) {
@@ -194,9 +209,10 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
         double bsum[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) { bsum[e] = 0.0; f[e] = 0.0; }
+        int st = 0, ph = 0;
         for (int step = 0; step < nsteps; ++step) {
-            const int j = j0 - 2 * step, st = step % NSL;
-            mbar_wait(&bar_full[st], (step / NSL) & 1);
+            const int j = j0 - 2 * step;
+            mbar_wait(&bar_full[st], ph);
             load_g(j, st, gv);
             double rhs[NE];
             const double beta = 2.0 * dt * (j + 2.0);
@@ -207,9 +223,11 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
             }
             double* buf = sR + (size_t)(step & 1) * BT * LDL;
             put_rhs(buf, rhs);
-            __syncthreads();
-            issue(step + NSL - 1);  // its stage was last read in step-1, which every warp has left
+            asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // compute warps only
             gemm(sL + (size_t)st * 2 * MAT, buf, f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[st]);   // operator + tiles of this stage are consumed
+            if (++st == NSL) { st = 0; ph ^= 1; }
             store_out(j, f);
         }
     } else {
@@ -224,11 +242,12 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
         //     f_j = L_inv_j @ ( g_j + dt*bjt*(L1_j @ f_e + IR4 @ bf_e) - bjt*IR2 @ f_e )
         // is evaluated as  L_inv_j @ rhs_elem + (L_inv_j @ D2) @ (dt*bjt*f_e)  with the product L_inv_j @ D2 formed
         // once on the host: one barrier and one (double-width) GEMM round per chain step instead of two.
+        int st = 0, ph = 0;
         for (int step = 0; step < nsteps; ++step) {
-            const int j = j0 - 2 * step, st = step % NSL;
+            const int j = j0 - 2 * step;
             const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
             double rhs[NE], sfe[NE];
-            mbar_wait(&bar_full[st], (step / NSL) & 1);
+            mbar_wait(&bar_full[st], ph);
             load_g(j - 1, st, gv);
             if (step == 0) {
 #pragma unroll
@@ -245,10 +264,12 @@ __global__ void __launch_bounds__(256) solve_kernel(SolveParams p) {
             double* bB = bufB + (size_t)(step & 1) * 2 * BT * LDL;
             put_rhs(bA, sfe);
             put_rhs(bB, rhs);
-            __syncthreads();
-            issue(step + NSL - 1);
+            asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // compute warps only
             const double* Lm = sL + (size_t)st * 2 * MAT;
             gemm2(Lm, bB, Lm + MAT, bA, f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[st]);
+            if (++st == NSL) { st = 0; ph ^= 1; }
             store_out(j - 1, f);
 #pragma unroll
             for (int e = 0; e < NE; ++e) bfe[e] += (step == 0) ? bj * f[e] : (bj * f[e] + bjt * fe[e]);

@@ -22,6 +22,9 @@ namespace {
 
 thread_local std::string g_create_error;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
+#ifndef SOLVE_NTB
+#define SOLVE_NTB 2  // members per back-substitution CTA = 8 * SOLVE_NTB (1 and 4 measured slower)
+#endif
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -331,10 +334,10 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     sp.field_mask = 7; sp.field_base = field_base;
     sp.dt_psi = pl->dt_psi; sp.dt_T = pl->dt_T; sp.dt_S = pl->dt_S; sp.nsl = pl->solve_nsl;
     // single-field calls pass field offsets of 0; the operator stack follows field_base
-    dim3 grid((B + 15) / 16, 2, nfields);
+    dim3 grid((B + 8 * SOLVE_NTB - 1) / (8 * SOLVE_NTB), 2, nfields);
     StageTimer tm(pl, SDDC_STAGE_SOLVE, st);
-    if (sm) solve_kernel<2, true><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
-    else solve_kernel<2, false><<<grid, 32 * pl->g.nt8, pl->solve_smem, st>>>(sp);
+    if (sm) solve_kernel<SOLVE_NTB, true><<<grid, 32 * (pl->g.nt8 + 1), pl->solve_smem, st>>>(sp);
+    else solve_kernel<SOLVE_NTB, false><<<grid, 32 * (pl->g.nt8 + 1), pl->solve_smem, st>>>(sp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
@@ -547,10 +550,16 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             TRY(set_smem(pl, synth_ws_kernel<4>, pl->ws_smem));
         }
     }
-    pl->solve_nsl = (solve_smem_doubles<2>(n8, 3) * sizeof(double) <= SMEM_LIMIT) ? 3 : 2;
-    pl->solve_smem = solve_smem_doubles<2>(n8, pl->solve_nsl) * sizeof(double);
-    TRY(set_smem(pl, solve_kernel<2, true>, pl->solve_smem));
-    TRY(set_smem(pl, solve_kernel<2, false>, pl->solve_smem));
+    {
+        const char* env = getenv("SDDC_SOLVE_STAGES");
+        int want = env ? atoi(env) : 3;
+        want = std::max(2, std::min(want, SOLVE_NSL));
+        while (want > 2 && solve_smem_doubles<SOLVE_NTB>(n8, want) * sizeof(double) > SMEM_LIMIT) --want;
+        pl->solve_nsl = want;
+    }
+    pl->solve_smem = solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double);
+    TRY(set_smem(pl, solve_kernel<SOLVE_NTB, true>, pl->solve_smem));
+    TRY(set_smem(pl, solve_kernel<SOLVE_NTB, false>, pl->solve_smem));
     TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8)));
     TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8)));
     TRY(set_smem(pl, prep_kernel<5>, prep_smem_bytes(n8)));
