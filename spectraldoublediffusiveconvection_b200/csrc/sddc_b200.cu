@@ -15,6 +15,7 @@
 #include "k_solve.cuh"
 #include "k_synth.cuh"
 #include "k_synth_ws.cuh"
+#include "k_synth2.cuh"
 
 using namespace sddc;
 
@@ -70,6 +71,8 @@ struct sddc_plan {
     std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
     bool dfx_ok = true;
+    int synth_variant = 0;    // 0: synth_kernel, 1: persistent warp-specialised, 2: two-CTAs-per-SM (k_synth2.cuh)
+    size_t s2_smem = 0;
     bool ws_ok = false;       // persistent warp-specialised synthesis available for this shape
     size_t ws_smem = 0;
     int num_sms = 148;
@@ -302,7 +305,15 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     const int nt = dfx ? pl->synth_nt_dfx : pl->synth_nt_fx;
     const int tiles = pl->g.Mhp / (8 * nt);
     StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-    if (!dfx && pl->ws_ok) {
+    if (!dfx && pl->ws_ok && pl->synth_variant == 2) {
+        sp.tab = pl->tab1d;  // W = 16 table tiling
+        dim3 grid2(pl->g.Mhp / S2_W, B);
+        synth2_kernel<4><<<grid2, S2_NTHR, pl->s2_smem, st>>>(sp);
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+        return SDDC_OK;
+    }
+    if (!dfx && pl->ws_ok && pl->synth_variant == 1) {
         sp.tab = pl->tab1d;  // W = 16 table tiling
         const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
         const int grid = std::min(nwork, pl->num_sms);
@@ -546,7 +557,13 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         const char* env = getenv("SDDC_SYNTH_WS");
         pl->ws_ok = g.nt8 == 4 && pl->synth_nt_dfx == SWS_NT && pl->dfx_ok && pl->ws_smem <= SMEM_LIMIT &&
                     !(env && env[0] == '0');
+        {
+            const char* v = getenv("SDDC_SYNTH_VARIANT");
+            pl->synth_variant = pl->ws_ok ? (v ? atoi(v) : 2) : 0;
+            pl->s2_smem = synth2_smem_doubles(n, n8) * sizeof(double);
+        }
         if (pl->ws_ok) {
+            TRY(set_smem(pl, synth2_kernel<4>, pl->s2_smem));
             TRY(set_smem(pl, synth_ws_kernel<4>, pl->ws_smem));
         }
     }
