@@ -20,8 +20,14 @@ namespace sddc {
 #endif
 // pipeline granularity: MMA k-steps (4 wavenumbers each) per stage, and ring depth (same bytes in flight either way)
 constexpr int SWS_KS = SWS_KS_PER_STAGE, SWS_STAGES = 6 / SWS_KS_PER_STAGE;
-constexpr int SWS_NT = 2, SWS_W = 16, SWS_NEW = 8;  // 12 MMA + 1 producer + 8 epilogue warps
-constexpr int SWS_NMMA = 12, SWS_TPW = 6, SWS_NTHR = 32 * (SWS_NMMA + 1 + SWS_NEW);
+#ifndef SWS_NMMA_CFG
+#define SWS_NMMA_CFG 12
+#endif
+#ifndef SWS_NEW_CFG
+#define SWS_NEW_CFG 8
+#endif
+constexpr int SWS_NT = 2, SWS_W = 16, SWS_NEW = SWS_NEW_CFG;  // MMA + 1 producer + epilogue warps
+constexpr int SWS_NMMA = SWS_NMMA_CFG, SWS_TPW = 72 / SWS_NMMA, SWS_NTHR = 32 * (SWS_NMMA + 1 + SWS_NEW);
 
 __host__ __device__ inline size_t synth_ws_smem_doubles(int n, int n8) {
     const size_t rs = 9 * (size_t)n8;
@@ -75,8 +81,9 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_ws_kernel(SynthParams p, in
     } else if (warp < NMMA) {
         // ---------------- MMA warps: (parity, group of 6 row tiles) ----------------
         constexpr int TPW = SWS_TPW;
-        static_assert(NF * NT8 == 6 * TPW, "warp-specialised synthesis is laid out for 36 row tiles per parity");
-        const int par = warp / 6, q = warp - par * 6;
+        constexpr int WPP = NMMA / 2;   // MMA warps per parity
+        static_assert(NF * NT8 == WPP * TPW, "warp-specialised synthesis is laid out for 36 row tiles per parity");
+        const int par = warp / WPP, q = warp - par * WPP;
         const int tile0 = q * TPW;                       // first 8-row tile of this warp (fields = tile / NT8)
         // table type per tile: fields 0-4 cosine (tiles 0..19), fields 5-8 sine (tiles 20..35); only q == 3 is mixed
         const int split = min(TPW, max(0, 5 * NT8 - tile0));   // tiles [0, split) cosine, [split, TPW) sine

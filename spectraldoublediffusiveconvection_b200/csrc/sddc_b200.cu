@@ -559,7 +559,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
                     !(env && env[0] == '0');
         {
             const char* v = getenv("SDDC_SYNTH_VARIANT");
-            pl->synth_variant = pl->ws_ok ? (v ? atoi(v) : 2) : 0;
+            pl->synth_variant = pl->ws_ok ? (v ? atoi(v) : 1) : 0;
             pl->s2_smem = synth2_smem_doubles(n, n8) * sizeof(double);
         }
         if (pl->ws_ok) {
