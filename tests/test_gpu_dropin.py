@@ -12,6 +12,14 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
+def _dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+def _rep(x, B):
+    return _dev(np.tile(np.asarray(x)[None, :], (B, 1)))
+
+
 @pytest.fixture(scope="module")
 def modules():
     import spectraldoublediffusiveconvection_b200.compat as compat
@@ -118,3 +126,47 @@ def test_newton_history_matches_cpu_path(modules):
     # both land on the steady branch of the reference's wide-gap test (KE = 2.57522e-2)
     ke = orc.kinetic_energy(Xg, orc.Operators(N_fm, N_r, d, 1.0, Pr, Tau), sym)
     assert abs(ke / 2.5752204992e-2 - 1) < 1e-6
+
+
+def test_batched_newton_and_arclength_lockstep(modules):
+    """BASELINE configs 4-5 in miniature: B concurrent Newton solves with batched GPU JVPs converge to the states
+    the reference-style host Newton (SciPy LGMRES) finds; one lock-step pseudo-arc-length step lands on the branch."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    from spectraldoublediffusiveconvection_b200.krylov import arclength_batched, newton_batched
+    MO, _ = modules
+    N_fm, N_r, d, Pr, Tau, Ra_s, sym = 32, 16, 2.0, 10.0, 1.0, 0.0, True
+    nr = N_r - 1
+    Ras = np.array([6780.0, 6800.0, 6850.0, 6900.0])
+    B = len(Ras)
+    pt = EnsemblePlan(N_fm, N_r, d, 0.075, Pr, Tau, symmetric=sym, max_batch=B)
+    X0 = np.random.default_rng(0).random(3 * nr * N_fm)
+    X0 = 1e-3 * X0 / np.linalg.norm(X0) * orc.sym_mask(N_fm, nr).reshape(-1)
+    Xs = pt.step(_rep(X0, B), _dev(Ras), Ra_s, nsteps=13000)          # four transients, one per Rayleigh number
+    pt.close()
+    pn = EnsemblePlan(N_fm, N_r, d, 1.0, Pr, Tau, symmetric=sym, max_batch=B)   # dt = 1 as in Main._Newton
+    Xn, hist, conv, njvp = newton_batched(pn, Xs, _dev(Ras), Ra_s, tol_newton=1e-8, max_it=6)
+    assert bool(conv.all()), hist
+    res = pn.residual(Xn, _dev(Ras), Ra_s)
+    assert float(torch.linalg.vector_norm(res, dim=1).max()) < 1e-6
+    Xn_h = Xn.cpu().numpy()
+    for m in (0, 3):
+        Xh, hh, _ = drv.newton(MO, Xs[m].cpu().numpy(), Ras[m], Ra_s, Tau, Pr, d, N_fm, N_r, sym, max_it=6)
+        assert rel_l2(Xn_h[m], Xh) < 1e-6                       # same steady state as the host LGMRES Newton
+    ke = pn.diagnostics(Xn).cpu().numpy()[:, 1]
+    assert abs(ke[0] / 2.5752204992e-2 - 1) < 1e-6              # KAT of the reference's wide-gap test (SURVEY section 4)
+    assert np.all(np.diff(ke) > 0)                              # kinetic energy grows with Ra along the branch
+    # one pseudo-arc-length step from the converged points: secant-free start with tangent (0, 1) in (X, mu)
+    n = Xn.shape[1]
+    Xd0 = torch.zeros_like(Xn)
+    mud0 = torch.ones(B, dtype=torch.float64, device="cuda")
+    ds = torch.full((B,), 5.0, dtype=torch.float64, device="cuda")
+    Xa, mua, Xd, mud, h2, nj2 = arclength_batched(pn, Xn, _dev(Ras), Xd0, mud0, ds, Ra_s, max_it=8)
+    resa = pn.residual(Xa, mua, Ra_s)
+    assert float(torch.linalg.vector_norm(resa, dim=1).max()) < 1e-6
+    delta = 1.0 / n
+    cons = delta * (Xd0 * (Xa - Xn)).sum(dim=1) + (1 - delta) * mud0 * (mua - _dev(Ras)) - ds
+    assert float(cons.abs().max()) < 1e-6                       # arclength constraint (Main.py:910)
+    nrm = torch.sqrt(delta * (Xd ** 2).sum(dim=1) + (1 - delta) * mud ** 2)
+    assert torch.allclose(nrm, torch.ones_like(nrm), atol=1e-10) and bool((mud > 0).all())
+    pn.close()
