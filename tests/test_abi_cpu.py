@@ -59,3 +59,21 @@ def test_product_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("test-only oracle", ""), f
+
+
+def test_checkpoint_schema_roundtrip(tmp_path):
+    """Output keeps the reference's HDF5 key paths (Main.py:305-321), with an .npz fallback when h5py is absent."""
+    from spectraldoublediffusiveconvection_b200 import io as sio
+    rng = np.random.default_rng(0)
+    states = rng.random((2, 3, 12))
+    hist = rng.random((5, 3, 6))
+    files = sio.save_ensemble(str(tmp_path / "TimeStep"), states, hist, np.arange(5) * 1e-3, [1.0, 2.0, 3.0], [0.0] * 3,
+                              {"Tau": 1.0, "Pr": 1.0, "d": 0.3, "N_r": 3, "N_fm": 2, "dt": 1e-3, "start_time": 0,
+                               "symmetric": False})
+    assert len(files) == 3
+    back = sio.load_time_step(files[1])
+    assert np.array_equal(back["Checkpoints/X_DATA"], states[:, 1])
+    assert np.array_equal(back["Scalar_Data/KE"], hist[:, 1, 1])
+    assert float(back["Parameters/Ra"]) == 2.0
+    for key in ("Scalar_Data/Norm", "Scalar_Data/Nu_T", "Scalar_Data/Nu_S", "Scalar_Data/Time", "Parameters/N_fm"):
+        assert key in back

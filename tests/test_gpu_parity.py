@@ -232,3 +232,32 @@ def test_time_step_host_matches_device_loop():
             assert np.array_equal(ck[s // 4 - 1], cur.cpu().numpy())
     assert np.array_equal(out, cur.cpu().numpy())
     pl.close()
+
+
+def test_step_is_cuda_graph_capturable():
+    """The device entry points are allocation-free and stream-ordered: a member-step can be captured in a CUDA graph
+    and replayed (include/sddc_b200.h contract)."""
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    K, N_r, d, dt, Pr, Tau = 32, 20, 0.5, 5e-3, 1.0, 0.5
+    B = 4
+    pl = EnsemblePlan(K, N_r, d, dt, Pr, Tau, max_batch=B)
+    rng = np.random.default_rng(3)
+    X = _dev(rng.random((B, 3 * pl.N)) * 1e-2)
+    Ra = _dev(np.linspace(2000.0, 4000.0, B))
+    Ras = _dev(np.zeros(B))
+    ref = pl.step(pl.step(X, Ra, Ras), Ra, Ras)
+    buf_in, buf_out = X.clone(), torch.empty_like(X)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        pl.step(buf_in, Ra, Ras, out=buf_out)            # warm-up on the side stream
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        pl.step(buf_in, Ra, Ras, out=buf_out)
+    g.replay()
+    buf_in.copy_(buf_out)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(buf_out, ref)
+    pl.close()
