@@ -93,3 +93,42 @@ class Ensemble:
 
     def close(self):
         self.plan.close()
+
+
+class GapSweep:
+    """Ensemble over shell gaps d (plus Ra, Ra_s): the pre-inverted operators depend on d (SURVEY.md section 7,
+    "operator sharing"), so members are grouped by their gap and every group gets its own plan; groups are stepped
+    one after the other on the same GPU.  Members keep their global order in every array this class returns."""
+
+    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, Ra, Ra_s, symmetric=False, device=None):
+        import numpy as np
+        from .plan import EnsemblePlan
+        d = np.atleast_1d(np.asarray(d, dtype=np.float64))
+        Ra = np.broadcast_to(np.atleast_1d(np.asarray(Ra, dtype=np.float64)), d.shape)
+        Ra_s = np.broadcast_to(np.atleast_1d(np.asarray(Ra_s, dtype=np.float64)), d.shape)
+        self.n_members = int(d.shape[0])
+        self.groups = []
+        for dv in np.unique(d):
+            idx = np.nonzero(d == dv)[0]
+            plan = EnsemblePlan(N_fm, N_r, float(dv), dt, Pr, Tau, symmetric=symmetric, max_batch=len(idx), device=device)
+            dev = plan.device
+            self.groups.append((torch.as_tensor(idx, device=dev), plan,
+                                torch.as_tensor(np.ascontiguousarray(Ra[idx])).to(dev),
+                                torch.as_tensor(np.ascontiguousarray(Ra_s[idx])).to(dev)))
+
+    def step(self, X, nsteps=1):
+        """X: [B, 3N] device tensor in global member order -> new tensor in the same order."""
+        out = torch.empty_like(X)
+        for idx, plan, Ra, Ra_s in self.groups:
+            out[idx] = plan.step(X[idx], Ra, Ra_s, nsteps=nsteps)
+        return out
+
+    def diagnostics(self, X):
+        out = torch.empty((X.shape[0], 6), dtype=torch.float64, device=X.device)
+        for idx, plan, _, _ in self.groups:
+            out[idx] = plan.diagnostics(X[idx])
+        return out
+
+    def close(self):
+        for _, plan, _, _ in self.groups:
+            plan.close()

@@ -261,3 +261,22 @@ def test_step_is_cuda_graph_capturable():
     torch.cuda.synchronize()
     assert torch.equal(buf_out, ref)
     pl.close()
+
+
+def test_gap_sweep_groups_members_by_gap():
+    """Shell-gap sweep: members with different d use different operator sets; results match per-member oracle runs."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200.ensemble import GapSweep
+    K, N_r, dt, Pr, Tau = 16, 18, 5e-3, 1.0, 1.0
+    d = np.array([0.3, 0.5, 0.3, 0.4, 0.5])
+    Ra = np.linspace(2000.0, 4000.0, 5)
+    gs = GapSweep(K, N_r, d, dt, Pr, Tau, Ra, 100.0)
+    assert len(gs.groups) == 3
+    rng = np.random.default_rng(8)
+    X = rng.random((5, 3 * (N_r - 1) * K)) * 1e-2
+    out = gs.step(_dev(X), nsteps=2).cpu().numpy()
+    for m in range(5):
+        op = orc.Operators(K, N_r, float(d[m]), dt, Pr, Tau)
+        ref = orc.step(orc.step(X[m], op, Ra[m], 100.0), op, Ra[m], 100.0)
+        assert rel_l2(out[m], ref) < 1e-10
+    gs.close()
