@@ -1,0 +1,21 @@
+"""Small end-to-end exercise of every entry point for compute-sanitizer runs."""
+import sys; sys.path.insert(0, '.')
+import numpy as np, torch
+from spectraldoublediffusiveconvection_b200 import EnsemblePlan, plan as P
+for (K, N_r, sym, B) in [(16, 10, False, 3), (32, 30, True, 17), (24, 41, False, 2), (16, 65, False, 2)]:
+    pl = EnsemblePlan(K, N_r, 0.4, 1e-2, 1.0, 0.5, symmetric=sym, max_batch=B)
+    X = torch.rand((B, 3 * pl.N), dtype=torch.float64, device='cuda') * 1e-2
+    dv = torch.randn_like(X)
+    Ra = torch.full((B,), 3000.0, dtype=torch.float64, device='cuda'); Ras = torch.zeros_like(Ra)
+    Y = pl.step(X, Ra, Ras, nsteps=3)
+    pl.nlin_fx(X); pl.residual(X, Ra, Ras); pl.dF_dRa(X); pl.diagnostics(Y)
+    if N_r <= 41:
+        pl.jvp(dv, X, Ra, Ras); pl.nlin_dfx(dv, X)
+    for op in range(6):
+        pl.linear_op(op, X[:, :pl.N].contiguous())
+    pl.solve_a4(X[:, :pl.N].contiguous()); pl.solve_nab2(X[:, :pl.N].contiguous(), 1)
+    out, hist = pl.time_step_host(X.cpu().numpy(), 3000.0, 0.0, 4, diag_every=2)
+    P.transform(P.T_IDCT, X[:, :K].contiguous(), 3 * K // 2)
+    torch.cuda.synchronize()
+    print("ok", K, N_r, sym, float(Y.abs().max()))
+    pl.close()
