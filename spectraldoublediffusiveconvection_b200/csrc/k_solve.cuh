@@ -103,13 +103,22 @@ __global__ void __launch_bounds__(288) solve_kernel(SolveParams p) {
             v[e] = x;
         }
     };
+    // residual / JVP: out = f - sub.  The subtrahend is fetched at the top of the chain step so that its (scattered)
+    // load latency is hidden behind the step's GEMM instead of stalling the store.
+    double subv[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) subv[e] = 0.0;
+    auto load_sub = [&](int row) {
+        if (p.sub) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (ok[e]) subv[e] = p.sub[ooff[e] + (long long)row * n];
+        }
+    };
     auto store_out = [&](int row, const double* f) {
 #pragma unroll
         for (int e = 0; e < NE; ++e)
-            if (ok[e]) {
-                const long long o = ooff[e] + (long long)row * n;
-                p.out[o] = p.sub ? f[e] - p.sub[o] : f[e];
-            }
+            if (ok[e]) p.out[ooff[e] + (long long)row * n] = f[e] - subv[e];
     };
     auto put_rhs = [&](double* buf, const double* v) {
 #pragma unroll
@@ -164,7 +173,10 @@ __global__ void __launch_bounds__(288) solve_kernel(SolveParams p) {
         double z[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) z[e] = 0.0;
-        for (int j = j0; j >= jend; j -= 2) store_out(is_psi ? j - 1 : j, z);
+        for (int j = j0; j >= jend; j -= 2) {
+            load_sub(is_psi ? j - 1 : j);
+            store_out(is_psi ? j - 1 : j, z);
+        }
         return;
     }
     const double* Lg = is_psi ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
@@ -212,6 +224,7 @@ __global__ void __launch_bounds__(288) solve_kernel(SolveParams p) {
         int st = 0, ph = 0;
         for (int step = 0; step < nsteps; ++step) {
             const int j = j0 - 2 * step;
+            load_sub(j);
             mbar_wait(&bar_full[st], ph);
             load_g(j, st, gv);
             double rhs[NE];
@@ -247,6 +260,7 @@ __global__ void __launch_bounds__(288) solve_kernel(SolveParams p) {
             const int j = j0 - 2 * step;
             const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
             double rhs[NE], sfe[NE];
+            load_sub(j - 1);
             mbar_wait(&bar_full[st], ph);
             load_g(j - 1, st, gv);
             if (step == 0) {
