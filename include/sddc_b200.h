@@ -121,6 +121,12 @@ int sddc_residual(sddc_plan* plan, const double* X, double* out, const double* R
 /* PDFX(dv, X) (Main.py:498-521, 804-827) */
 int sddc_jvp(sddc_plan* plan, const double* dv, const double* X, double* out, const double* Ra,
              const double* Ra_s, int B, void* stream);
+/* The same JVP split for Krylov solves, where X is fixed over many products (Main.py:528-534, 905-920):
+ * sddc_jvp_set_base synthesises and caches the base state's grid fields once, sddc_jvp_apply then costs one
+ * synthesis (of dv) instead of two.  B must match between the two calls. */
+int sddc_jvp_set_base(sddc_plan* plan, const double* X, int B, void* stream);
+int sddc_jvp_apply(sddc_plan* plan, const double* dv, double* out, const double* Ra, const double* Ra_s, int B,
+                   void* stream);
 /* PDFmu(X) (Main.py:829-837) */
 int sddc_dF_dRa(sddc_plan* plan, const double* X, double* out, int B, void* stream);
 /* per member [ ||X||_2, KE, Nu_T, Nu_S, Nu_T(outer wall), Nu_S(outer wall) ]: Main.py:292-295, Kinetic_Energy

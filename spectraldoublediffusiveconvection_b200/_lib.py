@@ -45,6 +45,8 @@ SYMBOLS = {
     "sddc_step": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _i, _i, _vp]),
     "sddc_residual": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _vp]),
     "sddc_jvp": (_i, [_vp, _dp, _dp, _dp, _dp, _dp, _i, _vp]),
+    "sddc_jvp_set_base": (_i, [_vp, _dp, _i, _vp]),
+    "sddc_jvp_apply": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _vp]),
     "sddc_dF_dRa": (_i, [_vp, _dp, _dp, _i, _vp]),
     "sddc_diagnostics": (_i, [_vp, _dp, _dp, _i, _vp]),
     "sddc_transform": (_i, [_i, _dp, _dp, _i, _i, _i, _vp]),

@@ -33,6 +33,7 @@ struct SynthParams {
     const double* wr;        // [n] radial trapezoid weights     (EPI_KE)
     const double* wth;       // [Mhp_tab] w_theta(j') sin(theta_j') (EPI_KE), zero padded
     double* kepart;          // [B][gridDim.x] partial sums      (EPI_KE)
+    double* gridc;           // [B][9][2][n8][Mhp] cached base-state grid fields (k_synth_ws.cuh, JVP with cached base)
     Geo g;
 };
 

@@ -35,7 +35,15 @@ __host__ __device__ inline size_t synth_ws_smem_doubles(int n, int n8) {
     return SWS_STAGES * stage + 2 * rs * SWS_W + 2 * (size_t)n * SWS_W + (size_t)n * n;
 }
 
-template <int NT8>
+// MODE: SWS_FX   products of the fields of one state (NLIN_FX);
+//       SWS_GRID no products: the nine grid fields of the state are stored to p.gridc (base state of a Newton /
+//                GMRES solve: computed once, reused by every Jacobian-vector product);
+//       SWS_JVPC the MMA operand is the perturbation dv, the base-state grid fields are read back from p.gridc and
+//                the bilinear products of NLIN_DFX (Matrix_Operators.py:884-887) are formed -- a JVP then costs one
+//                synthesis instead of two.
+enum { SWS_FX = 0, SWS_GRID = 1, SWS_JVPC = 2 };
+
+template <int NT8, int MODE>
 __global__ void __launch_bounds__(SWS_NTHR, 1) synth_ws_kernel(SynthParams p, int ntiles_j, int nwork) {
     constexpr int NF = 9, RS = NF * NT8 * 8, NT = SWS_NT, W = SWS_W, KS = SWS_KS, LDE = W;
     constexpr int A_SET = KS * 2 * RS * 4, B_ST = KS * 4 * W * 4, STAGE = A_SET + B_ST;
@@ -158,6 +166,9 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_ws_kernel(SynthParams p, in
             };
             mbar_wait(&bar_eo_full, tcount & 1);
             double qv[PTS][2];
+            // cached base-state grid fields: gridc[b][a][mirror][i][j']
+            double* gc = (MODE != SWS_FX) ? p.gridc + (long long)b * 9 * 2 * n8 * g.Mhp : nullptr;
+            const long long gms = (long long)n8 * g.Mhp;   // mirror stride; field stride = 2*gms
 #pragma unroll
             for (int s = 0; s < PTS; ++s) {
                 const int pt = et + s * NTHR_E;
@@ -170,12 +181,42 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_ws_kernel(SynthParams p, in
                         const double e = E[(size_t)(a * n8 + i) * LDE + c], o = O[(size_t)(a * n8 + i) * LDE + c];
                         if (a < 5) { f0[a] = e + o; f1[a] = e - o; } else { f0[a] = o + e; f1[a] = o - e; }
                     }
-                    sA1[(size_t)i * W + c] = f0[0] * f0[5];
-                    sA1[(size_t)(n + i) * W + c] = f1[0] * f1[5];
-                    qv[s][0] = f0[1] * f0[5] + f0[6] * f0[2];
-                    qv[s][1] = f1[1] * f1[5] + f1[6] * f1[2];
-                    const double nt0 = f0[0] * f0[3] - f0[6] * f0[7], nt1 = f1[0] * f1[3] - f1[6] * f1[7];
-                    const double ns0 = f0[0] * f0[4] - f0[6] * f0[8], ns1 = f1[0] * f1[4] - f1[6] * f1[8];
+                    if (MODE == SWS_GRID) {
+                        const long long go = (long long)i * g.Mhp + jt * W + c;
+#pragma unroll
+                        for (int a = 0; a < 9; ++a) {
+                            gc[(a * 2 + 0) * gms + go] = f0[a];
+                            gc[(a * 2 + 1) * gms + go] = f1[a];
+                        }
+                        continue;
+                    }
+                    double a1_0, a1_1, nt0, nt1, ns0, ns1;
+                    if (MODE == SWS_FX) {
+                        a1_0 = f0[0] * f0[5];                     a1_1 = f1[0] * f1[5];
+                        qv[s][0] = f0[1] * f0[5] + f0[6] * f0[2]; qv[s][1] = f1[1] * f1[5] + f1[6] * f1[2];
+                        nt0 = f0[0] * f0[3] - f0[6] * f0[7];      nt1 = f1[0] * f1[3] - f1[6] * f1[7];
+                        ns0 = f0[0] * f0[4] - f0[6] * f0[8];      ns1 = f1[0] * f1[4] - f1[6] * f1[8];
+                    } else {
+                        // h = perturbation fields (just synthesised), f = base-state fields (cached)
+                        double h0[9], h1[9];
+                        const long long go = (long long)i * g.Mhp + jt * W + c;
+#pragma unroll
+                        for (int a = 0; a < 9; ++a) {
+                            h0[a] = f0[a]; h1[a] = f1[a];
+                            f0[a] = gc[(a * 2 + 0) * gms + go];
+                            f1[a] = gc[(a * 2 + 1) * gms + go];
+                        }
+                        a1_0 = f0[0] * h0[5] + h0[0] * f0[5];
+                        a1_1 = f1[0] * h1[5] + h1[0] * f1[5];
+                        qv[s][0] = (f0[1] * h0[5] + f0[6] * h0[2]) + (h0[1] * f0[5] + h0[6] * f0[2]);
+                        qv[s][1] = (f1[1] * h1[5] + f1[6] * h1[2]) + (h1[1] * f1[5] + h1[6] * f1[2]);
+                        nt0 = (h0[0] * f0[3] - h0[6] * f0[7]) + (f0[0] * h0[3] - f0[6] * h0[7]);
+                        nt1 = (h1[0] * f1[3] - h1[6] * f1[7]) + (f1[0] * h1[3] - f1[6] * h1[7]);
+                        ns0 = (h0[0] * f0[4] - h0[6] * f0[8]) + (f0[0] * h0[4] - f0[6] * h0[8]);
+                        ns1 = (h1[0] * f1[4] - h1[6] * f1[8]) + (f1[0] * h1[4] - f1[6] * h1[8]);
+                    }
+                    sA1[(size_t)i * W + c] = a1_0;
+                    sA1[(size_t)(n + i) * W + c] = a1_1;
                     const long long oT = prd_off(1, i, c), oS = prd_off(2, i, c);
                     prd[oT] = nt0 + nt1;
                     prd[pps + oT] = nt0 - nt1;
@@ -186,6 +227,7 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_ws_kernel(SynthParams p, in
             // all E/O reads of this tile are done -> the MMA warps may overwrite sEO; sA1 is complete
             asm volatile("bar.sync 1, %0;" ::"n"(NTHR_E) : "memory");
             if (lane == 0) mbar_arrive(&bar_eo_free);
+            if (MODE != SWS_GRID) {   // compile-time: the grid-cache mode has no Dr stage
 #pragma unroll
             for (int s = 0; s < PTS; ++s) {
                 const int pt = et + s * NTHR_E;
@@ -206,6 +248,7 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_ws_kernel(SynthParams p, in
             }
             // sA1 is rewritten by the next tile's first phase only after every epilogue thread is past this point
             asm volatile("bar.sync 2, %0;" ::"n"(NTHR_E) : "memory");
+            }
         }
     }
 }

@@ -61,6 +61,8 @@ struct sddc_plan {
     double* coef1 = nullptr;
     long long coef_member_stride = 0;
     double *lin_sm = nullptr, *f_sm = nullptr;  // solve-major [3][K][bstride][n8+2]
+    double *gridc = nullptr, *xbase = nullptr;  // cached base state of sddc_jvp_set_base (lazily allocated)
+    int base_B = 0;
     long long bstride = 0;
     // host-API staging
     double *hX0 = nullptr, *hX1 = nullptr, *hX2 = nullptr, *hRa = nullptr, *hRas = nullptr, *hDiag = nullptr;
@@ -317,7 +319,7 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
         sp.tab = pl->tab1d;  // W = 16 table tiling
         const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
         const int grid = std::min(nwork, pl->num_sms);
-        synth_ws_kernel<4><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+        synth_ws_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
         pl->launches++;
         PLAN_CUDA(pl, cudaGetLastError());
         return SDDC_OK;
@@ -564,7 +566,9 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         }
         if (pl->ws_ok) {
             TRY(set_smem(pl, synth2_kernel<4>, pl->s2_smem));
-            TRY(set_smem(pl, synth_ws_kernel<4>, pl->ws_smem));
+            TRY(set_smem(pl, (synth_ws_kernel<4, SWS_FX>), pl->ws_smem));
+            TRY(set_smem(pl, (synth_ws_kernel<4, SWS_GRID>), pl->ws_smem));
+            TRY(set_smem(pl, (synth_ws_kernel<4, SWS_JVPC>), pl->ws_smem));
         }
     }
     {
@@ -714,6 +718,53 @@ int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, cons
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
+    if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
+    return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+}
+
+// launch the persistent warp-specialised synthesis in one of its cached-base modes
+static int run_synth_ws_mode(sddc_plan* pl, int mode, const double* coef, int B, cudaStream_t st) {
+    SynthParams sp{};
+    sp.coef0 = coef; sp.coef_stride = pl->coef_member_stride; sp.tab = pl->tab1d; sp.Dr = pl->Dr; sp.prd = pl->prd;
+    sp.gridc = pl->gridc; sp.g = pl->g;
+    const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
+    const int grid = std::min(nwork, pl->num_sms);
+    StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
+    if (mode == SWS_GRID) synth_ws_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+    else synth_ws_kernel<4, SWS_JVPC><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int sddc_jvp_set_base(sddc_plan* pl, const double* X, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Geo& g = pl->g;
+    if (!pl->xbase) {
+        if ((rc = dev_alloc(pl, &pl->xbase, (size_t)pl->cfg.max_batch * 3 * g.N, false))) return rc;
+        if (pl->ws_ok && (rc = dev_alloc(pl, &pl->gridc, (size_t)pl->cfg.max_batch * 9 * 2 * g.n8 * g.Mhp, true))) return rc;
+    }
+    PLAN_CUDA(pl, cudaMemcpyAsync(pl->xbase, X, sizeof(double) * (size_t)B * 3 * g.N, cudaMemcpyDeviceToDevice, st));
+    pl->base_B = B;
+    if (pl->ws_ok) {
+        if ((rc = run_prep(pl, pl->xbase, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
+        return run_synth_ws_mode(pl, SWS_GRID, pl->coef, B, st);
+    }
+    return SDDC_OK;
+}
+
+int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* Ra, const double* Ras, int B, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (!pl->xbase || B != pl->base_B) { pl->err = "sddc_jvp_apply: call sddc_jvp_set_base with the same batch first"; return SDDC_ERR_INVALID; }
+    if (dv == out) { pl->err = "out must not alias dv"; return SDDC_ERR_INVALID; }
+    if (!pl->ws_ok) return sddc_jvp(pl, dv, pl->xbase, out, Ra, Ras, B, stream);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long N3 = 3LL * pl->g.N;
+    if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
+    if ((rc = run_synth_ws_mode(pl, SWS_JVPC, pl->coef1, B, st))) return rc;
     if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
     return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
 }

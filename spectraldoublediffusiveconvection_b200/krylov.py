@@ -100,10 +100,10 @@ def newton_batched(plan, X, Ra, Ra_s, tol_newton=1e-8, tol_gmres=1e-4, krylov=80
     for _ in range(max_it):
         fx = plan.residual(X, Ra, Ra_s)                           # PFX (Main.py:473-496)
         fx = torch.where(active[:, None], fx, torch.zeros_like(fx))
-        Xc = X
+        plan.jvp_set_base(X)                                      # X is fixed during the linear solve
 
         def DF(v):
-            return plan.jvp(v, Xc, Ra, Ra_s)                      # PDFX (Main.py:498-521)
+            return plan.jvp_apply(v, Ra, Ra_s)                    # PDFX (Main.py:498-521)
 
         dv, info = batched_gmres(DF, fx, rtol=tol_gmres, m=krylov, max_restarts=max_restarts)
         njvp += info["iters"]
@@ -137,10 +137,11 @@ def arclength_batched(plan, X0, mu0, X_dot, mu_dot, ds, Ra_s, tol_newton=1e-8, t
 
     def make_DG(Xc, muc):
         dfmu = plan.dF_dRa(Xc)                                    # PDFmu (Main.py:829-837)
+        plan.jvp_set_base(Xc)
 
         def DG(dY):
             dX, dmu = dY[:, :n].contiguous(), dY[:, n]
-            top = plan.jvp(dX, Xc, muc, Ra_s) + dfmu * dmu[:, None]
+            top = plan.jvp_apply(dX, muc, Ra_s) + dfmu * dmu[:, None]
             bot = delta * (X_dot * dX).sum(dim=1) + (1.0 - delta) * mu_dot * dmu
             return torch.cat([top, bot[:, None]], dim=1)
 

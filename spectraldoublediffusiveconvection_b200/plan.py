@@ -193,6 +193,22 @@ class EnsemblePlan:
                                       Ra_s.data_ptr(), B, self._stream()))
         return out
 
+    def jvp_set_base(self, X):
+        """Cache the base state X of the following jvp_apply calls (one synthesis of X instead of one per product)."""
+        X = self._in(X, 3 * self.N)
+        self._check(self.lib.sddc_jvp_set_base(self._h, X.data_ptr(), X.shape[0], self._stream()))
+        self._base_B = X.shape[0]
+
+    def jvp_apply(self, dv, Ra, Ra_s, out=None):
+        """PDFX(dv, X_base) for the state given to jvp_set_base."""
+        dv = self._in(dv, 3 * self.N)
+        B = dv.shape[0]
+        Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
+        out = torch.empty_like(dv) if out is None else out
+        self._check(self.lib.sddc_jvp_apply(self._h, dv.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
+                                            self._stream()))
+        return out
+
     def dF_dRa(self, X, out=None):
         X = self._in(X, 3 * self.N)
         out = torch.empty_like(X) if out is None else out

@@ -280,3 +280,19 @@ def test_gap_sweep_groups_members_by_gap():
         ref = orc.step(orc.step(X[m], op, Ra[m], 100.0), op, Ra[m], 100.0)
         assert rel_l2(out[m], ref) < 1e-10
     gs.close()
+
+
+@pytest.mark.parametrize("name", ["cfg3_member", "cfg1_sym", "small_nosym"])
+def test_cached_base_jvp_equals_jvp(name):
+    """jvp_set_base + jvp_apply (one synthesis per product) == jvp (two syntheses), and matches the reference."""
+    g = load_golden(name)
+    pl = _plan(g)
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    Xb, dv = _dev(g["Xb"]), _dev(g["dv"])
+    pl.jvp_set_base(Xb)
+    j1 = pl.jvp_apply(dv, Ra, Ra_s).cpu().numpy().ravel()
+    j2 = pl.jvp_apply(2.0 * dv, Ra, Ra_s).cpu().numpy().ravel()      # the cache survives several products
+    assert rel_l2(j1, g["jvp_Xb"]) < 1e-10
+    assert rel_l2(j2, 2.0 * g["jvp_Xb"]) < 1e-10
+    assert rel_l2(j1, pl.jvp(dv, Xb, Ra, Ra_s).cpu().numpy().ravel()) < 1e-12
+    pl.close()
