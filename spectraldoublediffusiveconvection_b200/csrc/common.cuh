@@ -82,6 +82,20 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;  // valid in warp 0
 }
 
+// Order of the wavenumbers inside one 8-wide chunk of a parity block of the synthesis operands.  Odd k keep their
+// natural order.  Even k (k = 2k') are stored with the k' even ones first (MMA k-step 0) and the k' odd ones second
+// (k-step 1), so that the two classes k = 0 and k = 2 (mod 4) can be contracted separately (second mirror level,
+// k_synth_ws.cuh); kernels that contract a whole chunk are indifferent to the order as long as coefficients and
+// tables agree.
+__host__ __device__ __forceinline__ int chunk_pos(int kp, int par) {
+    const int r = kp & 7;
+    return (kp & ~7) | (par == 0 ? (((r & 1) << 2) | (r >> 1)) : r);
+}
+__host__ __device__ __forceinline__ int chunk_pos_inv(int pos, int par) {
+    const int r = pos & 7;
+    return (pos & ~7) | (par == 0 ? (((r & 3) << 1) | (r >> 2)) : r);
+}
+
 // Geometry shared by all kernels.
 struct Geo {
     int n;      // interior radial points

@@ -33,7 +33,8 @@ __global__ void fill_table_kernel(double* tab, int mode, int M, int Kh, int Mh, 
             chunk = (int)(r % nchunk); r /= nchunk; tile = (int)(r % nA); par = (int)(r / nA);
         }
         const int inner = 8 * chunk + 4 * ks + kk, outer = tile * W + col;
-        const int kp = (mode == 0) ? inner : outer, jp = (mode == 0) ? outer : inner;
+        // synthesis tables follow the coefficient order inside a chunk (chunk_pos)
+        const int kp = (mode == 0) ? chunk_pos_inv(inner, par) : outer, jp = (mode == 0) ? outer : inner;
         double v = 0.0;
         if (kp < Kh && jp < Mh) {
             const int k = 2 * kp + par;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) ke_prep_kernel(KEPrepParams p) {
     __syncthreads();
     const int c = c0 + lane;
     if (c >= K) return;
-    const int par = c & 1, kp = c >> 1;
+    const int par = c & 1, kp = chunk_pos(c >> 1, par);
     double* cf = p.coef + (long long)b * p.coef_stride;
     const double* Jb = p.JJ + (long long)b * (K + 1) * n;
     for (int i = warp; i < n; i += 8) {

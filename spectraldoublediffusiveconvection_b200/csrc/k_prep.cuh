@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
             const double jj = sJ[col * LDX + i];
             const double tv = sT[col * LDX + i], sv = sS[col * LDX + i];
             if (cf) {
-                const int kp = c >> 1;  // parity of c is e (c0 is a multiple of 32)
+                const int kp = chunk_pos(c >> 1, e);  // parity of c is e (c0 is a multiple of 32); position in the chunk
                 const long long o = (((long long)((kp >> 2) * 2 + e) * R9) + i) * 4 + (kp & 3);
                 const long long fs = (long long)n8 * 4;
                 double om = 0.0, dp = 0.0;
