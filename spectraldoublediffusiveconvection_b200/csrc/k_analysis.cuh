@@ -18,6 +18,8 @@ struct AnaParams {
     double* out;         // F(X): state layout [B][3N] (bstride == 0) or solve-major [3][K][bstride][n8+2] (k_solve.cuh);
                          // the -dt factor and the linear terms are applied by the solve kernel
     long long bstride;
+    int quarter;         // products / table follow the second mirror level (k_synth_wsq.cuh): even-k CTAs contract over
+                         // M/4 positions only and own one class (k' even or k' odd) of output columns
     Geo g;
 };
 
@@ -72,7 +74,11 @@ __global__ void __launch_bounds__(416, (NT8 <= 5 && ANA_NT == 2) ? 2 : 1) analys
         return;
     }
 
-    const int nchunk = Mhp / ANA_KC;
+    const bool qpar0 = p.quarter && par == 0;
+    const int nkt_half = gridDim.x / 2, cls = qpar0 ? kt / nkt_half : 0;
+    const int nchunk_full = Mhp / ANA_KC;
+    const int nchunk = qpar0 ? nchunk_full / 2 : nchunk_full;   // even-k CTAs: positions of their class only
+    const int chunk0 = qpar0 ? cls * nchunk : 0;
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NCW); }
         mbar_fence_init();
@@ -87,8 +93,8 @@ __global__ void __launch_bounds__(416, (NT8 <= 5 && ANA_NT == 2) ? 2 : 1) analys
 
     if (warp == NCW) {
         if (lane == 0) {
-            const double* gA = p.prd + ((long long)b * 2 + par) * Mhp * ROWS3;
-            const double* gB = p.tab2 + ((long long)par * gridDim.x + kt) * nchunk * B_ST;
+            const double* gA = p.prd + ((long long)b * 2 + par) * Mhp * ROWS3 + (long long)chunk0 * A_ST;
+            const double* gB = p.tab2 + ((long long)par * gridDim.x + kt) * nchunk_full * B_ST;
             int st = 0, ph = 0;
             for (int c = 0; c < nchunk; ++c) {
                 if (c >= nstage) mbar_wait(&bar_empty[st], ph ^ 1);
@@ -137,7 +143,8 @@ __global__ void __launch_bounds__(416, (NT8 <= 5 && ANA_NT == 2) ? 2 : 1) analys
             for (int nt = 0; nt < NT3; ++nt) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int kp = kt * KT3 + (cg * NT3 + nt) * 8 + 2 * tq + e;
+                    const int colt = (cg * NT3 + nt) * 8 + 2 * tq + e;
+                    const int kp = qpar0 ? 2 * ((kt % nkt_half) * KT3 + colt) + cls : kt * KT3 + colt;
                     if (kp >= g.Kh) continue;
                     const int k = 2 * kp + par;
                     const double v = acc[mt][nt][e];

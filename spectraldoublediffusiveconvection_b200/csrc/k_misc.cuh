@@ -48,6 +48,63 @@ __global__ void fill_table_kernel(double* tab, int mode, int M, int Kh, int Mh, 
     }
 }
 
+// Tables of the second mirror level ("quarter-wave" split, k_synth_ws.cuh).  Mirror pairs j' come in orbits
+// (L = j'', R = Mh-1-j''), j'' < Mq = Mh/2, with theta_R = pi/2 - theta_L.
+// mode 2 (synthesis, W = 16 columns per tile = 8 orbits):  tab[jt][chunk][ks][type][par][16][kk]
+//     par 1: col < 8 -> angle theta_L(jt*8+col), col >= 8 -> theta_R(jt*8+col-8);  k' = 8 chunk + 4 ks + kk
+//     par 0: col < 8 -> theta_L, k' = chunk_pos_inv(8 chunk + 4 ks + kk) (ks 0: k' even, ks 1: k' odd); col >= 8 -> 0
+// mode 3 (analysis, 64 output columns per tile): tab[par][kt][chunk][ks][type][64][kk], contraction position
+//     p = 8 chunk + 4 ks + kk
+//     par 1: p < Mq -> theta_L(p), p >= Mq -> theta_R(p - Mq);  k' = kt*64 + col
+//     par 0: only p < Mq (theta_L(p)); output columns are class-ordered: class = kt / (nkt/2),
+//            k' = 2*((kt % (nkt/2))*64 + col) + class
+__global__ void fill_table_quarter_kernel(double* tab, int mode, int M, int Kh, int Mh, int W, int nA, int nchunk) {
+    const long long total = 8LL * nA * nchunk * W * 4;
+    const int Mq = Mh / 2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx;
+        const int kk = (int)(r & 3); r >>= 2;
+        const int col = (int)(r % W); r /= W;
+        int type, par, ks, chunk, tile;
+        if (mode == 2) {
+            par = (int)(r & 1); r >>= 1; type = (int)(r & 1); r >>= 1; ks = (int)(r & 1); r >>= 1;
+            chunk = (int)(r % nchunk); tile = (int)(r / nchunk);
+        } else {
+            type = (int)(r & 1); r >>= 1; ks = (int)(r & 1); r >>= 1;
+            chunk = (int)(r % nchunk); r /= nchunk; tile = (int)(r % nA); par = (int)(r / nA);
+        }
+        const int inner = 8 * chunk + 4 * ks + kk;
+        int kp = -1, jp = -1;   // wavenumber index k' and mirror-pair index j' (angle theta_{j'}); -1 = zero entry
+        if (mode == 2) {
+            const int jq = tile * 8 + (col & 7);
+            if (jq < Mq) {
+                if (par == 1) { kp = inner; jp = (col < 8) ? jq : Mh - 1 - jq; }
+                else if (col < 8) { kp = chunk_pos_inv(inner, 0); jp = jq; }
+            }
+        } else {
+            if (par == 1) {
+                kp = tile * W + col;
+                if (inner < Mq) jp = inner; else if (inner < 2 * Mq) jp = Mh - 1 - (inner - Mq);
+            } else {
+                const int half = nA / 2, cls = tile / half;
+                kp = 2 * ((tile % half) * W + col) + cls;
+                if (inner < Mq) jp = inner;
+            }
+        }
+        double v = 0.0;
+        if (kp >= 0 && jp >= 0 && kp < Kh && jp < Mh) {
+            const int k = 2 * kp + par;
+            double c, s;
+            trig_kj(k, jp, M, c, s);
+            v = type == 0 ? c : s;
+            if (k == 0 && type == 1) v = 0.0;
+            if (mode == 3) v *= (type == 0 && k == 0) ? (1.0 / M) : (2.0 / M);
+        }
+        tab[idx] = v;
+    }
+}
+
 // w[j'] = trapezoid weight(theta_j') * sin(theta_j') on the M3-point grid for j' < M3/2 (mirror point has the
 // same value); np.trapz with x = theta on interior nodes only (Main.py:117,130).
 __global__ void fill_ke_weights_kernel(double* w, int M3, int Jp) {

@@ -116,12 +116,21 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
     double dps[2][2] = {}, d2r[2][2] = {}, dsq[2][2] = {}, dT[2][2] = {}, dS[2][2] = {};
     {
         const int arow = (mt * 8 + gq) * LDX + tq;
-        const int bcol = (nh * 16 + gq) * LDX + tq;
+        // MMA column slot (nl, j) -> sinusoid column of the 16-column half tile: odd columns (odd wavenumbers) in
+        // natural order, even columns class-split like chunk_pos, so that the four lanes sharing an accumulator row
+        // write four consecutive doubles of the tile-major coefficient arrays for both parities
+        int bcol[2];
+#pragma unroll
+        for (int nl = 0; nl < 2; ++nl) {
+            const int e = gq & 1, tt = gq >> 1;
+            const int kloc = (e == 0) ? 2 * tt + nl : 4 * nl + tt;
+            bcol[nl] = (nh * 16 + 2 * kloc + e) * LDX + tq;
+        }
         for (int ks = 0; ks < n8 / 4; ++ks) {
             const double aDr = mDr[arow + ks * 4], aD2r = mD2r[arow + ks * 4], aDsq = mDsq[arow + ks * 4];
 #pragma unroll
             for (int nl = 0; nl < 2; ++nl) {
-                const int o = bcol + nl * 8 * LDX + ks * 4;
+                const int o = bcol[nl] + ks * 4;
                 const double bP = sP[o], bT = sT[o], bS = sS[o];
                 mma884(dps[nl][0], dps[nl][1], aDr, bP);
                 mma884(d2r[nl][0], d2r[nl][1], aD2r, bP);
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
     for (int nl = 0; nl < 2; ++nl) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int col = nh * 16 + nl * 8 + 2 * tq + e;
+            const int col = nh * 16 + 2 * ((e == 0) ? 2 * tq + nl : 4 * nl + tq) + e;   // see the slot map above
             const int c = c0 + col;
             if (c >= K) continue;
             const double jj = sJ[col * LDX + i];

@@ -1,0 +1,249 @@
+// Stage 2, second mirror level ("quarter-wave" split) on top of the persistent warp-specialised schedule of
+// k_synth_ws.cuh.
+//
+// Mirror pairs j' of the grid come in orbits (L = j'', R = M/2-1-j''), j'' < M/4, with theta_R = pi/2 - theta_L, hence
+//     cos(2k' theta_R) = (-1)^k' cos(2k' theta_L),      sin(2k' theta_R) = (-1)^(k'+1) sin(2k' theta_L):
+// the even-wavenumber half E of every synthesis splits once more into the classes k' even (EE) and k' odd (EO),
+//     cosine rows: E(L) = EE + EO, E(R) = EE - EO;        sine rows: E(L) = EE + EO, E(R) = EO - EE,
+// each a contraction over K/4 wavenumbers at the L angles only.  The odd-wavenumber half O is contracted at L and
+// at R as before.  Per orbit and row that is 2*K/2 + 2*K/4 multiply-adds instead of 4*K/2: 25 % less tensor work;
+// the analysis GEMM gets the same saving from the doubly folded products written here (k_analysis.cuh, quarter mode).
+//
+// One tile = 8 orbits.  Each of the 12 MMA warps owns 3 of the 36 row tiles for BOTH parities: per 8-wavenumber
+// stage 12 DMMAs for O (2 column tiles x 2 k-steps) and 6 for EE/EO (k-step 0 holds the k' even coefficients,
+// k-step 1 the k' odd ones: chunk_pos in common.cuh) -- every warp does identical work.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+#include "k_synth.cuh"
+#include "k_synth_ws.cuh"
+
+namespace sddc {
+
+constexpr int SWQ_TPW = 3;  // row tiles per MMA warp (36 / 12)
+
+template <int NT8, int MODE>
+__global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, int ntiles_j, int nwork) {
+    constexpr int NF = 9, RS = NF * NT8 * 8, W = SWS_W, KS = 2, TPW = SWQ_TPW;
+    constexpr int A_SET = KS * 2 * RS * 4, B_ST = KS * 4 * W * 4, STAGE = A_SET + B_ST;
+    constexpr int NS = 3, NMMA = 12, NEW = SWS_NEW, NTHR_E = 32 * NEW;
+    constexpr int n8 = NT8 * 8, ROWS3 = 3 * n8, LDE = 8;
+    static_assert(NF * NT8 == NMMA * TPW, "laid out for 36 row tiles");
+    static_assert(SWS_NMMA == 12 && SWS_KS == 2 && SWS_STAGES == 3, "shares launch geometry with synth_ws_kernel");
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_eo_full, bar_eo_free;
+    const Geo& g = p.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const int nchunk = g.Khp / 8, n = g.n, Mq = g.Mh / 2;
+    double* sEO = smem + (size_t)NS * STAGE;      // [4 classes: O_L, O_R, EE, EO][RS][8]
+    double* sA1 = sEO + (size_t)4 * RS * LDE;     // [4 points][n][8]
+    double* sDr = sA1 + (size_t)4 * n * 8;        // [n][n]
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NMMA); }
+        mbar_init(&bar_eo_full, NMMA);
+        mbar_init(&bar_eo_free, NEW);
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < n * n; idx += SWS_NTHR) sDr[idx] = p.Dr[idx];
+    __syncthreads();
+
+    if (warp == NMMA) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            int st = 0, ph = 0;
+            long long it = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int b = w / ntiles_j, jt = w - b * ntiles_j;
+                const double* gA = p.coef0 + (long long)b * p.coef_stride;
+                const double* gB = p.tab + (long long)jt * nchunk * B_ST;
+                for (int c = 0; c < nchunk; ++c, ++it) {
+                    if (it >= NS) mbar_wait(&bar_empty[st], ph ^ 1);
+                    double* sA = smem + (size_t)st * STAGE;
+                    mbar_expect_tx(&bar_full[st], (unsigned)(STAGE * sizeof(double)));
+                    bulk_g2s(sA, gA + (long long)c * A_SET, A_SET * sizeof(double), &bar_full[st]);
+                    bulk_g2s(sA + A_SET, gB + (long long)c * B_ST, B_ST * sizeof(double), &bar_full[st]);
+                    if (++st == NS) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp < NMMA) {
+        // ---------------- MMA warps: 3 row tiles, both parities ----------------
+        const int tile0 = warp * TPW;
+        const int split = min(TPW, max(0, 5 * NT8 - tile0));   // tiles [0, split) cosine rows, [split, TPW) sine rows
+        const int a0_off = (tile0 * 8 + gq) * 4 + tq;                    // parity-0 rows (+ ks*2*RS*4 + mt*32)
+        const int a1_off = (RS + tile0 * 8 + gq) * 4 + tq;               // parity-1 rows
+        const int b_off = A_SET + gq * 4 + tq;                           // + ks*4*W*4 + (ty*2+par)*W*4 + nt*32
+        int st = 0, ph = 0, tcount = 0;
+        double accO[TPW][2][2], accE[TPW][2][2];   // O at the L / R column tile; EE / EO at the L column tile
+        auto stage_mma = [&](const double* sS, auto split_tag) {
+            constexpr int SPLIT = decltype(split_tag)::value;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double* sB = sS + b_off + ks * 4 * W * 4;
+                double b1c[2], b1s[2], b0c = 0.0, b0s = 0.0, a0[TPW], a1[TPW];
+                if (SPLIT > 0) { b1c[0] = sB[(0 * 2 + 1) * W * 4]; b1c[1] = sB[(0 * 2 + 1) * W * 4 + 32]; b0c = sB[0]; }
+                if (SPLIT < TPW) { b1s[0] = sB[(1 * 2 + 1) * W * 4]; b1s[1] = sB[(1 * 2 + 1) * W * 4 + 32]; b0s = sB[(1 * 2 + 0) * W * 4]; }
+#pragma unroll
+                for (int mt = 0; mt < TPW; ++mt) {
+                    a0[mt] = sS[a0_off + ks * 2 * RS * 4 + mt * 32];
+                    a1[mt] = sS[a1_off + ks * 2 * RS * 4 + mt * 32];
+                }
+#pragma unroll
+                for (int mt = 0; mt < TPW; ++mt) {
+                    mma884(accO[mt][0][0], accO[mt][0][1], a1[mt], mt < SPLIT ? b1c[0] : b1s[0]);
+                    mma884(accO[mt][1][0], accO[mt][1][1], a1[mt], mt < SPLIT ? b1c[1] : b1s[1]);
+                    mma884(accE[mt][ks][0], accE[mt][ks][1], a0[mt], mt < SPLIT ? b0c : b0s);
+                }
+            }
+        };
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++tcount) {
+#pragma unroll
+            for (int mt = 0; mt < TPW; ++mt)
+#pragma unroll
+                for (int x = 0; x < 2; ++x) accO[mt][x][0] = accO[mt][x][1] = accE[mt][x][0] = accE[mt][x][1] = 0.0;
+            for (int c = 0; c < nchunk; ++c) {
+                mbar_wait(&bar_full[st], ph);
+                const double* sS = smem + (size_t)st * STAGE;
+                if (split == TPW) stage_mma(sS, std::integral_constant<int, TPW>{});
+                else if (split == 0) stage_mma(sS, std::integral_constant<int, 0>{});
+                else stage_mma(sS, std::integral_constant<int, (5 * NT8) % TPW>{});
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[st]);
+                if (++st == NS) { st = 0; ph ^= 1; }
+            }
+            if (tcount > 0) mbar_wait(&bar_eo_free, (tcount - 1) & 1);
+#pragma unroll
+            for (int mt = 0; mt < TPW; ++mt) {
+                const size_t row = (size_t)(tile0 + mt) * 8 + gq;
+                *reinterpret_cast<double2*>(&sEO[(0 * RS + row) * LDE + 2 * tq]) = make_double2(accO[mt][0][0], accO[mt][0][1]);
+                *reinterpret_cast<double2*>(&sEO[(1 * RS + row) * LDE + 2 * tq]) = make_double2(accO[mt][1][0], accO[mt][1][1]);
+                *reinterpret_cast<double2*>(&sEO[(2 * RS + row) * LDE + 2 * tq]) = make_double2(accE[mt][0][0], accE[mt][0][1]);
+                *reinterpret_cast<double2*>(&sEO[(3 * RS + row) * LDE + 2 * tq]) = make_double2(accE[mt][1][0], accE[mt][1][1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_eo_full);
+        }
+    } else {
+        // ---------------- epilogue warps: one (radial row, orbit) item = 4 grid points per thread ----------------
+        const int et = tid - 32 * (NMMA + 1);
+        const int nitem = n * 8;
+        constexpr int PTS = (n8 * 8 + NTHR_E - 1) / NTHR_E;
+        int tcount = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++tcount) {
+            const int b = w / ntiles_j, jt = w - b * ntiles_j;
+            double* prd = p.prd + (long long)b * 2 * g.Mhp * ROWS3;
+            const long long pps = (long long)g.Mhp * ROWS3;   // parity stride
+            auto prd_off = [&](int f, int i, int pos) { return ((long long)(pos >> 2) * ROWS3 + f * n8 + i) * 4 + (pos & 3); };
+            double* gc = (MODE != SWS_FX) ? p.gridc + (long long)b * 9 * 2 * n8 * g.Mhp : nullptr;
+            const long long gms = (long long)n8 * g.Mhp;
+            mbar_wait(&bar_eo_full, tcount & 1);
+            double qv[PTS][4];
+#pragma unroll
+            for (int s = 0; s < PTS; ++s) {
+                const int it = et + s * NTHR_E;
+                qv[s][0] = qv[s][1] = qv[s][2] = qv[s][3] = 0.0;
+                if (it < nitem) {
+                    const int i = it >> 3, c = it & 7;
+                    const int jq = jt * 8 + c;                      // orbit index: L = jq, R = Mh-1-jq
+                    double nt[4], ns[4];   // [L, mirror(L), R, mirror(R)]
+                    // the two mirror pairs of the orbit are processed one after the other to bound register use
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        double f[9][2];    // [field][point of the pair, its mirror point]
+#pragma unroll
+                        for (int a = 0; a < 9; ++a) {
+                            const size_t r = ((size_t)a * n8 + i) * LDE + c;
+                            const double o = sEO[(size_t)pr * RS * LDE + r];          // O at L (pr 0) or R (pr 1)
+                            const double ee = sEO[(size_t)2 * RS * LDE + r], eo = sEO[(size_t)3 * RS * LDE + r];
+                            if (a < 5) {
+                                const double e = pr == 0 ? ee + eo : ee - eo;
+                                f[a][0] = e + o; f[a][1] = e - o;
+                            } else {
+                                const double e = pr == 0 ? ee + eo : eo - ee;
+                                f[a][0] = o + e; f[a][1] = o - e;
+                            }
+                        }
+                        const long long gp = (long long)i * g.Mhp + (pr == 0 ? jq : g.Mh - 1 - jq);
+                        if (MODE == SWS_GRID) {
+#pragma unroll
+                            for (int a = 0; a < 9; ++a) {
+                                gc[(a * 2 + 0) * gms + gp] = f[a][0];
+                                gc[(a * 2 + 1) * gms + gp] = f[a][1];
+                            }
+                            continue;
+                        }
+                        double a1[2];
+                        if (MODE == SWS_FX) {
+#pragma unroll
+                            for (int x = 0; x < 2; ++x) {
+                                a1[x] = f[0][x] * f[5][x];
+                                qv[s][2 * pr + x] = f[1][x] * f[5][x] + f[6][x] * f[2][x];
+                                nt[2 * pr + x] = f[0][x] * f[3][x] - f[6][x] * f[7][x];
+                                ns[2 * pr + x] = f[0][x] * f[4][x] - f[6][x] * f[8][x];
+                            }
+                        } else {
+                            double h[9][2];   // perturbation fields (just synthesised); f <- cached base-state fields
+#pragma unroll
+                            for (int a = 0; a < 9; ++a) {
+                                h[a][0] = f[a][0]; h[a][1] = f[a][1];
+                                f[a][0] = gc[(a * 2 + 0) * gms + gp];
+                                f[a][1] = gc[(a * 2 + 1) * gms + gp];
+                            }
+#pragma unroll
+                            for (int x = 0; x < 2; ++x) {
+                                a1[x] = f[0][x] * h[5][x] + h[0][x] * f[5][x];
+                                qv[s][2 * pr + x] = (f[1][x] * h[5][x] + f[6][x] * h[2][x]) + (h[1][x] * f[5][x] + h[6][x] * f[2][x]);
+                                nt[2 * pr + x] = (h[0][x] * f[3][x] - h[6][x] * f[7][x]) + (f[0][x] * h[3][x] - f[6][x] * h[7][x]);
+                                ns[2 * pr + x] = (h[0][x] * f[4][x] - h[6][x] * f[8][x]) + (f[0][x] * h[4][x] - f[6][x] * h[8][x]);
+                            }
+                        }
+                        sA1[((size_t)(2 * pr + 0) * n + i) * 8 + c] = a1[0];
+                        sA1[((size_t)(2 * pr + 1) * n + i) * 8 + c] = a1[1];
+                    }
+                    if (MODE != SWS_GRID) {
+                        // cosine-type analysis (T, S).  odd k: difference of a pair at its own position (L -> jq,
+                        // R -> Mq+jq).  even k: pair sums, folded once more into the k' even / k' odd classes.
+                        const long long oT0 = prd_off(1, i, jq), oT1 = prd_off(1, i, Mq + jq);
+                        const long long oS0 = prd_off(2, i, jq), oS1 = prd_off(2, i, Mq + jq);
+                        const double tL = nt[0] + nt[1], tR = nt[2] + nt[3], sL = ns[0] + ns[1], sR = ns[2] + ns[3];
+                        prd[pps + oT0] = nt[0] - nt[1]; prd[pps + oT1] = nt[2] - nt[3];
+                        prd[oT0] = tL + tR;             prd[oT1] = tL - tR;
+                        prd[pps + oS0] = ns[0] - ns[1]; prd[pps + oS1] = ns[2] - ns[3];
+                        prd[oS0] = sL + sR;             prd[oS1] = sL - sR;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NTHR_E) : "memory");
+            if (lane == 0) mbar_arrive(&bar_eo_free);
+            if (MODE != SWS_GRID) {
+#pragma unroll
+                for (int s = 0; s < PTS; ++s) {
+                    const int it = et + s * NTHR_E;
+                    if (it < nitem) {
+                        const int i = it >> 3, c = it & 7;
+                        const int jq = jt * 8 + c;
+                        double v[4] = {0.0, 0.0, 0.0, 0.0};
+                        for (int ip = 0; ip < n; ++ip) {
+                            const double dr = sDr[i * n + ip];
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) v[x] = fma(dr, sA1[((size_t)x * n + ip) * 8 + c], v[x]);
+                        }
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) v[x] -= qv[s][x];
+                        // sine-type analysis (psi).  odd k: pair sums at their own positions.  even k: pair
+                        // differences, class k' even: L - R, class k' odd: L + R.
+                        const long long o0 = prd_off(0, i, jq), o1 = prd_off(0, i, Mq + jq);
+                        const double dL = v[0] - v[1], dR = v[2] - v[3];
+                        prd[pps + o0] = v[0] + v[1]; prd[pps + o1] = v[2] + v[3];
+                        prd[o0] = dL - dR;           prd[o1] = dL + dR;
+                    }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(NTHR_E) : "memory");
+            }
+        }
+    }
+}
+
+}  // namespace sddc

@@ -16,6 +16,7 @@
 #include "k_synth.cuh"
 #include "k_synth_ws.cuh"
 #include "k_synth2.cuh"
+#include "k_synth_wsq.cuh"
 
 using namespace sddc;
 
@@ -55,6 +56,8 @@ struct sddc_plan {
     double *ir2 = nullptr, *ir4 = nullptr, *r2 = nullptr, *dT0 = nullptr, *gb = nullptr, *a4_ir2 = nullptr,
            *a4_ir4 = nullptr, *ir = nullptr, *nu_in = nullptr, *nu_out = nullptr, *wr = nullptr;
     double *tab1 = nullptr, *tab1d = nullptr, *tab2 = nullptr, *tab3 = nullptr, *wth = nullptr;
+    double *tab1q = nullptr, *tab2q = nullptr;  // second-mirror-level tables (k_synth_wsq.cuh)
+    bool quarter = false;
     // scratch
     double *JJ = nullptr, *coef = nullptr, *prd = nullptr, *lin = nullptr, *rhs = nullptr, *xtmp = nullptr,
            *kepart = nullptr, *zeroRa = nullptr;
@@ -319,7 +322,12 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
         sp.tab = pl->tab1d;  // W = 16 table tiling
         const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
         const int grid = std::min(nwork, pl->num_sms);
-        synth_ws_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+        if (pl->quarter) {
+            sp.tab = pl->tab1q;
+            synth_wsq_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+        } else {
+            synth_ws_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+        }
         pl->launches++;
         PLAN_CUDA(pl, cudaGetLastError());
         return SDDC_OK;
@@ -328,9 +336,10 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     return launch_synth<EPI_FX>(pl, sp, pl->synth_stage_fx, pl->synth_smem_fx, tiles, B, st);
 }
 
-int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream_t st) {
+int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream_t st, bool quarter) {
     AnaParams ap{};
-    ap.prd = pl->prd; ap.tab2 = pl->tab2; ap.out = out; ap.bstride = solve_major ? pl->bstride : 0; ap.g = pl->g;
+    ap.prd = pl->prd; ap.tab2 = quarter ? pl->tab2q : pl->tab2; ap.quarter = quarter ? 1 : 0;
+    ap.out = out; ap.bstride = solve_major ? pl->bstride : 0; ap.g = pl->g;
     StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
     return launch_analysis(pl, ap, B, st);
 }
@@ -365,7 +374,7 @@ int run_member_step(sddc_plan* pl, const double* X, double* out, const double* s
     const double* fnl = nullptr;
     if (!linear) {
         if ((rc = run_synth_nl(pl, false, B, st))) return rc;
-        if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
+        if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
     }
     return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
@@ -564,11 +573,28 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             pl->synth_variant = pl->ws_ok ? (v ? atoi(v) : 1) : 0;
             pl->s2_smem = synth2_smem_doubles(n, n8) * sizeof(double);
         }
+        {
+            const char* qe = getenv("SDDC_QUARTER");
+            pl->quarter = pl->ws_ok && pl->synth_variant == 1 && g.Kh % 128 == 0 && g.Mh % 16 == 0 && g.Mhp == g.Mh &&
+                          !(qe && qe[0] == '0');
+            if (pl->quarter) {
+                const int nch = g.Khp / 8, KT3q = 32 * pl->ana_nt;
+                TRY(dev_alloc(pl, &pl->tab1q, 4ull * g.Mhp * g.Khp, false));
+                TRY(dev_alloc(pl, &pl->tab2q, 4ull * g.Khp2 * g.Mhp, false));
+                fill_table_quarter_kernel<<<296, 256>>>(pl->tab1q, 2, g.M, g.Kh, g.Mh, 16, (g.Mh / 2) / 8, nch);
+                fill_table_quarter_kernel<<<296, 256>>>(pl->tab2q, 3, g.M, g.Kh, g.Mh, KT3q, g.Khp2 / KT3q, g.Mhp / 8);
+                pl->launches += 2;
+                TRYC(cudaGetLastError());
+            }
+        }
         if (pl->ws_ok) {
             TRY(set_smem(pl, synth2_kernel<4>, pl->s2_smem));
             TRY(set_smem(pl, (synth_ws_kernel<4, SWS_FX>), pl->ws_smem));
             TRY(set_smem(pl, (synth_ws_kernel<4, SWS_GRID>), pl->ws_smem));
             TRY(set_smem(pl, (synth_ws_kernel<4, SWS_JVPC>), pl->ws_smem));
+            TRY(set_smem(pl, (synth_wsq_kernel<4, SWS_FX>), pl->ws_smem));
+            TRY(set_smem(pl, (synth_wsq_kernel<4, SWS_GRID>), pl->ws_smem));
+            TRY(set_smem(pl, (synth_wsq_kernel<4, SWS_JVPC>), pl->ws_smem));
         }
     }
     {
@@ -633,7 +659,7 @@ int sddc_nlin_fx(sddc_plan* pl, const double* X, double* F, int B, void* stream)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, false, B, st))) return rc;
-    return run_analysis(pl, F, false, B, st);
+    return run_analysis(pl, F, false, B, st, pl->quarter);
 }
 
 int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, int B, void* stream) {
@@ -643,7 +669,7 @@ int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, i
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
-    return run_analysis(pl, F, false, B, st);
+    return run_analysis(pl, F, false, B, st, false);
 }
 
 int sddc_linear_op(sddc_plan* pl, int op, const double* in, double* out, int B, void* stream) {
@@ -718,7 +744,7 @@ int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, cons
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
-    if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
+    if ((rc = run_analysis(pl, pl->f_sm, true, B, st, false))) return rc;
     return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
 }
 
@@ -730,7 +756,11 @@ static int run_synth_ws_mode(sddc_plan* pl, int mode, const double* coef, int B,
     const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
     const int grid = std::min(nwork, pl->num_sms);
     StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-    if (mode == SWS_GRID) synth_ws_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+    if (pl->quarter) {
+        sp.tab = pl->tab1q;
+        if (mode == SWS_GRID) synth_wsq_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+        else synth_wsq_kernel<4, SWS_JVPC><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+    } else if (mode == SWS_GRID) synth_ws_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
     else synth_ws_kernel<4, SWS_JVPC><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -765,7 +795,7 @@ int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* R
     const long long N3 = 3LL * pl->g.N;
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_ws_mode(pl, SWS_JVPC, pl->coef1, B, st))) return rc;
-    if ((rc = run_analysis(pl, pl->f_sm, true, B, st))) return rc;
+    if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
     return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
 }
 
