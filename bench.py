@@ -280,7 +280,12 @@ def run_ours(a):
     M = 3 * K // 2
     # algorithmic flops of the dominant kernel per member: 9 syntheses as mirror-split dense contractions
     # (2 flops x 9n rows x K/2 modes x M/2 mirror pairs x 2 parities) + products + the Dr@ grid mat-vec
-    synth_flops = 2.0 * 9 * nr * (K // 2) * (M // 2) * 2 + 2.0 * nr * nr * M + 30.0 * nr * M
+    info = plan.info()
+    if info["quarter_wave"]:
+        # second mirror level: per orbit of 4 grid points 2 x K/2 (odd k at L and R) + 2 x K/4 (even k classes) MACs
+        synth_flops = 2.0 * 9 * nr * (M // 4) * (2 * (K // 2) + 2 * (K // 4)) + 2.0 * nr * nr * M + 30.0 * nr * M
+    else:
+        synth_flops = 2.0 * 9 * nr * (K // 2) * (M // 2) * 2 + 2.0 * nr * nr * M + 30.0 * nr * M
     synth_tflops = Bl * synth_flops / (stage_ms["synth"] * 1e-3) / 1e12 if stage_ms["synth"] > 0 else 0.0
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
@@ -295,7 +300,9 @@ def run_ours(a):
                 "frac": synth_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": traffic,
                 "peak_source": "fp64 DMMA peak measured with tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.txt); "
                                "MEASURED_PEAKS.json has no fp64 entry",
-                "launch_ms": stage_ms["synth"], "members_per_launch": Bl, "flops_per_member": synth_flops}
+                "launch_ms": stage_ms["synth"], "members_per_launch": Bl, "flops_per_member": synth_flops,
+                "algorithm": "dense mirror-split transforms, " + ("two mirror levels (quarter-wave)" if info["quarter_wave"] else "one mirror level"),
+                "kernel_variant": info}
     step_bytes = 48.0 * nr * K   # read X once, write X once
     per_gpu_rate = value / world
     hbm_view = {"bound": "hbm", "achieved": per_gpu_rate * step_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s",

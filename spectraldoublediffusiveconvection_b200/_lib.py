@@ -35,6 +35,7 @@ SYMBOLS = {
     "sddc_plan_destroy": (None, [_vp]),
     "sddc_last_error": (C.c_char_p, [_vp]),
     "sddc_launch_count": (_ll, [_vp]),
+    "sddc_plan_info": (_i, [_vp, _i]),
     "sddc_plan_set_linv": (_i, [_vp, _i, _dp, C.c_double]),
     "sddc_plan_set_a4_aux": (_i, [_vp, _dp, _dp, _dp]),
     "sddc_nlin_fx": (_i, [_vp, _dp, _dp, _i, _vp]),

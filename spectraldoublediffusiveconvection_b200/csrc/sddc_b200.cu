@@ -412,6 +412,17 @@ const char* sddc_last_error(const sddc_plan* plan) { return plan ? plan->err.c_s
 
 long long sddc_launch_count(const sddc_plan* plan) { return plan ? plan->launches : 0; }
 
+int sddc_plan_info(const sddc_plan* plan, int what) {
+    if (!plan) return -1;
+    switch (what) {
+        case 0: return plan->quarter ? 1 : 0;       // second mirror level active on the hot path
+        case 1: return plan->synth_variant;         // 0 generic, 1 persistent warp-specialised, 2 two-CTAs-per-SM
+        case 2: return plan->dfx_ok ? 1 : 0;        // two-state JVP synthesis available
+        case 3: return plan->g.n8;
+        default: return -1;
+    }
+}
+
 void sddc_plan_destroy(sddc_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);

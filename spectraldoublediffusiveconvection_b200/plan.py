@@ -101,6 +101,11 @@ class EnsemblePlan:
             return v.contiguous()
         return torch.full((B,), float(v), dtype=torch.float64, device=self.device)
 
+    def info(self):
+        """Kernel-selection facts: quarter-wave split active, synthesis variant, JVP availability, padded n."""
+        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8")
+        return {nm: int(self.lib.sddc_plan_info(self._h, i)) for i, nm in enumerate(names)}
+
     @property
     def launch_count(self):
         return int(self.lib.sddc_launch_count(self._h))
