@@ -23,7 +23,7 @@ using namespace sddc;
 namespace {
 
 thread_local std::string g_create_error;
-constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr size_t SMEM_LIMIT = 227 * 1024 - 1024;  // dynamic shared memory we opt in to (1 KB left for static barriers)
 #ifndef SOLVE_NTB
 #define SOLVE_NTB 2  // members per back-substitution CTA = 8 * SOLVE_NTB (1 and 4 measured slower)
 #endif
@@ -174,9 +174,12 @@ std::vector<double> build_a4_stack(const double* Linv, const double* D2, int K, 
     return o;
 }
 
+// The opt-in limit is a property of the kernel function, shared by every plan in the process: always raise it to
+// the architectural maximum so that plans of different shapes cannot lower each other's limit.
 template <typename Kern>
 int set_smem(sddc_plan* pl, Kern kern, size_t bytes) {
-    PLAN_CUDA(pl, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (bytes > SMEM_LIMIT) { pl->err = "kernel needs more shared memory than an SM has"; return SDDC_ERR_UNSUPPORTED; }
+    PLAN_CUDA(pl, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     return SDDC_OK;
 }
 
@@ -200,7 +203,7 @@ template <int NT8, int EPI>
 void launch_synth_inst(const SynthParams& sp, int nstage, size_t smem, dim3 grid, cudaStream_t st, bool set_attr) {
     constexpr int NF = (EPI == EPI_KE) ? 2 : 9;
     if (set_attr) {
-        cudaFuncSetAttribute(synth_kernel<NT8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(synth_kernel<NT8, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         return;
     }
     synth_kernel<NT8, EPI><<<grid, 32 * (2 * NF + 1), smem, st>>>(sp, nstage);
@@ -227,7 +230,7 @@ int launch_synth(sddc_plan* pl, const SynthParams& sp, int nstage, size_t smem, 
 template <int NT8>
 void launch_ana_inst(const AnaParams& ap, int nstage, size_t smem, dim3 grid, cudaStream_t st, bool set_attr) {
     if (set_attr) {
-        cudaFuncSetAttribute(analysis_kernel<NT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(analysis_kernel<NT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
         return;
     }
     analysis_kernel<NT8><<<grid, 416, smem, st>>>(ap, nstage);

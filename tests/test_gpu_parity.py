@@ -296,3 +296,22 @@ def test_cached_base_jvp_equals_jvp(name):
     assert rel_l2(j2, 2.0 * g["jvp_Xb"]) < 1e-10
     assert rel_l2(j1, pl.jvp(dv, Xb, Ra, Ra_s).cpu().numpy().ravel()) < 1e-12
     pl.close()
+
+
+def test_plans_of_different_shapes_coexist():
+    """Several live plans (different N_r, same kernel instantiations) must not disturb each other's launches."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    cfgs = [(32, 32, 0.4), (32, 26, 0.5), (32, 30, 0.45)]
+    plans = [EnsemblePlan(K, N_r, d, 5e-3, 1.0, 0.5, max_batch=2) for (K, N_r, d) in cfgs]
+    rng = np.random.default_rng(12)
+    for _ in range(2):
+        for (K, N_r, d), pl in zip(cfgs, plans):
+            X = rng.random((2, 3 * pl.N)) * 1e-2
+            out = pl.step(_dev(X), 3000.0, 100.0).cpu().numpy()
+            op = orc.Operators(K, N_r, d, 5e-3, 1.0, 0.5)
+            assert rel_l2(out[1], orc.step(X[1], op, 3000.0, 100.0)) < 1e-10
+            dg = pl.diagnostics(_dev(X)).cpu().numpy()
+            assert np.allclose(dg[0, :4], orc.diagnostics(X[0], op), rtol=1e-10)
+    for pl in plans:
+        pl.close()
