@@ -17,6 +17,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
 }
+// 8-byte asynchronous copy with zero fill when !valid (nothing is read from gmem_src then)
+__device__ __forceinline__ void cp_async8_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem_src), "r"(valid ? 8 : 0) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -92,23 +92,27 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
 
     const double* Xb = p.X + (long long)b * p.x_stride;
     const double* Jb = p.JJ + (long long)b * (K + 1) * n;
+    // all tile loads are asynchronous copies issued back to back (zero fill for masked / padded entries), so the
+    // global-memory latency is paid once per CTA
     for (int idx = tid; idx < TQ * LDX; idx += nthr) {
         const int q = idx / LDX, i = idx - q * LDX;
         const int bp = c0 - 1 + q, bt = c0 + q;
-        double vp = 0.0, vt = 0.0, vs = 0.0, vj = 0.0;
-        if (i < n) {
-            if (bp >= 0 && bp < K && !(g.symmetric && (bp & 1) == 0)) vp = Xb[(long long)bp * n + i];
-            if (bt < K && !(g.symmetric && (bt & 1) == 1)) {
-                vt = Xb[(long long)N + (long long)bt * n + i];
-                vs = Xb[2LL * N + (long long)bt * n + i];
-            }
-            if (bt <= K) vj = Jb[(long long)bt * n + i];
-        }
-        sP[idx] = vp; sT[idx] = vt; sS[idx] = vs; sJ[idx] = vj;
+        const bool in = i < n;
+        const bool okp = in && bp >= 0 && bp < K && !(g.symmetric && (bp & 1) == 0);
+        const bool okt = in && bt < K && !(g.symmetric && (bt & 1) == 1);
+        const bool okj = in && bt <= K;
+        cp_async8_zfill(&sP[idx], okp ? Xb + (long long)bp * n + i : Xb, okp);
+        cp_async8_zfill(&sT[idx], okt ? Xb + (long long)N + (long long)bt * n + i : Xb, okt);
+        cp_async8_zfill(&sS[idx], okt ? Xb + 2LL * N + (long long)bt * n + i : Xb, okt);
+        cp_async8_zfill(&sJ[idx], okj ? Jb + (long long)bt * n + i : Jb, okj);
     }
-    for (int idx = tid; idx < n8 * LDX; idx += nthr) {
-        mDr[idx] = p.DrP[idx]; mD2r[idx] = p.D2rP[idx]; mDsq[idx] = p.DsqP[idx];
+    for (int idx = tid; idx < n8 * LDX / 2; idx += nthr) {
+        cp_async16(&mDr[2 * idx], p.DrP + 2 * idx);
+        cp_async16(&mD2r[2 * idx], p.D2rP + 2 * idx);
+        cp_async16(&mDsq[2 * idx], p.DsqP + 2 * idx);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
 
     const int mt = warp >> 1, nh = warp & 1;
