@@ -1,0 +1,227 @@
+// Stage 4, hot path: the back-substitution chains of k_solve.cuh specialised for the solve-major layout with every
+// size a compile-time constant.  One chain step is a serial dependency (f_j needs f_{j+2}), and a CTA has only one
+// warp per scheduler, so the step time is the *instruction count* of the loop body times the issue latency: here
+// all shared-memory offsets are immediates, the output pointers are carried and decremented, and the special cases
+// of the recurrences (first step, mode 0) are folded into data instead of branches.
+//
+// The stream-function chains do twice the tensor work per step (L_inv_j and L_inv_j @ D2); they run on narrower
+// member tiles (SOLVE_NTB_PSI) than the scalar chains (SOLVE_NTB_TS) so that every CTA of the launch has about the
+// same step time.
+//
+// Reference semantics: A4_BSub_TSTEP_V2 (Matrix_Operators.py:1115-1194) and NAB2_BSub_TSTEP_V2 (1033-1086).
+#pragma once
+#include "k_solve.cuh"
+
+namespace sddc {
+
+#ifndef SOLVE_NTB_PSI
+#define SOLVE_NTB_PSI 1
+#endif
+#ifndef SOLVE_NTB_TS
+#define SOLVE_NTB_TS 2
+#endif
+
+template <int NTB, bool PSI>
+__host__ __device__ constexpr size_t solve_hot_doubles(int n8, int nsl) {
+    const int LDL = n8 + 4, LDG = n8 + 2, NM = PSI ? 2 : 1;
+    return (size_t)nsl * NM * n8 * LDL + (size_t)2 * NM * (8 * NTB) * LDL + (size_t)nsl * 2 * (8 * NTB) * LDG;
+}
+// nsl = pipeline stages (operator + right-hand-side tiles): 3, or 2 when three do not fit an SM
+__host__ inline size_t solve_hot_smem_bytes(int n8, int nsl) {
+    const size_t a = solve_hot_doubles<SOLVE_NTB_PSI, true>(n8, nsl), b = solve_hot_doubles<SOLVE_NTB_TS, false>(n8, nsl);
+    return sizeof(double) * (a > b ? a : b);
+}
+
+template <int NT8, int NSL, int NTB, bool PSI>
+__device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* smem, uint64_t* bar_full,
+                                                uint64_t* bar_empty, int fld, int which, int b0) {
+    constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
+    constexpr int NM = PSI ? 2 : 1, NTHR = 32 * NT8;
+    constexpr int NCH = NTB >= 2 ? 1 : 2;   // accumulator chains per product and member tile (k-steps interleaved)
+    const Geo& G = p.geo;
+    const int n = G.n, K = G.K;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+    const bool is_producer = warp == NT8;
+    double* sL = smem;                              // [NSL][NM][n8][LDL]
+    double* sR = sL + (size_t)NSL * NM * MAT;       // [2 step parities][NM][BT][LDL]
+    double* sG = sR + (size_t)2 * NM * BT * LDL;    // [NSL][2][BT][LDG]   (lin, F)
+    const int i = warp * 8 + gq;
+    const bool row_ok = i < n;
+    const bool has_f = p.fnl != nullptr, has_sub = p.sub != nullptr;
+
+    const int j0 = PSI ? (K - which) : (which == 0 ? K - 2 : K - 1);
+    const int jend = PSI ? 1 : 0;
+    const int row0 = PSI ? j0 - 1 : j0;
+    const int nsteps = (j0 - jend) / 2 + 1;
+
+    double* outp[NE];
+    bool ok[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int m = (e >> 1) * 8 + 2 * tq + (e & 1);
+        ok[e] = row_ok && (b0 + m) < p.B;
+        outp[e] = p.out + (long long)(b0 + m) * p.out_stride + (long long)fld * p.out_field_off + (long long)row0 * n + i;
+    }
+    const long long sub_delta = has_sub ? (p.sub - p.out) : 0;
+    const long long rstep = -2LL * n;
+
+    if (G.symmetric && which == 1) {   // these modes are identically zero under the equatorial symmetry
+        if (is_producer) return;
+        for (int s = 0; s < nsteps; ++s) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (ok[e]) outp[e][0] = has_sub ? -outp[e][sub_delta] : 0.0;
+                outp[e] += rstep;
+            }
+        }
+        return;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NSL; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NT8); }
+        mbar_fence_init();
+    }
+    for (int idx = tid; idx < 2 * NM * BT * LDL; idx += blockDim.x) sR[idx] = 0.0;   // padded rows stay zero
+    __syncthreads();
+
+    if (is_producer) {
+        if (lane != 0) return;
+        const double* Lg = PSI ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
+        constexpr unsigned tile_bytes = GT * sizeof(double), mat_bytes = NM * MAT * sizeof(double);
+        const unsigned bytes = mat_bytes + tile_bytes * (has_f ? 2u : 1u);
+        int st = 0, ph = 0;
+        for (int step = 0; step < nsteps; ++step) {
+            const int j = j0 - 2 * step;
+            const int jj = PSI ? (K - j) : (K - 1 - j), row = PSI ? j - 1 : j;
+            if (step >= NSL) mbar_wait(&bar_empty[st], ph ^ 1);
+            mbar_expect_tx(&bar_full[st], bytes);
+            bulk_g2s(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st]);
+            const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
+            bulk_g2s(sG + (size_t)st * 2 * GT, p.g + o, tile_bytes, &bar_full[st]);
+            if (has_f) bulk_g2s(sG + (size_t)st * 2 * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
+            if (++st == NSL) { st = 0; ph ^= 1; }
+        }
+        return;
+    }
+
+    // per-thread shared-memory bases; everything below is base + stage * constant + immediate
+    const double* gT = sG + (2 * tq) * LDG + i;          // right-hand-side tile element (member 2tq, row i)
+    double* rW = sR + (2 * tq) * LDL + i;                // GEMM operand element (member 2tq, row i)
+    const double* aP = sL + (warp * 8 + gq) * LDL + tq;  // A fragment: L_inv[8w+g][4ks+t]
+    const double* bP = sR + gq * LDL + tq;               // B fragment: rhs[4ks+t][member g]
+
+    double f[NE], subv[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { f[e] = 0.0; subv[e] = 0.0; }
+    double s1[NE], s2[NE];   // T,S: s1 = running sum b;   psi: s1 = f_e, s2 = bf_e
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { s1[e] = 0.0; s2[e] = 0.0; }
+    const double dt = PSI ? p.dt_psi : (fld == 1 ? p.dt_T : p.dt_S);
+    const double ir2 = (PSI && row_ok) ? p.ir2[i] : 0.0, ir4 = (PSI && row_ok) ? p.ir4[i] : 0.0;
+
+    int st = 0, ph = 0;
+    for (int step = 0; step < nsteps; ++step) {
+        const int j = j0 - 2 * step;
+        if (has_sub) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e)
+                if (ok[e]) subv[e] = outp[e][sub_delta];
+        }
+        mbar_wait(&bar_full[st], ph);
+        const double* gt = gT + st * (2 * GT);
+        double gv[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int off = ((e >> 1) * 8 + (e & 1)) * LDG;
+            gv[e] = gt[off];
+            if (has_f) gv[e] = fma(p.mdt, gt[GT + off], gv[e]);
+        }
+        double* buf = rW + (step & 1) * (NM * BT * LDL);
+        if (!PSI) {
+            // b += 2 dt (j+2) f_{j+2};  rhs = g_j - b   (halved for mode 0)       (Matrix_Operators.py:1063-1079)
+            const double beta = 2.0 * dt * (j + 2.0), scale = (j == 0) ? -0.5 : -1.0;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                s1[e] = fma(beta, f[e], s1[e]);
+                const double rhs = fma(scale, s1[e], gv[e]);
+                if (row_ok) buf[((e >> 1) * 8 + (e & 1)) * LDL] = rhs;
+            }
+        } else {
+            // f_j = L_inv_j ( g_j + dt bjt (L1_j f_e + IR4 bf_e) - bjt IR2 f_e ),  L1_j = D2 + b_j IR4
+            //     = L_inv_j ( g_j + c1 f_e + c2 bf_e ) + (L_inv_j D2) (dt bjt f_e)   (Matrix_Operators.py:1149-1180)
+            const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
+            const double c3 = dt * bjt, c2 = c3 * ir4, c1 = bjt * (dt * bj * ir4 - ir2);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                s1[e] += f[e];
+                const double rhs = fma(c2, s2[e], fma(c1, s1[e], gv[e]));
+                if (row_ok) {
+                    buf[((e >> 1) * 8 + (e & 1)) * LDL] = rhs;
+                    buf[BT * LDL + ((e >> 1) * 8 + (e & 1)) * LDL] = c3 * s1[e];
+                }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");   // compute warps only
+        {
+            const double* a = aP + st * (NM * MAT);
+            const double* b = bP + (step & 1) * (NM * BT * LDL);
+            double c[NM][NCH][NE];
+#pragma unroll
+            for (int q = 0; q < NM; ++q)
+#pragma unroll
+                for (int h = 0; h < NCH; ++h)
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) c[q][h][e] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < n8 / 4; ++ks) {
+#pragma unroll
+                for (int q = 0; q < NM; ++q) {
+                    const double av = a[q * MAT + ks * 4];
+#pragma unroll
+                    for (int nt = 0; nt < NTB; ++nt)
+                        mma884(c[q][ks % NCH][2 * nt], c[q][ks % NCH][2 * nt + 1], av,
+                               b[q * BT * LDL + nt * 8 * LDL + ks * 4]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < NM; ++q)
+#pragma unroll
+                    for (int h = 0; h < NCH; ++h) s += c[q][h][e];
+                f[e] = s;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);   // operator + tiles of this stage are consumed
+        if (++st == NSL) { st = 0; ph ^= 1; }
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            if (ok[e]) outp[e][0] = f[e] - subv[e];
+            outp[e] += rstep;
+        }
+        if (PSI) {
+            const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) s2[e] += fma(bj, f[e], bjt * s1[e]);
+        }
+    }
+}
+
+// grid = 2 * (psi member tiles) + 4 * (T,S member tiles) CTAs, stream-function chains first; block = 32 * (NT8 + 1):
+// compute warp w owns radial rows 8w..8w+7 in MMA accumulator layout, the last warp is the TMA producer.
+template <int NT8, int NSL>
+__global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
+    const int bid = blockIdx.x;
+    if (bid < 2 * npsi_tiles) {
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
+    } else {
+        const int r = bid - 2 * npsi_tiles;
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
+                                                  (r >> 2) * 8 * SOLVE_NTB_TS);
+    }
+}
+
+}  // namespace sddc

@@ -13,6 +13,7 @@
 #include "k_misc.cuh"
 #include "k_prep.cuh"
 #include "k_solve.cuh"
+#include "k_solve_hot.cuh"
 #include "k_synth.cuh"
 #include "k_synth_ws.cuh"
 #include "k_synth2.cuh"
@@ -85,8 +86,8 @@ struct sddc_plan {
     size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
     int ana_nt = 0, ana_stage = 0;
     size_t ana_smem = 0;
-    size_t solve_smem = 0;
-    int solve_nsl = 3;
+    size_t solve_smem = 0, solve_hot_smem = 0;
+    int solve_nsl = 3, solve_hot_nsl = 3;
     double dt_psi = 0, dt_T = 0, dt_S = 0;  // effective time steps of the three operator stacks
     // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
     bool profiling = false;
@@ -361,8 +362,22 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     // single-field calls pass field offsets of 0; the operator stack follows field_base
     dim3 grid((B + 8 * SOLVE_NTB - 1) / (8 * SOLVE_NTB), 2, nfields);
     StageTimer tm(pl, SDDC_STAGE_SOLVE, st);
-    if (sm) solve_kernel<SOLVE_NTB, true><<<grid, 32 * (pl->g.nt8 + 1), pl->solve_smem, st>>>(sp);
-    else solve_kernel<SOLVE_NTB, false><<<grid, 32 * (pl->g.nt8 + 1), pl->solve_smem, st>>>(sp);
+    if (sm) {
+        // hot path: all three fields from the solve-major buffers (k_solve_hot.cuh)
+        const int npsi = (B + 8 * SOLVE_NTB_PSI - 1) / (8 * SOLVE_NTB_PSI), nts = (B + 8 * SOLVE_NTB_TS - 1) / (8 * SOLVE_NTB_TS);
+        const int nblk = 2 * npsi + 4 * nts, nthr = 32 * (pl->g.nt8 + 1);
+        const size_t smb = pl->solve_hot_smem;
+        const bool n3 = pl->solve_hot_nsl == 3;
+        switch (pl->g.nt8) {
+            case 3: if (n3) solve_hot_kernel<3, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<3, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            case 4: if (n3) solve_hot_kernel<4, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<4, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            case 5: if (n3) solve_hot_kernel<5, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<5, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            case 6: if (n3) solve_hot_kernel<6, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<6, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            case 7: if (n3) solve_hot_kernel<7, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<7, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            case 8: if (n3) solve_hot_kernel<8, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<8, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            default: pl->err = "unsupported radial tile count"; return SDDC_ERR_UNSUPPORTED;
+        }
+    } else solve_kernel<SOLVE_NTB, false><<<grid, 32 * (pl->g.nt8 + 1), pl->solve_smem, st>>>(sp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
@@ -619,7 +634,20 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         pl->solve_nsl = want;
     }
     pl->solve_smem = solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double);
-    TRY(set_smem(pl, solve_kernel<SOLVE_NTB, true>, pl->solve_smem));
+    pl->solve_hot_nsl = solve_hot_smem_bytes(n8, 3) <= SMEM_LIMIT ? 3 : 2;
+    pl->solve_hot_smem = solve_hot_smem_bytes(n8, pl->solve_hot_nsl);
+    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<3, 3>), pl->solve_hot_smem));
+    else TRY(set_smem(pl, (solve_hot_kernel<3, 2>), pl->solve_hot_smem));
+    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<4, 3>), pl->solve_hot_smem));
+    else TRY(set_smem(pl, (solve_hot_kernel<4, 2>), pl->solve_hot_smem));
+    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<5, 3>), pl->solve_hot_smem));
+    else TRY(set_smem(pl, (solve_hot_kernel<5, 2>), pl->solve_hot_smem));
+    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<6, 3>), pl->solve_hot_smem));
+    else TRY(set_smem(pl, (solve_hot_kernel<6, 2>), pl->solve_hot_smem));
+    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<7, 3>), pl->solve_hot_smem));
+    else TRY(set_smem(pl, (solve_hot_kernel<7, 2>), pl->solve_hot_smem));
+    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<8, 3>), pl->solve_hot_smem));
+    else TRY(set_smem(pl, (solve_hot_kernel<8, 2>), pl->solve_hot_smem));
     TRY(set_smem(pl, solve_kernel<SOLVE_NTB, false>, pl->solve_smem));
     TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8)));
     TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8)));
