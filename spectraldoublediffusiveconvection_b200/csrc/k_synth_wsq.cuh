@@ -23,6 +23,12 @@ namespace sddc {
 
 constexpr int SWQ_TPW = 3;  // row tiles per MMA warp (36 / 12)
 
+__host__ __device__ inline size_t synth_wsq_smem_doubles(int n8) {
+    const size_t rs = 9 * (size_t)n8;
+    const size_t stage = (size_t)SWS_KS * 2 * rs * 4 + (size_t)SWS_KS * 4 * SWS_W * 4;
+    return SWS_STAGES * stage + 2 * rs * SWS_W + 2 * (size_t)4 * n8 * 8 + (size_t)n8 * (n8 + 4);
+}
+
 template <int NT8, int MODE>
 __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, int ntiles_j, int nwork) {
     constexpr int NF = 9, RS = NF * NT8 * 8, W = SWS_W, KS = 2, TPW = SWQ_TPW;
@@ -36,9 +42,11 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
     const Geo& g = p.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const int nchunk = g.Khp / 8, n = g.n, Mq = g.Mh / 2;
+    constexpr int LDD = n8 + 4;
     double* sEO = smem + (size_t)NS * STAGE;      // [4 classes: O_L, O_R, EE, EO][RS][8]
-    double* sA1 = sEO + (size_t)4 * RS * LDE;     // [4 points][n][8]
-    double* sDr = sA1 + (size_t)4 * n * 8;        // [n][n]
+    double* sA1 = sEO + (size_t)4 * RS * LDE;     // [4 points][n8][8]  (rows >= n stay zero)
+    double* sQ = sA1 + (size_t)4 * n8 * 8;        // [4 points][n8][8]
+    double* sDr = sQ + (size_t)4 * n8 * 8;        // [n8][LDD] zero padded
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NMMA); }
@@ -46,7 +54,11 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
         mbar_init(&bar_eo_free, NEW);
         mbar_fence_init();
     }
-    for (int idx = tid; idx < n * n; idx += SWS_NTHR) sDr[idx] = p.Dr[idx];
+    for (int idx = tid; idx < n8 * LDD; idx += SWS_NTHR) {
+        const int r = idx / LDD, c = idx - r * LDD;
+        sDr[idx] = (r < n && c < n) ? p.Dr[r * n + c] : 0.0;
+    }
+    for (int idx = tid; idx < 4 * n8 * 8; idx += SWS_NTHR) sA1[idx] = 0.0;
     __syncthreads();
 
     if (warp == NMMA) {
@@ -139,11 +151,9 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
             double* gc = (MODE != SWS_FX) ? p.gridc + (long long)b * 9 * 2 * n8 * g.Mhp : nullptr;
             const long long gms = (long long)n8 * g.Mhp;
             mbar_wait(&bar_eo_full, tcount & 1);
-            double qv[PTS][4];
 #pragma unroll
             for (int s = 0; s < PTS; ++s) {
                 const int it = et + s * NTHR_E;
-                qv[s][0] = qv[s][1] = qv[s][2] = qv[s][3] = 0.0;
                 if (it < nitem) {
                     const int i = it >> 3, c = it & 7;
                     const int jq = jt * 8 + c;                      // orbit index: L = jq, R = Mh-1-jq
@@ -174,12 +184,12 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
                             }
                             continue;
                         }
-                        double a1[2];
+                        double a1[2], qv[2];
                         if (MODE == SWS_FX) {
 #pragma unroll
                             for (int x = 0; x < 2; ++x) {
                                 a1[x] = f[0][x] * f[5][x];
-                                qv[s][2 * pr + x] = f[1][x] * f[5][x] + f[6][x] * f[2][x];
+                                qv[x] = f[1][x] * f[5][x] + f[6][x] * f[2][x];
                                 nt[2 * pr + x] = f[0][x] * f[3][x] - f[6][x] * f[7][x];
                                 ns[2 * pr + x] = f[0][x] * f[4][x] - f[6][x] * f[8][x];
                             }
@@ -194,13 +204,15 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
 #pragma unroll
                             for (int x = 0; x < 2; ++x) {
                                 a1[x] = f[0][x] * h[5][x] + h[0][x] * f[5][x];
-                                qv[s][2 * pr + x] = (f[1][x] * h[5][x] + f[6][x] * h[2][x]) + (h[1][x] * f[5][x] + h[6][x] * f[2][x]);
+                                qv[x] = (f[1][x] * h[5][x] + f[6][x] * h[2][x]) + (h[1][x] * f[5][x] + h[6][x] * f[2][x]);
                                 nt[2 * pr + x] = (h[0][x] * f[3][x] - h[6][x] * f[7][x]) + (f[0][x] * h[3][x] - f[6][x] * h[7][x]);
                                 ns[2 * pr + x] = (h[0][x] * f[4][x] - h[6][x] * f[8][x]) + (f[0][x] * h[4][x] - f[6][x] * h[8][x]);
                             }
                         }
-                        sA1[((size_t)(2 * pr + 0) * n + i) * 8 + c] = a1[0];
-                        sA1[((size_t)(2 * pr + 1) * n + i) * 8 + c] = a1[1];
+                        sA1[((size_t)(2 * pr + 0) * n8 + i) * 8 + c] = a1[0];
+                        sA1[((size_t)(2 * pr + 1) * n8 + i) * 8 + c] = a1[1];
+                        sQ[((size_t)(2 * pr + 0) * n8 + i) * 8 + c] = qv[0];
+                        sQ[((size_t)(2 * pr + 1) * n8 + i) * 8 + c] = qv[1];
                     }
                     if (MODE != SWS_GRID) {
                         // cosine-type analysis (T, S).  odd k: difference of a pair at its own position (L -> jq,
@@ -218,26 +230,43 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
             asm volatile("bar.sync 1, %0;" ::"n"(NTHR_E) : "memory");
             if (lane == 0) mbar_arrive(&bar_eo_free);
             if (MODE != SWS_GRID) {
+                // Dr @ (n x 32 points) on the tensor pipe: DFMAs issued from here would queue behind the MMA warps'
+                // DMMAs on the shared fp64 pipe one by one.  Warp e < NT8 owns radial rows 8e..8e+7 of all four
+                // point classes; accumulator element (row g, columns 2t, 2t+1).
+                const int ew = warp - (NMMA + 1);
+                if (ew < NT8) {
+                    double acc[4][2] = {};
+                    const double* ar = sDr + (ew * 8 + gq) * LDD + tq;
+                    const double* br = sA1 + tq * 8 + gq;
 #pragma unroll
-                for (int s = 0; s < PTS; ++s) {
-                    const int it = et + s * NTHR_E;
-                    if (it < nitem) {
-                        const int i = it >> 3, c = it & 7;
-                        const int jq = jt * 8 + c;
-                        double v[4] = {0.0, 0.0, 0.0, 0.0};
-                        for (int ip = 0; ip < n; ++ip) {
-                            const double dr = sDr[i * n + ip];
+                    for (int ks = 0; ks < n8 / 4; ++ks) {
+                        const double av = ar[ks * 4];
 #pragma unroll
-                            for (int x = 0; x < 4; ++x) v[x] = fma(dr, sA1[((size_t)x * n + ip) * 8 + c], v[x]);
+                        for (int x = 0; x < 4; ++x) mma884(acc[x][0], acc[x][1], av, br[(x * n8 + ks * 4) * 8]);
+                    }
+                    const int i = ew * 8 + gq;
+                    if (i < n) {
+                        const int c = 2 * tq, jq = jt * 8 + c;
+                        double v[4][2];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x) {
+                            const double2 q = *reinterpret_cast<const double2*>(&sQ[((size_t)x * n8 + i) * 8 + c]);
+                            v[x][0] = acc[x][0] - q.x; v[x][1] = acc[x][1] - q.y;
                         }
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) v[x] -= qv[s][x];
                         // sine-type analysis (psi).  odd k: pair sums at their own positions.  even k: pair
-                        // differences, class k' even: L - R, class k' odd: L + R.
+                        // differences, class k' even: L - R, class k' odd: L + R.   (columns c, c+1: one 16-byte store)
                         const long long o0 = prd_off(0, i, jq), o1 = prd_off(0, i, Mq + jq);
-                        const double dL = v[0] - v[1], dR = v[2] - v[3];
-                        prd[pps + o0] = v[0] + v[1]; prd[pps + o1] = v[2] + v[3];
-                        prd[o0] = dL - dR;           prd[o1] = dL + dR;
+                        double2 s0, s1, d0, d1;
+                        s0.x = v[0][0] + v[1][0]; s0.y = v[0][1] + v[1][1];
+                        s1.x = v[2][0] + v[3][0]; s1.y = v[2][1] + v[3][1];
+                        const double dLx = v[0][0] - v[1][0], dLy = v[0][1] - v[1][1];
+                        const double dRx = v[2][0] - v[3][0], dRy = v[2][1] - v[3][1];
+                        d0.x = dLx - dRx; d0.y = dLy - dRy;
+                        d1.x = dLx + dRx; d1.y = dLy + dRy;
+                        *reinterpret_cast<double2*>(&prd[pps + o0]) = s0;
+                        *reinterpret_cast<double2*>(&prd[pps + o1]) = s1;
+                        *reinterpret_cast<double2*>(&prd[o0]) = d0;
+                        *reinterpret_cast<double2*>(&prd[o1]) = d1;
                     }
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(NTHR_E) : "memory");

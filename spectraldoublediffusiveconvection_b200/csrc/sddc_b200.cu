@@ -593,7 +593,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         cudaDeviceProp prop;
         TRYC(cudaGetDeviceProperties(&prop, pl->device));
         pl->num_sms = prop.multiProcessorCount;
-        pl->ws_smem = synth_ws_smem_doubles(n, n8) * sizeof(double);
+        pl->ws_smem = std::max(synth_ws_smem_doubles(n, n8), synth_wsq_smem_doubles(n8)) * sizeof(double);
         const char* env = getenv("SDDC_SYNTH_WS");
         pl->ws_ok = g.nt8 == 4 && pl->synth_nt_dfx == SWS_NT && pl->dfx_ok && pl->ws_smem <= SMEM_LIMIT &&
                     !(env && env[0] == '0');
