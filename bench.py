@@ -295,7 +295,8 @@ def run_ours(a):
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "synth_ws_kernel (persistent warp-specialised synthesis + products, DMMA m8n8k4, TMA bulk staging)", "bound": "tensor",
+    kname = ("synth_wsq_kernel" if info["quarter_wave"] else "synth_ws_kernel" if info["synth_variant"] == 1 else "synth_kernel")
+    roofline = {"kernel": kname + " (synthesis + pointwise products, DMMA m8n8k4, TMA bulk staging)", "bound": "tensor",
                 "achieved": synth_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": synth_tflops / FP64_DMMA_PEAK_TFLOPS, "traffic": traffic,
                 "peak_source": "fp64 DMMA peak measured with tools/fp64_peak.cu on this pool (profiles/r01_fp64_peak.txt); "
