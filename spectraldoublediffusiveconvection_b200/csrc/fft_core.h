@@ -1,0 +1,464 @@
+// FFT formulation of the latitudinal transforms of NLIN_FX / NLIN_DFX (Matrix_Operators.py:743-898,
+// Transforms.py:73-129), written as per-thread "phase" functions that compile for the device (k_nlin_fft.cuh) and
+// for the host (tests/fft_emul.cpp runs the very same code thread by thread on the CPU against the oracle).
+//
+// One WORKER (64 threads) processes one radial row i of one member:
+//   build   : the nine sinusoid coefficient rows of Derivatives (Matrix_Operators.py:630-740) are formed from seven
+//             stored rows (JT, Dpsi, omega, DT, DS, T, S; the factors k and -k are applied here) and packed two real
+//             fields per complex sequence.  For a field with DCT-III input X_k (cos type: X_k = c_k, k < K; sine type:
+//             X_k = s_{M-k}, using sin(k th_j) = (-1)^j cos((M-k) th_j)) Makhoul's reordering gives
+//                 v_n = Re sum_k X_k w_k e^{2 pi i k n / M},  w_k = e^{i pi k / 2M},  v_n = y_{2n}, v_{M-1-n} = y_{2n+1}
+//             and with the Hermitian completion V_k = w_k (X_k - i X_{M-k}) / 2 (V_0 = X_0) two fields a, b share one
+//             complex inverse DFT of Z_k = V^a_k + i V^b_k:  Re z_n = v^a_n, Im z_n = v^b_n.
+//   inverse : length-M complex DFT as 8 x RD x 6 Cooley-Tukey passes in shared memory (M = 6 L, L = 8 RD).
+//   I3F1    : the last inverse pass (radix 6) leaves, in registers, all nine fields at the six grid points
+//             n = n1 + L n2; the Jacobian products (Matrix_Operators.py:791-793 / 884-887) are formed there and fed
+//             straight into the first (radix 6) pass of the forward transform.  The (-1)^j signs of the sine-type
+//             fields cancel in every product, so they are never applied.  The radial derivative of the first
+//             product, Dr @ (JT * omega), commutes with the latitudinal analysis and is applied afterwards on the
+//             spectral coefficients (post_kernel), so a row never needs its neighbours.
+//   forward : RD x 8 passes, then the two packed real sequences are separated and scaled
+//             (DCT: (2/M) Re[conj(w_k) V_k], k = 0 halved; DST: the same at index M - k).
+#pragma once
+#include <cmath>
+#ifdef __CUDACC__
+#define SDDC_HD __host__ __device__ __forceinline__
+#else
+#define SDDC_HD inline
+#endif
+
+namespace sddc {
+namespace fftp {
+
+constexpr int NTW = 64;  // threads per worker
+
+template <int M_>
+struct Cfg {
+    static constexpr int M = M_;
+    static constexpr int K = 2 * M_ / 3;
+    static constexpr int L = M_ / 6;
+    static constexpr int RD = L / 8;
+    static constexpr int PL = M_ + M_ / 8;  // doubles per padded plane (one pad double after every 8)
+    static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16), "supported grids: M = 192, 384, 768");
+};
+
+// table sizes (doubles)
+template <int M> constexpr int tab_wk_doubles() { return 2 * (M / 2 + 1); }
+template <int M> constexpr int tab_t6_doubles() { return 2 * M; }
+template <int M> constexpr int tab_tL_doubles() { return 2 * (M / 6); }
+template <int M> constexpr int tab_doubles() { return tab_wk_doubles<M>() + tab_t6_doubles<M>() + tab_tL_doubles<M>(); }
+
+struct Tables {
+    const double* wk;  // [M/2+1][2] : (cos, sin)(pi k / 2M) / 2
+    const double* t6;  // [6][L][2]  : (cos, sin)(2 pi k2 n1 / M)
+    const double* tL;  // [RD][8][2] : (cos, sin)(2 pi d a / L)
+};
+
+struct C {
+    double r, i;
+};
+SDDC_HD C operator+(C a, C b) { return C{a.r + b.r, a.i + b.i}; }
+SDDC_HD C operator-(C a, C b) { return C{a.r - b.r, a.i - b.i}; }
+SDDC_HD C cmul(C a, double c, double s) { return C{a.r * c - a.i * s, a.r * s + a.i * c}; }   // a * (c + i s)
+SDDC_HD C cmulc(C a, double c, double s) { return C{a.r * c + a.i * s, a.i * c - a.r * s}; }  // a * (c - i s)
+template <int SIGN>
+SDDC_HD C mul_i(C a) {  // a * (SIGN i)
+    return SIGN > 0 ? C{-a.i, a.r} : C{a.i, -a.r};
+}
+
+// cos / sin of 2 pi k / 16
+SDDC_HD constexpr double cos16(int k) {
+    return k == 0 ? 1.0
+         : k == 1 ? 0.92387953251128673848
+         : k == 2 ? 0.70710678118654752440
+         : k == 3 ? 0.38268343236508977173
+         : k == 4 ? 0.0
+         : k == 5 ? -0.38268343236508977173
+         : k == 6 ? -0.70710678118654752440
+         : k == 7 ? -0.92387953251128673848
+                  : -1.0;
+}
+SDDC_HD constexpr double sin16(int k) { return k <= 4 ? cos16(4 - k) : cos16(k - 4); }
+
+// O * e^{SIGN 2 pi i k / R}
+template <int R, int K_, int SIGN>
+SDDC_HD C twmul(C o) {
+    if (K_ == 0) return o;
+    if (4 * K_ == R) return mul_i<SIGN>(o);
+    constexpr int k16 = K_ * (16 / R);
+    constexpr double c = cos16(k16), s = SIGN * sin16(k16);
+    if (8 * K_ == R || 8 * K_ == 3 * R) {
+        // |c| = |s| = 1/sqrt2
+        constexpr double h = 0.70710678118654752440;
+        const C m = (8 * K_ == R) ? (o + mul_i<SIGN>(o)) : (mul_i<SIGN>(o) - o);
+        return C{m.r * h, m.i * h};
+    }
+    return cmul(o, c, s);
+}
+
+template <int R, int SIGN>
+struct Dft;
+template <int SIGN>
+struct Dft<2, SIGN> {
+    static SDDC_HD void run(const C (&in)[2], C (&out)[2]) {
+        out[0] = in[0] + in[1];
+        out[1] = in[0] - in[1];
+    }
+};
+template <int R, int SIGN, int K_>
+struct Combine {
+    static SDDC_HD void run(const C (&E)[R / 2], const C (&O)[R / 2], C (&out)[R]) {
+        const C t = twmul<R, K_, SIGN>(O[K_]);
+        out[K_] = E[K_] + t;
+        out[K_ + R / 2] = E[K_] - t;
+        Combine<R, SIGN, K_ + 1>::run(E, O, out);
+    }
+};
+template <int R, int SIGN>
+struct Combine<R, SIGN, R / 2> {
+    static SDDC_HD void run(const C (&)[R / 2], const C (&)[R / 2], C (&)[R]) {}
+};
+// radix-2 decimation in time, natural order in and out, everything in registers
+template <int R, int SIGN>
+struct Dft {
+    static SDDC_HD void run(const C (&in)[R], C (&out)[R]) {
+        C e[R / 2], o[R / 2], E[R / 2], O[R / 2];
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) {
+            e[j] = in[2 * j];
+            o[j] = in[2 * j + 1];
+        }
+        Dft<R / 2, SIGN>::run(e, E);
+        Dft<R / 2, SIGN>::run(o, O);
+        Combine<R, SIGN, 0>::run(E, O, out);
+    }
+};
+
+template <int SIGN>
+SDDC_HD void dft3(C x0, C x1, C x2, C& X0, C& X1, C& X2) {
+    constexpr double h = 0.86602540378443864676;
+    const C t1 = x1 + x2;
+    X0 = x0 + t1;
+    const C t2 = C{x0.r - 0.5 * t1.r, x0.i - 0.5 * t1.i};
+    const C d = x1 - x2;
+    const C t3 = mul_i<SIGN>(C{h * d.r, h * d.i});
+    X1 = t2 + t3;
+    X2 = t2 - t3;
+}
+// length-6 DFT by the prime-factor map n = (3 n1 + 2 n2) mod 6, k = (3 k1 + 4 k2) mod 6 (no twiddles)
+template <int SIGN>
+SDDC_HD void dft6(const C (&x)[6], C (&X)[6]) {
+    C A0, A1, A2, B0, B1, B2;
+    dft3<SIGN>(x[0], x[2], x[4], A0, A1, A2);
+    dft3<SIGN>(x[3], x[5], x[1], B0, B1, B2);
+    X[0] = A0 + B0;
+    X[3] = A0 - B0;
+    X[4] = A1 + B1;
+    X[1] = A1 - B1;
+    X[2] = A2 + B2;
+    X[5] = A2 - B2;
+}
+
+SDDC_HD int pad(int p) { return p + (p >> 3); }
+// storage position of spectral index k (input order of the inverse, output order of the forward transform)
+template <int M>
+SDDC_HD int kpos(int k) {
+    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD;
+    const int k2 = k % 6, k1 = k / 6;
+    return pad(L * k2 + 8 * (k1 % RD) + k1 / RD);
+}
+
+// ---- build: spectral rows -> packed complex sequences of five inverse transforms -------------------------------
+// cr: [7][K] = JT, Dpsi, omega, DT, DS, T, S of one radial row, sinusoid indexing (column k <-> wavenumber k).
+// buf: five (re, im) plane pairs, plane stride PL.
+template <int M>
+SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ buf, const Tables& tb) {
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
+    for (int k = t; k <= M / 2; k += NTW) {
+        const int kp = M - k;
+        const bool hasp = k > 0 && kp < K;  // the mirror index lies inside the truncated spectrum
+        double v[7], vp[7];
+#pragma unroll
+        for (int f = 0; f < 7; ++f) v[f] = cr[f * K + k];
+#pragma unroll
+        for (int f = 0; f < 7; ++f) vp[f] = hasp ? cr[f * K + kp] : 0.0;
+        const double fk = (double)k, fkp = (double)kp;
+        // (cos-type a, sine-type b) per transform
+        const double a[5] = {v[0], fk * v[1], fk * v[2], v[3], v[4]};
+        const double b[5] = {v[2], v[1], -fk * v[5], -fk * v[6], 0.0};
+        const double ap[5] = {vp[0], fkp * vp[1], fkp * vp[2], vp[3], vp[4]};
+        const double bp[5] = {vp[2], vp[1], -fkp * vp[5], -fkp * vp[6], 0.0};
+        const double wc = tb.wk[2 * k], ws = tb.wk[2 * k + 1];  // w_k / 2 ;  w_{M-k} / 2 = (ws, wc)
+        const int p = kpos<M>(k), pp = kpos<M>(kp % M);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            double* re = buf + (2 * q) * PL;
+            double* im = re + PL;
+            if (k == 0) {
+                re[p] = a[q];  // V_0 = X_0; the sine-type entry 0 is ignored (Transforms.py:41-54)
+                im[p] = 0.0;
+            } else {
+                const double P = a[q] + b[q], Q = bp[q] - ap[q];
+                re[p] = wc * P - ws * Q;
+                im[p] = wc * Q + ws * P;
+                if (kp != k) {
+                    const double P2 = ap[q] + bp[q], Q2 = b[q] - a[q];
+                    re[pp] = ws * P2 - wc * Q2;
+                    im[pp] = ws * Q2 + wc * P2;
+                }
+            }
+        }
+    }
+}
+
+// ---- radix-8 pass over c (contiguous storage) ----------------------------------------------------------------------
+// inverse (SIGN = +1): DFT over c -> a, then twiddle e^{+2 pi i d a / L};  forward (SIGN = -1): plain DFT over a -> c
+template <int M, int NF, int SIGN>
+SDDC_HD void pass_c(int t, double* __restrict__ buf, const Tables& tb) {
+    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD, PL = Cfg<M>::PL;
+    for (int u = t; u < NF * 6 * RD; u += NTW) {
+        const int q = u / (6 * RD), rem = u - q * (6 * RD), k2 = rem / RD, d = rem - k2 * RD;
+        double* re = buf + (2 * q) * PL + pad(L * k2 + 8 * d);
+        double* im = re + PL;
+        C x[8], y[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = C{re[c], im[c]};
+        Dft<8, SIGN>::run(x, y);
+        if (SIGN > 0) {
+#pragma unroll
+            for (int a = 1; a < 8; ++a) y[a] = cmul(y[a], tb.tL[2 * (d * 8 + a)], tb.tL[2 * (d * 8 + a) + 1]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            re[c] = y[c].r;
+            im[c] = y[c].i;
+        }
+    }
+}
+
+// ---- radix-RD pass over d (stride-8 storage) -------------------------------------------------------------------------
+// inverse: plain DFT over d -> b;  forward: DFT over b -> d, then twiddle e^{-2 pi i d a / L}
+template <int M, int NF, int SIGN>
+SDDC_HD void pass_d(int t, double* __restrict__ buf, const Tables& tb) {
+    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD, PL = Cfg<M>::PL;
+    for (int u = t; u < NF * 48; u += NTW) {
+        const int q = u / 48, rem = u - q * 48, k2 = rem >> 3, a = rem & 7;
+        double* re = buf + (2 * q) * PL + pad(L * k2) + a;  // element d at offset 9 d
+        double* im = re + PL;
+        C x[RD], y[RD];
+#pragma unroll
+        for (int d = 0; d < RD; ++d) x[d] = C{re[9 * d], im[9 * d]};
+        Dft<RD, SIGN>::run(x, y);
+        if (SIGN < 0) {
+#pragma unroll
+            for (int d = 1; d < RD; ++d) y[d] = cmulc(y[d], tb.tL[2 * (d * 8 + a)], tb.tL[2 * (d * 8 + a) + 1]);
+        }
+#pragma unroll
+        for (int d = 0; d < RD; ++d) {
+            re[9 * d] = y[d].r;
+            im[9 * d] = y[d].i;
+        }
+    }
+}
+
+// last inverse pass of transform q at column n1: six grid values z[n2] <-> grid point n = n1 + L n2
+template <int M>
+SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, int n1, const Tables& tb, C (&z)[6]) {
+    constexpr int L = Cfg<M>::L;
+    C x[6];
+#pragma unroll
+    for (int k2 = 0; k2 < 6; ++k2) {
+        const int p = pad(L * k2) + pad(n1);
+        x[k2] = C{re[p], im[p]};
+        if (k2 > 0) x[k2] = cmul(x[k2], tb.t6[2 * (k2 * L + n1)], tb.t6[2 * (k2 * L + n1) + 1]);
+    }
+    dft6<+1>(x, z);
+}
+
+// ---- I3F1: last inverse pass + Jacobian products + first forward pass ------------------------------------------------
+// FX : buffers 0..4 hold the transforms of X.                 Products of NLIN_FX  (Matrix_Operators.py:791-793)
+// DFX: buffers 0..4 hold the base state, 5..9 the perturbation. Products of NLIN_DFX (Matrix_Operators.py:884-887)
+// Output: buffer 0 <- P1 + i P2 (sine type: JT*om | kDpsi*om + Dpsi*kom), buffer 1 <- N_T + i N_S (cosine type),
+// already through the forward radix-6 pass and its twiddle.
+template <int M, bool DFX>
+SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
+    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
+    for (int n1 = t; n1 < L; n1 += NTW) {
+        int pos[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) pos[m] = pad(L * m) + pad(n1);
+        double* base = buf;
+        double* pert = buf + (DFX ? 10 * PL : 0);
+        if (DFX) {
+            // base-state grid values, written back in place (only this thread touches these positions)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                C z[6];
+                inv6<M>(base + 2 * q * PL, base + (2 * q + 1) * PL, n1, tb, z);
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    base[2 * q * PL + pos[m]] = z[m].r;
+                    base[(2 * q + 1) * PL + pos[m]] = z[m].i;
+                }
+            }
+        }
+        // grid field g of the base state at point m (DFX only): plane index = 2 q + part
+        auto bg = [&](int plane, int m) { return base[plane * PL + pos[m]]; };
+        enum { JT = 0, OM = 1, KDP = 2, DP = 3, KOM = 4, KT = 5, DT = 6, KS = 7, DS = 8 };
+        double jt[6], dp[6], P1[6], P2[6], NT[6], NS[6];
+        {
+            C z0[6], z1[6];
+            inv6<M>(pert, pert + PL, n1, tb, z0);           // JT | omega
+            inv6<M>(pert + 2 * PL, pert + 3 * PL, n1, tb, z1);  // k Dpsi | Dpsi
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                jt[m] = z0[m].r;
+                dp[m] = z1[m].i;
+                if (DFX) {
+                    P1[m] = bg(JT, m) * z0[m].i + jt[m] * bg(OM, m);
+                    P2[m] = bg(KDP, m) * z0[m].i + z1[m].r * bg(OM, m);
+                } else {
+                    P1[m] = jt[m] * z0[m].i;
+                    P2[m] = z1[m].r * z0[m].i;
+                }
+            }
+        }
+        {
+            C z2[6];
+            inv6<M>(pert + 4 * PL, pert + 5 * PL, n1, tb, z2);  // k omega | -k T
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                if (DFX) {
+                    P2[m] += bg(DP, m) * z2[m].r + dp[m] * bg(KOM, m);
+                    NT[m] = -(dp[m] * bg(KT, m) + bg(DP, m) * z2[m].i);
+                } else {
+                    P2[m] += dp[m] * z2[m].r;
+                    NT[m] = -(dp[m] * z2[m].i);
+                }
+            }
+        }
+        {
+            C z3[6];
+            inv6<M>(pert + 6 * PL, pert + 7 * PL, n1, tb, z3);  // DT | -k S
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                if (DFX) {
+                    NT[m] += jt[m] * bg(DT, m) + bg(JT, m) * z3[m].r;
+                    NS[m] = -(dp[m] * bg(KS, m) + bg(DP, m) * z3[m].i);
+                } else {
+                    NT[m] += jt[m] * z3[m].r;
+                    NS[m] = -(dp[m] * z3[m].i);
+                }
+            }
+        }
+        {
+            C z4[6];
+            inv6<M>(pert + 8 * PL, pert + 9 * PL, n1, tb, z4);  // DS | 0
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                if (DFX) NS[m] += jt[m] * bg(DS, m) + bg(JT, m) * z4[m].r;
+                else NS[m] += jt[m] * z4[m].r;
+            }
+        }
+        // forward radix-6 over n2 -> k2, twiddle e^{-2 pi i k2 n1 / M}
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            C x[6], y[6];
+#pragma unroll
+            for (int m = 0; m < 6; ++m) x[m] = q == 0 ? C{P1[m], P2[m]} : C{NT[m], NS[m]};
+            dft6<-1>(x, y);
+            double* re = buf + 2 * q * PL;
+            double* im = re + PL;
+#pragma unroll
+            for (int k2 = 0; k2 < 6; ++k2) {
+                if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6[2 * (k2 * L + n1)], tb.t6[2 * (k2 * L + n1) + 1]);
+                re[pos[k2]] = y[k2].r;
+                im[pos[k2]] = y[k2].i;
+            }
+        }
+    }
+}
+
+// ---- post: separate the packed sequences, scale, truncate to K --------------------------------------------------------
+// out: [4][K] = DST(JT*om), DST(kDpsi*om + Dpsi*kom), DCT(N_T), DCT(N_S)   (sinusoid indexing; Transforms.py:28-39,56-70)
+template <int M>
+SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ out, const Tables& tb) {
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
+    constexpr double sc = 2.0 / M;  // the table holds w_k / 2, which absorbs the 1/2 of the Hermitian split
+    for (int k = t; k <= M / 2; k += NTW) {
+        const int kp = M - k;
+        const int p = kpos<M>(k), pp = kpos<M>(kp % M);
+        const double hc = tb.wk[2 * k], hs = tb.wk[2 * k + 1];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double* re = buf + 2 * q * PL;
+            const double* im = re + PL;
+            const double A = re[p], Bv = im[p], Cc = re[pp], D = im[pp];
+            // C_k = Re[conj(w_k) V_k] for the two packed fields, at k and at M - k
+            const double ca_k = sc * (hc * (A + Cc) + hs * (Bv - D));
+            const double cb_k = sc * (hc * (Bv + D) - hs * (A - Cc));
+            const double ca_kp = sc * (hs * (A + Cc) + hc * (D - Bv));
+            const double cb_kp = sc * (hs * (Bv + D) - hc * (Cc - A));
+            double* oa = out + (2 * q) * K;
+            double* ob = oa + K;
+            if (q == 0) {
+                // sine type: out[k] = (2/M) C_{M-k}  (k = 1 .. K-1), out[0] = 0
+                if (k == 0) {
+                    oa[0] = 0.0;
+                    ob[0] = 0.0;
+                } else {
+                    oa[k] = ca_kp;
+                    ob[k] = cb_kp;
+                    if (kp < K && kp != k) {
+                        oa[kp] = ca_k;
+                        ob[kp] = cb_k;
+                    }
+                }
+            } else {
+                if (k == 0) {
+                    oa[0] = A * (1.0 / M);
+                    ob[0] = Bv * (1.0 / M);
+                } else {
+                    oa[k] = ca_k;
+                    ob[k] = cb_k;
+                    if (kp < K && kp != k) {
+                        oa[kp] = ca_kp;
+                        ob[kp] = cb_kp;
+                    }
+                }
+            }
+        }
+    }
+}
+
+#ifndef __CUDA_ARCH__
+// host: fill [wk | t6 | tL] (tab_doubles<M>() doubles), long-double arguments
+template <int M>
+inline void fill_tables(double* out) {
+    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    double* wk = out;
+    double* t6 = wk + tab_wk_doubles<M>();
+    double* tL = t6 + tab_t6_doubles<M>();
+    for (int k = 0; k <= M / 2; ++k) {
+        const long double x = pi * k / (2.0L * M);
+        wk[2 * k] = (double)(0.5L * cosl(x));
+        wk[2 * k + 1] = (double)(0.5L * sinl(x));
+    }
+    for (int k2 = 0; k2 < 6; ++k2)
+        for (int n1 = 0; n1 < L; ++n1) {
+            const long double x = 2.0L * pi * ((k2 * n1) % M) / M;
+            t6[2 * (k2 * L + n1)] = (double)cosl(x);
+            t6[2 * (k2 * L + n1) + 1] = (double)sinl(x);
+        }
+    for (int d = 0; d < RD; ++d)
+        for (int a = 0; a < 8; ++a) {
+            const long double x = 2.0L * pi * ((d * a) % L) / L;
+            tL[2 * (d * 8 + a)] = (double)cosl(x);
+            tL[2 * (d * 8 + a) + 1] = (double)sinl(x);
+        }
+}
+#endif
+
+}  // namespace fftp
+}  // namespace sddc

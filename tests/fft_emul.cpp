@@ -1,0 +1,86 @@
+// CPU emulation of one worker of nlin_fft_kernel (csrc/fft_core.h): the per-thread phase functions are the ones the
+// device kernel runs; here they are executed thread by thread with the barriers of the kernel as loop boundaries.
+// Test infrastructure only (tests/test_fft_core_cpu.py builds it with g++ and compares against the oracle).
+#include <complex>
+#include <cstdio>
+#include <vector>
+
+#include "../spectraldoublediffusiveconvection_b200/csrc/fft_core.h"
+
+using namespace sddc::fftp;
+
+template <int M, bool DFX>
+static void run_rows(const double* coef0, const double* coef1, double* out, int nrows) {
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 10 : 5;
+    std::vector<double> tab(tab_doubles<M>());
+    fill_tables<M>(tab.data());
+    Tables tb{tab.data(), tab.data() + tab_wk_doubles<M>(), tab.data() + tab_wk_doubles<M>() + tab_t6_doubles<M>()};
+    std::vector<double> buf((size_t)2 * NF * PL);
+    for (int row = 0; row < nrows; ++row) {
+        for (auto& v : buf) v = 1e300;  // poison: every position that is read must have been written
+        for (int t = 0; t < NTW; ++t) {
+            build<M>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
+            if (DFX) build<M>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
+        }
+        for (int t = 0; t < NTW; ++t) pass_c<M, NF, +1>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) pass_d<M, NF, +1>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) i3f1<M, DFX>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) pass_d<M, 2, -1>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) pass_c<M, 2, -1>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) post<M>(t, buf.data(), out + (size_t)row * 4 * K, tb);
+    }
+}
+
+template <int R, int SIGN>
+static double check_dft() {
+    C x[R], y[R];
+    for (int j = 0; j < R; ++j) x[j] = C{0.3 + 0.7 * j - 0.05 * j * j, -0.2 + 0.11 * j * j};
+    Dft<R, SIGN>::run(x, y);
+    double err = 0;
+    for (int k = 0; k < R; ++k) {
+        std::complex<double> s = 0;
+        for (int j = 0; j < R; ++j) s += std::complex<double>(x[j].r, x[j].i) * std::polar(1.0, SIGN * 2 * M_PI * ((j * k) % R) / R);
+        err = std::max(err, std::abs(s - std::complex<double>(y[k].r, y[k].i)));
+    }
+    return err;
+}
+template <int SIGN>
+static double check_dft6() {
+    C x[6], y[6];
+    for (int j = 0; j < 6; ++j) x[j] = C{0.3 + 0.7 * j - 0.05 * j * j, -0.2 + 0.11 * j * j};
+    dft6<SIGN>(x, y);
+    double err = 0;
+    for (int k = 0; k < 6; ++k) {
+        std::complex<double> s = 0;
+        for (int j = 0; j < 6; ++j) s += std::complex<double>(x[j].r, x[j].i) * std::polar(1.0, SIGN * 2 * M_PI * ((j * k) % 6) / 6);
+        err = std::max(err, std::abs(s - std::complex<double>(y[k].r, y[k].i)));
+    }
+    return err;
+}
+
+extern "C" {
+
+// worst absolute error of the register butterflies against a direct DFT
+double fft_emul_butterfly_error() {
+    double e = 0;
+    e = std::max(e, check_dft<4, +1>());
+    e = std::max(e, check_dft<4, -1>());
+    e = std::max(e, check_dft<8, +1>());
+    e = std::max(e, check_dft<8, -1>());
+    e = std::max(e, check_dft<16, +1>());
+    e = std::max(e, check_dft<16, -1>());
+    e = std::max(e, check_dft6<+1>());
+    e = std::max(e, check_dft6<-1>());
+    return e;
+}
+
+// coef0 / coef1: [nrows][7][K]; out: [nrows][4][K].  Returns 0, or -1 for an unsupported grid size.
+int fft_emul_rows(int M, int dfx, const double* coef0, const double* coef1, double* out, int nrows) {
+    switch (M) {
+        case 192: dfx ? run_rows<192, true>(coef0, coef1, out, nrows) : run_rows<192, false>(coef0, coef1, out, nrows); return 0;
+        case 384: dfx ? run_rows<384, true>(coef0, coef1, out, nrows) : run_rows<384, false>(coef0, coef1, out, nrows); return 0;
+        case 768: dfx ? run_rows<768, true>(coef0, coef1, out, nrows) : run_rows<768, false>(coef0, coef1, out, nrows); return 0;
+        default: return -1;
+    }
+}
+}

@@ -1,0 +1,89 @@
+"""CPU check of the FFT formulation used by nlin_fft_kernel: the per-thread phase functions of csrc/fft_core.h are
+compiled for the host (tests/fft_emul.cpp) and run thread by thread against the oracle's dense-sum transforms
+(Transforms.py:73-129, Matrix_Operators.py:776-799 / 884-887)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import sddc_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("fft_emul") / "libfft_emul.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", so,
+                    os.path.join(HERE, "fft_emul.cpp")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.fft_emul_butterfly_error.restype = ctypes.c_double
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.fft_emul_rows.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_int]
+    return lib
+
+
+def _rows(X3, op, symmetric):
+    """[n][7][K] stored rows (JT, Dpsi, omega, DT, DS, T, S) and the nine grid-ready arrays of the oracle."""
+    c, s = orc._spectral_fields(X3, op, symmetric)
+    K, n = op.K, op.n
+    if symmetric:
+        X3 = X3 * orc.sym_mask(K, n)
+    rows = np.stack([c["JT"], s["Dpsi"], s["om"], c["DT"], c["DS"], X3[1].T, X3[2].T], axis=1)
+    return np.ascontiguousarray(rows)
+
+
+def _expected(g, h=None):
+    """[n][4][K] analysed products (Matrix_Operators.py:791-799; bilinear form 884-887 when h is given)."""
+    if h is None:
+        P1 = g["JT"] * g["om"]
+        P2 = g["kDpsi"] * g["om"] + g["Dpsi"] * g["kom"]
+        NT = g["JT"] * g["DT"] - g["Dpsi"] * g["kT"]
+        NS = g["JT"] * g["DS"] - g["Dpsi"] * g["kS"]
+    else:
+        P1 = g["JT"] * h["om"] + h["JT"] * g["om"]
+        P2 = (g["kDpsi"] * h["om"] + g["Dpsi"] * h["kom"]) + (h["kDpsi"] * g["om"] + h["Dpsi"] * g["kom"])
+        NT = (h["JT"] * g["DT"] - h["Dpsi"] * g["kT"]) + (g["JT"] * h["DT"] - g["Dpsi"] * h["kT"])
+        NS = (h["JT"] * g["DS"] - h["Dpsi"] * g["kS"]) + (g["JT"] * h["DS"] - g["Dpsi"] * h["kS"])
+    K = (2 * P1.shape[1]) // 3
+    return np.stack([orc.DST(P1)[:, :K], orc.DST(P2)[:, :K], orc.DCT(NT)[:, :K], orc.DCT(NS)[:, :K]], axis=1)
+
+
+def _call(lib, M, rows0, rows1=None):
+    n, _, K = rows0.shape
+    out = np.full((n, 4, K), np.nan)
+    dp = ctypes.POINTER(ctypes.c_double)
+    r1 = rows1 if rows1 is not None else rows0
+    rc = lib.fft_emul_rows(M, int(rows1 is not None), rows0.ctypes.data_as(dp), r1.ctypes.data_as(dp),
+                           out.ctypes.data_as(dp), n)
+    assert rc == 0
+    return out
+
+
+def test_register_butterflies(emul):
+    assert emul.fft_emul_butterfly_error() < 5e-14
+
+
+@pytest.mark.parametrize("K,N_r,symmetric", [(128, 8, False), (256, 6, False), (256, 6, True), (512, 5, False)])
+def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
+    op = orc.Operators(K, N_r, 0.4, 1e-2, 1.0, 0.5)
+    rng = np.random.default_rng(K + N_r)
+    X3 = rng.standard_normal((3, K, op.n))
+    Y3 = rng.standard_normal((3, K, op.n))
+    M = 3 * K // 2
+    rows = _rows(X3, op, symmetric)
+    g = orc._grid_fields(X3, op, symmetric)
+    exp = _expected(g)
+    got = _call(emul, M, rows)
+    assert np.isfinite(got).all()
+    scale = np.abs(exp).max(axis=(0, 2), keepdims=True)
+    assert (np.abs(got - exp) / scale).max() < 1e-12  # white spectra times k: the dense sums themselves round at this level
+    # two-state (Jacobian-vector product) variant
+    rows1 = _rows(Y3, op, symmetric)
+    h = orc._grid_fields(Y3, op, symmetric)
+    exp2 = _expected(g, h)
+    got2 = _call(emul, M, rows, rows1)
+    scale2 = np.abs(exp2).max(axis=(0, 2), keepdims=True)
+    assert (np.abs(got2 - exp2) / scale2).max() < 1e-12
