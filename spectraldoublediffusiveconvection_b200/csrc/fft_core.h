@@ -43,10 +43,10 @@ struct Cfg {
 };
 
 // table sizes (doubles)
-template <int M> constexpr int tab_wk_doubles() { return 2 * (M / 2 + 1); }
-template <int M> constexpr int tab_t6_doubles() { return 2 * M; }
-template <int M> constexpr int tab_tL_doubles() { return 2 * (M / 6); }
-template <int M> constexpr int tab_doubles() { return tab_wk_doubles<M>() + tab_t6_doubles<M>() + tab_tL_doubles<M>(); }
+template <int M> SDDC_HD constexpr int tab_wk_doubles() { return 2 * (M / 2 + 1); }
+template <int M> SDDC_HD constexpr int tab_t6_doubles() { return 2 * M; }
+template <int M> SDDC_HD constexpr int tab_tL_doubles() { return 2 * (M / 6); }
+template <int M> SDDC_HD constexpr int tab_doubles() { return tab_wk_doubles<M>() + tab_t6_doubles<M>() + tab_tL_doubles<M>(); }
 
 struct Tables {
     const double* wk;  // [M/2+1][2] : (cos, sin)(pi k / 2M) / 2
@@ -431,7 +431,6 @@ SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ ou
     }
 }
 
-#ifndef __CUDA_ARCH__
 // host: fill [wk | t6 | tL] (tab_doubles<M>() doubles), long-double arguments
 template <int M>
 inline void fill_tables(double* out) {
@@ -458,7 +457,6 @@ inline void fill_tables(double* out) {
             tL[2 * (d * 8 + a) + 1] = (double)sinl(x);
         }
 }
-#endif
 
 }  // namespace fftp
 }  // namespace sddc

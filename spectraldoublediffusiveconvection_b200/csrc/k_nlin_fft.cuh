@@ -1,0 +1,124 @@
+// Stage 2+3 of a member-step in the FFT formulation (fft_core.h): the nonlinear term NLIN_FX / NLIN_DFX
+// (Matrix_Operators.py:743-898) with the latitudinal transforms as mixed-radix complex FFTs in shared memory.
+//
+//   nlin_fft_kernel : persistent, one CTA per SM.  A CTA holds NW independent workers of 64 threads (two warps);
+//                     a worker takes one (member, radial row) at a time through
+//                         build | radix-8 | radix-RD | radix-6 + products + radix-6 | radix-RD | radix-8 | post
+//                     with a named barrier (bar.sync id, 64) between phases, so the workers of a CTA are never in
+//                     lock step and fill each other's barrier / memory latencies.  All transform data stays in the
+//                     worker's shared-memory planes; HBM sees 7 coefficient rows in and 4 spectral rows out.
+//   post_kernel     : Dr @ DST(JT*omega) - DST(..) per wavenumber, un-shift of the sine coefficients
+//                     (Matrix_Operators.py:797-802), equatorial-symmetry mask, and the transposition into the state /
+//                     solve-major layout.
+#pragma once
+#include "common.cuh"
+#include "fft_core.h"
+
+namespace sddc {
+
+struct NlinFftParams {
+    const double* coef0;  // [rows][7][K] spectral rows of the (base) state, rows = B * n
+    const double* coef1;  // [rows][7][K] rows of the perturbation (two-state mode)
+    double* spec;         // [rows][4][K] analysed products
+    const double* tab;    // fftp::tab_doubles<M>() table doubles (fftp::fill_tables)
+    int nrows;
+};
+
+template <int M>
+__host__ __device__ constexpr int nlin_fft_tab_pad() { return (fftp::tab_doubles<M>() + 15) / 16 * 16; }
+template <int M, bool DFX>
+__host__ __device__ constexpr size_t nlin_fft_smem_bytes(int nw) {
+    return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + (size_t)nw * 2 * (DFX ? 10 : 5) * fftp::Cfg<M>::PL);
+}
+
+__device__ __forceinline__ void worker_sync(int w) {
+    asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
+}
+
+template <int M, bool DFX, int NW>
+__global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
+    using namespace fftp;
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 10 : 5;
+    extern __shared__ __align__(128) double smem[];
+    double* stab = smem;
+    for (int i = threadIdx.x; i < tab_doubles<M>(); i += 64 * NW) stab[i] = p.tab[i];
+    __syncthreads();
+    const Tables tb{stab, stab + tab_wk_doubles<M>(), stab + tab_wk_doubles<M>() + tab_t6_doubles<M>()};
+    const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
+    double* buf = smem + nlin_fft_tab_pad<M>() + (size_t)w * 2 * NF * PL;
+    for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
+        build<M>(t, p.coef0 + (size_t)row * 7 * K, buf, tb);
+        if (DFX) build<M>(t, p.coef1 + (size_t)row * 7 * K, buf + 10 * PL, tb);
+        worker_sync(w);
+        pass_c<M, NF, +1>(t, buf, tb);
+        worker_sync(w);
+        pass_d<M, NF, +1>(t, buf, tb);
+        worker_sync(w);
+        i3f1<M, DFX>(t, buf, tb);
+        worker_sync(w);
+        pass_d<M, 2, -1>(t, buf, tb);
+        worker_sync(w);
+        pass_c<M, 2, -1>(t, buf, tb);
+        worker_sync(w);
+        post<M>(t, buf, p.spec + (size_t)row * 4 * K, tb);
+        worker_sync(w);
+    }
+}
+
+struct PostParams {
+    const double* spec;  // [B][n][4][K]
+    const double* DrT;   // [n][n8]: DrT[i'][i] = Dr[i][i']
+    double* out;         // F(X): state layout [B][3N] (bstride == 0) or solve-major [3][K][bstride][n8+2]
+    long long bstride;
+    Geo g;
+};
+
+constexpr int POST_TC = 32;
+
+__host__ __device__ inline size_t post_smem_bytes(int n, int n8) {
+    return sizeof(double) * ((size_t)4 * n * (POST_TC + 1) + (size_t)n * n8);
+}
+
+// grid = (K / 32, B), 256 threads
+__global__ void __launch_bounds__(256) post_kernel(PostParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const Geo& g = p.g;
+    const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDT = POST_TC + 1;
+    const int k0 = blockIdx.x * POST_TC, b = blockIdx.y, tid = threadIdx.x;
+    double* sT = smem;                   // [4][n][33]
+    double* sD = smem + 4 * n * LDT;     // [n][n8]
+    const double* sb = p.spec + (size_t)b * n * 4 * K;
+    for (int idx = tid; idx < 4 * n * POST_TC; idx += 256) {
+        const int c = idx & (POST_TC - 1), fi = idx / POST_TC, f = fi & 3, i = fi >> 2;
+        sT[(f * n + i) * LDT + c] = (k0 + c < K) ? sb[((size_t)i * 4 + f) * K + k0 + c] : 0.0;
+    }
+    for (int idx = tid; idx < n * n8; idx += 256) sD[idx] = p.DrT[idx];
+    __syncthreads();
+    const bool sm = p.bstride != 0;
+    const int LDG = n8 + 2;
+    auto out_at = [&](int f, int blk, int i) -> double& {
+        return sm ? p.out[(((long long)f * K + blk) * p.bstride + b) * LDG + i]
+                  : p.out[(long long)b * 3 * N + (long long)f * N + (long long)blk * n + i];
+    };
+    for (int idx = tid; idx < 3 * POST_TC * n; idx += 256) {
+        const int i = idx % n, fc = idx / n, col = fc & (POST_TC - 1), f = fc / POST_TC;
+        const int k = k0 + col;
+        if (k >= K) continue;
+        const bool masked = g.symmetric && (k & 1);  // every odd sinusoid index is masked (Matrix_Operators.py:536-556)
+        if (f == 0) {
+            // sinusoid index k -> code block k-1; k = 0 is dropped and block K-1 gets no nonlinear contribution
+            if (k == 0) {
+                out_at(0, K - 1, i) = 0.0;
+                continue;
+            }
+            double acc = 0.0;
+            for (int ip = 0; ip < n; ++ip) acc = fma(sD[ip * n8 + i], sT[ip * LDT + col], acc);
+            const double v = acc - sT[(n + i) * LDT + col];
+            out_at(0, k - 1, i) = masked ? 0.0 : v;
+        } else {
+            out_at(f, k, i) = masked ? 0.0 : sT[((f + 1) * n + i) * LDT + col];
+        }
+    }
+}
+
+}  // namespace sddc

@@ -50,7 +50,8 @@ struct PrepParams {
     const double* X;        // [B][3N] state (or perturbation)
     long long x_stride;
     const double* JJ;       // [B][K+1][n] from scan_kernel on the same X
-    double* coef;           // coefficient set, tile-major [B][Khp/8][2 ks][2 par][9*n8][4] (see k_synth.cuh), or null
+    double* coef;           // coefficient set, tile-major [B][Khp/8][2 ks][2 par][9*n8][4] (see k_synth.cuh), or null;
+                            // FFTL kernels: the seven spectral rows [B][n][7][K] of fft_core.h instead
     long long coef_stride;  // member stride of coef in doubles
     double* lin;            // linear right-hand side in solve-major order [3][K][bstride][n8+2] (k_solve.cuh), or null
     long long bstride;      // members per (field, mode) slab of lin
@@ -74,7 +75,9 @@ __host__ __device__ inline size_t prep_smem_bytes(int n8) {
 // whose accumulator fragments are written straight into (a) the tile-major coefficient arrays of the synthesis
 // GEMM -- one accumulator tile is one contiguous 256-byte A-fragment block there -- and (b) the linear
 // right-hand sides of Step_Python (Main.py:266-280) in the state layout.
-template <int NT8>
+// FFTL selects the output of the FFT formulation (k_nlin_fft.cuh): seven row-major spectral rows per radial point
+// (JT, Dpsi, omega, DT, DS, T, S) and the natural MMA column order, so that a quad writes 64 contiguous bytes.
+template <int NT8, bool FFTL = false>
 __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(PrepParams p) {
     extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
         for (int nl = 0; nl < 2; ++nl) {
             const int e = gq & 1, tt = gq >> 1;
             const int kloc = (e == 0) ? 2 * tt + nl : 4 * nl + tt;
-            bcol[nl] = (nh * 16 + 2 * kloc + e) * LDX + tq;
+            bcol[nl] = (FFTL ? (nh * 16 + nl * 8 + gq) : (nh * 16 + 2 * kloc + e)) * LDX + tq;
         }
         for (int ks = 0; ks < n8 / 4; ++ks) {
             const double aDr = mDr[arow + ks * 4], aD2r = mD2r[arow + ks * 4], aDsq = mDsq[arow + ks * 4];
@@ -156,14 +159,37 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
     const double dtPr = g.dt * g.Pr;
 #pragma unroll
     for (int nl = 0; nl < 2; ++nl) {
+        if (FFTL && p.coef) {
+            // columns (col, col+1) of the accumulator pair; K is even and c0 a multiple of 32, so both are < K together
+            const int col = nh * 16 + nl * 8 + 2 * tq, c = c0 + col;
+            if (c < K) {
+                const double j0 = sJ[col * LDX + i], j1 = sJ[(col + 1) * LDX + i];
+                double2 om, dp;
+                om.x = (c >= 1) ? d2r[nl][0] - (double)c * (ir4 * j0) : 0.0;
+                dp.x = (c >= 1) ? dps[nl][0] : 0.0;
+                om.y = d2r[nl][1] - (double)(c + 1) * (ir4 * j1);
+                dp.y = dps[nl][1];
+                double* r7 = p.coef + ((long long)b * n + i) * 7 * K + c;
+                *reinterpret_cast<double2*>(r7) = make_double2(j0, j1);                       // JT
+                *reinterpret_cast<double2*>(r7 + (long long)K) = dp;                          // Dpsi
+                *reinterpret_cast<double2*>(r7 + 2LL * K) = om;                               // omega
+                *reinterpret_cast<double2*>(r7 + 3LL * K) = make_double2(dT[nl][0], dT[nl][1]);
+                *reinterpret_cast<double2*>(r7 + 4LL * K) = make_double2(dS[nl][0], dS[nl][1]);
+                *reinterpret_cast<double2*>(r7 + 5LL * K) = make_double2(sT[col * LDX + i], sT[(col + 1) * LDX + i]);
+                *reinterpret_cast<double2*>(r7 + 6LL * K) = make_double2(sS[col * LDX + i], sS[(col + 1) * LDX + i]);
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const int col = nh * 16 + 2 * ((e == 0) ? 2 * tq + nl : 4 * nl + tq) + e;   // see the slot map above
+            const int col = FFTL ? nh * 16 + nl * 8 + 2 * tq + e
+                                 : nh * 16 + 2 * ((e == 0) ? 2 * tq + nl : 4 * nl + tq) + e;   // see the slot map above
             const int c = c0 + col;
             if (c >= K) continue;
             const double jj = sJ[col * LDX + i];
             const double tv = sT[col * LDX + i], sv = sS[col * LDX + i];
-            if (cf) {
+            if (FFTL) {
+                // written above, two adjacent columns per 16-byte store
+            } else if (cf) {
                 const int kp = chunk_pos(c >> 1, e);  // parity of c is e (c0 is a multiple of 32); position in the chunk
                 const long long o = (((long long)((kp >> 2) * 2 + e) * R9) + i) * 4 + (kp & 3);
                 const long long fs = (long long)n8 * 4;

@@ -18,6 +18,7 @@
 #include "k_synth_ws.cuh"
 #include "k_synth2.cuh"
 #include "k_synth_wsq.cuh"
+#include "k_nlin_fft.cuh"
 
 using namespace sddc;
 
@@ -66,6 +67,11 @@ struct sddc_plan {
     long long coef_member_stride = 0;
     double *lin_sm = nullptr, *f_sm = nullptr;  // solve-major [3][K][bstride][n8+2]
     double *gridc = nullptr, *xbase = nullptr;  // cached base state of sddc_jvp_set_base (lazily allocated)
+    // FFT formulation of the nonlinear term (k_nlin_fft.cuh): available for N_fm = 128, 256, 512
+    int fft_M = 0;              // 3 N_fm / 2 when the FFT path is active, else 0
+    bool fft_dfx = false;       // two-state (JVP) variant available
+    int fft_nw = 0, fft_nw_dfx = 0;
+    double *coef7 = nullptr, *coef7b = nullptr, *coef7base = nullptr, *spec4 = nullptr, *fft_tab = nullptr;
     int base_B = 0;
     long long bstride = 0;
     // host-API staging
@@ -275,12 +281,13 @@ int run_scan(sddc_plan* pl, const double* X, long long stride, int B, cudaStream
 
 // scan + prep of state X into coefficient set `set` (and optionally the linear right-hand side)
 int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* lin, const double* Ra,
-             const double* Ras, int B, cudaStream_t st) {
+             const double* Ras, int B, cudaStream_t st, double* coef7 = nullptr) {
     int rc = run_scan(pl, X, 3LL * pl->g.N, B, st);
     if (rc) return rc;
     PrepParams pp{};
     pp.X = X; pp.x_stride = 3LL * pl->g.N; pp.JJ = pl->JJ;
-    pp.coef = want_coef ? (set == 0 ? pl->coef : pl->coef1) : nullptr;
+    const bool fftl = coef7 != nullptr;  // seven spectral rows per radial point for the FFT formulation
+    pp.coef = want_coef ? (fftl ? coef7 : (set == 0 ? pl->coef : pl->coef1)) : nullptr;
     pp.coef_stride = pl->coef_member_stride;
     pp.lin = lin; pp.bstride = pl->bstride; pp.Ra = Ra; pp.Ras = Ras;
     pp.DrP = pl->DrP; pp.D2rP = pl->D2rP; pp.DsqP = pl->DsqP;
@@ -289,13 +296,24 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
     StageTimer tm(pl, SDDC_STAGE_PREP, st);
     const size_t smem = prep_smem_bytes(pl->g.n8);
-    switch (pl->g.nt8) {
-        case 3: prep_kernel<3><<<grid, 192, smem, st>>>(pp); break;
-        case 4: prep_kernel<4><<<grid, 256, smem, st>>>(pp); break;
-        case 5: prep_kernel<5><<<grid, 320, smem, st>>>(pp); break;
-        case 6: prep_kernel<6><<<grid, 384, smem, st>>>(pp); break;
-        case 7: prep_kernel<7><<<grid, 448, smem, st>>>(pp); break;
-        default: prep_kernel<8><<<grid, 512, smem, st>>>(pp); break;
+    if (fftl) {
+        switch (pl->g.nt8) {
+            case 3: prep_kernel<3, true><<<grid, 192, smem, st>>>(pp); break;
+            case 4: prep_kernel<4, true><<<grid, 256, smem, st>>>(pp); break;
+            case 5: prep_kernel<5, true><<<grid, 320, smem, st>>>(pp); break;
+            case 6: prep_kernel<6, true><<<grid, 384, smem, st>>>(pp); break;
+            case 7: prep_kernel<7, true><<<grid, 448, smem, st>>>(pp); break;
+            default: prep_kernel<8, true><<<grid, 512, smem, st>>>(pp); break;
+        }
+    } else {
+        switch (pl->g.nt8) {
+            case 3: prep_kernel<3><<<grid, 192, smem, st>>>(pp); break;
+            case 4: prep_kernel<4><<<grid, 256, smem, st>>>(pp); break;
+            case 5: prep_kernel<5><<<grid, 320, smem, st>>>(pp); break;
+            case 6: prep_kernel<6><<<grid, 384, smem, st>>>(pp); break;
+            case 7: prep_kernel<7><<<grid, 448, smem, st>>>(pp); break;
+            default: prep_kernel<8><<<grid, 512, smem, st>>>(pp); break;
+        }
     }
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -348,6 +366,53 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
     return launch_analysis(pl, ap, B, st);
 }
 
+// FFT formulation: coefficient rows -> analysed products spec4 (k_nlin_fft.cuh)
+template <int M>
+int launch_nlin_fft(sddc_plan* pl, const NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
+    if (set_attr) {
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, (M <= 384 ? 6 : 3)>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        if (M <= 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<(M <= 384 ? M : 384), true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        return SDDC_OK;
+    }
+    if (dfx) {
+        constexpr int MD = M <= 384 ? M : 384;  // the two-state variant is instantiated up to M = 384 only
+        const int grid = std::min((np.nrows + 2) / 3, pl->num_sms);
+        nlin_fft_kernel<MD, true, 3><<<grid, 192, nlin_fft_smem_bytes<MD, true>(3), st>>>(np);
+    } else {
+        constexpr int NW = M <= 384 ? 6 : 3;
+        const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
+        nlin_fft_kernel<M, false, NW><<<grid, 64 * NW, nlin_fft_smem_bytes<M, false>(NW), st>>>(np);
+    }
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
+int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, int B, cudaStream_t st, bool set_attr = false) {
+    NlinFftParams np{};
+    np.coef0 = c0; np.coef1 = c1; np.spec = pl->spec4; np.tab = pl->fft_tab; np.nrows = B * pl->g.n;
+    const bool dfx = c1 != nullptr;
+    if (dfx && !pl->fft_dfx) { pl->err = "two-state FFT variant not available for this N_fm"; return SDDC_ERR_UNSUPPORTED; }
+    StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
+    switch (pl->fft_M) {
+        case 192: return launch_nlin_fft<192>(pl, np, dfx, st, set_attr);
+        case 384: return launch_nlin_fft<384>(pl, np, dfx, st, set_attr);
+        case 768: return launch_nlin_fft<768>(pl, np, dfx, st, set_attr);
+        default: pl->err = "FFT path not available for this N_fm"; return SDDC_ERR_UNSUPPORTED;
+    }
+}
+
+int run_post(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream_t st) {
+    PostParams pp{};
+    pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = out; pp.bstride = solve_major ? pl->bstride : 0; pp.g = pl->g;
+    dim3 grid((pl->g.K + POST_TC - 1) / POST_TC, B);
+    StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
+    post_kernel<<<grid, 256, post_smem_bytes(pl->g.n, pl->g.n8), st>>>(pp);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
 // gs < 0 selects the solve-major layout for g / fnl
 int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, long long gf, double* out, long long os,
               long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st) {
@@ -387,10 +452,15 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
 int run_member_step(sddc_plan* pl, const double* X, double* out, const double* sub, const double* Ra,
                     const double* Ras, int B, bool linear, cudaStream_t st) {
     const long long N3 = 3LL * pl->g.N;
-    int rc = run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st);
+    const bool fft = pl->fft_M != 0 && !linear;
+    int rc = run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st, fft ? pl->coef7 : nullptr);
     if (rc) return rc;
     const double* fnl = nullptr;
-    if (!linear) {
+    if (fft) {
+        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, B, st))) return rc;
+        if ((rc = run_post(pl, pl->f_sm, true, B, st))) return rc;
+        fnl = pl->f_sm;
+    } else if (!linear) {
         if ((rc = run_synth_nl(pl, false, B, st))) return rc;
         if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
@@ -437,6 +507,8 @@ int sddc_plan_info(const sddc_plan* plan, int what) {
         case 1: return plan->synth_variant;         // 0 generic, 1 persistent warp-specialised, 2 two-CTAs-per-SM
         case 2: return plan->dfx_ok ? 1 : 0;        // two-state JVP synthesis available
         case 3: return plan->g.n8;
+        case 4: return plan->fft_M;                 // grid size of the FFT formulation of the nonlinear term (0: dense DMMA path)
+        case 5: return plan->fft_dfx ? 1 : 0;       // FFT formulation also used for the two-state (JVP) products
         default: return -1;
     }
 }
@@ -627,6 +699,33 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         }
     }
     {
+        // FFT formulation of the nonlinear term (k_nlin_fft.cuh); SDDC_FFT=0 keeps the dense DMMA transforms
+        const char* fe = getenv("SDDC_FFT");
+        const bool want = !(fe && fe[0] == '0');
+        if (want && (K == 128 || K == 256 || K == 512)) {
+            pl->fft_M = g.M;
+            pl->fft_dfx = K <= 256;
+            std::vector<double> tab;
+            switch (g.M) {
+                case 192: tab.resize(fftp::tab_doubles<192>()); fftp::fill_tables<192>(tab.data()); break;
+                case 384: tab.resize(fftp::tab_doubles<384>()); fftp::fill_tables<384>(tab.data()); break;
+                default: tab.resize(fftp::tab_doubles<768>()); fftp::fill_tables<768>(tab.data()); break;
+            }
+            TRY(upload(pl, &pl->fft_tab, tab));
+            TRY(dev_alloc(pl, &pl->coef7, Bm * 7 * g.N, false));
+            if (pl->fft_dfx) TRY(dev_alloc(pl, &pl->coef7b, Bm * 7 * g.N, false));
+            TRY(dev_alloc(pl, &pl->spec4, Bm * 4 * g.N, false));
+            TRY(run_nlin_fft(pl, nullptr, nullptr, 1, nullptr, true));
+            TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
+            TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8)));
+            TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8)));
+            TRY(set_smem(pl, (prep_kernel<5, true>), prep_smem_bytes(n8)));
+            TRY(set_smem(pl, (prep_kernel<6, true>), prep_smem_bytes(n8)));
+            TRY(set_smem(pl, (prep_kernel<7, true>), prep_smem_bytes(n8)));
+            TRY(set_smem(pl, (prep_kernel<8, true>), prep_smem_bytes(n8)));
+        }
+    }
+    {
         const char* env = getenv("SDDC_SOLVE_STAGES");
         int want = env ? atoi(env) : 3;
         want = std::max(2, std::min(want, SOLVE_NSL));
@@ -699,6 +798,11 @@ int sddc_nlin_fx(sddc_plan* pl, const double* X, double* F, int B, void* stream)
     int rc = check_batch(pl, B);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pl->fft_M) {
+        if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, B, st))) return rc;
+        return run_post(pl, F, false, B, st);
+    }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, false, B, st))) return rc;
     return run_analysis(pl, F, false, B, st, pl->quarter);
@@ -708,6 +812,12 @@ int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, i
     int rc = check_batch(pl, B);
     if (rc) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pl->fft_dfx) {
+        if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
+        if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st, pl->coef7b))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7, pl->coef7b, B, st))) return rc;
+        return run_post(pl, F, false, B, st);
+    }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
@@ -783,6 +893,13 @@ int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, cons
     if (dv == out || X == out) { pl->err = "out must not alias dv or X"; return SDDC_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long N3 = 3LL * pl->g.N;
+    if (pl->fft_dfx) {
+        if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
+        if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7, pl->coef7b, B, st))) return rc;
+        if ((rc = run_post(pl, pl->f_sm, true, B, st))) return rc;
+        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+    }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_nl(pl, true, B, st))) return rc;
@@ -816,10 +933,15 @@ int sddc_jvp_set_base(sddc_plan* pl, const double* X, int B, void* stream) {
     const Geo& g = pl->g;
     if (!pl->xbase) {
         if ((rc = dev_alloc(pl, &pl->xbase, (size_t)pl->cfg.max_batch * 3 * g.N, false))) return rc;
-        if (pl->ws_ok && (rc = dev_alloc(pl, &pl->gridc, (size_t)pl->cfg.max_batch * 9 * 2 * g.n8 * g.Mhp, true))) return rc;
+        if (pl->fft_dfx) {
+            if ((rc = dev_alloc(pl, &pl->coef7base, (size_t)pl->cfg.max_batch * 7 * g.N, false))) return rc;
+        } else if (pl->ws_ok && (rc = dev_alloc(pl, &pl->gridc, (size_t)pl->cfg.max_batch * 9 * 2 * g.n8 * g.Mhp, true))) return rc;
     }
     PLAN_CUDA(pl, cudaMemcpyAsync(pl->xbase, X, sizeof(double) * (size_t)B * 3 * g.N, cudaMemcpyDeviceToDevice, st));
     pl->base_B = B;
+    // FFT formulation: the base state is kept as its seven spectral rows; its grid values are re-synthesised inside
+    // every product kernel (cheaper than reading 9 n M cached grid values per member back from HBM)
+    if (pl->fft_dfx) return run_prep(pl, pl->xbase, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7base);
     if (pl->ws_ok) {
         if ((rc = run_prep(pl, pl->xbase, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
         return run_synth_ws_mode(pl, SWS_GRID, pl->coef, B, st);
@@ -832,9 +954,15 @@ int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* R
     if (rc) return rc;
     if (!pl->xbase || B != pl->base_B) { pl->err = "sddc_jvp_apply: call sddc_jvp_set_base with the same batch first"; return SDDC_ERR_INVALID; }
     if (dv == out) { pl->err = "out must not alias dv"; return SDDC_ERR_INVALID; }
-    if (!pl->ws_ok) return sddc_jvp(pl, dv, pl->xbase, out, Ra, Ras, B, stream);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long N3 = 3LL * pl->g.N;
+    if (pl->fft_dfx) {
+        if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7base, pl->coef7b, B, st))) return rc;
+        if ((rc = run_post(pl, pl->f_sm, true, B, st))) return rc;
+        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+    }
+    if (!pl->ws_ok) return sddc_jvp(pl, dv, pl->xbase, out, Ra, Ras, B, stream);
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_ws_mode(pl, SWS_JVPC, pl->coef1, B, st))) return rc;
     if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;

@@ -102,8 +102,9 @@ class EnsemblePlan:
         return torch.full((B,), float(v), dtype=torch.float64, device=self.device)
 
     def info(self):
-        """Kernel-selection facts: quarter-wave split active, synthesis variant, JVP availability, padded n."""
-        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8")
+        """Kernel-selection facts: quarter-wave split active, synthesis variant, JVP availability, padded n, grid size
+        of the FFT formulation of the nonlinear term (0 = dense DMMA transforms), FFT formulation used for JVPs."""
+        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8", "fft_M", "fft_jvp")
         return {nm: int(self.lib.sddc_plan_info(self._h, i)) for i, nm in enumerate(names)}
 
     @property

@@ -175,7 +175,8 @@ def test_error_behaviour():
 
 
 @pytest.mark.parametrize("K,N_r,sym", [(128, 20, False), (512, 40, False), (64, 33, True), (40, 50, False),
-                                        (24, 65, False), (8, 18, True)])
+                                        (24, 65, False), (8, 18, True), (128, 26, True), (256, 12, True),
+                                        (512, 9, True), (256, 50, False)])
 def test_other_shapes_against_oracle(K, N_r, sym):
     """Every kernel instantiation (radial tile counts 3..8, BASELINE configs 2 and 5 shapes, ragged mode counts):
     one step, one JVP, diagnostics and the nonlinear term against the NumPy oracle on seeded inputs."""
@@ -192,7 +193,9 @@ def test_other_shapes_against_oracle(K, N_r, sym):
     Xd, dvd = _dev(X), _dev(dv)
     F = pl.nlin_fx(Xd).cpu().numpy()
     st = pl.step(Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
-    has_jvp = N_r <= 41           # the two-state synthesis needs 2x the staging shared memory
+    # the dense two-state synthesis needs 2x the staging shared memory; the FFT formulation
+    # (N_fm = 128, 256) has no such limit
+    has_jvp = N_r <= 41 or K in (128, 256)
     if has_jvp:
         jv = pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
     else:
@@ -296,6 +299,29 @@ def test_cached_base_jvp_equals_jvp(name):
     assert rel_l2(j2, 2.0 * g["jvp_Xb"]) < 1e-10
     assert rel_l2(j1, pl.jvp(dv, Xb, Ra, Ra_s).cpu().numpy().ravel()) < 1e-12
     pl.close()
+
+
+def test_dense_transform_path_still_matches(monkeypatch):
+    """SDDC_FFT=0 keeps the dense DMMA transforms (the path every N_fm other than 128/256/512 takes) at the
+    headline shape; FFT and dense formulations of the same plan shape agree to rounding."""
+    g = load_golden("cfg3_member")
+    pl_fft = _plan(g)
+    assert pl_fft.info()["fft_M"] == 384 and pl_fft.info()["fft_jvp"] == 1
+    monkeypatch.setenv("SDDC_FFT", "0")
+    pl = _plan(g)
+    monkeypatch.delenv("SDDC_FFT")
+    assert pl.info()["fft_M"] == 0
+    Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
+    Xb, dv = _dev(g["Xb"]), _dev(g["dv"])
+    F = pl.nlin_fx(Xb).cpu().numpy().ravel()
+    assert rel_l2(F, g["NLIN_FX"]) < TOL_CALL
+    assert rel_l2(F, pl_fft.nlin_fx(Xb).cpu().numpy().ravel()) < TOL_CALL
+    assert rel_l2(pl.nlin_dfx(dv, Xb).cpu().numpy().ravel(), g["NLIN_DFX"]) < TOL_CALL
+    assert rel_l2(pl.step(Xb, Ra, Ra_s).cpu().numpy().ravel(), g["step_Xb"]) < TOL_CALL
+    pl.jvp_set_base(Xb)
+    assert rel_l2(pl.jvp_apply(dv, Ra, Ra_s).cpu().numpy().ravel(), g["jvp_Xb"]) < 1e-10
+    pl.close()
+    pl_fft.close()
 
 
 def test_plans_of_different_shapes_coexist():

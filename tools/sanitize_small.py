@@ -2,7 +2,11 @@
 import sys; sys.path.insert(0, '.')
 import numpy as np, torch
 from spectraldoublediffusiveconvection_b200 import EnsemblePlan, plan as P
-for (K, N_r, sym, B) in [(16, 10, False, 3), (32, 30, True, 17), (24, 41, False, 2), (16, 65, False, 2)]:
+import os
+SHAPES = [(16, 10, False, 3), (32, 30, True, 17), (24, 41, False, 2), (16, 65, False, 2)]
+if os.environ.get('SANITIZE_FFT'):   # the FFT formulation (k_nlin_fft.cuh): N_fm = 128 / 256 / 512
+    SHAPES = [(128, 10, False, 3), (256, 8, True, 2), (512, 6, False, 1)]
+for (K, N_r, sym, B) in SHAPES:
     pl = EnsemblePlan(K, N_r, 0.4, 1e-2, 1.0, 0.5, symmetric=sym, max_batch=B)
     X = torch.rand((B, 3 * pl.N), dtype=torch.float64, device='cuda') * 1e-2
     dv = torch.randn_like(X)
@@ -11,6 +15,7 @@ for (K, N_r, sym, B) in [(16, 10, False, 3), (32, 30, True, 17), (24, 41, False,
     pl.nlin_fx(X); pl.residual(X, Ra, Ras); pl.dF_dRa(X); pl.diagnostics(Y)
     if N_r <= 41:
         pl.jvp(dv, X, Ra, Ras); pl.nlin_dfx(dv, X)
+        pl.jvp_set_base(X); pl.jvp_apply(dv, Ra, Ras)
     for op in range(6):
         pl.linear_op(op, X[:, :pl.N].contiguous())
     pl.solve_a4(X[:, :pl.N].contiguous()); pl.solve_nab2(X[:, :pl.N].contiguous(), 1)
