@@ -32,27 +32,48 @@ namespace fftp {
 
 constexpr int NTW = 64;  // threads per worker
 
+// Shared-memory layout of one plane (re or im) of a length-M sequence: 8-element blocks, block index
+//     j = 6 d + k2   (spectral side: k = 6 (RD c + d) + k2 is element c of block j = k mod 6RD;
+//                     grid side:     n1 = a + 8 b of sub-transform k2 is element a of block 6 b + k2)
+// stored XOR-swizzled: element c of block j sits at 8 (j ^ bit3(j)) + (c ^ (j & 7)).  Bank = address mod 16 (doubles),
+// a bijection of (j mod 16, c) for fixed c, so every access pattern of the passes is conflict free per half-warp:
+//   16 consecutive blocks, same element (build, radix-8 pass, post)        -> 16 distinct residues of j
+//   blocks (2i, 2i+1), elements 0..7 (radix-RD pass)                          -> bit0(j) flips the upper bank half
+//   elements 0..15 of blocks j, j+6 (radix-6 pass; 2-way conflict only when j mod 8 < 2)
 template <int M_>
 struct Cfg {
     static constexpr int M = M_;
     static constexpr int K = 2 * M_ / 3;
     static constexpr int L = M_ / 6;
     static constexpr int RD = L / 8;
-    static constexpr int PL = M_ + M_ / 8;  // doubles per padded plane (one pad double after every 8)
+    static constexpr int NBLK = M_ / 8;  // = 6 RD
+    static constexpr int PL = M_;        // doubles per plane
     static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16), "supported grids: M = 192, 384, 768");
 };
+SDDC_HD int at(int j, int c) { return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7)); }
 
-// table sizes (doubles)
-template <int M> SDDC_HD constexpr int tab_wk_doubles() { return 2 * (M / 2 + 1); }
-template <int M> SDDC_HD constexpr int tab_t6_doubles() { return 2 * M; }
-template <int M> SDDC_HD constexpr int tab_tL_doubles() { return 2 * (M / 6); }
-template <int M> SDDC_HD constexpr int tab_doubles() { return tab_wk_doubles<M>() + tab_t6_doubles<M>() + tab_tL_doubles<M>(); }
+// table sizes (doubles): wk cos | wk sin | t6 cos | t6 sin | tL cos | tL sin
+template <int M> SDDC_HD constexpr int tab_wk_doubles() { return M / 2 + 1; }
+template <int M> SDDC_HD constexpr int tab_t6_doubles() { return M; }
+template <int M> SDDC_HD constexpr int tab_tL_doubles() { return 9 * (M / 48); }
+template <int M> SDDC_HD constexpr int tab_doubles() { return 2 * (tab_wk_doubles<M>() + tab_t6_doubles<M>() + tab_tL_doubles<M>()); }
 
 struct Tables {
-    const double* wk;  // [M/2+1][2] : (cos, sin)(pi k / 2M) / 2
-    const double* t6;  // [6][L][2]  : (cos, sin)(2 pi k2 n1 / M)
-    const double* tL;  // [RD][8][2] : (cos, sin)(2 pi d a / L)
+    const double *wkc, *wks;  // [M/2+1] : cos, sin (pi k / 2M) / 2
+    const double *t6c, *t6s;  // [6][L]  : cos, sin (2 pi k2 n1 / M)
+    const double *tLc, *tLs;  // [RD][9] : cos, sin (2 pi d a / L), a < 8 (row stride 9: conflict-free column reads)
 };
+template <int M>
+SDDC_HD Tables make_tables(const double* base) {
+    Tables tb;
+    tb.wkc = base;
+    tb.wks = tb.wkc + tab_wk_doubles<M>();
+    tb.t6c = tb.wks + tab_wk_doubles<M>();
+    tb.t6s = tb.t6c + tab_t6_doubles<M>();
+    tb.tLc = tb.t6s + tab_t6_doubles<M>();
+    tb.tLs = tb.tLc + tab_tL_doubles<M>();
+    return tb;
+}
 
 struct C {
     double r, i;
@@ -159,13 +180,11 @@ SDDC_HD void dft6(const C (&x)[6], C (&X)[6]) {
     X[5] = A2 - B2;
 }
 
-SDDC_HD int pad(int p) { return p + (p >> 3); }
-// storage position of spectral index k (input order of the inverse, output order of the forward transform)
+// storage offset of spectral index k (input order of the inverse, output order of the forward transform)
 template <int M>
 SDDC_HD int kpos(int k) {
-    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD;
-    const int k2 = k % 6, k1 = k / 6;
-    return pad(L * k2 + 8 * (k1 % RD) + k1 / RD);
+    constexpr int NBLK = Cfg<M>::NBLK;
+    return at(k % NBLK, k / NBLK);
 }
 
 // ---- build: spectral rows -> packed complex sequences of five inverse transforms -------------------------------
@@ -188,7 +207,7 @@ SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ bu
         const double b[5] = {v[2], v[1], -fk * v[5], -fk * v[6], 0.0};
         const double ap[5] = {vp[0], fkp * vp[1], fkp * vp[2], vp[3], vp[4]};
         const double bp[5] = {vp[2], vp[1], -fkp * vp[5], -fkp * vp[6], 0.0};
-        const double wc = tb.wk[2 * k], ws = tb.wk[2 * k + 1];  // w_k / 2 ;  w_{M-k} / 2 = (ws, wc)
+        const double wc = tb.wkc[k], ws = tb.wks[k];  // w_k / 2 ;  w_{M-k} / 2 = (ws, wc)
         const int p = kpos<M>(k), pp = kpos<M>(kp % M);
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
@@ -211,66 +230,78 @@ SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ bu
     }
 }
 
-// ---- radix-8 pass over c (contiguous storage) ----------------------------------------------------------------------
-// inverse (SIGN = +1): DFT over c -> a, then twiddle e^{+2 pi i d a / L};  forward (SIGN = -1): plain DFT over a -> c
+// ---- radix-8 pass over c (the eight elements of a block) ---------------------------------------------------------------
+// inverse (SIGN = +1): DFT over c -> a;  forward (SIGN = -1): DFT over a -> c.  The twiddle e^{+-2 pi i d a / L} between
+// the two passes of the length-L transform is applied by pass_d, where it depends on the thread only.
 template <int M, int NF, int SIGN>
-SDDC_HD void pass_c(int t, double* __restrict__ buf, const Tables& tb) {
-    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD, PL = Cfg<M>::PL;
-    for (int u = t; u < NF * 6 * RD; u += NTW) {
-        const int q = u / (6 * RD), rem = u - q * (6 * RD), k2 = rem / RD, d = rem - k2 * RD;
-        double* re = buf + (2 * q) * PL + pad(L * k2 + 8 * d);
+SDDC_HD void pass_c(int t, double* __restrict__ buf) {
+    constexpr int NBLK = Cfg<M>::NBLK, PL = Cfg<M>::PL;
+    for (int u = t; u < NF * NBLK; u += NTW) {
+        const int q = u / NBLK, j = u - q * NBLK;
+        const int sw = j & 7;
+        double* re = buf + (2 * q) * PL + ((j ^ ((j >> 3) & 1)) << 3);
         double* im = re + PL;
         C x[8], y[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = C{re[c], im[c]};
+        for (int c = 0; c < 8; ++c) x[c] = C{re[c ^ sw], im[c ^ sw]};
         Dft<8, SIGN>::run(x, y);
-        if (SIGN > 0) {
-#pragma unroll
-            for (int a = 1; a < 8; ++a) y[a] = cmul(y[a], tb.tL[2 * (d * 8 + a)], tb.tL[2 * (d * 8 + a) + 1]);
-        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            re[c] = y[c].r;
-            im[c] = y[c].i;
+            re[c ^ sw] = y[c].r;
+            im[c ^ sw] = y[c].i;
         }
     }
 }
 
-// ---- radix-RD pass over d (stride-8 storage) -------------------------------------------------------------------------
-// inverse: plain DFT over d -> b;  forward: DFT over b -> d, then twiddle e^{-2 pi i d a / L}
+// twiddles e^{2 pi i d a / L}, d < RD, of thread t: pass_d always works on element a = t & 7 (48 and 64 are multiples of 8)
+template <int M>
+SDDC_HD void load_tw(int t, const Tables& tb, C (&tw)[Cfg<M>::RD]) {
+#pragma unroll
+    for (int d = 0; d < Cfg<M>::RD; ++d) tw[d] = C{tb.tLc[d * 9 + (t & 7)], tb.tLs[d * 9 + (t & 7)]};
+}
+
+// ---- radix-RD pass over d (same element of the blocks 6 d + k2) ------------------------------------------------------
+// inverse: twiddle e^{+2 pi i d a / L}, then DFT over d -> b;  forward: DFT over b -> d, then twiddle e^{-2 pi i d a / L}
 template <int M, int NF, int SIGN>
-SDDC_HD void pass_d(int t, double* __restrict__ buf, const Tables& tb) {
-    constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD, PL = Cfg<M>::PL;
+SDDC_HD void pass_d(int t, double* __restrict__ buf, const C (&tw)[Cfg<M>::RD]) {
+    constexpr int RD = Cfg<M>::RD, PL = Cfg<M>::PL;
     for (int u = t; u < NF * 48; u += NTW) {
         const int q = u / 48, rem = u - q * 48, k2 = rem >> 3, a = rem & 7;
-        double* re = buf + (2 * q) * PL + pad(L * k2) + a;  // element d at offset 9 d
+        double* re = buf + (2 * q) * PL;
         double* im = re + PL;
+        int o[RD];
+#pragma unroll
+        for (int d = 0; d < RD; ++d) o[d] = at(6 * d + k2, a);
         C x[RD], y[RD];
 #pragma unroll
-        for (int d = 0; d < RD; ++d) x[d] = C{re[9 * d], im[9 * d]};
+        for (int d = 0; d < RD; ++d) x[d] = C{re[o[d]], im[o[d]]};
+        if (SIGN > 0) {
+#pragma unroll
+            for (int d = 1; d < RD; ++d) x[d] = cmul(x[d], tw[d].r, tw[d].i);
+        }
         Dft<RD, SIGN>::run(x, y);
         if (SIGN < 0) {
 #pragma unroll
-            for (int d = 1; d < RD; ++d) y[d] = cmulc(y[d], tb.tL[2 * (d * 8 + a)], tb.tL[2 * (d * 8 + a) + 1]);
+            for (int d = 1; d < RD; ++d) y[d] = cmulc(y[d], tw[d].r, tw[d].i);
         }
 #pragma unroll
         for (int d = 0; d < RD; ++d) {
-            re[9 * d] = y[d].r;
-            im[9 * d] = y[d].i;
+            re[o[d]] = y[d].r;
+            im[o[d]] = y[d].i;
         }
     }
 }
 
-// last inverse pass of transform q at column n1: six grid values z[n2] <-> grid point n = n1 + L n2
+// last inverse pass of one transform at column n1: six grid values z[n2] <-> grid point n = n1 + L n2
 template <int M>
-SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, int n1, const Tables& tb, C (&z)[6]) {
+SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, const int (&pos)[6], int n1,
+                  const Tables& tb, C (&z)[6]) {
     constexpr int L = Cfg<M>::L;
     C x[6];
 #pragma unroll
     for (int k2 = 0; k2 < 6; ++k2) {
-        const int p = pad(L * k2) + pad(n1);
-        x[k2] = C{re[p], im[p]};
-        if (k2 > 0) x[k2] = cmul(x[k2], tb.t6[2 * (k2 * L + n1)], tb.t6[2 * (k2 * L + n1) + 1]);
+        x[k2] = C{re[pos[k2]], im[pos[k2]]};
+        if (k2 > 0) x[k2] = cmul(x[k2], tb.t6c[k2 * L + n1], tb.t6s[k2 * L + n1]);
     }
     dft6<+1>(x, z);
 }
@@ -286,7 +317,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
     for (int n1 = t; n1 < L; n1 += NTW) {
         int pos[6];
 #pragma unroll
-        for (int m = 0; m < 6; ++m) pos[m] = pad(L * m) + pad(n1);
+        for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
         double* base = buf;
         double* pert = buf + (DFX ? 10 * PL : 0);
         if (DFX) {
@@ -294,7 +325,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
 #pragma unroll
             for (int q = 0; q < 5; ++q) {
                 C z[6];
-                inv6<M>(base + 2 * q * PL, base + (2 * q + 1) * PL, n1, tb, z);
+                inv6<M>(base + 2 * q * PL, base + (2 * q + 1) * PL, pos, n1, tb, z);
 #pragma unroll
                 for (int m = 0; m < 6; ++m) {
                     base[2 * q * PL + pos[m]] = z[m].r;
@@ -308,8 +339,8 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
         double jt[6], dp[6], P1[6], P2[6], NT[6], NS[6];
         {
             C z0[6], z1[6];
-            inv6<M>(pert, pert + PL, n1, tb, z0);           // JT | omega
-            inv6<M>(pert + 2 * PL, pert + 3 * PL, n1, tb, z1);  // k Dpsi | Dpsi
+            inv6<M>(pert, pert + PL, pos, n1, tb, z0);               // JT | omega
+            inv6<M>(pert + 2 * PL, pert + 3 * PL, pos, n1, tb, z1);  // k Dpsi | Dpsi
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 jt[m] = z0[m].r;
@@ -325,7 +356,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
         }
         {
             C z2[6];
-            inv6<M>(pert + 4 * PL, pert + 5 * PL, n1, tb, z2);  // k omega | -k T
+            inv6<M>(pert + 4 * PL, pert + 5 * PL, pos, n1, tb, z2);  // k omega | -k T
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 if (DFX) {
@@ -339,7 +370,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
         }
         {
             C z3[6];
-            inv6<M>(pert + 6 * PL, pert + 7 * PL, n1, tb, z3);  // DT | -k S
+            inv6<M>(pert + 6 * PL, pert + 7 * PL, pos, n1, tb, z3);  // DT | -k S
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 if (DFX) {
@@ -353,7 +384,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
         }
         {
             C z4[6];
-            inv6<M>(pert + 8 * PL, pert + 9 * PL, n1, tb, z4);  // DS | 0
+            inv6<M>(pert + 8 * PL, pert + 9 * PL, pos, n1, tb, z4);  // DS | 0
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 if (DFX) NS[m] += jt[m] * bg(DS, m) + bg(JT, m) * z4[m].r;
@@ -371,7 +402,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
             double* im = re + PL;
 #pragma unroll
             for (int k2 = 0; k2 < 6; ++k2) {
-                if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6[2 * (k2 * L + n1)], tb.t6[2 * (k2 * L + n1) + 1]);
+                if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6c[k2 * L + n1], tb.t6s[k2 * L + n1]);
                 re[pos[k2]] = y[k2].r;
                 im[pos[k2]] = y[k2].i;
             }
@@ -388,7 +419,7 @@ SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ ou
     for (int k = t; k <= M / 2; k += NTW) {
         const int kp = M - k;
         const int p = kpos<M>(k), pp = kpos<M>(kp % M);
-        const double hc = tb.wk[2 * k], hs = tb.wk[2 * k + 1];
+        const double hc = tb.wkc[k], hs = tb.wks[k];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const double* re = buf + 2 * q * PL;
@@ -431,30 +462,33 @@ SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ ou
     }
 }
 
-// host: fill [wk | t6 | tL] (tab_doubles<M>() doubles), long-double arguments
+// host: fill the tables (tab_doubles<M>() doubles, layout of make_tables), long-double arguments
 template <int M>
 inline void fill_tables(double* out) {
     constexpr int L = Cfg<M>::L, RD = Cfg<M>::RD;
     const long double pi = 3.14159265358979323846264338327950288L;
-    double* wk = out;
-    double* t6 = wk + tab_wk_doubles<M>();
-    double* tL = t6 + tab_t6_doubles<M>();
+    double* wkc = out;
+    double* wks = wkc + tab_wk_doubles<M>();
+    double* t6c = wks + tab_wk_doubles<M>();
+    double* t6s = t6c + tab_t6_doubles<M>();
+    double* tLc = t6s + tab_t6_doubles<M>();
+    double* tLs = tLc + tab_tL_doubles<M>();
     for (int k = 0; k <= M / 2; ++k) {
         const long double x = pi * k / (2.0L * M);
-        wk[2 * k] = (double)(0.5L * cosl(x));
-        wk[2 * k + 1] = (double)(0.5L * sinl(x));
+        wkc[k] = (double)(0.5L * cosl(x));
+        wks[k] = (double)(0.5L * sinl(x));
     }
     for (int k2 = 0; k2 < 6; ++k2)
         for (int n1 = 0; n1 < L; ++n1) {
             const long double x = 2.0L * pi * ((k2 * n1) % M) / M;
-            t6[2 * (k2 * L + n1)] = (double)cosl(x);
-            t6[2 * (k2 * L + n1) + 1] = (double)sinl(x);
+            t6c[k2 * L + n1] = (double)cosl(x);
+            t6s[k2 * L + n1] = (double)sinl(x);
         }
     for (int d = 0; d < RD; ++d)
-        for (int a = 0; a < 8; ++a) {
+        for (int a = 0; a < 9; ++a) {
             const long double x = 2.0L * pi * ((d * a) % L) / L;
-            tL[2 * (d * 8 + a)] = (double)cosl(x);
-            tL[2 * (d * 8 + a) + 1] = (double)sinl(x);
+            tLc[d * 9 + a] = a < 8 ? (double)cosl(x) : 0.0;
+            tLs[d * 9 + a] = a < 8 ? (double)sinl(x) : 0.0;
         }
 }
 

@@ -43,22 +43,24 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     double* stab = smem;
     for (int i = threadIdx.x; i < tab_doubles<M>(); i += 64 * NW) stab[i] = p.tab[i];
     __syncthreads();
-    const Tables tb{stab, stab + tab_wk_doubles<M>(), stab + tab_wk_doubles<M>() + tab_t6_doubles<M>()};
+    const Tables tb = make_tables<M>(stab);
     const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
     double* buf = smem + nlin_fft_tab_pad<M>() + (size_t)w * 2 * NF * PL;
+    C tw[Cfg<M>::RD];
+    load_tw<M>(t, tb, tw);
     for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
         build<M>(t, p.coef0 + (size_t)row * 7 * K, buf, tb);
         if (DFX) build<M>(t, p.coef1 + (size_t)row * 7 * K, buf + 10 * PL, tb);
         worker_sync(w);
-        pass_c<M, NF, +1>(t, buf, tb);
+        pass_c<M, NF, +1>(t, buf);
         worker_sync(w);
-        pass_d<M, NF, +1>(t, buf, tb);
+        pass_d<M, NF, +1>(t, buf, tw);
         worker_sync(w);
         i3f1<M, DFX>(t, buf, tb);
         worker_sync(w);
-        pass_d<M, 2, -1>(t, buf, tb);
+        pass_d<M, 2, -1>(t, buf, tw);
         worker_sync(w);
-        pass_c<M, 2, -1>(t, buf, tb);
+        pass_c<M, 2, -1>(t, buf);
         worker_sync(w);
         post<M>(t, buf, p.spec + (size_t)row * 4 * K, tb);
         worker_sync(w);
@@ -74,6 +76,9 @@ struct PostParams {
 };
 
 constexpr int POST_TC = 32;
+#ifndef NLIN_FFT_NW
+#define NLIN_FFT_NW 6  // workers (of 64 threads) per CTA of the one-state kernel
+#endif
 
 __host__ __device__ inline size_t post_smem_bytes(int n, int n8) {
     return sizeof(double) * ((size_t)4 * n * (POST_TC + 1) + (size_t)n * n8);
@@ -94,6 +99,21 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p) {
     }
     for (int idx = tid; idx < n * n8; idx += 256) sD[idx] = p.DrT[idx];
     __syncthreads();
+    // F_psi[i][k] = sum_i' Dr[i][i'] P1[i'][k] - P2[i][k]: thread = (column, four consecutive rows); the operator row
+    // segment is a warp-wide broadcast, the column read is conflict free.  The result replaces P2 (read by no one else).
+    for (int i0 = (tid >> 5) * 4; i0 < n; i0 += 32) {   // i0 + 3 < n8: padded operator columns are zero
+        const int col = tid & 31;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int ip = 0; ip < n; ++ip) {
+            const double p1 = sT[ip * LDT + col];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fma(sD[ip * n8 + i0 + r], p1, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (i0 + r < n) sT[(n + i0 + r) * LDT + col] = acc[r] - sT[(n + i0 + r) * LDT + col];
+    }
+    __syncthreads();
     const bool sm = p.bstride != 0;
     const int LDG = n8 + 2;
     auto out_at = [&](int f, int blk, int i) -> double& {
@@ -105,18 +125,14 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p) {
         const int k = k0 + col;
         if (k >= K) continue;
         const bool masked = g.symmetric && (k & 1);  // every odd sinusoid index is masked (Matrix_Operators.py:536-556)
+        const double v = masked ? 0.0 : sT[((f + 1) * n + i) * LDT + col];
         if (f == 0) {
             // sinusoid index k -> code block k-1; k = 0 is dropped and block K-1 gets no nonlinear contribution
-            if (k == 0) {
-                out_at(0, K - 1, i) = 0.0;
-                continue;
-            }
-            double acc = 0.0;
-            for (int ip = 0; ip < n; ++ip) acc = fma(sD[ip * n8 + i], sT[ip * LDT + col], acc);
-            const double v = acc - sT[(n + i) * LDT + col];
-            out_at(0, k - 1, i) = masked ? 0.0 : v;
+            // (Matrix_Operators.py:802)
+            if (k == 0) out_at(0, K - 1, i) = 0.0;
+            else out_at(0, k - 1, i) = v;
         } else {
-            out_at(f, k, i) = masked ? 0.0 : sT[((f + 1) * n + i) * LDT + col];
+            out_at(f, k, i) = v;
         }
     }
 }

@@ -370,7 +370,7 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
 template <int M>
 int launch_nlin_fft(sddc_plan* pl, const NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
     if (set_attr) {
-        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, (M <= 384 ? 6 : 3)>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, (M <= 384 ? NLIN_FFT_NW : 3)>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         if (M <= 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<(M <= 384 ? M : 384), true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
@@ -379,7 +379,7 @@ int launch_nlin_fft(sddc_plan* pl, const NlinFftParams& np, bool dfx, cudaStream
         const int grid = std::min((np.nrows + 2) / 3, pl->num_sms);
         nlin_fft_kernel<MD, true, 3><<<grid, 192, nlin_fft_smem_bytes<MD, true>(3), st>>>(np);
     } else {
-        constexpr int NW = M <= 384 ? 6 : 3;
+        constexpr int NW = M <= 384 ? NLIN_FFT_NW : 3;
         const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
         nlin_fft_kernel<M, false, NW><<<grid, 64 * NW, nlin_fft_smem_bytes<M, false>(NW), st>>>(np);
     }

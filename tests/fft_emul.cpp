@@ -14,7 +14,7 @@ static void run_rows(const double* coef0, const double* coef1, double* out, int 
     constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 10 : 5;
     std::vector<double> tab(tab_doubles<M>());
     fill_tables<M>(tab.data());
-    Tables tb{tab.data(), tab.data() + tab_wk_doubles<M>(), tab.data() + tab_wk_doubles<M>() + tab_t6_doubles<M>()};
+    const Tables tb = make_tables<M>(tab.data());
     std::vector<double> buf((size_t)2 * NF * PL);
     for (int row = 0; row < nrows; ++row) {
         for (auto& v : buf) v = 1e300;  // poison: every position that is read must have been written
@@ -22,11 +22,11 @@ static void run_rows(const double* coef0, const double* coef1, double* out, int 
             build<M>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
             if (DFX) build<M>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
         }
-        for (int t = 0; t < NTW; ++t) pass_c<M, NF, +1>(t, buf.data(), tb);
-        for (int t = 0; t < NTW; ++t) pass_d<M, NF, +1>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) pass_c<M, NF, +1>(t, buf.data());
+        for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, NF, +1>(t, buf.data(), tw); }
         for (int t = 0; t < NTW; ++t) i3f1<M, DFX>(t, buf.data(), tb);
-        for (int t = 0; t < NTW; ++t) pass_d<M, 2, -1>(t, buf.data(), tb);
-        for (int t = 0; t < NTW; ++t) pass_c<M, 2, -1>(t, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1>(t, buf.data(), tw); }
+        for (int t = 0; t < NTW; ++t) pass_c<M, 2, -1>(t, buf.data());
         for (int t = 0; t < NTW; ++t) post<M>(t, buf.data(), out + (size_t)row * 4 * K, tb);
     }
 }
