@@ -12,6 +12,7 @@ the per-step diagnostics all-gather is measured separately ("with_diagnostics").
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -304,6 +305,22 @@ def run_ours(a):
                 "launch_ms": stage_ms["synth"], "members_per_launch": Bl, "flops_per_member": synth_flops,
                 "algorithm": "dense mirror-split transforms, " + ("two mirror levels (quarter-wave)" if info["quarter_wave"] else "one mirror level"),
                 "kernel_variant": info}
+    if info.get("fft_M"):
+        # FFT formulation (k_nlin_fft.cuh): the dominant kernel reads 7 spectral rows and writes 4 per radial point and
+        # keeps every transform in shared memory -> graded against HBM: 11 * 8 * nr * K bytes
+        # per member.  Its fp64 work: 7 complex length-M FFTs per row (5 inverse, 2 forward) + packing + products.
+        fft_bytes = 88.0 * nr * K
+        fft_flops = nr * (7 * 5.0 * M * math.log2(M) + 60.0 * M)
+        gbs = Bl * fft_bytes / (stage_ms["synth"] * 1e-3) / 1e9 if stage_ms["synth"] > 0 else 0.0
+        roofline = {"kernel": "nlin_fft_kernel (5 inverse + 2 forward complex FFTs per radial row in shared memory, "
+                              "Jacobian products fused between the radix-6 passes)",
+                    "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": traffic, "peak_kind": peak_kind,
+                    "launch_ms": stage_ms["synth"], "members_per_launch": Bl, "bytes_per_member": fft_bytes,
+                    "fp64_tflops": Bl * fft_flops / (stage_ms["synth"] * 1e-3) / 1e12 if stage_ms["synth"] > 0 else 0.0,
+                    "fp64_peak_tflops_dfma": 33.6,
+                    "algorithm": "mixed-radix (8 x %d x 6) FFT, two real fields per complex transform" % (M // 48),
+                    "kernel_variant": info}
     step_bytes = 48.0 * nr * K   # read X once, write X once
     per_gpu_rate = value / world
     hbm_view = {"bound": "hbm", "achieved": per_gpu_rate * step_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -22,17 +22,91 @@ struct NlinFftParams {
     double* spec;         // [rows][4][K] analysed products
     const double* tab;    // fftp::tab_doubles<M>() table doubles (fftp::fill_tables)
     int nrows;
+    // fused finishing stage (what post_kernel does otherwise): the worker that completes the last radial row of a
+    // member applies Dr @ and transposes that member's products into the state / solve-major layout
+    int* next_row;        // row counter, zeroed before every launch: workers claim rows dynamically, so that a worker
+                          // delayed by a finishing stage simply takes fewer rows (with static striding the delayed
+                          // worker arrives last again and again and ends up finishing every member: measured 30x slower)
+    int* done;            // [B] arrival counters, zero between launches; nullptr: post_kernel runs as a separate launch
+    const double* DrT;    // [n][n8]: DrT[i'][i] = Dr[i][i']
+    double* out;          // F(X): state layout [B][3N] (bstride == 0) or solve-major [3][K][bstride][n8+2]
+    long long bstride;
+    int ftc;              // column tile of the finishing stage: 4 n (ftc + 1) doubles fit in one worker's planes
+    Geo g;
 };
+
+#ifndef NLIN_FFT_NW
+#define NLIN_FFT_NW 6  // workers (of 64 threads) per CTA of the one-state kernel
+#endif
 
 template <int M>
 __host__ __device__ constexpr int nlin_fft_tab_pad() { return (fftp::tab_doubles<M>() + 15) / 16 * 16; }
+__host__ __device__ inline int nlin_fft_dr_pad(int n, int n8) { return (n * n8 + 15) / 16 * 16; }
 template <int M, bool DFX>
-__host__ __device__ constexpr size_t nlin_fft_smem_bytes(int nw) {
-    return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + (size_t)nw * 2 * (DFX ? 10 : 5) * fftp::Cfg<M>::PL);
+__host__ __device__ constexpr size_t nlin_fft_worker_doubles() { return (size_t)2 * (DFX ? 10 : 5) * fftp::Cfg<M>::PL; }
+// dynamic shared memory: tables | DrT (fused finishing stage only) | nw workers
+template <int M, bool DFX>
+__host__ __device__ inline size_t nlin_fft_smem_bytes(int nw, int dr_doubles) {
+    return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + dr_doubles + (size_t)nw * nlin_fft_worker_doubles<M, DFX>());
 }
 
 __device__ __forceinline__ void worker_sync(int w) {
     asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
+}
+
+// Finishing stage of member b by one worker (64 threads), tile by tile of `tc` sinusoid columns:
+//   F_psi[i][k] = sum_i' Dr[i][i'] P1[i'][k] - P2[i][k]  -> code block k-1 (Matrix_Operators.py:791,797-802),
+//   F_T, F_S    = analysed products, equatorial-symmetry mask, state / solve-major layout.
+// The products were written by other SMs; the caller has fenced after observing the last arrival.
+__device__ __forceinline__ void finish_member(const NlinFftParams& p, int b, int w, int t, double* sT, const double* sD) {
+    const Geo& g = p.g;
+    const int n = g.n, n8 = g.n8, K = g.K, N = g.N, tc = p.ftc, LDT = tc + 1;
+    const double* sb = p.spec + (size_t)b * n * 4 * K;
+    const bool sm = p.bstride != 0;
+    const int LDG = n8 + 2;
+    auto out_at = [&](int f, int blk, int i) -> double& {
+        return sm ? p.out[(((long long)f * K + blk) * p.bstride + b) * LDG + i]
+                  : p.out[(long long)b * 3 * N + (long long)f * N + (long long)blk * n + i];
+    };
+    for (int k0 = 0; k0 < K; k0 += tc) {
+        // all tile loads in flight at once (asynchronous copies; none of these lines can be in this SM's L1: they were
+        // written by stores, which do not allocate, and L1 does not survive a kernel boundary)
+        for (int idx = t; idx < 4 * n * tc; idx += 64) {
+            const int c = idx % tc, fi = idx / tc, f = fi & 3, i = fi >> 2;
+            const bool ok = k0 + c < K;
+            cp_async8_zfill(&sT[(f * n + i) * LDT + c], ok ? sb + ((size_t)i * 4 + f) * K + k0 + c : sb, ok);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        worker_sync(w);
+        for (int u = t; u < tc * ((n + 3) / 4); u += 64) {
+            const int col = u % tc, i0 = (u / tc) * 4;   // i0 + 3 < n8: padded operator columns are zero
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int ip = 0; ip < n; ++ip) {
+                const double p1 = sT[ip * LDT + col];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[r] = fma(sD[ip * n8 + i0 + r], p1, acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (i0 + r < n) sT[(n + i0 + r) * LDT + col] = acc[r] - sT[(n + i0 + r) * LDT + col];
+        }
+        worker_sync(w);
+        for (int idx = t; idx < 3 * tc * n; idx += 64) {
+            const int i = idx % n, fc = idx / n, col = fc % tc, f = fc / tc;
+            const int k = k0 + col;
+            if (k >= K) continue;
+            const bool masked = g.symmetric && (k & 1);  // every odd sinusoid index is masked (Matrix_Operators.py:536-556)
+            const double v = masked ? 0.0 : sT[((f + 1) * n + i) * LDT + col];
+            if (f == 0) {
+                if (k == 0) out_at(0, K - 1, i) = 0.0;   // block K-1 gets no nonlinear contribution (Matrix_Operators.py:802)
+                else out_at(0, k - 1, i) = v;
+            } else {
+                out_at(f, k, i) = v;
+            }
+        }
+        worker_sync(w);
+    }
 }
 
 template <int M, bool DFX, int NW>
@@ -40,17 +114,36 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     using namespace fftp;
     constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 10 : 5;
     extern __shared__ __align__(128) double smem[];
+    __shared__ int s_last[NW], s_row[NW];
     double* stab = smem;
+    double* sD = smem + nlin_fft_tab_pad<M>();
+    const int dr_doubles = p.done ? nlin_fft_dr_pad(p.g.n, p.g.n8) : 0;
     for (int i = threadIdx.x; i < tab_doubles<M>(); i += 64 * NW) stab[i] = p.tab[i];
+    if (p.done)
+        for (int i = threadIdx.x; i < p.g.n * p.g.n8; i += 64 * NW) sD[i] = p.DrT[i];
     __syncthreads();
     const Tables tb = make_tables<M>(stab);
     const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
-    double* buf = smem + nlin_fft_tab_pad<M>() + (size_t)w * 2 * NF * PL;
+    double* buf = sD + dr_doubles + (size_t)w * nlin_fft_worker_doubles<M, DFX>();
     C tw[Cfg<M>::RD];
     load_tw<M>(t, tb, tw);
-    for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
+    const int stride = gridDim.x * NW;
+    for (;;) {
+        if (t == 0) s_row[w] = atomicAdd(p.next_row, 1);
+        worker_sync(w);
+        const int row = s_row[w];
+        if (row >= p.nrows) break;
         build<M>(t, p.coef0 + (size_t)row * 7 * K, buf, tb);
         if (DFX) build<M>(t, p.coef1 + (size_t)row * 7 * K, buf + 10 * PL, tb);
+        // pull the row that will be claimed one round from now from HBM into L2 while this one is transformed
+        if (row + stride < p.nrows) {
+            const char* nx = reinterpret_cast<const char*>(p.coef0 + (size_t)(row + stride) * 7 * K);
+            for (int o = t * 128; o < 7 * K * 8; o += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            if (DFX) {
+                const char* nx1 = reinterpret_cast<const char*>(p.coef1 + (size_t)(row + stride) * 7 * K);
+                for (int o = t * 128; o < 7 * K * 8; o += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx1 + o));
+            }
+        }
         worker_sync(w);
         pass_c<M, NF, +1>(t, buf);
         worker_sync(w);
@@ -63,6 +156,19 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
         pass_c<M, 2, -1>(t, buf);
         worker_sync(w);
         post<M>(t, buf, p.spec + (size_t)row * 4 * K, tb);
+        if (p.done) {
+            // last-arriver pattern: publish this row, count it, and let the worker that completes a member finish it
+            __threadfence();
+            worker_sync(w);
+            const int b = row / p.g.n;
+            if (t == 0) s_last[w] = (atomicAdd(p.done + b, 1) == p.g.n - 1);
+            worker_sync(w);
+            if (s_last[w]) {
+                __threadfence();
+                finish_member(p, b, w, t, buf, sD);
+                if (t == 0) p.done[b] = 0;
+            }
+        }
         worker_sync(w);
     }
 }
@@ -76,9 +182,6 @@ struct PostParams {
 };
 
 constexpr int POST_TC = 32;
-#ifndef NLIN_FFT_NW
-#define NLIN_FFT_NW 6  // workers (of 64 threads) per CTA of the one-state kernel
-#endif
 
 __host__ __device__ inline size_t post_smem_bytes(int n, int n8) {
     return sizeof(double) * ((size_t)4 * n * (POST_TC + 1) + (size_t)n * n8);

@@ -70,7 +70,8 @@ struct sddc_plan {
     // FFT formulation of the nonlinear term (k_nlin_fft.cuh): available for N_fm = 128, 256, 512
     int fft_M = 0;              // 3 N_fm / 2 when the FFT path is active, else 0
     bool fft_dfx = false;       // two-state (JVP) variant available
-    int fft_nw = 0, fft_nw_dfx = 0;
+    bool fft_fuse = false;      // finishing stage (post) fused into the FFT kernel (SDDC_FUSE_POST=1)
+    int* fft_done = nullptr;    // [1 + max_batch] dynamic row counter, then the arrival counters of the fused finishing stage
     double *coef7 = nullptr, *coef7b = nullptr, *coef7base = nullptr, *spec4 = nullptr, *fft_tab = nullptr;
     int base_B = 0;
     long long bstride = 0;
@@ -368,49 +369,77 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
 
 // FFT formulation: coefficient rows -> analysed products spec4 (k_nlin_fft.cuh)
 template <int M>
-int launch_nlin_fft(sddc_plan* pl, const NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
+constexpr int nlin_fft_nw(bool dfx) { return dfx ? 3 : (M <= 384 ? NLIN_FFT_NW : 3); }
+
+// column tile of the fused finishing stage that fits into one worker's planes (0: does not fit)
+template <int M, bool DFX>
+int nlin_fft_ftc(int n) {
+    for (int tc = 32; tc >= 8; tc >>= 1)
+        if ((size_t)4 * n * (tc + 1) <= nlin_fft_worker_doubles<M, DFX>()) return tc;
+    return 0;
+}
+
+template <int M>
+int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
+    constexpr int MD = M <= 384 ? M : 384;  // the two-state variant is instantiated up to M = 384 only
+    constexpr int NW = nlin_fft_nw<M>(false), NWD = nlin_fft_nw<M>(true);
     if (set_attr) {
-        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, (M <= 384 ? NLIN_FFT_NW : 3)>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        if (M <= 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<(M <= 384 ? M : 384), true, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        if (M <= 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
-    if (dfx) {
-        constexpr int MD = M <= 384 ? M : 384;  // the two-state variant is instantiated up to M = 384 only
-        const int grid = std::min((np.nrows + 2) / 3, pl->num_sms);
-        nlin_fft_kernel<MD, true, 3><<<grid, 192, nlin_fft_smem_bytes<MD, true>(3), st>>>(np);
+    const int n = pl->g.n, n8 = pl->g.n8;
+    // fused finishing stage when its operator copy and tiles fit next to the workers
+    int ftc = dfx ? nlin_fft_ftc<MD, true>(n) : nlin_fft_ftc<M, false>(n);
+    int drd = nlin_fft_dr_pad(n, n8);
+    size_t smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, drd) : nlin_fft_smem_bytes<M, false>(NW, drd);
+    const bool fuse = pl->fft_fuse && ftc > 0 && smem <= SMEM_LIMIT && np.out != nullptr;
+    if (!fuse) {
+        np.done = nullptr;
+        smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, 0) : nlin_fft_smem_bytes<M, false>(NW, 0);
     } else {
-        constexpr int NW = M <= 384 ? NLIN_FFT_NW : 3;
-        const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
-        nlin_fft_kernel<M, false, NW><<<grid, 64 * NW, nlin_fft_smem_bytes<M, false>(NW), st>>>(np);
+        np.done = pl->fft_done + 1; np.ftc = ftc;
+    }
+    np.next_row = pl->fft_done;   // counter 0: dynamic row claims; counters 1..: per-member arrivals
+    PLAN_CUDA(pl, cudaMemsetAsync(pl->fft_done, 0, sizeof(int), st));
+    {
+        StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
+        if (dfx) {
+            const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
+            nlin_fft_kernel<MD, true, NWD><<<grid, 64 * NWD, smem, st>>>(np);
+        } else {
+            const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
+            nlin_fft_kernel<M, false, NW><<<grid, 64 * NW, smem, st>>>(np);
+        }
     }
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
+    if (!fuse && np.out) {
+        PostParams pp{};
+        pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = np.out; pp.bstride = np.bstride; pp.g = pl->g;
+        dim3 grid((pl->g.K + POST_TC - 1) / POST_TC, np.nrows / n);
+        StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
+        post_kernel<<<grid, 256, post_smem_bytes(n, n8), st>>>(pp);
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+    }
     return SDDC_OK;
 }
 
-int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, int B, cudaStream_t st, bool set_attr = false) {
+// nonlinear term of the rows c0 (and, two-state, c1) into `out` (state layout or solve-major)
+int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out, bool solve_major, int B, cudaStream_t st,
+                 bool set_attr = false) {
     NlinFftParams np{};
     np.coef0 = c0; np.coef1 = c1; np.spec = pl->spec4; np.tab = pl->fft_tab; np.nrows = B * pl->g.n;
+    np.DrT = pl->DrT; np.out = out; np.bstride = solve_major ? pl->bstride : 0; np.g = pl->g;
     const bool dfx = c1 != nullptr;
     if (dfx && !pl->fft_dfx) { pl->err = "two-state FFT variant not available for this N_fm"; return SDDC_ERR_UNSUPPORTED; }
-    StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
     switch (pl->fft_M) {
         case 192: return launch_nlin_fft<192>(pl, np, dfx, st, set_attr);
         case 384: return launch_nlin_fft<384>(pl, np, dfx, st, set_attr);
         case 768: return launch_nlin_fft<768>(pl, np, dfx, st, set_attr);
         default: pl->err = "FFT path not available for this N_fm"; return SDDC_ERR_UNSUPPORTED;
     }
-}
-
-int run_post(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream_t st) {
-    PostParams pp{};
-    pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = out; pp.bstride = solve_major ? pl->bstride : 0; pp.g = pl->g;
-    dim3 grid((pl->g.K + POST_TC - 1) / POST_TC, B);
-    StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
-    post_kernel<<<grid, 256, post_smem_bytes(pl->g.n, pl->g.n8), st>>>(pp);
-    pl->launches++;
-    PLAN_CUDA(pl, cudaGetLastError());
-    return SDDC_OK;
 }
 
 // gs < 0 selects the solve-major layout for g / fnl
@@ -457,8 +486,7 @@ int run_member_step(sddc_plan* pl, const double* X, double* out, const double* s
     if (rc) return rc;
     const double* fnl = nullptr;
     if (fft) {
-        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, B, st))) return rc;
-        if ((rc = run_post(pl, pl->f_sm, true, B, st))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, pl->f_sm, true, B, st))) return rc;
         fnl = pl->f_sm;
     } else if (!linear) {
         if ((rc = run_synth_nl(pl, false, B, st))) return rc;
@@ -509,6 +537,7 @@ int sddc_plan_info(const sddc_plan* plan, int what) {
         case 3: return plan->g.n8;
         case 4: return plan->fft_M;                 // grid size of the FFT formulation of the nonlinear term (0: dense DMMA path)
         case 5: return plan->fft_dfx ? 1 : 0;       // FFT formulation also used for the two-state (JVP) products
+        case 6: return plan->fft_fuse ? 1 : 0;      // finishing stage fused into the FFT kernel (when it fits)
         default: return -1;
     }
 }
@@ -715,7 +744,16 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             TRY(dev_alloc(pl, &pl->coef7, Bm * 7 * g.N, false));
             if (pl->fft_dfx) TRY(dev_alloc(pl, &pl->coef7b, Bm * 7 * g.N, false));
             TRY(dev_alloc(pl, &pl->spec4, Bm * 4 * g.N, false));
-            TRY(run_nlin_fft(pl, nullptr, nullptr, 1, nullptr, true));
+            {
+                // measured and rejected as the default: a finishing stage run by the 64 threads
+                // of the last-arriving worker is latency bound (0.44 ms against 0.19 + 0.08 ms for two launches)
+                const char* fp = getenv("SDDC_FUSE_POST");
+                pl->fft_fuse = fp && fp[0] == '1';
+                double* cnt = nullptr;
+                TRY(dev_alloc(pl, &cnt, (Bm + 2) / 2 + 1, true));   // row counter + arrival counters of the fused finishing stage
+                pl->fft_done = reinterpret_cast<int*>(cnt);
+            }
+            TRY(run_nlin_fft(pl, nullptr, nullptr, nullptr, false, 1, nullptr, true));
             TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
             TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8)));
             TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8)));
@@ -800,8 +838,7 @@ int sddc_nlin_fx(sddc_plan* pl, const double* X, double* F, int B, void* stream)
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (pl->fft_M) {
         if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
-        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, B, st))) return rc;
-        return run_post(pl, F, false, B, st);
+        return run_nlin_fft(pl, pl->coef7, nullptr, F, false, B, st);
     }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_synth_nl(pl, false, B, st))) return rc;
@@ -815,8 +852,7 @@ int sddc_nlin_dfx(sddc_plan* pl, const double* dv, const double* X, double* F, i
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
         if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st, pl->coef7b))) return rc;
-        if ((rc = run_nlin_fft(pl, pl->coef7, pl->coef7b, B, st))) return rc;
-        return run_post(pl, F, false, B, st);
+        return run_nlin_fft(pl, pl->coef7, pl->coef7b, F, false, B, st);
     }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, nullptr, nullptr, nullptr, B, st))) return rc;
@@ -896,8 +932,7 @@ int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, cons
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
-        if ((rc = run_nlin_fft(pl, pl->coef7, pl->coef7b, B, st))) return rc;
-        if ((rc = run_post(pl, pl->f_sm, true, B, st))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7, pl->coef7b, pl->f_sm, true, B, st))) return rc;
         return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
     }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
@@ -958,8 +993,7 @@ int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* R
     const long long N3 = 3LL * pl->g.N;
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
-        if ((rc = run_nlin_fft(pl, pl->coef7base, pl->coef7b, B, st))) return rc;
-        if ((rc = run_post(pl, pl->f_sm, true, B, st))) return rc;
+        if ((rc = run_nlin_fft(pl, pl->coef7base, pl->coef7b, pl->f_sm, true, B, st))) return rc;
         return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
     }
     if (!pl->ws_ok) return sddc_jvp(pl, dv, pl->xbase, out, Ra, Ras, B, stream);
