@@ -462,6 +462,60 @@ SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ ou
     }
 }
 
+// ---- kinetic energy (Main.py:71-134): one complex transform per radial row on the M = 3K grid -----------------------
+// ca: K = M/3 cosine-type coefficients (J_theta(psi)/r), sb: K sine-type coefficients (Dr psi, sinusoid indexing).
+// Same packing as build(); the spectrum is empty between K and M - K.
+template <int M>
+SDDC_HD void build_ke(int t, const double* __restrict__ ca, const double* __restrict__ sb, double* __restrict__ buf,
+                      const Tables& tb) {
+    constexpr int Kc = M / 3, PL = Cfg<M>::PL;
+    double* re = buf;
+    double* im = buf + PL;
+    for (int k = t; k <= M / 2; k += NTW) {
+        const int kp = M - k, p = kpos<M>(k), pp = kpos<M>(kp % M);
+        if (k >= Kc) {
+            re[p] = 0.0; im[p] = 0.0;
+            if (kp != k) { re[pp] = 0.0; im[pp] = 0.0; }
+        } else if (k == 0) {
+            re[p] = ca[0]; im[p] = 0.0;
+        } else {
+            const double a = ca[k], b = sb[k], wc = tb.wkc[k], ws = tb.wks[k];
+            const double P = a + b, Q2 = b - a;   // Z_k = w_k P / 2,  Z_{M-k} = w_{M-k} (i Q2) / 2
+            re[p] = wc * P;   im[p] = ws * P;
+            re[pp] = -wc * Q2; im[pp] = ws * Q2;
+        }
+    }
+}
+
+// last inverse pass + weighted sum of squares: returns this thread's share of
+//   sum_n Wn[n] (Jpsi(n)^2 + Dpsi(n)^2),  Wn = theta trapezoid weight * sin(theta) in the transform's point order
+template <int M>
+SDDC_HD double ke6(int t, const double* __restrict__ buf, const Tables& tb, const double* __restrict__ Wn) {
+    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
+    double acc = 0.0;
+    for (int n1 = t; n1 < L; n1 += NTW) {
+        int pos[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
+        C z[6];
+        inv6<M>(buf, buf + PL, pos, n1, tb, z);
+#pragma unroll
+        for (int m = 0; m < 6; ++m) acc += Wn[n1 + L * m] * (z[m].r * z[m].r + z[m].i * z[m].i);
+    }
+    return acc;
+}
+
+// host: theta weights of Kinetic_Energy in the point order of the transform (n <-> grid index 2n, or 2(M-1-n)+1)
+template <int M>
+inline void fill_ke_weights(double* Wn) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int n = 0; n < M; ++n) {
+        const int j = n < M / 2 ? 2 * n : 2 * (M - 1 - n) + 1;
+        const long double th = pi * (2.0L * j + 1.0L) / (2.0L * M), dth = pi / M;
+        Wn[n] = (double)(((j == 0 || j == M - 1) ? 0.5L * dth : dth) * sinl(th));   // np.trapz over the midpoint nodes only
+    }
+}
+
 // host: fill the tables (tab_doubles<M>() doubles, layout of make_tables), long-double arguments
 template <int M>
 inline void fill_tables(double* out) {

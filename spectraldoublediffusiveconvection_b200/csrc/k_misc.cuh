@@ -128,6 +128,7 @@ struct KEPrepParams {
     const double* DrT;  // [n][n8]
     const double* ir;   // [n] 1/r
     Geo g;
+    int rows;           // 1: row-major output [B][n][2][K] for the FFT formulation (k_nlin_fft.cuh)
 };
 
 __global__ void __launch_bounds__(256) ke_prep_kernel(KEPrepParams p) {
@@ -156,6 +157,12 @@ __global__ void __launch_bounds__(256) ke_prep_kernel(KEPrepParams p) {
     for (int i = warp; i < n; i += 8) {
         double d = 0.0;
         for (int ip = 0; ip < n; ++ip) d = fma(mDr[ip * n8 + i], sP[lane * n + ip], d);
+        if (p.rows) {
+            double* r2 = p.coef + (((long long)b * n + i) * 2) * K + c;
+            r2[0] = p.ir[i] * Jb[(long long)c * n + i];
+            r2[K] = (c >= 1) ? d : 0.0;
+            continue;
+        }
         const long long o = (((long long)((kp >> 2) * 2 + par) * (2 * n8)) + i) * 4 + (kp & 3);
         cf[o] = p.ir[i] * Jb[(long long)c * n + i];
         cf[o + (long long)n8 * 4] = (c >= 1) ? d : 0.0;

@@ -173,6 +173,55 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     }
 }
 
+// Kinetic energy on the 3K grid (Main.py:71-134) in the FFT formulation: one complex transform per radial row
+// (J_theta(psi)/r and Dr psi packed), weighted sum of squares in the last pass.  kepart[row] = wr[i] * sum_theta.
+struct KeFftParams {
+    const double* rows;   // [B n][2][K]
+    const double* tab;    // fftp::fill_tables<3K>
+    const double* Wn;     // [3K] fftp::fill_ke_weights<3K>
+    const double* wr;     // [n] radial trapezoid weights
+    double* kepart;       // [B n]
+    int nrows, n;
+};
+template <int M>
+__host__ __device__ constexpr int ke_fft_shared_doubles() { return nlin_fft_tab_pad<M>() + M; }
+template <int M>
+__host__ __device__ constexpr size_t ke_fft_smem_bytes(int nw) {
+    return sizeof(double) * ((size_t)ke_fft_shared_doubles<M>() + (size_t)nw * 2 * fftp::Cfg<M>::PL);
+}
+
+template <int M, int NW>
+__global__ void __launch_bounds__(64 * NW, 1) ke_fft_kernel(KeFftParams p) {
+    using namespace fftp;
+    constexpr int Kc = M / 3, PL = Cfg<M>::PL;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ double s_part[NW][2];
+    double* stab = smem;
+    double* sW = smem + nlin_fft_tab_pad<M>();
+    for (int i = threadIdx.x; i < tab_doubles<M>(); i += 64 * NW) stab[i] = p.tab[i];
+    for (int i = threadIdx.x; i < M; i += 64 * NW) sW[i] = p.Wn[i];
+    __syncthreads();
+    const Tables tb = make_tables<M>(stab);
+    const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
+    double* buf = smem + ke_fft_shared_doubles<M>() + (size_t)w * 2 * PL;
+    C tw[Cfg<M>::RD];
+    load_tw<M>(t, tb, tw);
+    for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
+        const double* r = p.rows + (size_t)row * 2 * Kc;
+        build_ke<M>(t, r, r + Kc, buf, tb);
+        worker_sync(w);
+        pass_c<M, 1, +1>(t, buf);
+        worker_sync(w);
+        pass_d<M, 1, +1>(t, buf, tw);
+        worker_sync(w);
+        const double part = warp_sum(ke6<M>(t, buf, tb, sW));
+        if ((t & 31) == 0) s_part[w][t >> 5] = part;
+        worker_sync(w);
+        if (t == 0) p.kepart[row] = p.wr[row % p.n] * (s_part[w][0] + s_part[w][1]);
+        worker_sync(w);
+    }
+}
+
 struct PostParams {
     const double* spec;  // [B][n][4][K]
     const double* DrT;   // [n][n8]: DrT[i'][i] = Dr[i][i']
@@ -184,60 +233,86 @@ struct PostParams {
 constexpr int POST_TC = 32;
 
 __host__ __device__ inline size_t post_smem_bytes(int n, int n8) {
-    return sizeof(double) * ((size_t)4 * n * (POST_TC + 1) + (size_t)n * n8);
+    return sizeof(double) * ((size_t)2 * 4 * n * (POST_TC + 1) + (size_t)n * n8);
 }
 
-// grid = (K / 32, B), 256 threads
-__global__ void __launch_bounds__(256) post_kernel(PostParams p) {
+// Persistent: CTA c takes the tiles (member b, 32 sinusoid columns) c, c + gridDim.x, ...; the four product tiles of the
+// next tile are in flight (cp.async, two stages) while the current one is contracted with Dr and stored.
+__global__ void __launch_bounds__(256) post_kernel(PostParams p, int ntiles) {
     extern __shared__ __align__(16) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDT = POST_TC + 1;
-    const int k0 = blockIdx.x * POST_TC, b = blockIdx.y, tid = threadIdx.x;
-    double* sT = smem;                   // [4][n][33]
-    double* sD = smem + 4 * n * LDT;     // [n][n8]
-    const double* sb = p.spec + (size_t)b * n * 4 * K;
-    for (int idx = tid; idx < 4 * n * POST_TC; idx += 256) {
-        const int c = idx & (POST_TC - 1), fi = idx / POST_TC, f = fi & 3, i = fi >> 2;
-        sT[(f * n + i) * LDT + c] = (k0 + c < K) ? sb[((size_t)i * 4 + f) * K + k0 + c] : 0.0;
-    }
+    const int tid = threadIdx.x, nkt = (K + POST_TC - 1) / POST_TC, TS = 4 * n * LDT;
+    double* sD = smem + 2 * TS;   // [n][n8]
     for (int idx = tid; idx < n * n8; idx += 256) sD[idx] = p.DrT[idx];
-    __syncthreads();
-    // F_psi[i][k] = sum_i' Dr[i][i'] P1[i'][k] - P2[i][k]: thread = (column, four consecutive rows); the operator row
-    // segment is a warp-wide broadcast, the column read is conflict free.  The result replaces P2 (read by no one else).
-    for (int i0 = (tid >> 5) * 4; i0 < n; i0 += 32) {   // i0 + 3 < n8: padded operator columns are zero
-        const int col = tid & 31;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int ip = 0; ip < n; ++ip) {
-            const double p1 = sT[ip * LDT + col];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = fma(sD[ip * n8 + i0 + r], p1, acc[r]);
+    auto issue = [&](int tile, int stage) {
+        const int b = tile / nkt, k0 = (tile - b * nkt) * POST_TC;
+        const double* sb = p.spec + (size_t)b * n * 4 * K;
+        double* sT = smem + stage * TS;
+        for (int idx = tid; idx < 4 * n * POST_TC; idx += 256) {
+            const int c = idx & (POST_TC - 1), fi = idx / POST_TC, f = fi & 3, i = fi >> 2;
+            const bool ok = k0 + c < K;
+            cp_async8_zfill(&sT[(f * n + i) * LDT + c], ok ? sb + ((size_t)i * 4 + f) * K + k0 + c : sb, ok);
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (i0 + r < n) sT[(n + i0 + r) * LDT + col] = acc[r] - sT[(n + i0 + r) * LDT + col];
-    }
-    __syncthreads();
+    };
     const bool sm = p.bstride != 0;
     const int LDG = n8 + 2;
-    auto out_at = [&](int f, int blk, int i) -> double& {
-        return sm ? p.out[(((long long)f * K + blk) * p.bstride + b) * LDG + i]
-                  : p.out[(long long)b * 3 * N + (long long)f * N + (long long)blk * n + i];
-    };
-    for (int idx = tid; idx < 3 * POST_TC * n; idx += 256) {
-        const int i = idx % n, fc = idx / n, col = fc & (POST_TC - 1), f = fc / POST_TC;
-        const int k = k0 + col;
-        if (k >= K) continue;
-        const bool masked = g.symmetric && (k & 1);  // every odd sinusoid index is masked (Matrix_Operators.py:536-556)
-        const double v = masked ? 0.0 : sT[((f + 1) * n + i) * LDT + col];
-        if (f == 0) {
-            // sinusoid index k -> code block k-1; k = 0 is dropped and block K-1 gets no nonlinear contribution
-            // (Matrix_Operators.py:802)
-            if (k == 0) out_at(0, K - 1, i) = 0.0;
-            else out_at(0, k - 1, i) = v;
-        } else {
-            out_at(f, k, i) = v;
+    int tile = blockIdx.x, stage = 0;
+    if (tile < ntiles) issue(tile, 0);
+    cp_async_commit();
+    for (; tile < ntiles; tile += gridDim.x, stage ^= 1) {
+        const int nxt = tile + gridDim.x;
+        if (nxt < ntiles) issue(nxt, stage ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const int b = tile / nkt, k0 = (tile - b * nkt) * POST_TC;
+        double* sT = smem + stage * TS;   // [4][n][33]
+        // F_psi[i][k] = sum_i' Dr[i][i'] P1[i'][k] - P2[i][k]: thread = (column, four consecutive rows); the operator row
+        // segment is a warp-wide broadcast, the column read is conflict free.  The result replaces P2 (read by no one else).
+        for (int i0 = (tid >> 5) * 4; i0 < n; i0 += 32) {   // i0 + 3 < n8: padded operator columns are zero
+            const int col = tid & 31;
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double2* d2 = reinterpret_cast<const double2*>(sD + i0);   // 32-byte aligned: two 16-byte broadcasts per row
+            const int rs = n8 >> 1;
+#pragma unroll 4
+            for (int ip = 0; ip < n; ++ip) {
+                const double p1 = sT[ip * LDT + col];
+                const double2 a = d2[ip * rs], c2 = d2[ip * rs + 1];
+                acc[0] = fma(a.x, p1, acc[0]);
+                acc[1] = fma(a.y, p1, acc[1]);
+                acc[2] = fma(c2.x, p1, acc[2]);
+                acc[3] = fma(c2.y, p1, acc[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (i0 + r < n) sT[(n + i0 + r) * LDT + col] = acc[r] - sT[(n + i0 + r) * LDT + col];
         }
+        __syncthreads();
+        // store phase, radial index fastest (runs of n doubles in either layout); (i, column, field) advance incrementally
+        {
+            int i = tid % n, fc = tid / n;
+            const int di = 256 % n, dfc = 256 / n;
+            double* ob = sm ? p.out + (long long)b * LDG : p.out + (long long)b * 3 * N;
+            const long long blk_stride = sm ? p.bstride * LDG : n, fld_stride = sm ? (long long)K * p.bstride * LDG : N;
+            for (; fc < 3 * POST_TC; ) {
+                const int col = fc & (POST_TC - 1), f = fc >> 5;
+                const int k = k0 + col;
+                if (k < K) {
+                    const bool masked = g.symmetric && (k & 1);  // every odd sinusoid index is masked (Matrix_Operators.py:536-556)
+                    const double v = masked ? 0.0 : sT[((f + 1) * n + i) * LDT + col];
+                    // psi: sinusoid index k -> code block k-1; k = 0 is dropped and block K-1 gets no nonlinear
+                    // contribution (Matrix_Operators.py:802)
+                    const int blk = f == 0 ? (k == 0 ? K - 1 : k - 1) : k;
+                    ob[f * fld_stride + blk * blk_stride + i] = (f == 0 && k == 0) ? 0.0 : v;
+                }
+                i += di; fc += dfc;
+                if (i >= n) { i -= n; ++fc; }
+            }
+        }
+        __syncthreads();   // this stage is refilled two iterations from now, by copies issued after this point
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace sddc

@@ -70,6 +70,8 @@ struct sddc_plan {
     // FFT formulation of the nonlinear term (k_nlin_fft.cuh): available for N_fm = 128, 256, 512
     int fft_M = 0;              // 3 N_fm / 2 when the FFT path is active, else 0
     bool fft_dfx = false;       // two-state (JVP) variant available
+    int ke_M = 0;               // 3 N_fm when the kinetic-energy synthesis runs as an FFT (N_fm = 128, 256), else 0
+    double *ke_tab = nullptr, *ke_Wn = nullptr;
     bool fft_fuse = false;      // finishing stage (post) fused into the FFT kernel (SDDC_FUSE_POST=1)
     int* fft_done = nullptr;    // [1 + max_batch] dynamic row counter, then the arrival counters of the fused finishing stage
     double *coef7 = nullptr, *coef7b = nullptr, *coef7base = nullptr, *spec4 = nullptr, *fft_tab = nullptr;
@@ -417,9 +419,11 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
     if (!fuse && np.out) {
         PostParams pp{};
         pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = np.out; pp.bstride = np.bstride; pp.g = pl->g;
-        dim3 grid((pl->g.K + POST_TC - 1) / POST_TC, np.nrows / n);
+        const int ntiles = ((pl->g.K + POST_TC - 1) / POST_TC) * (np.nrows / n);
+        const size_t psm = post_smem_bytes(n, n8);
+        const int per_sm = std::max(1, std::min(4, (int)((SMEM_LIMIT + 1024) / (psm + 1024))));
         StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
-        post_kernel<<<grid, 256, post_smem_bytes(n, n8), st>>>(pp);
+        post_kernel<<<std::min(ntiles, per_sm * pl->num_sms), 256, psm, st>>>(pp, ntiles);
         pl->launches++;
         PLAN_CUDA(pl, cudaGetLastError());
     }
@@ -677,7 +681,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(dev_alloc(pl, &pl->rhs, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->xtmp, Bm * 3 * g.N, false));
     pl->nke = pl->Mh3p / (8 * pl->synth_nt_ke);
-    TRY(dev_alloc(pl, &pl->kepart, Bm * pl->nke, true));
+    TRY(dev_alloc(pl, &pl->kepart, Bm * std::max(pl->nke, n), true));
     TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
     // ---- opt in to large dynamic shared memory ----
     {
@@ -755,6 +759,20 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             }
             TRY(run_nlin_fft(pl, nullptr, nullptr, nullptr, false, 1, nullptr, true));
             TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
+            if (K <= 256) {
+                // kinetic energy on the 3K grid with the same transform code (M = 384 or 768)
+                pl->ke_M = 3 * K;
+                std::vector<double> kt, kw(pl->ke_M);
+                if (pl->ke_M == 384) {
+                    kt.resize(fftp::tab_doubles<384>()); fftp::fill_tables<384>(kt.data()); fftp::fill_ke_weights<384>(kw.data());
+                    TRY(set_smem(pl, (ke_fft_kernel<384, 8>), ke_fft_smem_bytes<384>(8)));
+                } else {
+                    kt.resize(fftp::tab_doubles<768>()); fftp::fill_tables<768>(kt.data()); fftp::fill_ke_weights<768>(kw.data());
+                    TRY(set_smem(pl, (ke_fft_kernel<768, 6>), ke_fft_smem_bytes<768>(6)));
+                }
+                TRY(upload(pl, &pl->ke_tab, kt));
+                TRY(upload(pl, &pl->ke_Wn, kw));
+            }
             TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8)));
             TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8)));
             TRY(set_smem(pl, (prep_kernel<5, true>), prep_smem_bytes(n8)));
@@ -1038,6 +1056,32 @@ int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* s
     kp.X = X; kp.x_stride = 3LL * g.N; kp.JJ = pl->JJ; kp.coef = pl->coef1; kp.coef_stride = pl->coef_member_stride;
     kp.DrT = pl->DrT; kp.ir = pl->ir; kp.g = g;
     dim3 grid((g.K + 31) / 32, B);
+    if (pl->ke_M) {
+        // FFT formulation: two row-major coefficient rows per radial point (scratch: coef7), one transform per row
+        kp.coef = pl->coef7; kp.rows = 1;
+        {
+            StageTimer tm(pl, SDDC_STAGE_KE_PREP, st);
+            ke_prep_kernel<<<grid, 256, sizeof(double) * ((size_t)32 * g.n + (size_t)g.n * g.n8), st>>>(kp);
+        }
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+        KeFftParams kf{};
+        kf.rows = pl->coef7; kf.tab = pl->ke_tab; kf.Wn = pl->ke_Wn; kf.wr = pl->wr; kf.kepart = pl->kepart;
+        kf.nrows = B * g.n; kf.n = g.n;
+        const int kgrid = std::min((kf.nrows + 7) / 8, pl->num_sms);
+        {
+            StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
+            if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<kgrid, 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
+            else ke_fft_kernel<768, 6><<<std::min((kf.nrows + 5) / 6, pl->num_sms), 384, ke_fft_smem_bytes<768>(6), st>>>(kf);
+        }
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+        StageTimer tm2(pl, SDDC_STAGE_DIAG, st);
+        diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, g.n, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+        return SDDC_OK;
+    }
     {
         StageTimer tm(pl, SDDC_STAGE_KE_PREP, st);
         ke_prep_kernel<<<grid, 256, sizeof(double) * ((size_t)32 * g.n + (size_t)g.n * g.n8), st>>>(kp);

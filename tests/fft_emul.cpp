@@ -58,7 +58,36 @@ static double check_dft6() {
     return err;
 }
 
+template <int M>
+static void run_ke_rows(const double* rows, double* out, int nrows) {
+    constexpr int Kc = M / 3, PL = Cfg<M>::PL;
+    std::vector<double> tab(tab_doubles<M>()), Wn(M);
+    fill_tables<M>(tab.data());
+    fill_ke_weights<M>(Wn.data());
+    const Tables tb = make_tables<M>(tab.data());
+    std::vector<double> buf((size_t)2 * PL);
+    for (int row = 0; row < nrows; ++row) {
+        for (auto& v : buf) v = 1e300;
+        const double* r = rows + (size_t)row * 2 * Kc;
+        for (int t = 0; t < NTW; ++t) build_ke<M>(t, r, r + Kc, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) pass_c<M, 1, +1>(t, buf.data());
+        for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 1, +1>(t, buf.data(), tw); }
+        double s = 0.0;
+        for (int t = 0; t < NTW; ++t) s += ke6<M>(t, buf.data(), tb, Wn.data());
+        out[row] = s;
+    }
+}
+
 extern "C" {
+
+// rows: [nrows][2][M/3] (cosine-type, sine-type coefficients); out[row] = sum_j w_j sin(th_j) (f_j^2 + g_j^2)
+int fft_emul_ke_rows(int M, const double* rows, double* out, int nrows) {
+    switch (M) {
+        case 384: run_ke_rows<384>(rows, out, nrows); return 0;
+        case 768: run_ke_rows<768>(rows, out, nrows); return 0;
+        default: return -1;
+    }
+}
 
 // worst absolute error of the register butterflies against a direct DFT
 double fft_emul_butterfly_error() {

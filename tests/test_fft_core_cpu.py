@@ -22,6 +22,7 @@ def emul(tmp_path_factory):
     lib.fft_emul_butterfly_error.restype = ctypes.c_double
     dp = ctypes.POINTER(ctypes.c_double)
     lib.fft_emul_rows.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_int]
+    lib.fft_emul_ke_rows.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int]
     return lib
 
 
@@ -87,3 +88,24 @@ def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
     got2 = _call(emul, M, rows, rows1)
     scale2 = np.abs(exp2).max(axis=(0, 2), keepdims=True)
     assert (np.abs(got2 - exp2) / scale2).max() < 1e-12
+
+
+@pytest.mark.parametrize("K", [128, 256])
+def test_fft_kinetic_energy_rows(emul, K):
+    """Weighted sum of squares of the two Kinetic_Energy fields on the 3K grid (Main.py:104-130)."""
+    rng = np.random.default_rng(K)
+    n, M3 = 7, 3 * K
+    a = rng.standard_normal((n, K))
+    b = rng.standard_normal((n, K))
+    b[:, 0] = 0.0
+    rows = np.ascontiguousarray(np.stack([a, b], axis=1))
+    out = np.full(n, np.nan)
+    dp = ctypes.POINTER(ctypes.c_double)
+    assert emul.fft_emul_ke_rows(M3, rows.ctypes.data_as(dp), out.ctypes.data_as(dp), n) == 0
+    th = orc.grid(M3)
+    wt = np.zeros(M3)
+    dth = np.diff(th)
+    wt[:-1] += 0.5 * dth
+    wt[1:] += 0.5 * dth
+    ref = ((orc.IDCT(a, n=M3) ** 2 + orc.IDST(b, n=M3) ** 2) * (wt * np.sin(th))[None, :]).sum(axis=1)
+    assert np.abs(out / ref - 1).max() < 1e-13
