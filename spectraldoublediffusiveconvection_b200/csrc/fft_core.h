@@ -1,6 +1,6 @@
 // FFT formulation of the latitudinal transforms of NLIN_FX / NLIN_DFX (Matrix_Operators.py:743-898,
 // Transforms.py:73-129), written as per-thread "phase" functions that compile for the device (k_nlin_fft.cuh) and
-// for the host (tests/fft_emul.cpp runs the very same code thread by thread on the CPU against the oracle).
+// for the host (tests/fft_emul.cpp runs the very same code thread by thread on the CPU against the test-only oracle).
 //
 // One WORKER (64 threads) processes one radial row i of one member:
 //   build   : the nine sinusoid coefficient rows of Derivatives (Matrix_Operators.py:630-740) are formed from seven
@@ -466,8 +466,8 @@ SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ ou
 // ca: K = M/3 cosine-type coefficients (J_theta(psi)/r), sb: K sine-type coefficients (Dr psi, sinusoid indexing).
 // Same packing as build(); the spectrum is empty between K and M - K.
 template <int M>
-SDDC_HD void build_ke(int t, const double* __restrict__ ca, const double* __restrict__ sb, double* __restrict__ buf,
-                      const Tables& tb) {
+SDDC_HD void build_ke(int t, const double* __restrict__ ca, const double* __restrict__ sb, double asc,
+                      double* __restrict__ buf, const Tables& tb) {   // asc scales the cosine-type row (1/r)
     constexpr int Kc = M / 3, PL = Cfg<M>::PL;
     double* re = buf;
     double* im = buf + PL;
@@ -477,9 +477,9 @@ SDDC_HD void build_ke(int t, const double* __restrict__ ca, const double* __rest
             re[p] = 0.0; im[p] = 0.0;
             if (kp != k) { re[pp] = 0.0; im[pp] = 0.0; }
         } else if (k == 0) {
-            re[p] = ca[0]; im[p] = 0.0;
+            re[p] = asc * ca[0]; im[p] = 0.0;
         } else {
-            const double a = ca[k], b = sb[k], wc = tb.wkc[k], ws = tb.wks[k];
+            const double a = asc * ca[k], b = sb[k], wc = tb.wkc[k], ws = tb.wks[k];
             const double P = a + b, Q2 = b - a;   // Z_k = w_k P / 2,  Z_{M-k} = w_{M-k} (i Q2) / 2
             re[p] = wc * P;   im[p] = ws * P;
             re[pp] = -wc * Q2; im[pp] = ws * Q2;

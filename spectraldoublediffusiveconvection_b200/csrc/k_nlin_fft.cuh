@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
 // Kinetic energy on the 3K grid (Main.py:71-134) in the FFT formulation: one complex transform per radial row
 // (J_theta(psi)/r and Dr psi packed), weighted sum of squares in the last pass.  kepart[row] = wr[i] * sum_theta.
 struct KeFftParams {
-    const double* rows;   // [B n][2][K]
+    const double* rows;   // [B n][2][K]; or the seven-row blocks of prep_kernel (row_stride = 7K, b_off = K, ascale = 1/r)
+    long long row_stride; // doubles between consecutive (member, radial point) rows
+    int b_off;            // offset of the sine-type row inside a block
+    const double* ascale; // [n] factor of the cosine-type row, or null
     const double* tab;    // fftp::fill_tables<3K>
     const double* Wn;     // [3K] fftp::fill_ke_weights<3K>
     const double* wr;     // [n] radial trapezoid weights
@@ -193,7 +196,7 @@ __host__ __device__ constexpr size_t ke_fft_smem_bytes(int nw) {
 template <int M, int NW>
 __global__ void __launch_bounds__(64 * NW, 1) ke_fft_kernel(KeFftParams p) {
     using namespace fftp;
-    constexpr int Kc = M / 3, PL = Cfg<M>::PL;
+    constexpr int PL = Cfg<M>::PL;
     extern __shared__ __align__(128) double smem[];
     __shared__ double s_part[NW][2];
     double* stab = smem;
@@ -207,8 +210,8 @@ __global__ void __launch_bounds__(64 * NW, 1) ke_fft_kernel(KeFftParams p) {
     C tw[Cfg<M>::RD];
     load_tw<M>(t, tb, tw);
     for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
-        const double* r = p.rows + (size_t)row * 2 * Kc;
-        build_ke<M>(t, r, r + Kc, buf, tb);
+        const double* r = p.rows + (size_t)row * p.row_stride;
+        build_ke<M>(t, r, r + p.b_off, p.ascale ? p.ascale[row % p.n] : 1.0, buf, tb);
         worker_sync(w);
         pass_c<M, 1, +1>(t, buf);
         worker_sync(w);

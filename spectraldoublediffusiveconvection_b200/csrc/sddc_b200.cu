@@ -481,13 +481,38 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     return SDDC_OK;
 }
 
+// kinetic energy by FFT from coefficient rows + the remaining diagnostics (norm, Nusselt numbers)
+int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row_stride, int b_off, const double* ascale,
+               double* out, int B, cudaStream_t st) {
+    const Geo& g = pl->g;
+    KeFftParams kf{};
+    kf.rows = rows; kf.row_stride = row_stride; kf.b_off = b_off; kf.ascale = ascale;
+    kf.tab = pl->ke_tab; kf.Wn = pl->ke_Wn; kf.wr = pl->wr; kf.kepart = pl->kepart;
+    kf.nrows = B * g.n; kf.n = g.n;
+    {
+        StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
+        if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<std::min((kf.nrows + 7) / 8, pl->num_sms), 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
+        else ke_fft_kernel<768, 6><<<std::min((kf.nrows + 5) / 6, pl->num_sms), 384, ke_fft_smem_bytes<768>(6), st>>>(kf);
+    }
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    StageTimer tm2(pl, SDDC_STAGE_DIAG, st);
+    diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, g.n, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
+    pl->launches++;
+    PLAN_CUDA(pl, cudaGetLastError());
+    return SDDC_OK;
+}
+
 // Step(X) [- sub]: the shared composition of Step_Python / PFX (Main.py:255-283, 473-496)
-int run_member_step(sddc_plan* pl, const double* X, double* out, const double* sub, const double* Ra,
-                    const double* Ras, int B, bool linear, cudaStream_t st) {
+int run_step_prep(sddc_plan* pl, const double* X, const double* Ra, const double* Ras, int B, bool linear, cudaStream_t st) {
+    const bool fft = pl->fft_M != 0 && !linear;
+    return run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st, fft ? pl->coef7 : nullptr);
+}
+
+int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool linear, cudaStream_t st) {
     const long long N3 = 3LL * pl->g.N;
     const bool fft = pl->fft_M != 0 && !linear;
-    int rc = run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st, fft ? pl->coef7 : nullptr);
-    if (rc) return rc;
+    int rc;
     const double* fnl = nullptr;
     if (fft) {
         if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, pl->f_sm, true, B, st))) return rc;
@@ -498,6 +523,13 @@ int run_member_step(sddc_plan* pl, const double* X, double* out, const double* s
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
     }
     return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
+}
+
+int run_member_step(sddc_plan* pl, const double* X, double* out, const double* sub, const double* Ra,
+                    const double* Ras, int B, bool linear, cudaStream_t st) {
+    int rc = run_step_prep(pl, X, Ra, Ras, B, linear, st);
+    if (rc) return rc;
+    return run_step_rest(pl, out, sub, B, linear, st);
 }
 
 int ensure_host_staging(sddc_plan* pl) {
@@ -1065,21 +1097,7 @@ int sddc_diagnostics(sddc_plan* pl, const double* X, double* out, int B, void* s
         }
         pl->launches++;
         PLAN_CUDA(pl, cudaGetLastError());
-        KeFftParams kf{};
-        kf.rows = pl->coef7; kf.tab = pl->ke_tab; kf.Wn = pl->ke_Wn; kf.wr = pl->wr; kf.kepart = pl->kepart;
-        kf.nrows = B * g.n; kf.n = g.n;
-        const int kgrid = std::min((kf.nrows + 7) / 8, pl->num_sms);
-        {
-            StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
-            if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<kgrid, 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
-            else ke_fft_kernel<768, 6><<<std::min((kf.nrows + 5) / 6, pl->num_sms), 384, ke_fft_smem_bytes<768>(6), st>>>(kf);
-        }
-        pl->launches++;
-        PLAN_CUDA(pl, cudaGetLastError());
-        StageTimer tm2(pl, SDDC_STAGE_DIAG, st);
-        diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, g.n, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
-        pl->launches++;
-        PLAN_CUDA(pl, cudaGetLastError());
+        if ((rc = run_ke_fft(pl, X, pl->coef7, 2LL * g.K, g.K, nullptr, out, B, st))) return rc;
         return SDDC_OK;
     }
     {
@@ -1210,17 +1228,36 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
     double* cur = pl->hX0;
     double* nxt = pl->hX1;
     bool ckpt_pending = false;
+    // With the FFT formulation the prep stage of step s+1 already holds J_theta(psi) and Dr psi of X_s as spectral rows:
+    // the kinetic energy of X_s is taken from them (no second scan / derivative pass); only the last record needs the
+    // stand-alone diagnostics.  (Symmetric runs: stepped states are masked already, so the masked prep loads are exact.)
+    const bool share = pl->fft_M != 0 && pl->ke_M != 0 && !linear;
+    int pending = -1;   // diagnostics record of the current state still to be produced
+    auto ship_record = [&](int r) -> int {
+        double* drec = pl->hHist + (size_t)r * B * 6;
+        PLAN_CUDA(pl, cudaEventRecord(pl->ev_done[0], cs));
+        PLAN_CUDA(pl, cudaStreamWaitEvent(pl->out_stream, pl->ev_done[0], 0));
+        PLAN_CUDA(pl, cudaMemcpyAsync(diag_hist + (size_t)r * B * 6, drec, sizeof(double) * B * 6,
+                                      cudaMemcpyDeviceToHost, pl->out_stream));
+        return SDDC_OK;
+    };
     for (int s = 1; s <= nsteps; ++s) {
-        if ((rc = run_member_step(pl, cur, nxt, nullptr, pl->hRa, pl->hRas, B, linear != 0, cs))) return rc;
+        if ((rc = run_step_prep(pl, cur, pl->hRa, pl->hRas, B, linear != 0, cs))) return rc;
+        if (pending >= 0) {
+            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs))) return rc;
+            if ((rc = ship_record(pending))) return rc;
+            pending = -1;
+        }
+        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs))) return rc;
         std::swap(cur, nxt);
         if (diag_every && s % diag_every == 0) {
             const int r = s / diag_every - 1;
-            double* drec = pl->hHist + (size_t)r * B * 6;
-            if ((rc = sddc_diagnostics(pl, cur, drec, B, cs))) return rc;
-            PLAN_CUDA(pl, cudaEventRecord(pl->ev_done[0], cs));
-            PLAN_CUDA(pl, cudaStreamWaitEvent(pl->out_stream, pl->ev_done[0], 0));
-            PLAN_CUDA(pl, cudaMemcpyAsync(diag_hist + (size_t)r * B * 6, drec, sizeof(double) * B * 6,
-                                          cudaMemcpyDeviceToHost, pl->out_stream));
+            if (share && s < nsteps) {
+                pending = r;
+            } else {
+                if ((rc = sddc_diagnostics(pl, cur, pl->hHist + (size_t)r * B * 6, B, cs))) return rc;
+                if ((rc = ship_record(r))) return rc;
+            }
         }
         if (ckpt_every && s % ckpt_every == 0) {
             const int r = s / ckpt_every - 1;

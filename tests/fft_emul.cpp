@@ -69,7 +69,7 @@ static void run_ke_rows(const double* rows, double* out, int nrows) {
     for (int row = 0; row < nrows; ++row) {
         for (auto& v : buf) v = 1e300;
         const double* r = rows + (size_t)row * 2 * Kc;
-        for (int t = 0; t < NTW; ++t) build_ke<M>(t, r, r + Kc, buf.data(), tb);
+        for (int t = 0; t < NTW; ++t) build_ke<M>(t, r, r + Kc, 1.0, buf.data(), tb);
         for (int t = 0; t < NTW; ++t) pass_c<M, 1, +1>(t, buf.data());
         for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 1, +1>(t, buf.data(), tw); }
         double s = 0.0;

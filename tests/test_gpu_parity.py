@@ -237,6 +237,31 @@ def test_time_step_host_matches_device_loop():
     pl.close()
 
 
+@pytest.mark.parametrize("sym", [False, True])
+def test_time_step_host_shares_prep_with_diagnostics(sym):
+    """FFT formulation: inside sddc_time_step_host the kinetic energy of X_s comes from the spectral rows that the prep
+    stage of step s+1 produces anyway; the history must equal the stand-alone diagnostics to rounding, the states
+    bit for bit."""
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    K, N_r, d, dt, Pr, Tau = 128, 14, 0.5, 5e-3, 1.0, 0.5
+    B, nsteps = 3, 7
+    pl = EnsemblePlan(K, N_r, d, dt, Pr, Tau, symmetric=sym, max_batch=B)
+    assert pl.info()["fft_M"] == 192
+    rng = np.random.default_rng(10)
+    X = rng.random((B, 3 * pl.N)) * 1e-2
+    Ra, Ra_s = np.linspace(2000.0, 4000.0, B), np.linspace(0.0, 200.0, B)
+    out, hist, ck = pl.time_step_host(X, Ra, Ra_s, nsteps, diag_every=1, ckpt_every=3)
+    cur = _dev(X)
+    for s in range(1, nsteps + 1):
+        cur = pl.step(cur, _dev(Ra), _dev(Ra_s))
+        ref = pl.diagnostics(cur).cpu().numpy()
+        assert np.allclose(hist[s - 1], ref, rtol=1e-11, atol=0.0), s
+        if s % 3 == 0:
+            assert np.array_equal(ck[s // 3 - 1], cur.cpu().numpy())
+    assert np.array_equal(out, cur.cpu().numpy())
+    pl.close()
+
+
 def test_step_is_cuda_graph_capturable():
     """The device entry points are allocation-free and stream-ordered: a member-step can be captured in a CUDA graph
     and replayed (include/sddc_b200.h contract)."""
