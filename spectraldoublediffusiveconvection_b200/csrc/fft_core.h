@@ -54,13 +54,13 @@ SDDC_HD int at(int j, int c) { return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7)
 
 // table sizes (doubles): wk cos | wk sin | t6 cos | t6 sin | tL cos | tL sin
 template <int M> SDDC_HD constexpr int tab_wk_doubles() { return M / 2 + 1; }
-template <int M> SDDC_HD constexpr int tab_t6_doubles() { return M; }
+template <int M> SDDC_HD constexpr int tab_t6_doubles() { return 5 * (M / 6); }
 template <int M> SDDC_HD constexpr int tab_tL_doubles() { return 9 * (M / 48); }
 template <int M> SDDC_HD constexpr int tab_doubles() { return 2 * (tab_wk_doubles<M>() + tab_t6_doubles<M>() + tab_tL_doubles<M>()); }
 
 struct Tables {
     const double *wkc, *wks;  // [M/2+1] : cos, sin (pi k / 2M) / 2
-    const double *t6c, *t6s;  // [6][L]  : cos, sin (2 pi k2 n1 / M)
+    const double *t6c, *t6s;  // [5][L]  : cos, sin (2 pi k2 n1 / M), k2 = 1..5 (row k2 - 1)
     const double *tLc, *tLs;  // [RD][9] : cos, sin (2 pi d a / L), a < 8 (row stride 9: conflict-free column reads)
 };
 template <int M>
@@ -189,10 +189,15 @@ SDDC_HD int kpos(int k) {
 
 // ---- build: spectral rows -> packed complex sequences of five inverse transforms -------------------------------
 // cr: [7][K] = JT, Dpsi, omega, DT, DS, T, S of one radial row, sinusoid indexing (column k <-> wavenumber k).
-// buf: five (re, im) plane pairs, plane stride PL.
-template <int M>
-SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ buf, const Tables& tb) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
+// buf: (re, im) plane pairs, plane stride PL.
+// MODE 0: one state, five transforms (the fifth packs DS with nothing).
+// MODE 1: base state of the two-state product; the fifth transform packs DS of the base state with DS of the
+//         perturbation row cr2 -- both cosine type -- so that the pair of states needs 9 transforms, not 10.
+// MODE 2: perturbation of the two-state product, transforms 0..3 only.
+template <int M, int MODE = 0>
+SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ buf, const Tables& tb,
+                   const double* __restrict__ cr2 = nullptr) {
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NQ = MODE == 2 ? 4 : 5;
     for (int k = t; k <= M / 2; k += NTW) {
         const int kp = M - k;
         const bool hasp = k > 0 && kp < K;  // the mirror index lies inside the truncated spectrum
@@ -209,19 +214,23 @@ SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ bu
         const double bp[5] = {vp[2], vp[1], -fkp * vp[5], -fkp * vp[6], 0.0};
         const double wc = tb.wkc[k], ws = tb.wks[k];  // w_k / 2 ;  w_{M-k} / 2 = (ws, wc)
         const int p = kpos<M>(k), pp = kpos<M>(kp % M);
+        // second cosine-type field of transform 4 (MODE 1): X^b_k = c[k], X^b_{M-k} = c[M-k]
+        const double c2 = MODE == 1 ? cr2[4 * K + k] : 0.0, c2p = (MODE == 1 && hasp) ? cr2[4 * K + kp] : 0.0;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             double* re = buf + (2 * q) * PL;
             double* im = re + PL;
+            // X^b at k and at M-k: a sine-type field is stored reversed (X_k = s_{M-k})
+            const double xb_k = (MODE == 1 && q == 4) ? c2 : bp[q], xb_kp = (MODE == 1 && q == 4) ? c2p : b[q];
             if (k == 0) {
                 re[p] = a[q];  // V_0 = X_0; the sine-type entry 0 is ignored (Transforms.py:41-54)
-                im[p] = 0.0;
+                im[p] = (MODE == 1 && q == 4) ? c2 : 0.0;
             } else {
-                const double P = a[q] + b[q], Q = bp[q] - ap[q];
+                const double P = a[q] + xb_kp, Q = xb_k - ap[q];
                 re[p] = wc * P - ws * Q;
                 im[p] = wc * Q + ws * P;
                 if (kp != k) {
-                    const double P2 = ap[q] + bp[q], Q2 = b[q] - a[q];
+                    const double P2 = ap[q] + xb_k, Q2 = xb_kp - a[q];
                     re[pp] = ws * P2 - wc * Q2;
                     im[pp] = ws * Q2 + wc * P2;
                 }
@@ -301,14 +310,15 @@ SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, 
 #pragma unroll
     for (int k2 = 0; k2 < 6; ++k2) {
         x[k2] = C{re[pos[k2]], im[pos[k2]]};
-        if (k2 > 0) x[k2] = cmul(x[k2], tb.t6c[k2 * L + n1], tb.t6s[k2 * L + n1]);
+        if (k2 > 0) x[k2] = cmul(x[k2], tb.t6c[(k2 - 1) * L + n1], tb.t6s[(k2 - 1) * L + n1]);
     }
     dft6<+1>(x, z);
 }
 
 // ---- I3F1: last inverse pass + Jacobian products + first forward pass ------------------------------------------------
 // FX : buffers 0..4 hold the transforms of X.                 Products of NLIN_FX  (Matrix_Operators.py:791-793)
-// DFX: buffers 0..4 hold the base state, 5..9 the perturbation. Products of NLIN_DFX (Matrix_Operators.py:884-887)
+// DFX: buffers 0..3 hold the base state, 4 packs DS of base and perturbation, 5..8 the perturbation.
+//      Products of NLIN_DFX (Matrix_Operators.py:884-887)
 // Output: buffer 0 <- P1 + i P2 (sine type: JT*om | kDpsi*om + Dpsi*kom), buffer 1 <- N_T + i N_S (cosine type),
 // already through the forward radix-6 pass and its twiddle.
 template <int M, bool DFX>
@@ -382,14 +392,15 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
                 }
             }
         }
-        {
+        if (DFX) {
+            // DS of the perturbation came out as the imaginary part of the base state's fifth transform (plane 9)
+#pragma unroll
+            for (int m = 0; m < 6; ++m) NS[m] += jt[m] * bg(DS, m) + bg(JT, m) * bg(9, m);
+        } else {
             C z4[6];
             inv6<M>(pert + 8 * PL, pert + 9 * PL, pos, n1, tb, z4);  // DS | 0
 #pragma unroll
-            for (int m = 0; m < 6; ++m) {
-                if (DFX) NS[m] += jt[m] * bg(DS, m) + bg(JT, m) * z4[m].r;
-                else NS[m] += jt[m] * z4[m].r;
-            }
+            for (int m = 0; m < 6; ++m) NS[m] += jt[m] * z4[m].r;
         }
         // forward radix-6 over n2 -> k2, twiddle e^{-2 pi i k2 n1 / M}
 #pragma unroll
@@ -402,7 +413,7 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
             double* im = re + PL;
 #pragma unroll
             for (int k2 = 0; k2 < 6; ++k2) {
-                if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6c[k2 * L + n1], tb.t6s[k2 * L + n1]);
+                if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6c[(k2 - 1) * L + n1], tb.t6s[(k2 - 1) * L + n1]);
                 re[pos[k2]] = y[k2].r;
                 im[pos[k2]] = y[k2].i;
             }
@@ -532,11 +543,11 @@ inline void fill_tables(double* out) {
         wkc[k] = (double)(0.5L * cosl(x));
         wks[k] = (double)(0.5L * sinl(x));
     }
-    for (int k2 = 0; k2 < 6; ++k2)
+    for (int k2 = 1; k2 < 6; ++k2)
         for (int n1 = 0; n1 < L; ++n1) {
             const long double x = 2.0L * pi * ((k2 * n1) % M) / M;
-            t6c[k2 * L + n1] = (double)cosl(x);
-            t6s[k2 * L + n1] = (double)sinl(x);
+            t6c[(k2 - 1) * L + n1] = (double)cosl(x);
+            t6s[(k2 - 1) * L + n1] = (double)sinl(x);
         }
     for (int d = 0; d < RD; ++d)
         for (int a = 0; a < 9; ++a) {

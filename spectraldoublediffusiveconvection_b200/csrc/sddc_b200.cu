@@ -371,7 +371,7 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
 
 // FFT formulation: coefficient rows -> analysed products spec4 (k_nlin_fft.cuh)
 template <int M>
-constexpr int nlin_fft_nw(bool dfx) { return dfx ? 3 : (M <= 384 ? NLIN_FFT_NW : 3); }
+constexpr int nlin_fft_nw(bool dfx) { return dfx ? 4 : (M <= 384 ? NLIN_FFT_NW : 3); }
 
 // column tile of the fused finishing stage that fits into one worker's planes (0: does not fit)
 template <int M, bool DFX>

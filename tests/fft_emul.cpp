@@ -11,7 +11,7 @@ using namespace sddc::fftp;
 
 template <int M, bool DFX>
 static void run_rows(const double* coef0, const double* coef1, double* out, int nrows) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 10 : 5;
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 9 : 5;
     std::vector<double> tab(tab_doubles<M>());
     fill_tables<M>(tab.data());
     const Tables tb = make_tables<M>(tab.data());
@@ -19,8 +19,12 @@ static void run_rows(const double* coef0, const double* coef1, double* out, int 
     for (int row = 0; row < nrows; ++row) {
         for (auto& v : buf) v = 1e300;  // poison: every position that is read must have been written
         for (int t = 0; t < NTW; ++t) {
-            build<M>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
-            if (DFX) build<M>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
+            if (DFX) {
+                build<M, 1>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb, coef1 + (size_t)row * 7 * K);
+                build<M, 2>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
+            } else {
+                build<M>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
+            }
         }
         for (int t = 0; t < NTW; ++t) pass_c<M, NF, +1>(t, buf.data());
         for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, NF, +1>(t, buf.data(), tw); }
