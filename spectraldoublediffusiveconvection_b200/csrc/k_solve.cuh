@@ -36,6 +36,9 @@ struct SolveParams {
     int field_base;         // field index of chain group 0 (for single-field calls)
     double dt_psi, dt_T, dt_S;  // Pr*dt, dt, Tau*dt
     int nsl;                    // pipeline stages in use (2 or 3)
+    double* jj_out;             // optional [B][K+1][n]: theta-coupling brackets of the NEW stream function, exactly what
+                                // scan_kernel would compute from the output (the running sum f_e of the A4 chain is that
+                                // suffix sum), so the next step of a multi-step call skips its scan (k_solve_hot.cuh)
 };
 
 #ifndef SOLVE_NSL_MAX

@@ -64,6 +64,14 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     }
     const long long sub_delta = has_sub ? (p.sub - p.out) : 0;
     const long long rstep = -2LL * n;
+    // JJ[b][m][i] of the new stream function (k_prep.cuh, scan_kernel), sine mode m = j of this chain
+    const bool want_jj = PSI && p.jj_out != nullptr;
+    double* jjp[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        const int m = (e >> 1) * 8 + 2 * tq + (e & 1);
+        jjp[e] = want_jj ? p.jj_out + ((long long)(b0 + m) * (K + 1) + j0) * n + i : nullptr;
+    }
 
     if (G.symmetric && which == 1) {   // these modes are identically zero under the equatorial symmetry
         if (is_producer) return;
@@ -72,6 +80,10 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
             for (int e = 0; e < NE; ++e) {
                 if (ok[e]) outp[e][0] = has_sub ? -outp[e][sub_delta] : 0.0;
                 outp[e] += rstep;
+                if (want_jj) {
+                    if (ok[e]) jjp[e][0] = 0.0;
+                    jjp[e] += rstep;
+                }
             }
         }
         return;
@@ -200,11 +212,25 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
             if (ok[e]) outp[e][0] = f[e] - subv[e];
             outp[e] += rstep;
         }
+        if (want_jj) {
+            // (j+1) psi^(j) + 2 S[j] with S[j] = f_e, rounded exactly like scan_kernel does it (product first)
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                if (ok[e]) jjp[e][0] = __fma_rn(s1[e], 2.0, __dmul_rn((double)j + 1.0, f[e]));
+                jjp[e] += rstep;
+            }
+        }
         if (PSI) {
             const double bj = -(double)j * (j + 1.0), bjt = -2.0 * j;
 #pragma unroll
             for (int e = 0; e < NE; ++e) s2[e] += fma(bj, f[e], bjt * s1[e]);
         }
+    }
+    if (want_jj && which == 0) {
+        // JJ[0] = S[0] = sum of all even sine modes: the chain ended at j = 2 and the pointers now sit at m = 0
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+            if (ok[e]) jjp[e][0] = s1[e] + f[e];
     }
 }
 

@@ -284,8 +284,9 @@ int run_scan(sddc_plan* pl, const double* X, long long stride, int B, cudaStream
 
 // scan + prep of state X into coefficient set `set` (and optionally the linear right-hand side)
 int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* lin, const double* Ra,
-             const double* Ras, int B, cudaStream_t st, double* coef7 = nullptr) {
-    int rc = run_scan(pl, X, 3LL * pl->g.N, B, st);
+             const double* Ras, int B, cudaStream_t st, double* coef7 = nullptr, bool have_jj = false) {
+    // have_jj: pl->JJ already holds the brackets of X (written by the previous step's back-substitution)
+    int rc = have_jj ? SDDC_OK : run_scan(pl, X, 3LL * pl->g.N, B, st);
     if (rc) return rc;
     PrepParams pp{};
     pp.X = X; pp.x_stride = 3LL * pl->g.N; pp.JJ = pl->JJ;
@@ -448,8 +449,9 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
 
 // gs < 0 selects the solve-major layout for g / fnl
 int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, long long gf, double* out, long long os,
-              long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st) {
+              long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st, double* jj_out = nullptr) {
     SolveParams sp{};
+    sp.jj_out = jj_out;
     const bool sm = gs < 0;
     sp.bstride = pl->bstride;
     sp.g = g; sp.fnl = fnl; sp.mdt = -pl->g.dt; sp.g_stride = gs; sp.g_field_off = gf; sp.out = out; sp.out_stride = os; sp.out_field_off = of;
@@ -504,12 +506,14 @@ int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row
 }
 
 // Step(X) [- sub]: the shared composition of Step_Python / PFX (Main.py:255-283, 473-496)
-int run_step_prep(sddc_plan* pl, const double* X, const double* Ra, const double* Ras, int B, bool linear, cudaStream_t st) {
+// have_jj: the previous member-step of this call left the theta-coupling brackets of X in pl->JJ (emit_jj below)
+int run_step_prep(sddc_plan* pl, const double* X, const double* Ra, const double* Ras, int B, bool linear, cudaStream_t st,
+                  bool have_jj = false) {
     const bool fft = pl->fft_M != 0 && !linear;
-    return run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st, fft ? pl->coef7 : nullptr);
+    return run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st, fft ? pl->coef7 : nullptr, have_jj);
 }
 
-int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool linear, cudaStream_t st) {
+int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool linear, cudaStream_t st, bool emit_jj = false) {
     const long long N3 = 3LL * pl->g.N;
     const bool fft = pl->fft_M != 0 && !linear;
     int rc;
@@ -522,14 +526,16 @@ int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool lin
         if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
     }
-    return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
+    return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, emit_jj ? pl->JJ : nullptr);
 }
 
+// have_jj / emit_jj chain the steps of a multi-step call: the A4 back-substitution of step s writes the suffix-sum
+// brackets of its output, step s+1 starts without its scan launch
 int run_member_step(sddc_plan* pl, const double* X, double* out, const double* sub, const double* Ra,
-                    const double* Ras, int B, bool linear, cudaStream_t st) {
-    int rc = run_step_prep(pl, X, Ra, Ras, B, linear, st);
+                    const double* Ras, int B, bool linear, cudaStream_t st, bool have_jj = false, bool emit_jj = false) {
+    int rc = run_step_prep(pl, X, Ra, Ras, B, linear, st, have_jj);
     if (rc) return rc;
-    return run_step_rest(pl, out, sub, B, linear, st);
+    return run_step_rest(pl, out, sub, B, linear, st, emit_jj);
 }
 
 int ensure_host_staging(sddc_plan* pl) {
@@ -959,7 +965,7 @@ int sddc_step(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, 
     const double* src = Xin;
     for (int s = 0; s < nsteps; ++s) {
         double* dst = ((nsteps - s) & 1) ? Xout : pl->xtmp;  // the last step lands in Xout
-        if ((rc = run_member_step(pl, src, dst, nullptr, Ra, Ras, B, linear != 0, st))) return rc;
+        if ((rc = run_member_step(pl, src, dst, nullptr, Ra, Ras, B, linear != 0, st, s > 0, s + 1 < nsteps))) return rc;
         src = dst;
     }
     return SDDC_OK;
@@ -1242,13 +1248,13 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
         return SDDC_OK;
     };
     for (int s = 1; s <= nsteps; ++s) {
-        if ((rc = run_step_prep(pl, cur, pl->hRa, pl->hRas, B, linear != 0, cs))) return rc;
+        if ((rc = run_step_prep(pl, cur, pl->hRa, pl->hRas, B, linear != 0, cs, s > 1))) return rc;
         if (pending >= 0) {
             if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs))) return rc;
             if ((rc = ship_record(pending))) return rc;
             pending = -1;
         }
-        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs))) return rc;
+        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs, s < nsteps))) return rc;
         std::swap(cur, nxt);
         if (diag_every && s % diag_every == 0) {
             const int r = s / diag_every - 1;
