@@ -372,7 +372,8 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
 
 // FFT formulation: coefficient rows -> analysed products spec4 (k_nlin_fft.cuh)
 template <int M>
-constexpr int nlin_fft_nw(bool dfx) { return dfx ? 4 : (M <= 384 ? NLIN_FFT_NW : 3); }
+// two-state kernel: 18 planes per worker -- four workers fit at M <= 384, a single one at M = 768 (111 KB)
+constexpr int nlin_fft_nw(bool dfx) { return dfx ? (M <= 384 ? 4 : 1) : (M <= 384 ? NLIN_FFT_NW : 3); }
 
 // column tile of the fused finishing stage that fits into one worker's planes (0: does not fit)
 template <int M, bool DFX>
@@ -384,11 +385,11 @@ int nlin_fft_ftc(int n) {
 
 template <int M>
 int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
-    constexpr int MD = M <= 384 ? M : 384;  // the two-state variant is instantiated up to M = 384 only
+    constexpr int MD = M;
     constexpr int NW = nlin_fft_nw<M>(false), NWD = nlin_fft_nw<M>(true);
     if (set_attr) {
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        if (M <= 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
     const int n = pl->g.n, n8 = pl->g.n8;
@@ -775,7 +776,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         const bool want = !(fe && fe[0] == '0');
         if (want && (K == 128 || K == 256 || K == 512)) {
             pl->fft_M = g.M;
-            pl->fft_dfx = K <= 256;
+            pl->fft_dfx = true;
             std::vector<double> tab;
             switch (g.M) {
                 case 192: tab.resize(fftp::tab_doubles<192>()); fftp::fill_tables<192>(tab.data()); break;

@@ -1,8 +1,11 @@
-# one GPU-box round trip: parity report, stage timings, GPU test suite, racecheck of the FFT kernels
+# one GPU-box round trip: GPU test suite, bench at the config-5 shape
 mkdir -p gpurun_out
-python tools/gpu_check.py cfg3_member > gpurun_out/check_fft.log 2>&1
-python tools/stage_times.py > gpurun_out/stages_fft.log 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
-SANITIZE_FFT=2 timeout 300 compute-sanitizer --tool racecheck python tools/sanitize_small.py > gpurun_out/san_race.log 2>&1
-SANITIZE_FFT=1 timeout 300 compute-sanitizer --tool memcheck python tools/sanitize_small.py > gpurun_out/san_mem.log 2>&1
-for f in check_fft stages_fft pytest_gpu san_race san_mem; do echo "== $f"; tail -n 4 gpurun_out/$f.log; done
+python bench.py --steps 50 --warmup 5 --N_r 40 --N_fm 512 --members-per-gpu 512 --no-cpu-baseline > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err
+tail -n 3 gpurun_out/pytest_gpu.log
+python - <<'PY'
+import json
+for f in ("bench_cfg5",):
+    d=json.load(open('gpurun_out/%s.json'%f))
+    print(f, d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], "jvp", d["jvp"]["value"], d["jvp"].get("uncached"), "diag", d["with_diagnostics"]["value"])
+PY
