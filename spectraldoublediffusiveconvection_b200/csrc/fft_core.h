@@ -30,7 +30,7 @@
 namespace sddc {
 namespace fftp {
 
-constexpr int NTW = 64;  // threads per worker
+constexpr int NTW = 64;  // threads per worker (default; the M = 768 kernels use 128: template parameter NTH)
 
 // Shared-memory layout of one plane (re or im) of a length-M sequence: 8-element blocks, block index
 //     j = 6 d + k2   (spectral side: k = 6 (RD c + d) + k2 is element c of block j = k mod 6RD;
@@ -194,11 +194,11 @@ SDDC_HD int kpos(int k) {
 // MODE 1: base state of the two-state product; the fifth transform packs DS of the base state with DS of the
 //         perturbation row cr2 -- both cosine type -- so that the pair of states needs 9 transforms, not 10.
 // MODE 2: perturbation of the two-state product, transforms 0..3 only.
-template <int M, int MODE = 0>
+template <int M, int MODE = 0, int NTH = NTW>
 SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ buf, const Tables& tb,
                    const double* __restrict__ cr2 = nullptr) {
     constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NQ = MODE == 2 ? 4 : 5;
-    for (int k = t; k <= M / 2; k += NTW) {
+    for (int k = t; k <= M / 2; k += NTH) {
         const int kp = M - k;
         const bool hasp = k > 0 && kp < K;  // the mirror index lies inside the truncated spectrum
         double v[7], vp[7];
@@ -242,10 +242,10 @@ SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ bu
 // ---- radix-8 pass over c (the eight elements of a block) ---------------------------------------------------------------
 // inverse (SIGN = +1): DFT over c -> a;  forward (SIGN = -1): DFT over a -> c.  The twiddle e^{+-2 pi i d a / L} between
 // the two passes of the length-L transform is applied by pass_d, where it depends on the thread only.
-template <int M, int NF, int SIGN>
+template <int M, int NF, int SIGN, int NTH = NTW>
 SDDC_HD void pass_c(int t, double* __restrict__ buf) {
     constexpr int NBLK = Cfg<M>::NBLK, PL = Cfg<M>::PL;
-    for (int u = t; u < NF * NBLK; u += NTW) {
+    for (int u = t; u < NF * NBLK; u += NTH) {
         const int q = u / NBLK, j = u - q * NBLK;
         const int sw = j & 7;
         double* re = buf + (2 * q) * PL + ((j ^ ((j >> 3) & 1)) << 3);
@@ -262,7 +262,8 @@ SDDC_HD void pass_c(int t, double* __restrict__ buf) {
     }
 }
 
-// twiddles e^{2 pi i d a / L}, d < RD, of thread t: pass_d always works on element a = t & 7 (48 and 64 are multiples of 8)
+// twiddles e^{2 pi i d a / L}, d < RD, of thread t: pass_d always works on element a = t & 7 (48 and the worker size
+// are multiples of 8)
 template <int M>
 SDDC_HD void load_tw(int t, const Tables& tb, C (&tw)[Cfg<M>::RD]) {
 #pragma unroll
@@ -271,10 +272,10 @@ SDDC_HD void load_tw(int t, const Tables& tb, C (&tw)[Cfg<M>::RD]) {
 
 // ---- radix-RD pass over d (same element of the blocks 6 d + k2) ------------------------------------------------------
 // inverse: twiddle e^{+2 pi i d a / L}, then DFT over d -> b;  forward: DFT over b -> d, then twiddle e^{-2 pi i d a / L}
-template <int M, int NF, int SIGN>
+template <int M, int NF, int SIGN, int NTH = NTW>
 SDDC_HD void pass_d(int t, double* __restrict__ buf, const C (&tw)[Cfg<M>::RD]) {
     constexpr int RD = Cfg<M>::RD, PL = Cfg<M>::PL;
-    for (int u = t; u < NF * 48; u += NTW) {
+    for (int u = t; u < NF * 48; u += NTH) {
         const int q = u / 48, rem = u - q * 48, k2 = rem >> 3, a = rem & 7;
         double* re = buf + (2 * q) * PL;
         double* im = re + PL;
@@ -321,10 +322,10 @@ SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, 
 //      Products of NLIN_DFX (Matrix_Operators.py:884-887)
 // Output: buffer 0 <- P1 + i P2 (sine type: JT*om | kDpsi*om + Dpsi*kom), buffer 1 <- N_T + i N_S (cosine type),
 // already through the forward radix-6 pass and its twiddle.
-template <int M, bool DFX>
+template <int M, bool DFX, int NTH = NTW>
 SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
     constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
-    for (int n1 = t; n1 < L; n1 += NTW) {
+    for (int n1 = t; n1 < L; n1 += NTH) {
         int pos[6];
 #pragma unroll
         for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
@@ -423,11 +424,11 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
 
 // ---- post: separate the packed sequences, scale, truncate to K --------------------------------------------------------
 // out: [4][K] = DST(JT*om), DST(kDpsi*om + Dpsi*kom), DCT(N_T), DCT(N_S)   (sinusoid indexing; Transforms.py:28-39,56-70)
-template <int M>
+template <int M, int NTH = NTW>
 SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ out, const Tables& tb) {
     constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
     constexpr double sc = 2.0 / M;  // the table holds w_k / 2, which absorbs the 1/2 of the Hermitian split
-    for (int k = t; k <= M / 2; k += NTW) {
+    for (int k = t; k <= M / 2; k += NTH) {
         const int kp = M - k;
         const int p = kpos<M>(k), pp = kpos<M>(kp % M);
         const double hc = tb.wkc[k], hs = tb.wks[k];

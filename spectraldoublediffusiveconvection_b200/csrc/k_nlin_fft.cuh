@@ -51,8 +51,9 @@ __host__ __device__ inline size_t nlin_fft_smem_bytes(int nw, int dr_doubles) {
     return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + dr_doubles + (size_t)nw * nlin_fft_worker_doubles<M, DFX>());
 }
 
+template <int NT = 64>
 __device__ __forceinline__ void worker_sync(int w) {
-    asm volatile("bar.sync %0, 64;" ::"r"(w + 1) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(w + 1), "n"(NT) : "memory");
 }
 
 // Finishing stage of member b by one worker (64 threads), tile by tile of `tc` sinusoid columns:
@@ -110,8 +111,9 @@ __device__ __forceinline__ void finish_member(const NlinFftParams& p, int b, int
     }
 }
 
-template <int M, bool DFX, int NW>
-__global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
+// NT = threads per worker: 64, or 128 where the last pass has 128 columns (M = 768)
+template <int M, bool DFX, int NW, int NT = 64>
+__global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     using namespace fftp;
     constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 9 : 5;
     extern __shared__ __align__(128) double smem[];
@@ -119,62 +121,62 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     double* stab = smem;
     double* sD = smem + nlin_fft_tab_pad<M>();
     const int dr_doubles = p.done ? nlin_fft_dr_pad(p.g.n, p.g.n8) : 0;
-    for (int i = threadIdx.x; i < tab_doubles<M>(); i += 64 * NW) stab[i] = p.tab[i];
+    for (int i = threadIdx.x; i < tab_doubles<M>(); i += NT * NW) stab[i] = p.tab[i];
     if (p.done)
-        for (int i = threadIdx.x; i < p.g.n * p.g.n8; i += 64 * NW) sD[i] = p.DrT[i];
+        for (int i = threadIdx.x; i < p.g.n * p.g.n8; i += NT * NW) sD[i] = p.DrT[i];
     __syncthreads();
     const Tables tb = make_tables<M>(stab);
-    const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int w = threadIdx.x / NT, t = threadIdx.x % NT;
     double* buf = sD + dr_doubles + (size_t)w * nlin_fft_worker_doubles<M, DFX>();
     C tw[Cfg<M>::RD];
     load_tw<M>(t, tb, tw);
     const int stride = gridDim.x * NW;
     for (;;) {
         if (t == 0) s_row[w] = atomicAdd(p.next_row, 1);
-        worker_sync(w);
+        worker_sync<NT>(w);
         const int row = s_row[w];
         if (row >= p.nrows) break;
         if (DFX) {
-            build<M, 1>(t, p.coef0 + (size_t)row * 7 * K, buf, tb, p.coef1 + (size_t)row * 7 * K);
-            build<M, 2>(t, p.coef1 + (size_t)row * 7 * K, buf + 10 * PL, tb);
+            build<M, 1, NT>(t, p.coef0 + (size_t)row * 7 * K, buf, tb, p.coef1 + (size_t)row * 7 * K);
+            build<M, 2, NT>(t, p.coef1 + (size_t)row * 7 * K, buf + 10 * PL, tb);
         } else {
-            build<M>(t, p.coef0 + (size_t)row * 7 * K, buf, tb);
+            build<M, 0, NT>(t, p.coef0 + (size_t)row * 7 * K, buf, tb);
         }
         // pull the row that will be claimed one round from now from HBM into L2 while this one is transformed
         if (row + stride < p.nrows) {
             const char* nx = reinterpret_cast<const char*>(p.coef0 + (size_t)(row + stride) * 7 * K);
-            for (int o = t * 128; o < 7 * K * 8; o += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            for (int o = t * 128; o < 7 * K * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
             if (DFX) {
                 const char* nx1 = reinterpret_cast<const char*>(p.coef1 + (size_t)(row + stride) * 7 * K);
-                for (int o = t * 128; o < 7 * K * 8; o += 64 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx1 + o));
+                for (int o = t * 128; o < 7 * K * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx1 + o));
             }
         }
-        worker_sync(w);
-        pass_c<M, NF, +1>(t, buf);
-        worker_sync(w);
-        pass_d<M, NF, +1>(t, buf, tw);
-        worker_sync(w);
-        i3f1<M, DFX>(t, buf, tb);
-        worker_sync(w);
-        pass_d<M, 2, -1>(t, buf, tw);
-        worker_sync(w);
-        pass_c<M, 2, -1>(t, buf);
-        worker_sync(w);
-        post<M>(t, buf, p.spec + (size_t)row * 4 * K, tb);
+        worker_sync<NT>(w);
+        pass_c<M, NF, +1, NT>(t, buf);
+        worker_sync<NT>(w);
+        pass_d<M, NF, +1, NT>(t, buf, tw);
+        worker_sync<NT>(w);
+        i3f1<M, DFX, NT>(t, buf, tb);
+        worker_sync<NT>(w);
+        pass_d<M, 2, -1, NT>(t, buf, tw);
+        worker_sync<NT>(w);
+        pass_c<M, 2, -1, NT>(t, buf);
+        worker_sync<NT>(w);
+        post<M, NT>(t, buf, p.spec + (size_t)row * 4 * K, tb);
         if (p.done) {
             // last-arriver pattern: publish this row, count it, and let the worker that completes a member finish it
             __threadfence();
-            worker_sync(w);
+            worker_sync<NT>(w);
             const int b = row / p.g.n;
             if (t == 0) s_last[w] = (atomicAdd(p.done + b, 1) == p.g.n - 1);
-            worker_sync(w);
+            worker_sync<NT>(w);
             if (s_last[w]) {
                 __threadfence();
-                finish_member(p, b, w, t, buf, sD);
+                if (NT == 64) finish_member(p, b, w, t, buf, sD);   // the opt-in fused stage exists for 64-thread workers only
                 if (t == 0) p.done[b] = 0;
             }
         }
-        worker_sync(w);
+        worker_sync<NT>(w);
     }
 }
 

@@ -387,9 +387,10 @@ template <int M>
 int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
     constexpr int MD = M;
     constexpr int NW = nlin_fft_nw<M>(false), NWD = nlin_fft_nw<M>(true);
+    constexpr int NT = M == 768 ? 128 : 64, NTD = M == 768 ? 128 : 64;   // threads per worker = columns of the radix-6 pass at M = 768
     if (set_attr) {
-        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD, NTD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
     const int n = pl->g.n, n8 = pl->g.n8;
@@ -397,7 +398,7 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
     int ftc = dfx ? nlin_fft_ftc<MD, true>(n) : nlin_fft_ftc<M, false>(n);
     int drd = nlin_fft_dr_pad(n, n8);
     size_t smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, drd) : nlin_fft_smem_bytes<M, false>(NW, drd);
-    const bool fuse = pl->fft_fuse && ftc > 0 && smem <= SMEM_LIMIT && np.out != nullptr;
+    const bool fuse = pl->fft_fuse && ftc > 0 && smem <= SMEM_LIMIT && np.out != nullptr && NT == 64;
     if (!fuse) {
         np.done = nullptr;
         smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, 0) : nlin_fft_smem_bytes<M, false>(NW, 0);
@@ -410,10 +411,10 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
         StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
         if (dfx) {
             const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
-            nlin_fft_kernel<MD, true, NWD><<<grid, 64 * NWD, smem, st>>>(np);
+            nlin_fft_kernel<MD, true, NWD, NTD><<<grid, NTD * NWD, smem, st>>>(np);
         } else {
             const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
-            nlin_fft_kernel<M, false, NW><<<grid, 64 * NW, smem, st>>>(np);
+            nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
         }
     }
     pl->launches++;

@@ -11,27 +11,27 @@ using namespace sddc::fftp;
 
 template <int M, bool DFX>
 static void run_rows(const double* coef0, const double* coef1, double* out, int nrows) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 9 : 5;
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 9 : 5, NT = M == 768 ? 128 : 64;   // threads per worker as launched
     std::vector<double> tab(tab_doubles<M>());
     fill_tables<M>(tab.data());
     const Tables tb = make_tables<M>(tab.data());
     std::vector<double> buf((size_t)2 * NF * PL);
     for (int row = 0; row < nrows; ++row) {
         for (auto& v : buf) v = 1e300;  // poison: every position that is read must have been written
-        for (int t = 0; t < NTW; ++t) {
+        for (int t = 0; t < NT; ++t) {
             if (DFX) {
-                build<M, 1>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb, coef1 + (size_t)row * 7 * K);
-                build<M, 2>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
+                build<M, 1, NT>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb, coef1 + (size_t)row * 7 * K);
+                build<M, 2, NT>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
             } else {
-                build<M>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
+                build<M, 0, NT>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
             }
         }
-        for (int t = 0; t < NTW; ++t) pass_c<M, NF, +1>(t, buf.data());
-        for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, NF, +1>(t, buf.data(), tw); }
-        for (int t = 0; t < NTW; ++t) i3f1<M, DFX>(t, buf.data(), tb);
-        for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1>(t, buf.data(), tw); }
-        for (int t = 0; t < NTW; ++t) pass_c<M, 2, -1>(t, buf.data());
-        for (int t = 0; t < NTW; ++t) post<M>(t, buf.data(), out + (size_t)row * 4 * K, tb);
+        for (int t = 0; t < NT; ++t) pass_c<M, NF, +1, NT>(t, buf.data());
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, NF, +1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) i3f1<M, DFX, NT>(t, buf.data(), tb);
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) pass_c<M, 2, -1, NT>(t, buf.data());
+        for (int t = 0; t < NT; ++t) post<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
     }
 }
 
