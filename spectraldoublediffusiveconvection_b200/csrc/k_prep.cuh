@@ -61,16 +61,23 @@ struct PrepParams {
     const double *ir2, *ir4, *r2, *dT0, *gb;  // [n]
     Geo g;
     int B;
+    int nstage;             // 2: the next tile's copies overlap the current tile (n8 >= 40: one CTA per SM anyway);
+                            // 1: n8 <= 32, where three single-stage CTAs per SM measured faster than two double-buffered
+                            //    ones (0.128 vs 0.138 ms), and n8 = 64, where two stages do not fit
 };
 
 constexpr int PREP_TC = 32;  // sinusoid columns per CTA
 
-__host__ __device__ inline size_t prep_smem_bytes(int n8) {
-    return sizeof(double) * (size_t)(4 * (PREP_TC + 1) + 3 * n8) * (n8 + 4);
+__host__ __device__ inline size_t prep_smem_bytes(int n8, int nstage) {
+    return sizeof(double) * (size_t)(nstage * 4 * (PREP_TC + 1) + 3 * n8) * (n8 + 4);
 }
 
-// One CTA per (member, tile of 32 sinusoid columns), 2*nt8 warps: warp = (8-row radial tile mt, half of the
-// columns).  The radial derivatives Dr psi, D2r psi, Dsq psi, Dr T, Dr S are DMMA GEMMs
+// CTA c takes the tiles (member, 32 sinusoid columns) c, c + gridDim.x, ...  For n8 >= 40 (one CTA per SM) the launch
+// is persistent: the operators are loaded once per CTA and the four state tiles of the next tile are in flight
+// (cp.async, two stages) while the current one goes through the MMAs and the epilogue stores (0.45 -> 0.39 ms at
+// (40,512)).  For n8 <= 32 the grid has one CTA per tile, three per SM: measured faster than two double-buffered or
+// three single-stage persistent CTAs (0.128 vs 0.138 / 0.142 ms at (30,256)).  2*nt8 warps: warp = (8-row radial tile mt, half of the columns).
+// The radial derivatives Dr psi, D2r psi, Dsq psi, Dr T, Dr S are DMMA GEMMs
 //     OUT[i, c] = sum_i' Mat[i, i'] * X[c][i']      (A = operator, B = 32 mode blocks of the state tile)
 // whose accumulator fragments are written straight into (a) the tile-major coefficient arrays of the synthesis
 // GEMM -- one accumulator tile is one contiguous 256-byte A-fragment block there -- and (b) the linear
@@ -78,61 +85,85 @@ __host__ __device__ inline size_t prep_smem_bytes(int n8) {
 // FFTL selects the output of the FFT formulation (k_nlin_fft.cuh): seven row-major spectral rows per radial point
 // (JT, Dpsi, omega, DT, DS, T, S) and the natural MMA column order, so that a quad writes 64 contiguous bytes.
 template <int NT8, bool FFTL = false>
-__global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(PrepParams p) {
+__global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(PrepParams p, int ntiles) {
     extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDX = n8 + 4;
-    const int b = blockIdx.y, c0 = blockIdx.x * PREP_TC;
+    const int nkt = (K + PREP_TC - 1) / PREP_TC;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, gq = lane >> 2, tq = lane & 3;
     constexpr int TQ = PREP_TC + 1;
-    double* sP = smem;               // psi blocks c0-1 .. c0+31   (q = 0..32), row stride LDX, padded entries zero
-    double* sT = sP + TQ * LDX;      // T   blocks c0   .. c0+32
-    double* sS = sT + TQ * LDX;      // S   blocks c0   .. c0+32
-    double* sJ = sS + TQ * LDX;      // JJ  modes  c0   .. c0+32
-    double* mDr = sJ + TQ * LDX;     // [n8][LDX]
+    const int TS = 4 * TQ * LDX;     // doubles per stage: psi | T | S | JJ tiles
+    const int nst = p.nstage;
+    double* mDr = smem + nst * TS;   // [n8][LDX]
     double* mD2r = mDr + n8 * LDX;
     double* mDsq = mD2r + n8 * LDX;
 
-    const double* Xb = p.X + (long long)b * p.x_stride;
-    const double* Jb = p.JJ + (long long)b * (K + 1) * n;
-    // all tile loads are asynchronous copies issued back to back (zero fill for masked / padded entries), so the
-    // global-memory latency is paid once per CTA
-    for (int idx = tid; idx < TQ * LDX; idx += nthr) {
-        const int q = idx / LDX, i = idx - q * LDX;
-        const int bp = c0 - 1 + q, bt = c0 + q;
-        const bool in = i < n;
-        const bool okp = in && bp >= 0 && bp < K && !(g.symmetric && (bp & 1) == 0);
-        const bool okt = in && bt < K && !(g.symmetric && (bt & 1) == 1);
-        const bool okj = in && bt <= K;
-        cp_async8_zfill(&sP[idx], okp ? Xb + (long long)bp * n + i : Xb, okp);
-        cp_async8_zfill(&sT[idx], okt ? Xb + (long long)N + (long long)bt * n + i : Xb, okt);
-        cp_async8_zfill(&sS[idx], okt ? Xb + 2LL * N + (long long)bt * n + i : Xb, okt);
-        cp_async8_zfill(&sJ[idx], okj ? Jb + (long long)bt * n + i : Jb, okj);
-    }
+    // all tile loads are asynchronous copies issued back to back (zero fill for masked / padded entries)
+    auto issue = [&](int tile, int stage) {
+        const int b = tile / nkt, c0 = (tile - b * nkt) * PREP_TC;
+        double* sP = smem + stage * TS;  // psi blocks c0-1 .. c0+31   (q = 0..32), row stride LDX, padded entries zero
+        double* sT = sP + TQ * LDX;      // T   blocks c0   .. c0+32
+        double* sS = sT + TQ * LDX;      // S   blocks c0   .. c0+32
+        double* sJ = sS + TQ * LDX;      // JJ  modes  c0   .. c0+32
+        const double* Xb = p.X + (long long)b * p.x_stride;
+        const double* Jb = p.JJ + (long long)b * (K + 1) * n;
+        for (int idx = tid; idx < TQ * LDX; idx += nthr) {
+            const int q = idx / LDX, i = idx - q * LDX;
+            const int bp = c0 - 1 + q, bt = c0 + q;
+            const bool in = i < n;
+            const bool okp = in && bp >= 0 && bp < K && !(g.symmetric && (bp & 1) == 0);
+            const bool okt = in && bt < K && !(g.symmetric && (bt & 1) == 1);
+            const bool okj = in && bt <= K;
+            cp_async8_zfill(&sP[idx], okp ? Xb + (long long)bp * n + i : Xb, okp);
+            cp_async8_zfill(&sT[idx], okt ? Xb + (long long)N + (long long)bt * n + i : Xb, okt);
+            cp_async8_zfill(&sS[idx], okt ? Xb + 2LL * N + (long long)bt * n + i : Xb, okt);
+            cp_async8_zfill(&sJ[idx], okj ? Jb + (long long)bt * n + i : Jb, okj);
+        }
+    };
     for (int idx = tid; idx < n8 * LDX / 2; idx += nthr) {
         cp_async16(&mDr[2 * idx], p.DrP + 2 * idx);
         cp_async16(&mD2r[2 * idx], p.D2rP + 2 * idx);
         cp_async16(&mDsq[2 * idx], p.DsqP + 2 * idx);
     }
+    int tile = blockIdx.x, stage = 0;
+    if (tile < ntiles) issue(tile, 0);
     cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
 
     const int mt = warp >> 1, nh = warp & 1;
     const bool want_lin = p.lin != nullptr;
-    double dps[2][2] = {}, d2r[2][2] = {}, dsq[2][2] = {}, dT[2][2] = {}, dS[2][2] = {};
-    {
-        const int arow = (mt * 8 + gq) * LDX + tq;
-        // MMA column slot (nl, j) -> sinusoid column of the 16-column half tile: odd columns (odd wavenumbers) in
-        // natural order, even columns class-split like chunk_pos, so that the four lanes sharing an accumulator row
-        // write four consecutive doubles of the tile-major coefficient arrays for both parities
-        int bcol[2];
+    const int i = mt * 8 + gq;
+    const double dtPr = g.dt * g.Pr;
+    const int R9 = 9 * n8;
+    const int LDG = n8 + 2;
+    double* lb = p.lin;
+    const int arow = (mt * 8 + gq) * LDX + tq;
+    // MMA column slot (nl, j) -> sinusoid column of the 16-column half tile: odd columns (odd wavenumbers) in
+    // natural order, even columns class-split like chunk_pos, so that the four lanes sharing an accumulator row
+    // write four consecutive doubles of the tile-major coefficient arrays for both parities
+    int bcol[2];
 #pragma unroll
-        for (int nl = 0; nl < 2; ++nl) {
-            const int e = gq & 1, tt = gq >> 1;
-            const int kloc = (e == 0) ? 2 * tt + nl : 4 * nl + tt;
-            bcol[nl] = (FFTL ? (nh * 16 + nl * 8 + gq) : (nh * 16 + 2 * kloc + e)) * LDX + tq;
+    for (int nl = 0; nl < 2; ++nl) {
+        const int e = gq & 1, tt = gq >> 1;
+        const int kloc = (e == 0) ? 2 * tt + nl : 4 * nl + tt;
+        bcol[nl] = (FFTL ? (nh * 16 + nl * 8 + gq) : (nh * 16 + 2 * kloc + e)) * LDX + tq;
+    }
+
+    for (; tile < ntiles; tile += gridDim.x, stage = (nst == 2 ? stage ^ 1 : 0)) {
+        const int nxt = tile + gridDim.x;
+        if (nst == 2) {
+            if (nxt < ntiles) issue(nxt, stage ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
+        __syncthreads();
+        const int b = tile / nkt, c0 = (tile - b * nkt) * PREP_TC;
+        const double* sP = smem + stage * TS;
+        const double* sT = sP + TQ * LDX;
+        const double* sS = sT + TQ * LDX;
+        const double* sJ = sS + TQ * LDX;
+        double dps[2][2] = {}, d2r[2][2] = {}, dsq[2][2] = {}, dT[2][2] = {}, dS[2][2] = {};
         for (int ks = 0; ks < n8 / 4; ++ks) {
             const double aDr = mDr[arow + ks * 4], aD2r = mD2r[arow + ks * 4], aDsq = mDsq[arow + ks * 4];
 #pragma unroll
@@ -146,84 +177,86 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
                 if (want_lin) mma884(dsq[nl][0], dsq[nl][1], aDsq, sP[o + LDX]);  // psi block c (sine mode c+1)
             }
         }
-    }
-    const int i = mt * 8 + gq;
-    if (i >= n) return;
-    const double ir2 = p.ir2[i], ir4 = p.ir4[i], r2 = p.r2[i], dT0 = p.dT0[i], gb = p.gb[i];
-    const int R9 = 9 * n8;
-    double* cf = p.coef ? p.coef + (long long)b * p.coef_stride : nullptr;
-    double* lb = p.lin;
-    const int LDG = n8 + 2;
-    auto lin_off = [&](int f, int blk) { return (((long long)f * K + blk) * p.bstride + b) * LDG + i; };
-    const double Ra = want_lin ? p.Ra[b] : 0.0, Ras = want_lin ? p.Ras[b] : 0.0;
-    const double dtPr = g.dt * g.Pr;
+        if (i < n) {
+        const double ir2 = p.ir2[i], ir4 = p.ir4[i], r2 = p.r2[i], dT0 = p.dT0[i], gb = p.gb[i];
+        double* cf = p.coef ? p.coef + (long long)b * p.coef_stride : nullptr;
+        auto lin_off = [&](int f, int blk) { return (((long long)f * K + blk) * p.bstride + b) * LDG + i; };
+        const double Ra = want_lin ? p.Ra[b] : 0.0, Ras = want_lin ? p.Ras[b] : 0.0;
 #pragma unroll
-    for (int nl = 0; nl < 2; ++nl) {
-        if (FFTL && p.coef) {
-            // columns (col, col+1) of the accumulator pair; K is even and c0 a multiple of 32, so both are < K together
-            const int col = nh * 16 + nl * 8 + 2 * tq, c = c0 + col;
-            if (c < K) {
-                const double j0 = sJ[col * LDX + i], j1 = sJ[(col + 1) * LDX + i];
-                double2 om, dp;
-                om.x = (c >= 1) ? d2r[nl][0] - (double)c * (ir4 * j0) : 0.0;
-                dp.x = (c >= 1) ? dps[nl][0] : 0.0;
-                om.y = d2r[nl][1] - (double)(c + 1) * (ir4 * j1);
-                dp.y = dps[nl][1];
-                double* r7 = p.coef + ((long long)b * n + i) * 7 * K + c;
-                *reinterpret_cast<double2*>(r7) = make_double2(j0, j1);                       // JT
-                *reinterpret_cast<double2*>(r7 + (long long)K) = dp;                          // Dpsi
-                *reinterpret_cast<double2*>(r7 + 2LL * K) = om;                               // omega
-                *reinterpret_cast<double2*>(r7 + 3LL * K) = make_double2(dT[nl][0], dT[nl][1]);
-                *reinterpret_cast<double2*>(r7 + 4LL * K) = make_double2(dS[nl][0], dS[nl][1]);
-                *reinterpret_cast<double2*>(r7 + 5LL * K) = make_double2(sT[col * LDX + i], sT[(col + 1) * LDX + i]);
-                *reinterpret_cast<double2*>(r7 + 6LL * K) = make_double2(sS[col * LDX + i], sS[(col + 1) * LDX + i]);
+        for (int nl = 0; nl < 2; ++nl) {
+            if (FFTL && p.coef) {
+                // columns (col, col+1) of the accumulator pair; K is even and c0 a multiple of 32, so both are < K together
+                const int col = nh * 16 + nl * 8 + 2 * tq, c = c0 + col;
+                if (c < K) {
+                    const double j0 = sJ[col * LDX + i], j1 = sJ[(col + 1) * LDX + i];
+                    double2 om, dp;
+                    om.x = (c >= 1) ? d2r[nl][0] - (double)c * (ir4 * j0) : 0.0;
+                    dp.x = (c >= 1) ? dps[nl][0] : 0.0;
+                    om.y = d2r[nl][1] - (double)(c + 1) * (ir4 * j1);
+                    dp.y = dps[nl][1];
+                    double* r7 = p.coef + ((long long)b * n + i) * 7 * K + c;
+                    *reinterpret_cast<double2*>(r7) = make_double2(j0, j1);                       // JT
+                    *reinterpret_cast<double2*>(r7 + (long long)K) = dp;                          // Dpsi
+                    *reinterpret_cast<double2*>(r7 + 2LL * K) = om;                               // omega
+                    *reinterpret_cast<double2*>(r7 + 3LL * K) = make_double2(dT[nl][0], dT[nl][1]);
+                    *reinterpret_cast<double2*>(r7 + 4LL * K) = make_double2(dS[nl][0], dS[nl][1]);
+                    *reinterpret_cast<double2*>(r7 + 5LL * K) = make_double2(sT[col * LDX + i], sT[(col + 1) * LDX + i]);
+                    *reinterpret_cast<double2*>(r7 + 6LL * K) = make_double2(sS[col * LDX + i], sS[(col + 1) * LDX + i]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = FFTL ? nh * 16 + nl * 8 + 2 * tq + e
+                                     : nh * 16 + 2 * ((e == 0) ? 2 * tq + nl : 4 * nl + tq) + e;   // see the slot map above
+                const int c = c0 + col;
+                if (c >= K) continue;
+                const double jj = sJ[col * LDX + i];
+                const double tv = sT[col * LDX + i], sv = sS[col * LDX + i];
+                if (FFTL) {
+                    // written above, two adjacent columns per 16-byte store
+                } else if (cf) {
+                    const int kp = chunk_pos(c >> 1, e);  // parity of c is e (c0 is a multiple of 32); position in the chunk
+                    const long long o = (((long long)((kp >> 2) * 2 + e) * R9) + i) * 4 + (kp & 3);
+                    const long long fs = (long long)n8 * 4;
+                    double om = 0.0, dp = 0.0;
+                    if (c >= 1) {
+                        om = d2r[nl][e] - (double)c * (ir4 * jj);
+                        dp = dps[nl][e];
+                    }
+                    cf[0 * fs + o] = jj;                  // JT
+                    cf[1 * fs + o] = (double)c * dp;      // k Dpsi
+                    cf[2 * fs + o] = (double)c * om;      // k omega
+                    cf[3 * fs + o] = dT[nl][e];           // DT
+                    cf[4 * fs + o] = dS[nl][e];           // DS
+                    cf[5 * fs + o] = om;                  // omega
+                    cf[6 * fs + o] = dp;                  // Dpsi
+                    cf[7 * fs + o] = -(double)c * tv;     // -k T
+                    cf[8 * fs + o] = -(double)c * sv;     // -k S
+                }
+                if (lb) {
+                    // psi equation, block c <-> sine mode m = c+1: A2_SINE(psi) + dt Pr G(Ra T - Ra_s S)
+                    const int m = c + 1;
+                    double a2 = dsq[nl][e] - (double)m * (ir2 * sJ[(col + 1) * LDX + i]);
+                    if (m <= K - 1) {
+                        const double w = Ra * sT[(col + 1) * LDX + i] - Ras * sS[(col + 1) * LDX + i];
+                        a2 += dtPr * ((-(double)m * gb) * w);
+                    }
+                    lb[lin_off(0, c)] = a2;
+                    // T, S equations, cosine mode c: r^2 T - dt * dT0 * J_theta(psi)
+                    const double pT0 = dT0 * jj;
+                    lb[lin_off(1, c)] = r2 * tv - g.dt * pT0;
+                    lb[lin_off(2, c)] = r2 * sv - g.dt * pT0;
+                }
             }
         }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int col = FFTL ? nh * 16 + nl * 8 + 2 * tq + e
-                                 : nh * 16 + 2 * ((e == 0) ? 2 * tq + nl : 4 * nl + tq) + e;   // see the slot map above
-            const int c = c0 + col;
-            if (c >= K) continue;
-            const double jj = sJ[col * LDX + i];
-            const double tv = sT[col * LDX + i], sv = sS[col * LDX + i];
-            if (FFTL) {
-                // written above, two adjacent columns per 16-byte store
-            } else if (cf) {
-                const int kp = chunk_pos(c >> 1, e);  // parity of c is e (c0 is a multiple of 32); position in the chunk
-                const long long o = (((long long)((kp >> 2) * 2 + e) * R9) + i) * 4 + (kp & 3);
-                const long long fs = (long long)n8 * 4;
-                double om = 0.0, dp = 0.0;
-                if (c >= 1) {
-                    om = d2r[nl][e] - (double)c * (ir4 * jj);
-                    dp = dps[nl][e];
-                }
-                cf[0 * fs + o] = jj;                  // JT
-                cf[1 * fs + o] = (double)c * dp;      // k Dpsi
-                cf[2 * fs + o] = (double)c * om;      // k omega
-                cf[3 * fs + o] = dT[nl][e];           // DT
-                cf[4 * fs + o] = dS[nl][e];           // DS
-                cf[5 * fs + o] = om;                  // omega
-                cf[6 * fs + o] = dp;                  // Dpsi
-                cf[7 * fs + o] = -(double)c * tv;     // -k T
-                cf[8 * fs + o] = -(double)c * sv;     // -k S
-            }
-            if (lb) {
-                // psi equation, block c <-> sine mode m = c+1: A2_SINE(psi) + dt Pr G(Ra T - Ra_s S)
-                const int m = c + 1;
-                double a2 = dsq[nl][e] - (double)m * (ir2 * sJ[(col + 1) * LDX + i]);
-                if (m <= K - 1) {
-                    const double w = Ra * sT[(col + 1) * LDX + i] - Ras * sS[(col + 1) * LDX + i];
-                    a2 += dtPr * ((-(double)m * gb) * w);
-                }
-                lb[lin_off(0, c)] = a2;
-                // T, S equations, cosine mode c: r^2 T - dt * dT0 * J_theta(psi)
-                const double pT0 = dT0 * jj;
-                lb[lin_off(1, c)] = r2 * tv - g.dt * pT0;
-                lb[lin_off(2, c)] = r2 * sv - g.dt * pT0;
-            }
+        }
+        __syncthreads();   // every read of this stage is done before the copies of the tile after next refill it
+        if (nst == 1) {
+            if (nxt < ntiles) issue(nxt, 0);
+            cp_async_commit();
         }
     }
+    cp_async_wait<0>();
 }
 
 // Generic single-field linear operators of the reference API (sddc_linear_op): in/out [B][K][n].

@@ -297,26 +297,28 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     pp.DrP = pl->DrP; pp.D2rP = pl->D2rP; pp.DsqP = pl->DsqP;
     pp.ir2 = pl->ir2; pp.ir4 = pl->ir4; pp.r2 = pl->r2; pp.dT0 = pl->dT0; pp.gb = pl->gb;
     pp.g = pl->g; pp.B = B;
-    dim3 grid((pl->g.K + PREP_TC - 1) / PREP_TC, B);
+    const int ntiles = ((pl->g.K + PREP_TC - 1) / PREP_TC) * B;
+    pp.nstage = (pl->g.nt8 > 4 && prep_smem_bytes(pl->g.n8, 2) <= SMEM_LIMIT) ? 2 : 1;
+    const size_t smem = prep_smem_bytes(pl->g.n8, pp.nstage);
+    const int grid = pl->g.nt8 <= 4 ? ntiles : std::min(ntiles, pl->num_sms);   // one CTA per tile, or persistent
     StageTimer tm(pl, SDDC_STAGE_PREP, st);
-    const size_t smem = prep_smem_bytes(pl->g.n8);
     if (fftl) {
         switch (pl->g.nt8) {
-            case 3: prep_kernel<3, true><<<grid, 192, smem, st>>>(pp); break;
-            case 4: prep_kernel<4, true><<<grid, 256, smem, st>>>(pp); break;
-            case 5: prep_kernel<5, true><<<grid, 320, smem, st>>>(pp); break;
-            case 6: prep_kernel<6, true><<<grid, 384, smem, st>>>(pp); break;
-            case 7: prep_kernel<7, true><<<grid, 448, smem, st>>>(pp); break;
-            default: prep_kernel<8, true><<<grid, 512, smem, st>>>(pp); break;
+            case 3: prep_kernel<3, true><<<grid, 192, smem, st>>>(pp, ntiles); break;
+            case 4: prep_kernel<4, true><<<grid, 256, smem, st>>>(pp, ntiles); break;
+            case 5: prep_kernel<5, true><<<grid, 320, smem, st>>>(pp, ntiles); break;
+            case 6: prep_kernel<6, true><<<grid, 384, smem, st>>>(pp, ntiles); break;
+            case 7: prep_kernel<7, true><<<grid, 448, smem, st>>>(pp, ntiles); break;
+            default: prep_kernel<8, true><<<grid, 512, smem, st>>>(pp, ntiles); break;
         }
     } else {
         switch (pl->g.nt8) {
-            case 3: prep_kernel<3><<<grid, 192, smem, st>>>(pp); break;
-            case 4: prep_kernel<4><<<grid, 256, smem, st>>>(pp); break;
-            case 5: prep_kernel<5><<<grid, 320, smem, st>>>(pp); break;
-            case 6: prep_kernel<6><<<grid, 384, smem, st>>>(pp); break;
-            case 7: prep_kernel<7><<<grid, 448, smem, st>>>(pp); break;
-            default: prep_kernel<8><<<grid, 512, smem, st>>>(pp); break;
+            case 3: prep_kernel<3><<<grid, 192, smem, st>>>(pp, ntiles); break;
+            case 4: prep_kernel<4><<<grid, 256, smem, st>>>(pp, ntiles); break;
+            case 5: prep_kernel<5><<<grid, 320, smem, st>>>(pp, ntiles); break;
+            case 6: prep_kernel<6><<<grid, 384, smem, st>>>(pp, ntiles); break;
+            case 7: prep_kernel<7><<<grid, 448, smem, st>>>(pp, ntiles); break;
+            default: prep_kernel<8><<<grid, 512, smem, st>>>(pp, ntiles); break;
         }
     }
     pl->launches++;
@@ -813,12 +815,12 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
                 TRY(upload(pl, &pl->ke_tab, kt));
                 TRY(upload(pl, &pl->ke_Wn, kw));
             }
-            TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8)));
-            TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8)));
-            TRY(set_smem(pl, (prep_kernel<5, true>), prep_smem_bytes(n8)));
-            TRY(set_smem(pl, (prep_kernel<6, true>), prep_smem_bytes(n8)));
-            TRY(set_smem(pl, (prep_kernel<7, true>), prep_smem_bytes(n8)));
-            TRY(set_smem(pl, (prep_kernel<8, true>), prep_smem_bytes(n8)));
+            TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<5, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<6, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<7, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<8, true>), prep_smem_bytes(n8, 1)));
         }
     }
     {
@@ -844,12 +846,12 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<8, 3>), pl->solve_hot_smem));
     else TRY(set_smem(pl, (solve_hot_kernel<8, 2>), pl->solve_hot_smem));
     TRY(set_smem(pl, solve_kernel<SOLVE_NTB, false>, pl->solve_smem));
-    TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8)));
-    TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8)));
-    TRY(set_smem(pl, prep_kernel<5>, prep_smem_bytes(n8)));
-    TRY(set_smem(pl, prep_kernel<6>, prep_smem_bytes(n8)));
-    TRY(set_smem(pl, prep_kernel<7>, prep_smem_bytes(n8)));
-    TRY(set_smem(pl, prep_kernel<8>, prep_smem_bytes(n8)));
+    TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8, 1)));
+    TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8, 1)));
+    TRY(set_smem(pl, prep_kernel<5>, prep_smem_bytes(n8, 1)));
+    TRY(set_smem(pl, prep_kernel<6>, prep_smem_bytes(n8, 1)));
+    TRY(set_smem(pl, prep_kernel<7>, prep_smem_bytes(n8, 1)));
+    TRY(set_smem(pl, prep_kernel<8>, prep_smem_bytes(n8, 1)));
     TRY(set_smem(pl, linop_kernel, sizeof(double) * ((size_t)PREP_TC * n + (size_t)n * n8)));
     TRY(set_smem(pl, ke_prep_kernel, sizeof(double) * ((size_t)32 * n + (size_t)n * n8)));
     TRYC(cudaDeviceSynchronize());
