@@ -132,7 +132,7 @@ def _cpu_worker(args):
     orc.set_accel(True)
     op = orc.Operators(N_fm, N_r, PHYS["d"], PHYS["dt"], PHYS["Pr"], PHYS["Tau"])
     X = make_ics(seed, 1, 3 * op.n * op.K)[0]
-    for _ in range(warm):
+    for _ in range(max(warm, 2)):     # the first call compiles the numba loops in this process: never inside the timing
         X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
     t0 = time.perf_counter()
     for _ in range(nsteps):

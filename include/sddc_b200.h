@@ -89,8 +89,10 @@ void sddc_plan_destroy(sddc_plan* plan);
 const char* sddc_last_error(const sddc_plan* plan); /* plan may be NULL: error of the last failed create */
 /* number of this library's kernel launches issued through the plan so far */
 long long sddc_launch_count(const sddc_plan* plan);
-/* kernel-selection facts of a plan: what = 0 second mirror level (quarter-wave split) active, 1 synthesis kernel
- * variant, 2 two-state JVP synthesis available, 3 padded radial size */
+/* kernel-selection facts of a plan: what = 0 second mirror level (quarter-wave split) of the dense transforms active,
+ * 1 dense synthesis kernel variant, 2 dense two-state JVP synthesis available, 3 padded radial size,
+ * 4 grid size M of the FFT formulation of the nonlinear term (N_fm = 128, 256, 512; 0: dense DMMA transforms),
+ * 5 FFT formulation also used for the two-state (JVP) products, 6 finishing stage fused into the FFT kernel */
 int sddc_plan_info(const sddc_plan* plan, int what);
 
 /* Replace one pre-inverted operator stack (which: 0 = A4 / psi, 1 = NAB2 / T, 2 = NAB2 / S) and the effective
