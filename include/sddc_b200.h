@@ -152,6 +152,14 @@ enum sddc_stage {
 int sddc_profile_begin(sddc_plan* plan);
 int sddc_profile_end(sddc_plan* plan, double* ms, int* counts);
 
+/* The loop of Main._Time_Step (Main.py:286-329) device resident: nsteps member-steps from Xin to Xout (caller-owned
+ * device buffers, Xout must not alias Xin) and the diagnostics {|X|, KE, Nu_T, Nu_S, Nu_T(outer), Nu_S(outer)} of every
+ * diag_every-th step into the device buffer diag_hist[nsteps/diag_every][B][6] (diag_every = 0: none). Stream ordered,
+ * allocation free. With the FFT formulation the kinetic energy of step s comes from the spectral rows the prep stage
+ * of step s+1 produces anyway, and steps 2.. skip the scan launch. */
+int sddc_time_step(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
+                   int nsteps, int linear, int diag_every, double* diag_hist, void* stream);
+
 /* Host-buffer variants (blocking; copies included): what a ctypes / NumPy caller binds. */
 int sddc_step_host(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
                    int nsteps, int linear, double* diag_out /* [B][6] or NULL */);

@@ -53,6 +53,7 @@ SYMBOLS = {
     "sddc_transform": (_i, [_i, _dp, _dp, _i, _i, _i, _vp]),
     "sddc_profile_begin": (_i, [_vp]),
     "sddc_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "sddc_time_step": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _i, _i, _i, _dp, _vp]),
     "sddc_step_host": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _i, _i, _dp]),
     "sddc_time_step_host": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _i, _i, _i, _dp, _i, _dp]),
     "sddc_jvp_host": (_i, [_vp, _dp, _dp, _dp, _dp, _dp, _i]),

@@ -975,6 +975,36 @@ int sddc_step(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, 
     return SDDC_OK;
 }
 
+int sddc_time_step(sddc_plan* pl, const double* Xin, double* Xout, const double* Ra, const double* Ras, int B, int nsteps,
+                   int linear, int diag_every, double* diag_hist, void* stream) {
+    int rc = check_batch(pl, B);
+    if (rc) return rc;
+    if (nsteps < 1 || Xin == Xout || diag_every < 0 || (diag_every > 0 && !diag_hist)) {
+        pl->err = "sddc_time_step: nsteps >= 1, Xout must not alias Xin, diag_hist required when diag_every > 0";
+        return SDDC_ERR_INVALID;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool share = pl->fft_M != 0 && pl->ke_M != 0 && !linear;   // see sddc_time_step_host
+    const double* src = Xin;
+    int pending = -1;
+    for (int s = 1; s <= nsteps; ++s) {
+        double* dst = ((nsteps - s + 1) & 1) ? Xout : pl->xtmp;  // the last step lands in Xout
+        if ((rc = run_step_prep(pl, src, Ra, Ras, B, linear != 0, st, s > 1))) return rc;
+        if (pending >= 0) {
+            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, pl->g.K, pl->ir, diag_hist + (size_t)pending * B * 6, B, st))) return rc;
+            pending = -1;
+        }
+        if ((rc = run_step_rest(pl, dst, nullptr, B, linear != 0, st, s < nsteps))) return rc;
+        src = dst;
+        if (diag_every && s % diag_every == 0) {
+            const int r = s / diag_every - 1;
+            if (share && s < nsteps) pending = r;
+            else if ((rc = sddc_diagnostics(pl, src, diag_hist + (size_t)r * B * 6, B, stream))) return rc;
+        }
+    }
+    return SDDC_OK;
+}
+
 int sddc_residual(sddc_plan* pl, const double* X, double* out, const double* Ra, const double* Ras, int B, void* stream) {
     int rc = check_batch(pl, B);
     if (rc) return rc;

@@ -2,7 +2,7 @@
 step, sharded by member over the GPUs of one node.
 
 Members never exchange state, so there is no data-path collective; the only communication is the all-gather of
-the per-step diagnostics [B_local, 4] -> [B, 4] (Norm, KE, Nu_T, Nu_S: the four scalars Main._Time_Step appends
+the per-step diagnostics [B_local, 4] -> [B, 4] (one collective per run for the whole history) (Norm, KE, Nu_T, Nu_S: the four scalars Main._Time_Step appends
 per step, Main.py:292-295) and, on request, of the final states.  One process per GPU (torchrun); with a single
 process everything degenerates to the local plan.
 """
@@ -74,18 +74,14 @@ class Ensemble:
         """Advance the local members n_steps; every `diag_every` steps (0 = never) compute the diagnostics of all
         local members and all-gather them.  Returns (X_new, history) with history [n_records, B, 4] on every rank
         (the ensemble analogue of Scalar_Data/{Norm,KE,Nu_T,Nu_S}, Main.py:310-315)."""
-        hist = []
-        cur = X
-        done = 0
-        while done < n_steps:
-            k = n_steps - done if not diag_every else min(diag_every, n_steps - done)
-            cur = self.plan.step(cur, self.Ra, self.Ra_s, nsteps=k, linear=linear)
-            done += k
-            if diag_every:
-                d = self.plan.diagnostics(cur)[:, :4]
-                hist.append(gather_rows(d, self.n_members, self.group))
-        history = torch.stack(hist) if hist else torch.empty((0, self.n_members, 4), dtype=torch.float64,
-                                                             device=self.plan.device)
+        if not diag_every:
+            cur = self.plan.step(X, self.Ra, self.Ra_s, nsteps=n_steps, linear=linear)
+            return cur, torch.empty((0, self.n_members, 4), dtype=torch.float64, device=self.plan.device)
+        # one device-resident call for the whole run, one collective for the whole history: the records of the local
+        # members [n_records, B_local, 4] are gathered member-major and put back in record-major order
+        cur, hist = self.plan.time_step(X, self.Ra, self.Ra_s, n_steps, diag_every=diag_every, linear=linear)
+        local = hist[:, :, :4].permute(1, 0, 2).contiguous()                 # [B_local, n_records, 4]
+        history = gather_rows(local, self.n_members, self.group).permute(1, 0, 2).contiguous()
         return cur, history
 
     def gather_states(self, X):

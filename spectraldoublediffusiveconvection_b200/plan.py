@@ -182,6 +182,21 @@ class EnsemblePlan:
                                        int(nsteps), int(bool(linear)), self._stream()))
         return out
 
+    def time_step(self, X, Ra, Ra_s, nsteps, diag_every=1, linear=False, out=None):
+        """The loop of Main._Time_Step (Main.py:286-329), device resident: nsteps member-steps and the diagnostics of
+        every diag_every-th step.  Returns (X_new, history [nsteps // diag_every, B, 6]) as device tensors; one
+        stream-ordered C-ABI call (the kinetic energy of step s rides on the prep stage of step s+1)."""
+        X = self._in(X, 3 * self.N)
+        B = X.shape[0]
+        Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
+        out = torch.empty_like(X) if out is None else out
+        nrec = int(nsteps) // int(diag_every) if diag_every else 0
+        hist = torch.empty((nrec, B, 6), dtype=torch.float64, device=self.device)
+        self._check(self.lib.sddc_time_step(self._h, X.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
+                                            int(nsteps), int(bool(linear)), int(diag_every),
+                                            hist.data_ptr() if nrec else None, self._stream()))
+        return out, hist
+
     def residual(self, X, Ra, Ra_s, out=None):
         X = self._in(X, 3 * self.N)
         B = X.shape[0]

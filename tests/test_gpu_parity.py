@@ -262,6 +262,29 @@ def test_time_step_host_shares_prep_with_diagnostics(sym):
     pl.close()
 
 
+@pytest.mark.parametrize("K,N_r", [(128, 14), (32, 20)])
+def test_device_time_step_matches_step_plus_diagnostics(K, N_r):
+    """sddc_time_step (device resident, diagnostics history on the device) == step + diagnostics per step, for the FFT
+    formulation (shared prep stage) and the dense one."""
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    B, nsteps = 3, 7
+    pl = EnsemblePlan(K, N_r, 0.5, 5e-3, 1.0, 0.5, max_batch=B)
+    rng = np.random.default_rng(11)
+    X = _dev(rng.random((B, 3 * pl.N)) * 1e-2)
+    Ra, Ra_s = _dev(np.linspace(2000.0, 4000.0, B)), _dev(np.linspace(0.0, 200.0, B))
+    out, hist = pl.time_step(X, Ra, Ra_s, nsteps, diag_every=2)
+    assert hist.shape == (3, B, 6)
+    cur = X
+    for s in range(1, nsteps + 1):
+        cur = pl.step(cur, Ra, Ra_s)
+        if s % 2 == 0:
+            assert np.allclose(hist[s // 2 - 1].cpu().numpy(), pl.diagnostics(cur).cpu().numpy(), rtol=1e-11, atol=0.0), s
+    assert torch.equal(out, cur)
+    out0, hist0 = pl.time_step(X, Ra, Ra_s, 3, diag_every=0)
+    assert hist0.shape[0] == 0 and torch.equal(out0, pl.step(X, Ra, Ra_s, nsteps=3))
+    pl.close()
+
+
 def test_step_is_cuda_graph_capturable():
     """The device entry points are allocation-free and stream-ordered: a member-step can be captured in a CUDA graph
     and replayed (include/sddc_b200.h contract)."""
