@@ -97,6 +97,8 @@ struct sddc_plan {
     size_t ana_smem = 0;
     size_t solve_smem = 0, solve_hot_smem = 0;
     int solve_nsl = 3, solve_hot_nsl = 3;
+    bool solve_cluster = false; // 2-CTA clusters with operator multicast in the hot back-substitution (SDDC_SOLVE_CLUSTER=1);
+                                // measured slower (0.095 -> 0.217 ms at B = 512): opt-in only
     double dt_psi = 0, dt_T = 0, dt_S = 0;  // effective time steps of the three operator stacks
     // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
     bool profiling = false;
@@ -469,9 +471,18 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     if (sm) {
         // hot path: all three fields from the solve-major buffers (k_solve_hot.cuh)
         const int npsi = (B + 8 * SOLVE_NTB_PSI - 1) / (8 * SOLVE_NTB_PSI), nts = (B + 8 * SOLVE_NTB_TS - 1) / (8 * SOLVE_NTB_TS);
-        const int nblk = 2 * npsi + 4 * nts, nthr = 32 * (pl->g.nt8 + 1);
+        const int nthr = 32 * (pl->g.nt8 + 1);
         const size_t smb = pl->solve_hot_smem;
         const bool n3 = pl->solve_hot_nsl == 3;
+        if (pl->solve_cluster && pl->g.nt8 == 4 && n3) {
+            // pairs of member tiles as 2-CTA clusters sharing one multicast copy of every operator block
+            const int pp = (npsi + 1) / 2, pt = (nts + 1) / 2;
+            solve_hot_cluster_kernel<4, 3><<<2 * (2 * pp + 4 * pt), nthr, smb, st>>>(sp, pp);
+            pl->launches++;
+            PLAN_CUDA(pl, cudaGetLastError());
+            return SDDC_OK;
+        }
+        const int nblk = 2 * npsi + 4 * nts;
         switch (pl->g.nt8) {
             case 3: if (n3) solve_hot_kernel<3, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<3, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
             case 4: if (n3) solve_hot_kernel<4, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<4, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
@@ -716,7 +727,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(dev_alloc(pl, &pl->coef, Bm * pl->coef_member_stride, true));   // padded rows / columns stay zero
     TRY(dev_alloc(pl, &pl->coef1, Bm * pl->coef_member_stride, true));  // second set: dv (JVP) or KE rows
     TRY(dev_alloc(pl, &pl->prd, Bm * 3 * 2 * n8 * g.Mhp, true));
-    pl->bstride = (long long)round_up(cfg->max_batch, 16);
+    pl->bstride = (long long)round_up(cfg->max_batch, 32);   // a cluster pair of 16-member tiles never leaves its slab
     TRY(dev_alloc(pl, &pl->lin_sm, (size_t)3 * K * pl->bstride * (n8 + 2), true));
     TRY(dev_alloc(pl, &pl->f_sm, (size_t)3 * K * pl->bstride * (n8 + 2), true));
     TRY(dev_alloc(pl, &pl->lin, Bm * 3 * g.N, false));
@@ -833,6 +844,11 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->solve_smem = solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double);
     pl->solve_hot_nsl = solve_hot_smem_bytes(n8, 3) <= SMEM_LIMIT ? 3 : 2;
     pl->solve_hot_smem = solve_hot_smem_bytes(n8, pl->solve_hot_nsl);
+    {
+        const char* ce = getenv("SDDC_SOLVE_CLUSTER");
+        pl->solve_cluster = ce && ce[0] == '1';
+        if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_cluster_kernel<4, 3>), pl->solve_hot_smem));
+    }
     if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<3, 3>), pl->solve_hot_smem));
     else TRY(set_smem(pl, (solve_hot_kernel<3, 2>), pl->solve_hot_smem));
     if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<4, 3>), pl->solve_hot_smem));
