@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--members-per-gpu", type=int, default=512)
     ap.add_argument("--N_r", type=int, default=30)
     ap.add_argument("--N_fm", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: the same K as --steps, at most 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -377,7 +377,7 @@ def run_ours(a):
     # ---- end to end through the C ABI with HOST buffers (pinned): the ensemble analogue of Main._Time_Step
     # (Main.py:286-329): state H2D, K_e member-steps, the diagnostics of EVERY step copied back to the host, the
     # state checkpointed to the host every K_e/10 steps (the reference's N_save cadence) and at the end.
-    ne = max(10, a.e2e_steps)
+    ne = max(10, a.e2e_steps if a.e2e_steps > 0 else min(a.steps, 1000))   # the same K steps as the device-resident region
     ck = max(1, ne // 10)
     xin, xout = plan.pinned((Bl, W)), plan.pinned((Bl, W))
     hist = plan.pinned((ne, Bl, 6))

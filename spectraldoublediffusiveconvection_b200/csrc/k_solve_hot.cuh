@@ -40,7 +40,8 @@ __host__ inline size_t solve_hot_smem_bytes(int n8, int nsl) {
 // both CTAs have released it (remote mbarrier arrivals).  MEASURED (B200, B = 512): results identical, but 0.217 ms
 // against 0.095 ms for independent CTAs -- the chain is bound by per-step latency, and coupling two CTAs through
 // cluster-scope barriers and multicast delivery adds to exactly that.  Kept as an opt-in (SDDC_SOLVE_CLUSTER=1).
-template <int NT8, int NSL, int NTB, bool PSI, int CS = 1>
+// SUB: the call carries a subtrahend (residual / JVP); a compile-time switch so that the plain step keeps its registers
+template <int NT8, int NSL, int NTB, bool PSI, int CS = 1, bool SUB = true>
 __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* smem, uint64_t* bar_full,
                                                 uint64_t* bar_empty, int fld, int which, int b0) {
     constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
@@ -55,7 +56,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     double* sG = sR + (size_t)2 * NM * BT * LDL;    // [NSL][2][BT][LDG]   (lin, F)
     const int i = warp * 8 + gq;
     const bool row_ok = i < n;
-    const bool has_f = p.fnl != nullptr, has_sub = p.sub != nullptr;
+    const bool has_f = p.fnl != nullptr, has_sub = SUB && p.sub != nullptr;
 
     const int j0 = PSI ? (K - which) : (which == 0 ? K - 2 : K - 1);
     const int jend = PSI ? 1 : 0;
@@ -152,13 +153,24 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     const double dt = PSI ? p.dt_psi : (fld == 1 ? p.dt_T : p.dt_S);
     const double ir2 = (PSI && row_ok) ? p.ir2[i] : 0.0, ir4 = (PSI && row_ok) ? p.ir4[i] : 0.0;
 
+    // subtrahend of the residual / JVP (state layout, scattered 8-byte loads from HBM): fetched three chain steps ahead --
+    // ncu showed the consumers stalled on these loads (long scoreboard 6.5 per issue against 1.6 without a subtrahend)
+    double subq[3][NE];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) subq[d][e] = (has_sub && ok[e] && d < nsteps) ? outp[e][sub_delta + d * rstep] : 0.0;
     int st = 0, ph = 0;
     for (int step = 0; step < nsteps; ++step) {
         const int j = j0 - 2 * step;
         if (has_sub) {
 #pragma unroll
-            for (int e = 0; e < NE; ++e)
-                if (ok[e]) subv[e] = outp[e][sub_delta];
+            for (int e = 0; e < NE; ++e) {
+                subv[e] = subq[0][e];
+                subq[0][e] = subq[1][e];
+                subq[1][e] = subq[2][e];
+                if (ok[e] && step + 3 < nsteps) subq[2][e] = outp[e][sub_delta + 3 * rstep];
+            }
         }
         mbar_wait(&bar_full[st], ph);
         const double* gt = gT + st * (2 * GT);
@@ -281,17 +293,17 @@ solve_hot_cluster_kernel(SolveParams p, int npsi_pairs) {
     }
 }
 
-template <int NT8, int NSL>
+template <int NT8, int NSL, bool SUB = false>
 __global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
     const int bid = blockIdx.x;
     if (bid < 2 * npsi_tiles) {
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, 1, SUB>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
     } else {
         const int r = bid - 2 * npsi_tiles;
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
-                                                  (r >> 2) * 8 * SOLVE_NTB_TS);
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, 1, SUB>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
+                                                          (r >> 2) * 8 * SOLVE_NTB_TS);
     }
 }
 

@@ -483,15 +483,19 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
             return SDDC_OK;
         }
         const int nblk = 2 * npsi + 4 * nts;
+#define SDDC_LAUNCH_SOLVE_HOT(NT)                                                                                 \
+    if (sub) { if (n3) solve_hot_kernel<NT, 3, true><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, true><<<nblk, nthr, smb, st>>>(sp, npsi); } \
+    else { if (n3) solve_hot_kernel<NT, 3, false><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, false><<<nblk, nthr, smb, st>>>(sp, npsi); }
         switch (pl->g.nt8) {
-            case 3: if (n3) solve_hot_kernel<3, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<3, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
-            case 4: if (n3) solve_hot_kernel<4, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<4, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
-            case 5: if (n3) solve_hot_kernel<5, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<5, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
-            case 6: if (n3) solve_hot_kernel<6, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<6, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
-            case 7: if (n3) solve_hot_kernel<7, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<7, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
-            case 8: if (n3) solve_hot_kernel<8, 3><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<8, 2><<<nblk, nthr, smb, st>>>(sp, npsi); break;
+            case 3: SDDC_LAUNCH_SOLVE_HOT(3) break;
+            case 4: SDDC_LAUNCH_SOLVE_HOT(4) break;
+            case 5: SDDC_LAUNCH_SOLVE_HOT(5) break;
+            case 6: SDDC_LAUNCH_SOLVE_HOT(6) break;
+            case 7: SDDC_LAUNCH_SOLVE_HOT(7) break;
+            case 8: SDDC_LAUNCH_SOLVE_HOT(8) break;
             default: pl->err = "unsupported radial tile count"; return SDDC_ERR_UNSUPPORTED;
         }
+#undef SDDC_LAUNCH_SOLVE_HOT
     } else solve_kernel<SOLVE_NTB, false><<<grid, 32 * (pl->g.nt8 + 1), pl->solve_smem, st>>>(sp);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
@@ -849,18 +853,18 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         pl->solve_cluster = ce && ce[0] == '1';
         if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_cluster_kernel<4, 3>), pl->solve_hot_smem));
     }
-    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<3, 3>), pl->solve_hot_smem));
-    else TRY(set_smem(pl, (solve_hot_kernel<3, 2>), pl->solve_hot_smem));
-    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<4, 3>), pl->solve_hot_smem));
-    else TRY(set_smem(pl, (solve_hot_kernel<4, 2>), pl->solve_hot_smem));
-    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<5, 3>), pl->solve_hot_smem));
-    else TRY(set_smem(pl, (solve_hot_kernel<5, 2>), pl->solve_hot_smem));
-    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<6, 3>), pl->solve_hot_smem));
-    else TRY(set_smem(pl, (solve_hot_kernel<6, 2>), pl->solve_hot_smem));
-    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<7, 3>), pl->solve_hot_smem));
-    else TRY(set_smem(pl, (solve_hot_kernel<7, 2>), pl->solve_hot_smem));
-    if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_kernel<8, 3>), pl->solve_hot_smem));
-    else TRY(set_smem(pl, (solve_hot_kernel<8, 2>), pl->solve_hot_smem));
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<3, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<3, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<4, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<4, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 2, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<5, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 3, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<5, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 2, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<6, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 3, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<6, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 2, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<7, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 3, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<7, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 2, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<8, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 3, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<8, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 2, true>), pl->solve_hot_smem)); }
     TRY(set_smem(pl, solve_kernel<SOLVE_NTB, false>, pl->solve_smem));
     TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8, 1)));
     TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8, 1)));
