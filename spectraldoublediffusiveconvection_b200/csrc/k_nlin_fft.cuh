@@ -249,7 +249,7 @@ __host__ __device__ inline size_t post_smem_bytes(int n, int n8) {
 // Persistent: CTA c takes the tiles (member b, 32 sinusoid columns) c, c + gridDim.x, ...; the four product tiles of the
 // next tile are in flight (cp.async, two stages) while the current one is contracted with Dr and stored.
 __global__ void __launch_bounds__(256) post_kernel(PostParams p, int ntiles) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(128) double smem[];
     const Geo& g = p.g;
     const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDT = POST_TC + 1;
     const int tid = threadIdx.x, nkt = (K + POST_TC - 1) / POST_TC, TS = 4 * n * LDT;
