@@ -109,3 +109,55 @@ def test_fft_kinetic_energy_rows(emul, K):
     wt[1:] += 0.5 * dth
     ref = ((orc.IDCT(a, n=M3) ** 2 + orc.IDST(b, n=M3) ** 2) * (wt * np.sin(th))[None, :]).sum(axis=1)
     assert np.abs(out / ref - 1).max() < 1e-13
+
+
+def _at(j, c):
+    """fft_core.h at(): element c of block j of a plane."""
+    return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7))
+
+
+def _wavefronts(addrs):
+    """Shared-memory wavefronts of one 64-bit warp access (two half-warps; bank = address mod 16 in doubles)."""
+    tot = 0
+    for h in range(2):
+        lanes = {a for a in addrs[16 * h:16 * h + 16] if a is not None}
+        if lanes:
+            banks = {}
+            for a in lanes:
+                banks.setdefault(a % 16, set()).add(a)
+            tot += max(len(v) for v in banks.values())
+    return tot
+
+
+@pytest.mark.parametrize("M", [384, 768])
+def test_shared_memory_layout_is_conflict_free(M):
+    """The XOR-swizzled block layout of fft_core.h keeps the radix-8, radix-RD and packing passes free of bank
+    conflicts and the radix-6 pass within 4/3 of the ideal wavefront count."""
+    NBLK, L, RD, NT = M // 8, M // 6, M // 48, (128 if M == 768 else 64)
+    for warp in range(NT // 32):
+        lanes = [warp * 32 + l for l in range(32)]
+        # radix-8 pass: lane <-> block (five transforms back to back), one element index at a time
+        for r in range(0, 5 * NBLK, NT):
+            us = [t + r if t + r < 5 * NBLK else None for t in lanes]
+            for c in range(8):
+                ad = [None if u is None else 2 * (u // NBLK) * M + _at(u % NBLK, c) for u in us]
+                assert _wavefronts(ad) == sum(1 for h in range(2) if any(a is not None for a in ad[16 * h:16 * h + 16]))
+        # radix-RD pass: lane <-> (k2, element a), blocks 6 d + k2
+        for r in range(0, 5 * 48, NT):
+            us = [t + r if t + r < 5 * 48 else None for t in lanes]
+            for d in range(RD):
+                ad = [None if u is None else 2 * (u // 48) * M + _at(6 * d + ((u % 48) >> 3), (u % 48) & 7) for u in us]
+                assert _wavefronts(ad) == sum(1 for h in range(2) if any(a is not None for a in ad[16 * h:16 * h + 16]))
+        # packing: consecutive wavenumbers k -> consecutive blocks
+        for r in range(0, M // 2 + 1, NT):
+            ad = [_at((t + r) % NBLK, (t + r) // NBLK) if t + r <= M // 2 else None for t in lanes]
+            assert _wavefronts(ad) == sum(1 for h in range(2) if any(a is not None for a in ad[16 * h:16 * h + 16]))
+        # radix-6 pass: lane <-> column n1, blocks 6 (n1 >> 3) + m: at most 2-way, 4/3 of ideal overall
+        got = ideal = 0
+        for r in range(0, L, NT):
+            ns = [t + r if t + r < L else None for t in lanes]
+            for m in range(6):
+                ad = [None if n is None else _at(6 * (n >> 3) + m, n & 7) for n in ns]
+                got += _wavefronts(ad)
+                ideal += sum(1 for h in range(2) if any(a is not None for a in ad[16 * h:16 * h + 16]))
+        assert got <= ideal * 4 / 3 + 1e-9
