@@ -194,10 +194,13 @@ SDDC_HD int kpos(int k) {
 // MODE 1: base state of the two-state product; the fifth transform packs DS of the base state with DS of the
 //         perturbation row cr2 -- both cosine type -- so that the pair of states needs 9 transforms, not 10.
 // MODE 2: perturbation of the two-state product, transforms 0..3 only.
+// MODE 3 / 4: transforms (0, 1) / (2, 3) of the perturbation alone, written to plane pairs 0, 1 of buf (two-state kernel
+//         that transforms the perturbation two fields at a time, k_nlin_fft.cuh).
 template <int M, int MODE = 0, int NTH = NTW>
 SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ buf, const Tables& tb,
                    const double* __restrict__ cr2 = nullptr) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NQ = MODE == 2 ? 4 : 5;
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
+    constexpr int QLO = MODE == 4 ? 2 : 0, NQ = MODE == 2 ? 4 : MODE == 3 ? 2 : MODE == 4 ? 4 : 5;
     for (int k = t; k <= M / 2; k += NTH) {
         const int kp = M - k;
         const bool hasp = k > 0 && kp < K;  // the mirror index lies inside the truncated spectrum
@@ -217,8 +220,8 @@ SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ bu
         // second cosine-type field of transform 4 (MODE 1): X^b_k = c[k], X^b_{M-k} = c[M-k]
         const double c2 = MODE == 1 ? cr2[4 * K + k] : 0.0, c2p = (MODE == 1 && hasp) ? cr2[4 * K + kp] : 0.0;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            double* re = buf + (2 * q) * PL;
+        for (int q = QLO; q < NQ; ++q) {
+            double* re = buf + (2 * (q - QLO)) * PL;
             double* im = re + PL;
             // X^b at k and at M-k: a sine-type field is stored reversed (X_k = s_{M-k})
             const double xb_k = (MODE == 1 && q == 4) ? c2 : bp[q], xb_kp = (MODE == 1 && q == 4) ? c2p : b[q];
@@ -418,6 +421,86 @@ SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
                 re[pos[k2]] = y[k2].r;
                 im[pos[k2]] = y[k2].i;
             }
+        }
+    }
+}
+
+// ---- two-state products with the perturbation transformed two fields at a time ------------------------------------------
+// Planes: 0..9 base state (transform 4 packs DS of base and perturbation, build MODE 1), 10..13 the current pair of
+// perturbation transforms.  One column n1 per thread (L == threads per worker); what a thread carries from the first
+// pair to the second lives in its registers.
+struct Dfx2State {
+    double jt[6], dp[6], P1[6], P2[6];
+};
+
+// after the first round of inverse passes: base grid values (written back in place) and the pair (JT'|om'), (kDpsi'|Dpsi')
+template <int M>
+SDDC_HD void dfx2_first(int t, double* __restrict__ buf, const Tables& tb, Dfx2State& s) {
+    constexpr int PL = Cfg<M>::PL;
+    const int n1 = t;
+    int pos[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        C z[6];
+        inv6<M>(buf + 2 * q * PL, buf + (2 * q + 1) * PL, pos, n1, tb, z);
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+            buf[2 * q * PL + pos[m]] = z[m].r;
+            buf[(2 * q + 1) * PL + pos[m]] = z[m].i;
+        }
+    }
+    auto bg = [&](int plane, int m) { return buf[plane * PL + pos[m]]; };
+    enum { JT = 0, OM = 1, KDP = 2 };
+    C z0[6], z1[6];
+    inv6<M>(buf + 10 * PL, buf + 11 * PL, pos, n1, tb, z0);  // JT' | omega'
+    inv6<M>(buf + 12 * PL, buf + 13 * PL, pos, n1, tb, z1);  // k Dpsi' | Dpsi'
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        s.jt[m] = z0[m].r;
+        s.dp[m] = z1[m].i;
+        s.P1[m] = bg(JT, m) * z0[m].i + s.jt[m] * bg(OM, m);
+        s.P2[m] = bg(KDP, m) * z0[m].i + z1[m].r * bg(OM, m);
+    }
+}
+
+// after the second round: the pair (k om'|-k T'), (DT'|-k S'), the remaining products (Matrix_Operators.py:884-887) and the
+// first forward pass into planes 0..3
+template <int M>
+SDDC_HD void dfx2_second(int t, double* __restrict__ buf, const Tables& tb, Dfx2State& s) {
+    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
+    const int n1 = t;
+    int pos[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
+    auto bg = [&](int plane, int m) { return buf[plane * PL + pos[m]]; };
+    enum { JT = 0, DP = 3, KOM = 4, KT = 5, DT = 6, KS = 7, DS = 8, DSP = 9 };
+    C z2[6], z3[6];
+    inv6<M>(buf + 10 * PL, buf + 11 * PL, pos, n1, tb, z2);  // k omega' | -k T'
+    inv6<M>(buf + 12 * PL, buf + 13 * PL, pos, n1, tb, z3);  // DT' | -k S'
+    double NT[6], NS[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        s.P2[m] += bg(DP, m) * z2[m].r + s.dp[m] * bg(KOM, m);
+        NT[m] = -(s.dp[m] * bg(KT, m) + bg(DP, m) * z2[m].i);
+        NT[m] += s.jt[m] * bg(DT, m) + bg(JT, m) * z3[m].r;
+        NS[m] = -(s.dp[m] * bg(KS, m) + bg(DP, m) * z3[m].i);
+        NS[m] += s.jt[m] * bg(DS, m) + bg(JT, m) * bg(DSP, m);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        C x[6], y[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) x[m] = q == 0 ? C{s.P1[m], s.P2[m]} : C{NT[m], NS[m]};
+        dft6<-1>(x, y);
+        double* re = buf + 2 * q * PL;
+        double* im = re + PL;
+#pragma unroll
+        for (int k2 = 0; k2 < 6; ++k2) {
+            if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6c[(k2 - 1) * L + n1], tb.t6s[(k2 - 1) * L + n1]);
+            re[pos[k2]] = y[k2].r;
+            im[pos[k2]] = y[k2].i;
         }
     }
 }

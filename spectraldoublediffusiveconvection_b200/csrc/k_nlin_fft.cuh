@@ -180,6 +180,77 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     }
 }
 
+// Two-state (JVP) kernel with the perturbation transformed two fields at a time against the resident base planes:
+// 14 planes per worker instead of 18, so five 64-thread workers fit at M = 384 (four with the one-round kernel) and two
+// 128-thread workers at M = 768 (one).  One radix-6 column per thread (NT == M / 6); what a thread carries between the
+// two rounds (JT', Dpsi' and the partial products at its six points) stays in registers across the barriers.  Same
+// arithmetic as nlin_fft_kernel<M, true>: results are bit-identical (tests/test_fft_core_cpu.py).
+template <int M>
+__host__ __device__ constexpr size_t nlin_fft2_worker_doubles() { return (size_t)14 * fftp::Cfg<M>::PL; }
+template <int M>
+__host__ __device__ constexpr size_t nlin_fft2_smem_bytes(int nw) {
+    return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + (size_t)nw * nlin_fft2_worker_doubles<M>());
+}
+
+template <int M, int NW, int NT>
+__global__ void __launch_bounds__(NT * NW, 1) nlin_fft2_kernel(NlinFftParams p) {
+    using namespace fftp;
+    static_assert(NT == Cfg<M>::L, "one radix-6 column per thread");
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ int s_row[NW];
+    double* stab = smem;
+    for (int i = threadIdx.x; i < tab_doubles<M>(); i += NT * NW) stab[i] = p.tab[i];
+    __syncthreads();
+    const Tables tb = make_tables<M>(stab);
+    const int w = threadIdx.x / NT, t = threadIdx.x % NT;
+    double* buf = smem + nlin_fft_tab_pad<M>() + (size_t)w * nlin_fft2_worker_doubles<M>();
+    double* pair = buf + 10 * PL;
+    C tw[Cfg<M>::RD];
+    load_tw<M>(t, tb, tw);
+    const int stride = gridDim.x * NW;
+    for (;;) {
+        if (t == 0) s_row[w] = atomicAdd(p.next_row, 1);
+        worker_sync<NT>(w);
+        const int row = s_row[w];
+        if (row >= p.nrows) break;
+        const double* r0 = p.coef0 + (size_t)row * 7 * K;
+        const double* r1 = p.coef1 + (size_t)row * 7 * K;
+        build<M, 1, NT>(t, r0, buf, tb, r1);
+        build<M, 3, NT>(t, r1, pair, tb);
+        if (row + stride < p.nrows) {
+            const char* nx0 = reinterpret_cast<const char*>(p.coef0 + (size_t)(row + stride) * 7 * K);
+            const char* nx1 = reinterpret_cast<const char*>(p.coef1 + (size_t)(row + stride) * 7 * K);
+            for (int o = t * 128; o < 7 * K * 8; o += NT * 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx0 + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx1 + o));
+            }
+        }
+        worker_sync<NT>(w);
+        pass_c<M, 7, +1, NT>(t, buf);
+        worker_sync<NT>(w);
+        pass_d<M, 7, +1, NT>(t, buf, tw);
+        worker_sync<NT>(w);
+        Dfx2State st;
+        dfx2_first<M>(t, buf, tb, st);
+        worker_sync<NT>(w);                 // every column of the first pair is consumed before its planes are refilled
+        build<M, 4, NT>(t, r1, pair, tb);
+        worker_sync<NT>(w);
+        pass_c<M, 2, +1, NT>(t, pair);
+        worker_sync<NT>(w);
+        pass_d<M, 2, +1, NT>(t, pair, tw);
+        worker_sync<NT>(w);
+        dfx2_second<M>(t, buf, tb, st);
+        worker_sync<NT>(w);
+        pass_d<M, 2, -1, NT>(t, buf, tw);
+        worker_sync<NT>(w);
+        pass_c<M, 2, -1, NT>(t, buf);
+        worker_sync<NT>(w);
+        post<M, NT>(t, buf, p.spec + (size_t)row * 4 * K, tb);
+        worker_sync<NT>(w);
+    }
+}
+
 // Kinetic energy on the 3K grid (Main.py:71-134) in the FFT formulation: one complex transform per radial row
 // (J_theta(psi)/r and Dr psi packed), weighted sum of squares in the last pass.  kepart[row] = wr[i] * sum_theta.
 struct KeFftParams {

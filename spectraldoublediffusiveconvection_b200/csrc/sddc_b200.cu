@@ -70,6 +70,7 @@ struct sddc_plan {
     // FFT formulation of the nonlinear term (k_nlin_fft.cuh): available for N_fm = 128, 256, 512
     int fft_M = 0;              // 3 N_fm / 2 when the FFT path is active, else 0
     bool fft_dfx = false;       // two-state (JVP) variant available
+    bool fft_dfx2 = true;       // ... with the perturbation transformed two fields at a time (M = 384, 768; SDDC_DFX2=0: off)
     int ke_M = 0;               // 3 N_fm when the kinetic-energy synthesis runs as an FFT (N_fm = 128, 256), else 0
     double *ke_tab = nullptr, *ke_Wn = nullptr;
     bool fft_fuse = false;      // finishing stage (post) fused into the FFT kernel (SDDC_FUSE_POST=1)
@@ -395,6 +396,8 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
     if (set_attr) {
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD, NTD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        if (M == 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft2_kernel<384, 5, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        if (M == 768) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft2_kernel<768, 2, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
     const int n = pl->g.n, n8 = pl->g.n8;
@@ -402,7 +405,8 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
     int ftc = dfx ? nlin_fft_ftc<MD, true>(n) : nlin_fft_ftc<M, false>(n);
     int drd = nlin_fft_dr_pad(n, n8);
     size_t smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, drd) : nlin_fft_smem_bytes<M, false>(NW, drd);
-    const bool fuse = pl->fft_fuse && ftc > 0 && smem <= SMEM_LIMIT && np.out != nullptr && NT == 64;
+    const bool fuse = pl->fft_fuse && ftc > 0 && smem <= SMEM_LIMIT && np.out != nullptr && NT == 64 &&
+                      !(dfx && pl->fft_dfx2 && M >= 384);
     if (!fuse) {
         np.done = nullptr;
         smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, 0) : nlin_fft_smem_bytes<M, false>(NW, 0);
@@ -413,7 +417,12 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
     PLAN_CUDA(pl, cudaMemsetAsync(pl->fft_done, 0, sizeof(int), st));
     {
         StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-        if (dfx) {
+        if (dfx && pl->fft_dfx2 && M == 384) {
+            // perturbation transformed two fields at a time: 14 planes per worker, five workers per SM
+            nlin_fft2_kernel<384, 5, 64><<<std::min((np.nrows + 4) / 5, pl->num_sms), 320, nlin_fft2_smem_bytes<384>(5), st>>>(np);
+        } else if (dfx && pl->fft_dfx2 && M == 768) {
+            nlin_fft2_kernel<768, 2, 128><<<std::min((np.nrows + 1) / 2, pl->num_sms), 256, nlin_fft2_smem_bytes<768>(2), st>>>(np);
+        } else if (dfx) {
             const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
             nlin_fft_kernel<MD, true, NWD, NTD><<<grid, NTD * NWD, smem, st>>>(np);
         } else {
@@ -795,6 +804,10 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         if (want && (K == 128 || K == 256 || K == 512)) {
             pl->fft_M = g.M;
             pl->fft_dfx = true;
+            {
+                const char* d2 = getenv("SDDC_DFX2");
+                pl->fft_dfx2 = !(d2 && d2[0] == '0');
+            }
             std::vector<double> tab;
             switch (g.M) {
                 case 192: tab.resize(fftp::tab_doubles<192>()); fftp::fill_tables<192>(tab.data()); break;

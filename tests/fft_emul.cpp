@@ -35,6 +35,35 @@ static void run_rows(const double* coef0, const double* coef1, double* out, int 
     }
 }
 
+// the two-state kernel that transforms the perturbation two fields at a time (14 planes per worker)
+template <int M>
+static void run_rows_dfx2(const double* coef0, const double* coef1, double* out, int nrows) {
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NT = Cfg<M>::L;   // one radix-6 column per thread
+    std::vector<double> tab(tab_doubles<M>());
+    fill_tables<M>(tab.data());
+    const Tables tb = make_tables<M>(tab.data());
+    std::vector<double> buf((size_t)14 * PL);
+    std::vector<Dfx2State> st(NT);
+    auto twd = [&](int t, C (&tw)[Cfg<M>::RD]) { load_tw<M>(t, tb, tw); };
+    for (int row = 0; row < nrows; ++row) {
+        for (auto& v : buf) v = 1e300;
+        const double* r0 = coef0 + (size_t)row * 7 * K;
+        const double* r1 = coef1 + (size_t)row * 7 * K;
+        double* pp = buf.data() + 10 * PL;
+        for (int t = 0; t < NT; ++t) { build<M, 1, NT>(t, r0, buf.data(), tb, r1); build<M, 3, NT>(t, r1, pp, tb); }
+        for (int t = 0; t < NT; ++t) pass_c<M, 7, +1, NT>(t, buf.data());
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; twd(t, tw); pass_d<M, 7, +1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) dfx2_first<M>(t, buf.data(), tb, st[t]);
+        for (int t = 0; t < NT; ++t) build<M, 4, NT>(t, r1, pp, tb);
+        for (int t = 0; t < NT; ++t) pass_c<M, 2, +1, NT>(t, pp);
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; twd(t, tw); pass_d<M, 2, +1, NT>(t, pp, tw); }
+        for (int t = 0; t < NT; ++t) dfx2_second<M>(t, buf.data(), tb, st[t]);
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; twd(t, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) pass_c<M, 2, -1, NT>(t, buf.data());
+        for (int t = 0; t < NT; ++t) post<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
+    }
+}
+
 template <int R, int SIGN>
 static double check_dft() {
     C x[R], y[R];
@@ -105,6 +134,15 @@ double fft_emul_butterfly_error() {
     e = std::max(e, check_dft6<+1>());
     e = std::max(e, check_dft6<-1>());
     return e;
+}
+
+// two-state products, perturbation transformed two fields at a time (M = 384, 768)
+int fft_emul_rows_dfx2(int M, const double* coef0, const double* coef1, double* out, int nrows) {
+    switch (M) {
+        case 384: run_rows_dfx2<384>(coef0, coef1, out, nrows); return 0;
+        case 768: run_rows_dfx2<768>(coef0, coef1, out, nrows); return 0;
+        default: return -1;
+    }
 }
 
 // coef0 / coef1: [nrows][7][K]; out: [nrows][4][K].  Returns 0, or -1 for an unsupported grid size.
