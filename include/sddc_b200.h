@@ -40,7 +40,12 @@ typedef struct {
     int max_batch; /* largest B any call will use; scratch is sized for it */
     int device;    /* CUDA device ordinal */
     double dt, Pr, Tau, d;
+    int flags;     /* SDDC_FLAG_* (0: defaults) */
 } sddc_config;
+
+/* Keep the dense DMMA transforms where the FFT formulation of the nonlinear term would be used (N_fm = 128, 256,
+ * 512): lets the tests hold the path every other N_fm takes against the golden vectors of the headline shape. */
+#define SDDC_FLAG_DENSE_TRANSFORMS 1
 
 /* Host-built radial operators, computed with the reference's formulas (cheb_radial, Nabla2, Nabla4,
  * A4_TSTEP_MATS, NAB2_TSTEP_MATS: Matrix_Operators.py:10-76,1014-1030,1089-1112; Main.py:196-222).
@@ -90,9 +95,10 @@ const char* sddc_last_error(const sddc_plan* plan); /* plan may be NULL: error o
 /* number of this library's kernel launches issued through the plan so far */
 long long sddc_launch_count(const sddc_plan* plan);
 /* kernel-selection facts of a plan: what = 0 second mirror level (quarter-wave split) of the dense transforms active,
- * 1 dense synthesis kernel variant, 2 dense two-state JVP synthesis available, 3 padded radial size,
- * 4 grid size M of the FFT formulation of the nonlinear term (N_fm = 128, 256, 512; 0: dense DMMA transforms),
- * 5 FFT formulation also used for the two-state (JVP) products, 6 finishing stage fused into the FFT kernel */
+ * 1 dense synthesis kernel (0 generic, 1 persistent warp-specialised), 2 dense two-state JVP synthesis available,
+ * 3 padded radial size, 4 grid size M of the FFT formulation of the nonlinear term (N_fm = 128, 256, 512; 0: dense
+ * DMMA transforms), 5 FFT formulation also used for the two-state (JVP) products, 6 grid size of the kinetic-energy
+ * FFT (0: dense synthesis) */
 int sddc_plan_info(const sddc_plan* plan, int what);
 
 /* Replace one pre-inverted operator stack (which: 0 = A4 / psi, 1 = NAB2 / T, 2 = NAB2 / S) and the effective

@@ -16,7 +16,11 @@ c_double_p = C.POINTER(C.c_double)
 
 class SddcConfig(C.Structure):
     _fields_ = [("N_fm", C.c_int), ("N_r", C.c_int), ("symmetric", C.c_int), ("max_batch", C.c_int),
-                ("device", C.c_int), ("dt", C.c_double), ("Pr", C.c_double), ("Tau", C.c_double), ("d", C.c_double)]
+                ("device", C.c_int), ("dt", C.c_double), ("Pr", C.c_double), ("Tau", C.c_double), ("d", C.c_double),
+                ("flags", C.c_int)]
+
+
+FLAG_DENSE_TRANSFORMS = 1
 
 
 class SddcOperators(C.Structure):

@@ -66,47 +66,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                  : "memory");
 }
 
-// ---- thread-block cluster helpers (operator multicast of the back-substitution, k_solve_hot.cuh) -------------------
-__device__ __forceinline__ unsigned cluster_ctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release;\nbarrier.cluster.wait.acquire;" ::: "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, unsigned rank) {
-    asm volatile(
-        "{\n"
-        ".reg .b32 ra;\n"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-        "}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
-}
-// wait with cluster-scope acquire (the barrier also receives arrivals from the other CTAs of the cluster)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAITC:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONEC;\n"
-        "bra LAB_WAITC;\n"
-        "DONEC:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// contiguous global -> shared copy delivered to the same offset in every CTA of `mask`; completion is signalled on the
-// mbarrier at the same offset in each destination CTA
-__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar,
-                                                   unsigned short mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-        : "memory");
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -51,6 +51,13 @@ struct Cfg {
     static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16), "supported grids: M = 192, 384, 768");
 };
 SDDC_HD int at(int j, int c) { return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7)); }
+// offset of the (re, im) plane pair of transform q inside a worker's buffer.  Odd pairs are shifted by half a bank
+// period: a half-warp whose lanes straddle two transforms (blocks .., 23, 24 of pair q | blocks 1, 2, .. of pair q + 1)
+// then still hits 16 distinct banks.
+template <int M>
+SDDC_HD constexpr int pair_off(int q) { return q * (2 * Cfg<M>::PL + 8); }   // 2 PL is a multiple of 16
+template <int M>
+SDDC_HD constexpr int pairs_doubles(int nq) { return nq * (2 * Cfg<M>::PL + 8); }
 
 // table sizes (doubles): wk cos | wk sin | t6 cos | t6 sin | tL cos | tL sin
 template <int M> SDDC_HD constexpr int tab_wk_doubles() { return M / 2 + 1; }
@@ -280,7 +287,7 @@ SDDC_HD void pass_d(int t, double* __restrict__ buf, const C (&tw)[Cfg<M>::RD]) 
     constexpr int RD = Cfg<M>::RD, PL = Cfg<M>::PL;
     for (int u = t; u < NF * 48; u += NTH) {
         const int q = u / 48, rem = u - q * 48, k2 = rem >> 3, a = rem & 7;
-        double* re = buf + (2 * q) * PL;
+        double* re = buf + pair_off<M>(q);
         double* im = re + PL;
         int o[RD];
 #pragma unroll

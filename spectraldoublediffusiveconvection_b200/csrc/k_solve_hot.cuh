@@ -32,16 +32,8 @@ __host__ inline size_t solve_hot_smem_bytes(int n8, int nsl) {
     return sizeof(double) * (a > b ? a : b);
 }
 
-// CS = CTAs per cluster.  With CS = 2 the two CTAs of a cluster run the same chain (field, parity) on neighbouring
-// member tiles in lock step, and the operator blocks {L_inv_j (, L_inv_j @ D2)} -- identical for both -- are fetched
-// once per cluster: CTA 0 issues one multicast TMA copy that lands in both shared memories.  The kernel streams every
-// operator of its chain through every CTA (0.9 GB of L2 -> SM traffic per launch at B = 512, at the L2 throughput cap),
-// so halving that traffic was expected to shorten the launch.  CTA 0 refills a stage only after the consumer warps of
-// both CTAs have released it (remote mbarrier arrivals).  MEASURED (B200, B = 512): results identical, but 0.217 ms
-// against 0.095 ms for independent CTAs -- the chain is bound by per-step latency, and coupling two CTAs through
-// cluster-scope barriers and multicast delivery adds to exactly that.  Kept as an opt-in (SDDC_SOLVE_CLUSTER=1).
 // SUB: the call carries a subtrahend (residual / JVP); a compile-time switch so that the plain step keeps its registers
-template <int NT8, int NSL, int NTB, bool PSI, int CS = 1, bool SUB = true>
+template <int NT8, int NSL, int NTB, bool PSI, bool SUB = true>
 __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* smem, uint64_t* bar_full,
                                                 uint64_t* bar_empty, int fld, int which, int b0) {
     constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
@@ -83,7 +75,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     }
 
     if (G.symmetric && which == 1) {   // these modes are identically zero under the equatorial symmetry
-        if (is_producer) return;   // (both CTAs of a cluster take this branch: nothing cluster-wide has started yet)
+        if (is_producer) return;
         for (int s = 0; s < nsteps; ++s) {
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
@@ -97,15 +89,12 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
         }
         return;
     }
-    const unsigned crank = CS > 1 ? cluster_ctarank() : 0u;
     if (tid == 0) {
-        // CTA 0 of a cluster owns the operator stages of every CTA: its empty barriers also count the remote warps
-        for (int s = 0; s < NSL; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], (CS > 1 && crank == 0) ? NT8 * CS : NT8); }
+        for (int s = 0; s < NSL; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NT8); }
         mbar_fence_init();
     }
     for (int idx = tid; idx < 2 * NM * BT * LDL; idx += blockDim.x) sR[idx] = 0.0;   // padded rows stay zero
     __syncthreads();
-    if (CS > 1) cluster_sync_all();   // every barrier of the cluster is initialised before any remote arrive / multicast
 
     if (is_producer) {
       if (lane == 0) {
@@ -116,25 +105,15 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
         for (int step = 0; step < nsteps; ++step) {
             const int j = j0 - 2 * step;
             const int jj = PSI ? (K - j) : (K - 1 - j), row = PSI ? j - 1 : j;
-            if (step >= NSL) {
-                if (CS > 1) mbar_wait_cluster(&bar_empty[st], ph ^ 1);
-                else mbar_wait(&bar_empty[st], ph ^ 1);
-            }
+            if (step >= NSL) mbar_wait(&bar_empty[st], ph ^ 1);
             mbar_expect_tx(&bar_full[st], bytes);
-            if (CS > 1) {
-                if (crank == 0)
-                    bulk_g2s_multicast(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st],
-                                       (unsigned short)((1u << CS) - 1));
-            } else {
-                bulk_g2s(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st]);
-            }
+            bulk_g2s(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st]);
             const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
             bulk_g2s(sG + (size_t)st * 2 * GT, p.g + o, tile_bytes, &bar_full[st]);
             if (has_f) bulk_g2s(sG + (size_t)st * 2 * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
             if (++st == NSL) { st = 0; ph ^= 1; }
         }
       }
-      if (CS > 1) cluster_sync_all();   // nobody leaves while a peer may still signal its barriers or write its stages
       return;
     }
 
@@ -239,10 +218,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&bar_empty[st]);   // operator + tiles of this stage are consumed
-            if (CS > 1 && crank != 0) mbar_arrive_remote(&bar_empty[st], 0);   // ... and CTA 0 may refill the operator
-        }
+        if (lane == 0) mbar_arrive(&bar_empty[st]);   // operator + tiles of this stage are consumed
         if (++st == NSL) { st = 0; ph ^= 1; }
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
@@ -269,40 +245,20 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
         for (int e = 0; e < NE; ++e)
             if (ok[e]) jjp[e][0] = s1[e] + f[e];
     }
-    if (CS > 1) cluster_sync_all();
 }
 
 // grid = 2 * (psi member tiles) + 4 * (T,S member tiles) CTAs, stream-function chains first; block = 32 * (NT8 + 1):
 // compute warp w owns radial rows 8w..8w+7 in MMA accumulator layout, the last warp is the TMA producer.
-// Clustered launch (CS = 2): grid = 2 * (2 * psi tile pairs + 4 * T,S tile pairs); the CTAs (2c, 2c+1) of cluster c own
-// the member tiles (2 pair, 2 pair + 1) of the same chain.  A tile beyond the batch still runs its chain (its stores are
-// masked, its tile reads stay inside the padded solve-major buffers) so that the pair stays in lock step.
-template <int NT8, int NSL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (NT8 + 1))
-solve_hot_cluster_kernel(SolveParams p, int npsi_pairs) {
-    extern __shared__ __align__(128) double smem[];
-    __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
-    const int cid = blockIdx.x >> 1, rank = blockIdx.x & 1;
-    if (cid < 2 * npsi_pairs) {
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, 2>(p, smem, bar_full, bar_empty, 0, cid & 1,
-                                                       (2 * (cid >> 1) + rank) * 8 * SOLVE_NTB_PSI);
-    } else {
-        const int r = cid - 2 * npsi_pairs;
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, 2>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
-                                                       (2 * (r >> 2) + rank) * 8 * SOLVE_NTB_TS);
-    }
-}
-
 template <int NT8, int NSL, bool SUB = false>
 __global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
     const int bid = blockIdx.x;
     if (bid < 2 * npsi_tiles) {
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, 1, SUB>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, SUB>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
     } else {
         const int r = bid - 2 * npsi_tiles;
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, 1, SUB>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, SUB>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
                                                           (r >> 2) * 8 * SOLVE_NTB_TS);
     }
 }

@@ -1,5 +1,9 @@
-// Stage 2, second mirror level ("quarter-wave" split) on top of the persistent warp-specialised schedule of
-// k_synth_ws.cuh.
+// Stage 2 of the dense formulation, hot-path variant for 24 < n <= 32: persistent, warp-specialised synthesis kernel
+// with the second mirror level ("quarter-wave" split).  Schedule: one persistent CTA per SM walks over (member, column
+// tile) work items; 12 MMA warps (3 per SM sub-partition, so the four tensor pipes are evenly loaded) run the DMMA main
+// loop, a producer warp streams the operand stages with TMA bulk copies through an mbarrier ring that runs ahead across
+// tile boundaries, and 8 epilogue warps turn the accumulators of the *previous* tile into folded grid products while
+// the MMA warps already work on the next tile.  Other shapes use synth_kernel (k_synth.cuh).
 //
 // Mirror pairs j' of the grid come in orbits (L = j'', R = M/2-1-j''), j'' < M/4, with theta_R = pi/2 - theta_L, hence
 //     cos(2k' theta_R) = (-1)^k' cos(2k' theta_L),      sin(2k' theta_R) = (-1)^(k'+1) sin(2k' theta_L):
@@ -17,9 +21,21 @@
 
 #include "common.cuh"
 #include "k_synth.cuh"
-#include "k_synth_ws.cuh"
 
 namespace sddc {
+
+// pipeline granularity: MMA k-steps (4 wavenumbers each) per stage, and ring depth
+constexpr int SWS_KS = 2, SWS_STAGES = 3;
+constexpr int SWS_NT = 2, SWS_W = 16, SWS_NEW = 8;  // MMA + 1 producer + epilogue warps
+constexpr int SWS_NMMA = 12, SWS_NTHR = 32 * (SWS_NMMA + 1 + SWS_NEW);
+
+// MODE: SWS_FX   products of the fields of one state (NLIN_FX);
+//       SWS_GRID no products: the nine grid fields of the state are stored to p.gridc (base state of a Newton /
+//                GMRES solve: computed once, reused by every Jacobian-vector product);
+//       SWS_JVPC the MMA operand is the perturbation dv, the base-state grid fields are read back from p.gridc and
+//                the bilinear products of NLIN_DFX (Matrix_Operators.py:884-887) are formed -- a JVP then costs one
+//                synthesis instead of two.
+enum { SWS_FX = 0, SWS_GRID = 1, SWS_JVPC = 2 };
 
 constexpr int SWQ_TPW = 3;  // row tiles per MMA warp (36 / 12)
 
@@ -36,7 +52,7 @@ __global__ void __launch_bounds__(SWS_NTHR, 1) synth_wsq_kernel(SynthParams p, i
     constexpr int NS = 3, NMMA = 12, NEW = SWS_NEW, NTHR_E = 32 * NEW;
     constexpr int n8 = NT8 * 8, ROWS3 = 3 * n8, LDE = 8;
     static_assert(NF * NT8 == NMMA * TPW, "laid out for 36 row tiles");
-    static_assert(SWS_NMMA == 12 && SWS_KS == 2 && SWS_STAGES == 3, "shares launch geometry with synth_ws_kernel");
+    static_assert(SWS_NMMA == 12 && SWS_KS == 2 && SWS_STAGES == 3, "launch geometry");
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_eo_full, bar_eo_free;
     const Geo& g = p.g;

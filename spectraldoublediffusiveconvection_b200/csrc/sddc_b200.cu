@@ -15,8 +15,6 @@
 #include "k_solve.cuh"
 #include "k_solve_hot.cuh"
 #include "k_synth.cuh"
-#include "k_synth_ws.cuh"
-#include "k_synth2.cuh"
 #include "k_synth_wsq.cuh"
 #include "k_nlin_fft.cuh"
 
@@ -70,11 +68,9 @@ struct sddc_plan {
     // FFT formulation of the nonlinear term (k_nlin_fft.cuh): available for N_fm = 128, 256, 512
     int fft_M = 0;              // 3 N_fm / 2 when the FFT path is active, else 0
     bool fft_dfx = false;       // two-state (JVP) variant available
-    bool fft_dfx2 = true;       // ... with the perturbation transformed two fields at a time (M = 384, 768; SDDC_DFX2=0: off)
     int ke_M = 0;               // 3 N_fm when the kinetic-energy synthesis runs as an FFT (N_fm = 128, 256), else 0
     double *ke_tab = nullptr, *ke_Wn = nullptr;
-    bool fft_fuse = false;      // finishing stage (post) fused into the FFT kernel (SDDC_FUSE_POST=1)
-    int* fft_done = nullptr;    // [1 + max_batch] dynamic row counter, then the arrival counters of the fused finishing stage
+    int* fft_row = nullptr;     // dynamic row counter of nlin_fft_kernel (zeroed before every launch)
     double *coef7 = nullptr, *coef7b = nullptr, *coef7base = nullptr, *spec4 = nullptr, *fft_tab = nullptr;
     int base_B = 0;
     long long bstride = 0;
@@ -87,9 +83,7 @@ struct sddc_plan {
     std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
     bool dfx_ok = true;
-    int synth_variant = 0;    // 0: synth_kernel, 1: persistent warp-specialised, 2: two-CTAs-per-SM (k_synth2.cuh)
-    size_t s2_smem = 0;
-    bool ws_ok = false;       // persistent warp-specialised synthesis available for this shape
+    bool ws_ok = false;       // persistent warp-specialised quarter-wave synthesis (k_synth_wsq.cuh) available for this shape
     size_t ws_smem = 0;
     int num_sms = 148;
     int synth_nt_fx = 0, synth_nt_dfx = 0, synth_nt_ke = 0, synth_stage_fx = 0, synth_stage_dfx = 0, synth_stage_ke = 0;
@@ -98,8 +92,6 @@ struct sddc_plan {
     size_t ana_smem = 0;
     size_t solve_smem = 0, solve_hot_smem = 0;
     int solve_nsl = 3, solve_hot_nsl = 3;
-    bool solve_cluster = false; // 2-CTA clusters with operator multicast in the hot back-substitution (SDDC_SOLVE_CLUSTER=1);
-                                // measured slower (0.095 -> 0.217 ms at B = 512): opt-in only
     double dt_psi = 0, dt_T = 0, dt_S = 0;  // effective time steps of the three operator stacks
     // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
     bool profiling = false;
@@ -341,24 +333,11 @@ int run_synth_nl(sddc_plan* pl, bool dfx, int B, cudaStream_t st) {
     const int nt = dfx ? pl->synth_nt_dfx : pl->synth_nt_fx;
     const int tiles = pl->g.Mhp / (8 * nt);
     StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-    if (!dfx && pl->ws_ok && pl->synth_variant == 2) {
-        sp.tab = pl->tab1d;  // W = 16 table tiling
-        dim3 grid2(pl->g.Mhp / S2_W, B);
-        synth2_kernel<4><<<grid2, S2_NTHR, pl->s2_smem, st>>>(sp);
-        pl->launches++;
-        PLAN_CUDA(pl, cudaGetLastError());
-        return SDDC_OK;
-    }
-    if (!dfx && pl->ws_ok && pl->synth_variant == 1) {
-        sp.tab = pl->tab1d;  // W = 16 table tiling
+    if (!dfx && pl->ws_ok) {
+        sp.tab = pl->tab1q;
         const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
         const int grid = std::min(nwork, pl->num_sms);
-        if (pl->quarter) {
-            sp.tab = pl->tab1q;
-            synth_wsq_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
-        } else {
-            synth_ws_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
-        }
+        synth_wsq_kernel<4, SWS_FX><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
         pl->launches++;
         PLAN_CUDA(pl, cudaGetLastError());
         return SDDC_OK;
@@ -375,56 +354,30 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
     return launch_analysis(pl, ap, B, st);
 }
 
-// FFT formulation: coefficient rows -> analysed products spec4 (k_nlin_fft.cuh)
+// FFT formulation: coefficient rows -> analysed products spec4 (k_nlin_fft.cuh), then post_kernel
+// workers per CTA: 8 plane pairs... the one-state worker holds 4 plane pairs (8 M doubles), the two-state one 7
 template <int M>
-// two-state kernel: 18 planes per worker -- four workers fit at M <= 384, a single one at M = 768 (111 KB)
-constexpr int nlin_fft_nw(bool dfx) { return dfx ? (M <= 384 ? 4 : 1) : (M <= 384 ? NLIN_FFT_NW : 3); }
-
-// column tile of the fused finishing stage that fits into one worker's planes (0: does not fit)
-template <int M, bool DFX>
-int nlin_fft_ftc(int n) {
-    for (int tc = 32; tc >= 8; tc >>= 1)
-        if ((size_t)4 * n * (tc + 1) <= nlin_fft_worker_doubles<M, DFX>()) return tc;
-    return 0;
-}
+constexpr int nlin_fft_nw(bool dfx) { return dfx ? (M == 768 ? 2 : (M == 384 ? 5 : 8)) : (M == 768 ? 4 : NLIN_FFT_NW); }
 
 template <int M>
-int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st, bool set_attr) {
-    constexpr int MD = M;
+int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bstride, bool dfx, cudaStream_t st, bool set_attr) {
     constexpr int NW = nlin_fft_nw<M>(false), NWD = nlin_fft_nw<M>(true);
-    constexpr int NT = M == 768 ? 128 : 64, NTD = M == 768 ? 128 : 64;   // threads per worker = columns of the radix-6 pass at M = 768
+    constexpr int NT = M == 768 ? 128 : 64;   // threads per worker = columns of the radix-6 pass at M = 768
+    constexpr size_t smem = nlin_fft_smem_bytes<M, false>(NW), smem_d = nlin_fft_smem_bytes<M, true>(NWD);
+    static_assert(smem <= SMEM_LIMIT && smem_d <= SMEM_LIMIT, "workers do not fit into shared memory");
     if (set_attr) {
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<MD, true, NWD, NTD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        if (M == 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft2_kernel<384, 5, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        if (M == 768) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft2_kernel<768, 2, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, true, NWD, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
     const int n = pl->g.n, n8 = pl->g.n8;
-    // fused finishing stage when its operator copy and tiles fit next to the workers
-    int ftc = dfx ? nlin_fft_ftc<MD, true>(n) : nlin_fft_ftc<M, false>(n);
-    int drd = nlin_fft_dr_pad(n, n8);
-    size_t smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, drd) : nlin_fft_smem_bytes<M, false>(NW, drd);
-    const bool fuse = pl->fft_fuse && ftc > 0 && smem <= SMEM_LIMIT && np.out != nullptr && NT == 64 &&
-                      !(dfx && pl->fft_dfx2 && M >= 384);
-    if (!fuse) {
-        np.done = nullptr;
-        smem = dfx ? nlin_fft_smem_bytes<MD, true>(NWD, 0) : nlin_fft_smem_bytes<M, false>(NW, 0);
-    } else {
-        np.done = pl->fft_done + 1; np.ftc = ftc;
-    }
-    np.next_row = pl->fft_done;   // counter 0: dynamic row claims; counters 1..: per-member arrivals
-    PLAN_CUDA(pl, cudaMemsetAsync(pl->fft_done, 0, sizeof(int), st));
+    np.next_row = pl->fft_row;
+    PLAN_CUDA(pl, cudaMemsetAsync(pl->fft_row, 0, sizeof(int), st));
     {
         StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-        if (dfx && pl->fft_dfx2 && M == 384) {
-            // perturbation transformed two fields at a time: 14 planes per worker, five workers per SM
-            nlin_fft2_kernel<384, 5, 64><<<std::min((np.nrows + 4) / 5, pl->num_sms), 320, nlin_fft2_smem_bytes<384>(5), st>>>(np);
-        } else if (dfx && pl->fft_dfx2 && M == 768) {
-            nlin_fft2_kernel<768, 2, 128><<<std::min((np.nrows + 1) / 2, pl->num_sms), 256, nlin_fft2_smem_bytes<768>(2), st>>>(np);
-        } else if (dfx) {
+        if (dfx) {
             const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
-            nlin_fft_kernel<MD, true, NWD, NTD><<<grid, NTD * NWD, smem, st>>>(np);
+            nlin_fft_kernel<M, true, NWD, NT><<<grid, NT * NWD, smem_d, st>>>(np);
         } else {
             const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
             nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
@@ -432,9 +385,9 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, bool dfx, cudaStream_t st,
     }
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
-    if (!fuse && np.out) {
+    if (out) {
         PostParams pp{};
-        pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = np.out; pp.bstride = np.bstride; pp.g = pl->g;
+        pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = out; pp.bstride = bstride; pp.g = pl->g;
         const int ntiles = ((pl->g.K + POST_TC - 1) / POST_TC) * (np.nrows / n);
         const size_t psm = post_smem_bytes(n, n8);
         const int per_sm = std::max(1, std::min(4, (int)((SMEM_LIMIT + 1024) / (psm + 1024))));
@@ -451,13 +404,12 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
                  bool set_attr = false) {
     NlinFftParams np{};
     np.coef0 = c0; np.coef1 = c1; np.spec = pl->spec4; np.tab = pl->fft_tab; np.nrows = B * pl->g.n;
-    np.DrT = pl->DrT; np.out = out; np.bstride = solve_major ? pl->bstride : 0; np.g = pl->g;
+    const long long bstride = solve_major ? pl->bstride : 0;
     const bool dfx = c1 != nullptr;
-    if (dfx && !pl->fft_dfx) { pl->err = "two-state FFT variant not available for this N_fm"; return SDDC_ERR_UNSUPPORTED; }
     switch (pl->fft_M) {
-        case 192: return launch_nlin_fft<192>(pl, np, dfx, st, set_attr);
-        case 384: return launch_nlin_fft<384>(pl, np, dfx, st, set_attr);
-        case 768: return launch_nlin_fft<768>(pl, np, dfx, st, set_attr);
+        case 192: return launch_nlin_fft<192>(pl, np, out, bstride, dfx, st, set_attr);
+        case 384: return launch_nlin_fft<384>(pl, np, out, bstride, dfx, st, set_attr);
+        case 768: return launch_nlin_fft<768>(pl, np, out, bstride, dfx, st, set_attr);
         default: pl->err = "FFT path not available for this N_fm"; return SDDC_ERR_UNSUPPORTED;
     }
 }
@@ -483,14 +435,6 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
         const int nthr = 32 * (pl->g.nt8 + 1);
         const size_t smb = pl->solve_hot_smem;
         const bool n3 = pl->solve_hot_nsl == 3;
-        if (pl->solve_cluster && pl->g.nt8 == 4 && n3) {
-            // pairs of member tiles as 2-CTA clusters sharing one multicast copy of every operator block
-            const int pp = (npsi + 1) / 2, pt = (nts + 1) / 2;
-            solve_hot_cluster_kernel<4, 3><<<2 * (2 * pp + 4 * pt), nthr, smb, st>>>(sp, pp);
-            pl->launches++;
-            PLAN_CUDA(pl, cudaGetLastError());
-            return SDDC_OK;
-        }
         const int nblk = 2 * npsi + 4 * nts;
 #define SDDC_LAUNCH_SOLVE_HOT(NT)                                                                                 \
     if (sub) { if (n3) solve_hot_kernel<NT, 3, true><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, true><<<nblk, nthr, smb, st>>>(sp, npsi); } \
@@ -602,12 +546,12 @@ int sddc_plan_info(const sddc_plan* plan, int what) {
     if (!plan) return -1;
     switch (what) {
         case 0: return plan->quarter ? 1 : 0;       // second mirror level active on the hot path
-        case 1: return plan->synth_variant;         // 0 generic, 1 persistent warp-specialised, 2 two-CTAs-per-SM
+        case 1: return plan->ws_ok ? 1 : 0;         // dense path: 0 generic synthesis kernel, 1 persistent warp-specialised
         case 2: return plan->dfx_ok ? 1 : 0;        // two-state JVP synthesis available
         case 3: return plan->g.n8;
         case 4: return plan->fft_M;                 // grid size of the FFT formulation of the nonlinear term (0: dense DMMA path)
         case 5: return plan->fft_dfx ? 1 : 0;       // FFT formulation also used for the two-state (JVP) products
-        case 6: return plan->fft_fuse ? 1 : 0;      // finishing stage fused into the FFT kernel (when it fits)
+        case 6: return plan->ke_M;                  // grid size of the kinetic-energy FFT (0: dense synthesis)
         default: return -1;
     }
 }
@@ -764,50 +708,31 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         cudaDeviceProp prop;
         TRYC(cudaGetDeviceProperties(&prop, pl->device));
         pl->num_sms = prop.multiProcessorCount;
-        pl->ws_smem = std::max(synth_ws_smem_doubles(n, n8), synth_wsq_smem_doubles(n8)) * sizeof(double);
-        const char* env = getenv("SDDC_SYNTH_WS");
+        pl->ws_smem = synth_wsq_smem_doubles(n8) * sizeof(double);
+        // persistent quarter-wave synthesis: 24 < n <= 32 and a grid the second mirror level divides
         pl->ws_ok = g.nt8 == 4 && pl->synth_nt_dfx == SWS_NT && pl->dfx_ok && pl->ws_smem <= SMEM_LIMIT &&
-                    !(env && env[0] == '0');
-        {
-            const char* v = getenv("SDDC_SYNTH_VARIANT");
-            pl->synth_variant = pl->ws_ok ? (v ? atoi(v) : 1) : 0;
-            pl->s2_smem = synth2_smem_doubles(n, n8) * sizeof(double);
-        }
-        {
-            const char* qe = getenv("SDDC_QUARTER");
-            pl->quarter = pl->ws_ok && pl->synth_variant == 1 && g.Kh % 128 == 0 && g.Mh % 16 == 0 && g.Mhp == g.Mh &&
-                          !(qe && qe[0] == '0');
-            if (pl->quarter) {
-                const int nch = g.Khp / 8, KT3q = 32 * pl->ana_nt;
-                TRY(dev_alloc(pl, &pl->tab1q, 4ull * g.Mhp * g.Khp, false));
-                TRY(dev_alloc(pl, &pl->tab2q, 4ull * g.Khp2 * g.Mhp, false));
-                fill_table_quarter_kernel<<<296, 256>>>(pl->tab1q, 2, g.M, g.Kh, g.Mh, 16, (g.Mh / 2) / 8, nch);
-                fill_table_quarter_kernel<<<296, 256>>>(pl->tab2q, 3, g.M, g.Kh, g.Mh, KT3q, g.Khp2 / KT3q, g.Mhp / 8);
-                pl->launches += 2;
-                TRYC(cudaGetLastError());
-            }
-        }
-        if (pl->ws_ok) {
-            TRY(set_smem(pl, synth2_kernel<4>, pl->s2_smem));
-            TRY(set_smem(pl, (synth_ws_kernel<4, SWS_FX>), pl->ws_smem));
-            TRY(set_smem(pl, (synth_ws_kernel<4, SWS_GRID>), pl->ws_smem));
-            TRY(set_smem(pl, (synth_ws_kernel<4, SWS_JVPC>), pl->ws_smem));
+                    g.Kh % 128 == 0 && g.Mh % 16 == 0 && g.Mhp == g.Mh;
+        pl->quarter = pl->ws_ok;
+        if (pl->quarter) {
+            const int nch = g.Khp / 8, KT3q = 32 * pl->ana_nt;
+            TRY(dev_alloc(pl, &pl->tab1q, 4ull * g.Mhp * g.Khp, false));
+            TRY(dev_alloc(pl, &pl->tab2q, 4ull * g.Khp2 * g.Mhp, false));
+            fill_table_quarter_kernel<<<296, 256>>>(pl->tab1q, 2, g.M, g.Kh, g.Mh, 16, (g.Mh / 2) / 8, nch);
+            fill_table_quarter_kernel<<<296, 256>>>(pl->tab2q, 3, g.M, g.Kh, g.Mh, KT3q, g.Khp2 / KT3q, g.Mhp / 8);
+            pl->launches += 2;
+            TRYC(cudaGetLastError());
             TRY(set_smem(pl, (synth_wsq_kernel<4, SWS_FX>), pl->ws_smem));
             TRY(set_smem(pl, (synth_wsq_kernel<4, SWS_GRID>), pl->ws_smem));
             TRY(set_smem(pl, (synth_wsq_kernel<4, SWS_JVPC>), pl->ws_smem));
         }
     }
     {
-        // FFT formulation of the nonlinear term (k_nlin_fft.cuh); SDDC_FFT=0 keeps the dense DMMA transforms
-        const char* fe = getenv("SDDC_FFT");
-        const bool want = !(fe && fe[0] == '0');
+        // FFT formulation of the nonlinear term (k_nlin_fft.cuh); SDDC_FLAG_DENSE_TRANSFORMS keeps the dense DMMA
+        // transforms (validation of the path every other N_fm takes, at the headline shape)
+        const bool want = !(cfg->flags & SDDC_FLAG_DENSE_TRANSFORMS);
         if (want && (K == 128 || K == 256 || K == 512)) {
             pl->fft_M = g.M;
             pl->fft_dfx = true;
-            {
-                const char* d2 = getenv("SDDC_DFX2");
-                pl->fft_dfx2 = !(d2 && d2[0] == '0');
-            }
             std::vector<double> tab;
             switch (g.M) {
                 case 192: tab.resize(fftp::tab_doubles<192>()); fftp::fill_tables<192>(tab.data()); break;
@@ -819,13 +744,9 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             if (pl->fft_dfx) TRY(dev_alloc(pl, &pl->coef7b, Bm * 7 * g.N, false));
             TRY(dev_alloc(pl, &pl->spec4, Bm * 4 * g.N, false));
             {
-                // measured and rejected as the default: a finishing stage run by the 64 threads
-                // of the last-arriving worker is latency bound (0.44 ms against 0.19 + 0.08 ms for two launches)
-                const char* fp = getenv("SDDC_FUSE_POST");
-                pl->fft_fuse = fp && fp[0] == '1';
                 double* cnt = nullptr;
-                TRY(dev_alloc(pl, &cnt, (Bm + 2) / 2 + 1, true));   // row counter + arrival counters of the fused finishing stage
-                pl->fft_done = reinterpret_cast<int*>(cnt);
+                TRY(dev_alloc(pl, &cnt, 2, true));
+                pl->fft_row = reinterpret_cast<int*>(cnt);
             }
             TRY(run_nlin_fft(pl, nullptr, nullptr, nullptr, false, 1, nullptr, true));
             TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
@@ -851,21 +772,11 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             TRY(set_smem(pl, (prep_kernel<8, true>), prep_smem_bytes(n8, 1)));
         }
     }
-    {
-        const char* env = getenv("SDDC_SOLVE_STAGES");
-        int want = env ? atoi(env) : 3;
-        want = std::max(2, std::min(want, SOLVE_NSL));
-        while (want > 2 && solve_smem_doubles<SOLVE_NTB>(n8, want) * sizeof(double) > SMEM_LIMIT) --want;
-        pl->solve_nsl = want;
-    }
+    pl->solve_nsl = SOLVE_NSL;
+    while (pl->solve_nsl > 2 && solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double) > SMEM_LIMIT) --pl->solve_nsl;
     pl->solve_smem = solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double);
     pl->solve_hot_nsl = solve_hot_smem_bytes(n8, 3) <= SMEM_LIMIT ? 3 : 2;
     pl->solve_hot_smem = solve_hot_smem_bytes(n8, pl->solve_hot_nsl);
-    {
-        const char* ce = getenv("SDDC_SOLVE_CLUSTER");
-        pl->solve_cluster = ce && ce[0] == '1';
-        if (pl->solve_hot_nsl == 3) TRY(set_smem(pl, (solve_hot_cluster_kernel<4, 3>), pl->solve_hot_smem));
-    }
     if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<3, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, true>), pl->solve_hot_smem)); }
     else { TRY(set_smem(pl, (solve_hot_kernel<3, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, true>), pl->solve_hot_smem)); }
     if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<4, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, true>), pl->solve_hot_smem)); }
@@ -1073,12 +984,9 @@ static int run_synth_ws_mode(sddc_plan* pl, int mode, const double* coef, int B,
     const int ntj = pl->g.Mhp / SWS_W, nwork = ntj * B;
     const int grid = std::min(nwork, pl->num_sms);
     StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-    if (pl->quarter) {
-        sp.tab = pl->tab1q;
-        if (mode == SWS_GRID) synth_wsq_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
-        else synth_wsq_kernel<4, SWS_JVPC><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
-    } else if (mode == SWS_GRID) synth_ws_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
-    else synth_ws_kernel<4, SWS_JVPC><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+    sp.tab = pl->tab1q;
+    if (mode == SWS_GRID) synth_wsq_kernel<4, SWS_GRID><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
+    else synth_wsq_kernel<4, SWS_JVPC><<<grid, SWS_NTHR, pl->ws_smem, st>>>(sp, ntj, nwork);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;

@@ -29,7 +29,8 @@ class SddcError(RuntimeError):
 
 
 class EnsemblePlan:
-    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, symmetric=False, max_batch=1, device=None, operators=None):
+    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, symmetric=False, max_batch=1, device=None, operators=None,
+                 dense_transforms=False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise SddcError("no CUDA device: the B200 path has no CPU fallback")
@@ -44,7 +45,8 @@ class EnsemblePlan:
         self.max_batch = int(max_batch)
         self.dt, self.Pr, self.Tau, self.d = float(dt), float(Pr), float(Tau), float(d)
         cfg = _lib.SddcConfig(self.N_fm, self.N_r, int(self.symmetric), self.max_batch, self.device.index,
-                              self.dt, self.Pr, self.Tau, self.d)
+                              self.dt, self.Pr, self.Tau, self.d,
+                              _lib.FLAG_DENSE_TRANSFORMS if dense_transforms else 0)
         o = self.ops
         cops = _lib.SddcOperators(
             Dr=_ptr(o.Dr), Dsq=_ptr(o.Dsq), D2r=_ptr(o.D2r), D2=_ptr(o.D2), r2=_ptr(o.r2), ir2=_ptr(o.ir2),
@@ -104,7 +106,7 @@ class EnsemblePlan:
     def info(self):
         """Kernel-selection facts: quarter-wave split active, synthesis variant, JVP availability, padded n, grid size
         of the FFT formulation of the nonlinear term (0 = dense DMMA transforms), FFT formulation used for JVPs."""
-        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8", "fft_M", "fft_jvp")
+        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8", "fft_M", "fft_jvp", "ke_fft_M")
         return {nm: int(self.lib.sddc_plan_info(self._h, i)) for i, nm in enumerate(names)}
 
     @property

@@ -6,61 +6,32 @@
 #include <vector>
 
 #include "../spectraldoublediffusiveconvection_b200/csrc/fft_core.h"
+#include "../spectraldoublediffusiveconvection_b200/csrc/fft_fused.h"
 
 using namespace sddc::fftp;
 
 template <int M, bool DFX>
 static void run_rows(const double* coef0, const double* coef1, double* out, int nrows) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 9 : 5, NT = M == 768 ? 128 : 64;   // threads per worker as launched
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NF = DFX ? 7 : 4, NT = M == 768 ? 128 : 64;   // threads per worker as launched
     std::vector<double> tab(tab_doubles<M>());
     fill_tables<M>(tab.data());
     const Tables tb = make_tables<M>(tab.data());
-    std::vector<double> buf((size_t)2 * NF * PL);
+    std::vector<double> buf((size_t)pairs_doubles<M>(NF));
     for (int row = 0; row < nrows; ++row) {
         for (auto& v : buf) v = 1e300;  // poison: every position that is read must have been written
-        for (int t = 0; t < NT; ++t) {
-            if (DFX) {
-                build<M, 1, NT>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb, coef1 + (size_t)row * 7 * K);
-                build<M, 2, NT>(t, coef1 + (size_t)row * 7 * K, buf.data() + 10 * PL, tb);
-            } else {
-                build<M, 0, NT>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
-            }
-        }
-        for (int t = 0; t < NT; ++t) pass_c<M, NF, +1, NT>(t, buf.data());
-        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, NF, +1, NT>(t, buf.data(), tw); }
-        for (int t = 0; t < NT; ++t) i3f1<M, DFX, NT>(t, buf.data(), tb);
-        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
-        for (int t = 0; t < NT; ++t) pass_c<M, 2, -1, NT>(t, buf.data());
-        for (int t = 0; t < NT; ++t) post<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
-    }
-}
-
-// the two-state kernel that transforms the perturbation two fields at a time (14 planes per worker)
-template <int M>
-static void run_rows_dfx2(const double* coef0, const double* coef1, double* out, int nrows) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NT = Cfg<M>::L;   // one radix-6 column per thread
-    std::vector<double> tab(tab_doubles<M>());
-    fill_tables<M>(tab.data());
-    const Tables tb = make_tables<M>(tab.data());
-    std::vector<double> buf((size_t)14 * PL);
-    std::vector<Dfx2State> st(NT);
-    auto twd = [&](int t, C (&tw)[Cfg<M>::RD]) { load_tw<M>(t, tb, tw); };
-    for (int row = 0; row < nrows; ++row) {
-        for (auto& v : buf) v = 1e300;
         const double* r0 = coef0 + (size_t)row * 7 * K;
         const double* r1 = coef1 + (size_t)row * 7 * K;
-        double* pp = buf.data() + 10 * PL;
-        for (int t = 0; t < NT; ++t) { build<M, 1, NT>(t, r0, buf.data(), tb, r1); build<M, 3, NT>(t, r1, pp, tb); }
-        for (int t = 0; t < NT; ++t) pass_c<M, 7, +1, NT>(t, buf.data());
-        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; twd(t, tw); pass_d<M, 7, +1, NT>(t, buf.data(), tw); }
-        for (int t = 0; t < NT; ++t) dfx2_first<M>(t, buf.data(), tb, st[t]);
-        for (int t = 0; t < NT; ++t) build<M, 4, NT>(t, r1, pp, tb);
-        for (int t = 0; t < NT; ++t) pass_c<M, 2, +1, NT>(t, pp);
-        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; twd(t, tw); pass_d<M, 2, +1, NT>(t, pp, tw); }
-        for (int t = 0; t < NT; ++t) dfx2_second<M>(t, buf.data(), tb, st[t]);
-        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; twd(t, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
-        for (int t = 0; t < NT; ++t) pass_c<M, 2, -1, NT>(t, buf.data());
-        for (int t = 0; t < NT; ++t) post<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
+        for (int t = 0; t < NT; ++t) {
+            if (DFX) bc_inv_dfx<M, NT>(t, r0, r1, buf.data(), tb);
+            else bc_inv_fx<M, NT>(t, r0, buf.data(), tb);
+        }
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, NF, +1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) {
+            if (DFX) i3f1_dfx<M, NT>(t, buf.data(), tb);
+            else i3f1_fx<M, NT>(t, buf.data(), tb);
+        }
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) cp_fwd<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
     }
 }
 
@@ -134,15 +105,6 @@ double fft_emul_butterfly_error() {
     e = std::max(e, check_dft6<+1>());
     e = std::max(e, check_dft6<-1>());
     return e;
-}
-
-// two-state products, perturbation transformed two fields at a time (M = 384, 768)
-int fft_emul_rows_dfx2(int M, const double* coef0, const double* coef1, double* out, int nrows) {
-    switch (M) {
-        case 384: run_rows_dfx2<384>(coef0, coef1, out, nrows); return 0;
-        case 768: run_rows_dfx2<768>(coef0, coef1, out, nrows); return 0;
-        default: return -1;
-    }
 }
 
 // coef0 / coef1: [nrows][7][K]; out: [nrows][4][K].  Returns 0, or -1 for an unsupported grid size.

@@ -23,7 +23,6 @@ def emul(tmp_path_factory):
     dp = ctypes.POINTER(ctypes.c_double)
     lib.fft_emul_rows.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_int]
     lib.fft_emul_ke_rows.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int]
-    lib.fft_emul_rows_dfx2.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_int]
     return lib
 
 
@@ -89,13 +88,6 @@ def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
     got2 = _call(emul, M, rows, rows1)
     scale2 = np.abs(exp2).max(axis=(0, 2), keepdims=True)
     assert (np.abs(got2 - exp2) / scale2).max() < 1e-12
-    if K >= 256:
-        # the variant that transforms the perturbation two fields at a time performs the same arithmetic: bit-identical
-        got3 = np.full_like(got2, np.nan)
-        dp = ctypes.POINTER(ctypes.c_double)
-        assert emul.fft_emul_rows_dfx2(M, rows.ctypes.data_as(dp), rows1.ctypes.data_as(dp), got3.ctypes.data_as(dp),
-                                       rows.shape[0]) == 0
-        assert np.array_equal(got3, got2)
 
 
 @pytest.mark.parametrize("K", [128, 256])

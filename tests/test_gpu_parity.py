@@ -351,15 +351,15 @@ def test_cached_base_jvp_equals_jvp(name):
     pl.close()
 
 
-def test_dense_transform_path_still_matches(monkeypatch):
-    """SDDC_FFT=0 keeps the dense DMMA transforms (the path every N_fm other than 128/256/512 takes) at the
-    headline shape; FFT and dense formulations of the same plan shape agree to rounding."""
+def test_dense_transform_path_still_matches():
+    """dense_transforms=True keeps the dense DMMA transforms (the path every N_fm other than 128/256/512 takes) at
+    the headline shape; FFT and dense formulations of the same plan shape agree to rounding."""
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
     g = load_golden("cfg3_member")
     pl_fft = _plan(g)
     assert pl_fft.info()["fft_M"] == 384 and pl_fft.info()["fft_jvp"] == 1
-    monkeypatch.setenv("SDDC_FFT", "0")
-    pl = _plan(g)
-    monkeypatch.delenv("SDDC_FFT")
+    pl = EnsemblePlan(int(g["N_fm"]), int(g["N_r"]), float(g["d"]), float(g["dt"]), float(g["Pr"]), float(g["Tau"]),
+                      symmetric=bool(g["symmetric"]), max_batch=4, dense_transforms=True)
     assert pl.info()["fft_M"] == 0
     Ra, Ra_s = float(g["Ra"]), float(g["Ra_s"])
     Xb, dv = _dev(g["Xb"]), _dev(g["dv"])
