@@ -2,23 +2,16 @@
 // Transforms.py:73-129), written as per-thread "phase" functions that compile for the device (k_nlin_fft.cuh) and
 // for the host (tests/fft_emul.cpp runs the very same code thread by thread on the CPU against the test-only oracle).
 //
-// One WORKER (64 threads) processes one radial row i of one member:
-//   build   : the nine sinusoid coefficient rows of Derivatives (Matrix_Operators.py:630-740) are formed from seven
-//             stored rows (JT, Dpsi, omega, DT, DS, T, S; the factors k and -k are applied here) and packed two real
-//             fields per complex sequence.  For a field with DCT-III input X_k (cos type: X_k = c_k, k < K; sine type:
-//             X_k = s_{M-k}, using sin(k th_j) = (-1)^j cos((M-k) th_j)) Makhoul's reordering gives
-//                 v_n = Re sum_k X_k w_k e^{2 pi i k n / M},  w_k = e^{i pi k / 2M},  v_n = y_{2n}, v_{M-1-n} = y_{2n+1}
-//             and with the Hermitian completion V_k = w_k (X_k - i X_{M-k}) / 2 (V_0 = X_0) two fields a, b share one
-//             complex inverse DFT of Z_k = V^a_k + i V^b_k:  Re z_n = v^a_n, Im z_n = v^b_n.
+// Shared pieces: the plane layout, the register butterflies, the radix-8 / radix-RD passes, the tables, and the
+// kinetic-energy transform.  The packing / product / unpacking phases of the nonlinear term live in fft_fused.h.
+//   Makhoul's reordering: for a field with DCT-III input X_k (cos type: X_k = c_k, k < K; sine type: X_k = s_{M-k},
+//   using sin(k th_j) = (-1)^j cos((M-k) th_j))
+//       v_n = Re sum_k X_k w_k e^{2 pi i k n / M},  w_k = e^{i pi k / 2M},  v_n = y_{2n}, v_{M-1-n} = y_{2n+1}
+//   and with the Hermitian completion V_k = w_k (X_k - i X_{M-k}) / 2 (V_0 = X_0) two fields a, b share one complex
+//   inverse DFT of Z_k = V^a_k + i V^b_k:  Re z_n = v^a_n, Im z_n = v^b_n.
 //   inverse : length-M complex DFT as 8 x RD x 6 Cooley-Tukey passes in shared memory (M = 6 L, L = 8 RD).
-//   I3F1    : the last inverse pass (radix 6) leaves, in registers, all nine fields at the six grid points
-//             n = n1 + L n2; the Jacobian products (Matrix_Operators.py:791-793 / 884-887) are formed there and fed
-//             straight into the first (radix 6) pass of the forward transform.  The (-1)^j signs of the sine-type
-//             fields cancel in every product, so they are never applied.  The radial derivative of the first
-//             product, Dr @ (JT * omega), commutes with the latitudinal analysis and is applied afterwards on the
-//             spectral coefficients (post_kernel), so a row never needs its neighbours.
-//   forward : RD x 8 passes, then the two packed real sequences are separated and scaled
-//             (DCT: (2/M) Re[conj(w_k) V_k], k = 0 halved; DST: the same at index M - k).
+//   forward : the same passes backwards with conjugated twiddles; the two packed real sequences are separated and
+//             scaled afterwards (DCT: (2/M) Re[conj(w_k) V_k], k = 0 halved; DST: the same at index M - k).
 #pragma once
 #include <cmath>
 #ifdef __CUDACC__
@@ -51,13 +44,13 @@ struct Cfg {
     static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16), "supported grids: M = 192, 384, 768");
 };
 SDDC_HD int at(int j, int c) { return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7)); }
-// offset of the (re, im) plane pair of transform q inside a worker's buffer.  Odd pairs are shifted by half a bank
-// period: a half-warp whose lanes straddle two transforms (blocks .., 23, 24 of pair q | blocks 1, 2, .. of pair q + 1)
-// then still hits 16 distinct banks.
+// offset of the (re, im) plane pair of transform q inside a worker's buffer.  On the small grid (M = 192), where the lanes
+// of a half-warp straddle two transforms (blocks .., 11, 12 of pair q | blocks 1, 2, .. of pair q + 1), odd pairs are
+// shifted by half a bank period; for M >= 384 every warp round stays inside one transform.
 template <int M>
-SDDC_HD constexpr int pair_off(int q) { return q * (2 * Cfg<M>::PL + 8); }   // 2 PL is a multiple of 16
+SDDC_HD constexpr int pair_off(int q) { return q * (2 * Cfg<M>::PL + (M < 384 ? 8 : 0)); }   // 2 PL is a multiple of 16
 template <int M>
-SDDC_HD constexpr int pairs_doubles(int nq) { return nq * (2 * Cfg<M>::PL + 8); }
+SDDC_HD constexpr int pairs_doubles(int nq) { return nq * (2 * Cfg<M>::PL + (M < 384 ? 8 : 0)); }
 
 // table sizes (doubles): wk cos | wk sin | t6 cos | t6 sin | tL cos | tL sin
 template <int M> SDDC_HD constexpr int tab_wk_doubles() { return M / 2 + 1; }
@@ -194,61 +187,6 @@ SDDC_HD int kpos(int k) {
     return at(k % NBLK, k / NBLK);
 }
 
-// ---- build: spectral rows -> packed complex sequences of five inverse transforms -------------------------------
-// cr: [7][K] = JT, Dpsi, omega, DT, DS, T, S of one radial row, sinusoid indexing (column k <-> wavenumber k).
-// buf: (re, im) plane pairs, plane stride PL.
-// MODE 0: one state, five transforms (the fifth packs DS with nothing).
-// MODE 1: base state of the two-state product; the fifth transform packs DS of the base state with DS of the
-//         perturbation row cr2 -- both cosine type -- so that the pair of states needs 9 transforms, not 10.
-// MODE 2: perturbation of the two-state product, transforms 0..3 only.
-// MODE 3 / 4: transforms (0, 1) / (2, 3) of the perturbation alone, written to plane pairs 0, 1 of buf (two-state kernel
-//         that transforms the perturbation two fields at a time, k_nlin_fft.cuh).
-template <int M, int MODE = 0, int NTH = NTW>
-SDDC_HD void build(int t, const double* __restrict__ cr, double* __restrict__ buf, const Tables& tb,
-                   const double* __restrict__ cr2 = nullptr) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
-    constexpr int QLO = MODE == 4 ? 2 : 0, NQ = MODE == 2 ? 4 : MODE == 3 ? 2 : MODE == 4 ? 4 : 5;
-    for (int k = t; k <= M / 2; k += NTH) {
-        const int kp = M - k;
-        const bool hasp = k > 0 && kp < K;  // the mirror index lies inside the truncated spectrum
-        double v[7], vp[7];
-#pragma unroll
-        for (int f = 0; f < 7; ++f) v[f] = cr[f * K + k];
-#pragma unroll
-        for (int f = 0; f < 7; ++f) vp[f] = hasp ? cr[f * K + kp] : 0.0;
-        const double fk = (double)k, fkp = (double)kp;
-        // (cos-type a, sine-type b) per transform
-        const double a[5] = {v[0], fk * v[1], fk * v[2], v[3], v[4]};
-        const double b[5] = {v[2], v[1], -fk * v[5], -fk * v[6], 0.0};
-        const double ap[5] = {vp[0], fkp * vp[1], fkp * vp[2], vp[3], vp[4]};
-        const double bp[5] = {vp[2], vp[1], -fkp * vp[5], -fkp * vp[6], 0.0};
-        const double wc = tb.wkc[k], ws = tb.wks[k];  // w_k / 2 ;  w_{M-k} / 2 = (ws, wc)
-        const int p = kpos<M>(k), pp = kpos<M>(kp % M);
-        // second cosine-type field of transform 4 (MODE 1): X^b_k = c[k], X^b_{M-k} = c[M-k]
-        const double c2 = MODE == 1 ? cr2[4 * K + k] : 0.0, c2p = (MODE == 1 && hasp) ? cr2[4 * K + kp] : 0.0;
-#pragma unroll
-        for (int q = QLO; q < NQ; ++q) {
-            double* re = buf + (2 * (q - QLO)) * PL;
-            double* im = re + PL;
-            // X^b at k and at M-k: a sine-type field is stored reversed (X_k = s_{M-k})
-            const double xb_k = (MODE == 1 && q == 4) ? c2 : bp[q], xb_kp = (MODE == 1 && q == 4) ? c2p : b[q];
-            if (k == 0) {
-                re[p] = a[q];  // V_0 = X_0; the sine-type entry 0 is ignored (Transforms.py:41-54)
-                im[p] = (MODE == 1 && q == 4) ? c2 : 0.0;
-            } else {
-                const double P = a[q] + xb_kp, Q = xb_k - ap[q];
-                re[p] = wc * P - ws * Q;
-                im[p] = wc * Q + ws * P;
-                if (kp != k) {
-                    const double P2 = ap[q] + xb_k, Q2 = xb_kp - a[q];
-                    re[pp] = ws * P2 - wc * Q2;
-                    im[pp] = ws * Q2 + wc * P2;
-                }
-            }
-        }
-    }
-}
-
 // ---- radix-8 pass over c (the eight elements of a block) ---------------------------------------------------------------
 // inverse (SIGN = +1): DFT over c -> a;  forward (SIGN = -1): DFT over a -> c.  The twiddle e^{+-2 pi i d a / L} between
 // the two passes of the length-L transform is applied by pass_d, where it depends on the thread only.
@@ -312,6 +250,38 @@ SDDC_HD void pass_d(int t, double* __restrict__ buf, const C (&tw)[Cfg<M>::RD]) 
     }
 }
 
+// The same pass run by ONE warp on the transforms it owns (nlin_fft_staged_kernel): NTR plane pairs at `pa` and `pb`
+// (NTR = 1: pa only), 48 units each.
+template <int M, int NTR, int SIGN>
+SDDC_HD void pass_d_warp(int lane, double* __restrict__ pa, double* __restrict__ pb, const C (&tw)[Cfg<M>::RD]) {
+    constexpr int RD = Cfg<M>::RD, PL = Cfg<M>::PL;
+    for (int u = lane; u < NTR * 48; u += 32) {
+        const int sel = u / 48, rem = u - sel * 48, k2 = rem >> 3, a = rem & 7;
+        double* re = sel ? pb : pa;
+        double* im = re + PL;
+        int o[RD];
+#pragma unroll
+        for (int d = 0; d < RD; ++d) o[d] = at(6 * d + k2, a);
+        C x[RD], y[RD];
+#pragma unroll
+        for (int d = 0; d < RD; ++d) x[d] = C{re[o[d]], im[o[d]]};
+        if (SIGN > 0) {
+#pragma unroll
+            for (int d = 1; d < RD; ++d) x[d] = cmul(x[d], tw[d].r, tw[d].i);
+        }
+        Dft<RD, SIGN>::run(x, y);
+        if (SIGN < 0) {
+#pragma unroll
+            for (int d = 1; d < RD; ++d) y[d] = cmulc(y[d], tw[d].r, tw[d].i);
+        }
+#pragma unroll
+        for (int d = 0; d < RD; ++d) {
+            re[o[d]] = y[d].r;
+            im[o[d]] = y[d].i;
+        }
+    }
+}
+
 // last inverse pass of one transform at column n1: six grid values z[n2] <-> grid point n = n1 + L n2
 template <int M>
 SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, const int (&pos)[6], int n1,
@@ -324,244 +294,6 @@ SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, 
         if (k2 > 0) x[k2] = cmul(x[k2], tb.t6c[(k2 - 1) * L + n1], tb.t6s[(k2 - 1) * L + n1]);
     }
     dft6<+1>(x, z);
-}
-
-// ---- I3F1: last inverse pass + Jacobian products + first forward pass ------------------------------------------------
-// FX : buffers 0..4 hold the transforms of X.                 Products of NLIN_FX  (Matrix_Operators.py:791-793)
-// DFX: buffers 0..3 hold the base state, 4 packs DS of base and perturbation, 5..8 the perturbation.
-//      Products of NLIN_DFX (Matrix_Operators.py:884-887)
-// Output: buffer 0 <- P1 + i P2 (sine type: JT*om | kDpsi*om + Dpsi*kom), buffer 1 <- N_T + i N_S (cosine type),
-// already through the forward radix-6 pass and its twiddle.
-template <int M, bool DFX, int NTH = NTW>
-SDDC_HD void i3f1(int t, double* __restrict__ buf, const Tables& tb) {
-    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
-    for (int n1 = t; n1 < L; n1 += NTH) {
-        int pos[6];
-#pragma unroll
-        for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
-        double* base = buf;
-        double* pert = buf + (DFX ? 10 * PL : 0);
-        if (DFX) {
-            // base-state grid values, written back in place (only this thread touches these positions)
-#pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                C z[6];
-                inv6<M>(base + 2 * q * PL, base + (2 * q + 1) * PL, pos, n1, tb, z);
-#pragma unroll
-                for (int m = 0; m < 6; ++m) {
-                    base[2 * q * PL + pos[m]] = z[m].r;
-                    base[(2 * q + 1) * PL + pos[m]] = z[m].i;
-                }
-            }
-        }
-        // grid field g of the base state at point m (DFX only): plane index = 2 q + part
-        auto bg = [&](int plane, int m) { return base[plane * PL + pos[m]]; };
-        enum { JT = 0, OM = 1, KDP = 2, DP = 3, KOM = 4, KT = 5, DT = 6, KS = 7, DS = 8 };
-        double jt[6], dp[6], P1[6], P2[6], NT[6], NS[6];
-        {
-            C z0[6], z1[6];
-            inv6<M>(pert, pert + PL, pos, n1, tb, z0);               // JT | omega
-            inv6<M>(pert + 2 * PL, pert + 3 * PL, pos, n1, tb, z1);  // k Dpsi | Dpsi
-#pragma unroll
-            for (int m = 0; m < 6; ++m) {
-                jt[m] = z0[m].r;
-                dp[m] = z1[m].i;
-                if (DFX) {
-                    P1[m] = bg(JT, m) * z0[m].i + jt[m] * bg(OM, m);
-                    P2[m] = bg(KDP, m) * z0[m].i + z1[m].r * bg(OM, m);
-                } else {
-                    P1[m] = jt[m] * z0[m].i;
-                    P2[m] = z1[m].r * z0[m].i;
-                }
-            }
-        }
-        {
-            C z2[6];
-            inv6<M>(pert + 4 * PL, pert + 5 * PL, pos, n1, tb, z2);  // k omega | -k T
-#pragma unroll
-            for (int m = 0; m < 6; ++m) {
-                if (DFX) {
-                    P2[m] += bg(DP, m) * z2[m].r + dp[m] * bg(KOM, m);
-                    NT[m] = -(dp[m] * bg(KT, m) + bg(DP, m) * z2[m].i);
-                } else {
-                    P2[m] += dp[m] * z2[m].r;
-                    NT[m] = -(dp[m] * z2[m].i);
-                }
-            }
-        }
-        {
-            C z3[6];
-            inv6<M>(pert + 6 * PL, pert + 7 * PL, pos, n1, tb, z3);  // DT | -k S
-#pragma unroll
-            for (int m = 0; m < 6; ++m) {
-                if (DFX) {
-                    NT[m] += jt[m] * bg(DT, m) + bg(JT, m) * z3[m].r;
-                    NS[m] = -(dp[m] * bg(KS, m) + bg(DP, m) * z3[m].i);
-                } else {
-                    NT[m] += jt[m] * z3[m].r;
-                    NS[m] = -(dp[m] * z3[m].i);
-                }
-            }
-        }
-        if (DFX) {
-            // DS of the perturbation came out as the imaginary part of the base state's fifth transform (plane 9)
-#pragma unroll
-            for (int m = 0; m < 6; ++m) NS[m] += jt[m] * bg(DS, m) + bg(JT, m) * bg(9, m);
-        } else {
-            C z4[6];
-            inv6<M>(pert + 8 * PL, pert + 9 * PL, pos, n1, tb, z4);  // DS | 0
-#pragma unroll
-            for (int m = 0; m < 6; ++m) NS[m] += jt[m] * z4[m].r;
-        }
-        // forward radix-6 over n2 -> k2, twiddle e^{-2 pi i k2 n1 / M}
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            C x[6], y[6];
-#pragma unroll
-            for (int m = 0; m < 6; ++m) x[m] = q == 0 ? C{P1[m], P2[m]} : C{NT[m], NS[m]};
-            dft6<-1>(x, y);
-            double* re = buf + 2 * q * PL;
-            double* im = re + PL;
-#pragma unroll
-            for (int k2 = 0; k2 < 6; ++k2) {
-                if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6c[(k2 - 1) * L + n1], tb.t6s[(k2 - 1) * L + n1]);
-                re[pos[k2]] = y[k2].r;
-                im[pos[k2]] = y[k2].i;
-            }
-        }
-    }
-}
-
-// ---- two-state products with the perturbation transformed two fields at a time ------------------------------------------
-// Planes: 0..9 base state (transform 4 packs DS of base and perturbation, build MODE 1), 10..13 the current pair of
-// perturbation transforms.  One column n1 per thread (L == threads per worker); what a thread carries from the first
-// pair to the second lives in its registers.
-struct Dfx2State {
-    double jt[6], dp[6], P1[6], P2[6];
-};
-
-// after the first round of inverse passes: base grid values (written back in place) and the pair (JT'|om'), (kDpsi'|Dpsi')
-template <int M>
-SDDC_HD void dfx2_first(int t, double* __restrict__ buf, const Tables& tb, Dfx2State& s) {
-    constexpr int PL = Cfg<M>::PL;
-    const int n1 = t;
-    int pos[6];
-#pragma unroll
-    for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        C z[6];
-        inv6<M>(buf + 2 * q * PL, buf + (2 * q + 1) * PL, pos, n1, tb, z);
-#pragma unroll
-        for (int m = 0; m < 6; ++m) {
-            buf[2 * q * PL + pos[m]] = z[m].r;
-            buf[(2 * q + 1) * PL + pos[m]] = z[m].i;
-        }
-    }
-    auto bg = [&](int plane, int m) { return buf[plane * PL + pos[m]]; };
-    enum { JT = 0, OM = 1, KDP = 2 };
-    C z0[6], z1[6];
-    inv6<M>(buf + 10 * PL, buf + 11 * PL, pos, n1, tb, z0);  // JT' | omega'
-    inv6<M>(buf + 12 * PL, buf + 13 * PL, pos, n1, tb, z1);  // k Dpsi' | Dpsi'
-#pragma unroll
-    for (int m = 0; m < 6; ++m) {
-        s.jt[m] = z0[m].r;
-        s.dp[m] = z1[m].i;
-        s.P1[m] = bg(JT, m) * z0[m].i + s.jt[m] * bg(OM, m);
-        s.P2[m] = bg(KDP, m) * z0[m].i + z1[m].r * bg(OM, m);
-    }
-}
-
-// after the second round: the pair (k om'|-k T'), (DT'|-k S'), the remaining products (Matrix_Operators.py:884-887) and the
-// first forward pass into planes 0..3
-template <int M>
-SDDC_HD void dfx2_second(int t, double* __restrict__ buf, const Tables& tb, Dfx2State& s) {
-    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
-    const int n1 = t;
-    int pos[6];
-#pragma unroll
-    for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
-    auto bg = [&](int plane, int m) { return buf[plane * PL + pos[m]]; };
-    enum { JT = 0, DP = 3, KOM = 4, KT = 5, DT = 6, KS = 7, DS = 8, DSP = 9 };
-    C z2[6], z3[6];
-    inv6<M>(buf + 10 * PL, buf + 11 * PL, pos, n1, tb, z2);  // k omega' | -k T'
-    inv6<M>(buf + 12 * PL, buf + 13 * PL, pos, n1, tb, z3);  // DT' | -k S'
-    double NT[6], NS[6];
-#pragma unroll
-    for (int m = 0; m < 6; ++m) {
-        s.P2[m] += bg(DP, m) * z2[m].r + s.dp[m] * bg(KOM, m);
-        NT[m] = -(s.dp[m] * bg(KT, m) + bg(DP, m) * z2[m].i);
-        NT[m] += s.jt[m] * bg(DT, m) + bg(JT, m) * z3[m].r;
-        NS[m] = -(s.dp[m] * bg(KS, m) + bg(DP, m) * z3[m].i);
-        NS[m] += s.jt[m] * bg(DS, m) + bg(JT, m) * bg(DSP, m);
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        C x[6], y[6];
-#pragma unroll
-        for (int m = 0; m < 6; ++m) x[m] = q == 0 ? C{s.P1[m], s.P2[m]} : C{NT[m], NS[m]};
-        dft6<-1>(x, y);
-        double* re = buf + 2 * q * PL;
-        double* im = re + PL;
-#pragma unroll
-        for (int k2 = 0; k2 < 6; ++k2) {
-            if (k2 > 0) y[k2] = cmulc(y[k2], tb.t6c[(k2 - 1) * L + n1], tb.t6s[(k2 - 1) * L + n1]);
-            re[pos[k2]] = y[k2].r;
-            im[pos[k2]] = y[k2].i;
-        }
-    }
-}
-
-// ---- post: separate the packed sequences, scale, truncate to K --------------------------------------------------------
-// out: [4][K] = DST(JT*om), DST(kDpsi*om + Dpsi*kom), DCT(N_T), DCT(N_S)   (sinusoid indexing; Transforms.py:28-39,56-70)
-template <int M, int NTH = NTW>
-SDDC_HD void post(int t, const double* __restrict__ buf, double* __restrict__ out, const Tables& tb) {
-    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL;
-    constexpr double sc = 2.0 / M;  // the table holds w_k / 2, which absorbs the 1/2 of the Hermitian split
-    for (int k = t; k <= M / 2; k += NTH) {
-        const int kp = M - k;
-        const int p = kpos<M>(k), pp = kpos<M>(kp % M);
-        const double hc = tb.wkc[k], hs = tb.wks[k];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const double* re = buf + 2 * q * PL;
-            const double* im = re + PL;
-            const double A = re[p], Bv = im[p], Cc = re[pp], D = im[pp];
-            // C_k = Re[conj(w_k) V_k] for the two packed fields, at k and at M - k
-            const double ca_k = sc * (hc * (A + Cc) + hs * (Bv - D));
-            const double cb_k = sc * (hc * (Bv + D) - hs * (A - Cc));
-            const double ca_kp = sc * (hs * (A + Cc) + hc * (D - Bv));
-            const double cb_kp = sc * (hs * (Bv + D) - hc * (Cc - A));
-            double* oa = out + (2 * q) * K;
-            double* ob = oa + K;
-            if (q == 0) {
-                // sine type: out[k] = (2/M) C_{M-k}  (k = 1 .. K-1), out[0] = 0
-                if (k == 0) {
-                    oa[0] = 0.0;
-                    ob[0] = 0.0;
-                } else {
-                    oa[k] = ca_kp;
-                    ob[k] = cb_kp;
-                    if (kp < K && kp != k) {
-                        oa[kp] = ca_k;
-                        ob[kp] = cb_k;
-                    }
-                }
-            } else {
-                if (k == 0) {
-                    oa[0] = A * (1.0 / M);
-                    ob[0] = Bv * (1.0 / M);
-                } else {
-                    oa[k] = ca_k;
-                    ob[k] = cb_k;
-                    if (kp < K && kp != k) {
-                        oa[kp] = ca_kp;
-                        ob[kp] = cb_kp;
-                    }
-                }
-            }
-        }
-    }
 }
 
 // ---- kinetic energy (Main.py:71-134): one complex transform per radial row on the M = 3K grid -----------------------

@@ -41,40 +41,45 @@ SDDC_HD void load_block(const double* __restrict__ re, const double* __restrict_
     for (int c = 0; c < 8; ++c) x[c] = C{re[base + (c ^ sw)], im[base + (c ^ sw)]};
 }
 
-// Source of one packed transform: cosine-type row a (nullptr: none) and sine-type row b, the latter optionally
-// multiplied by -k (the theta-derivative of a cosine series, Matrix_Operators.py:711-716).
-// TYPE 0: (cosine | sine).  TYPE 1: (sine | sine): a is a sine-type row too and carries the same factor.
+// Stored rows of one radial point (k_prep.cuh, FFTL): 0 JT, 1 omega, 2 DT, 3 Dpsi, 4 DS, 5 -k T, 6 -k S (the factor -k of
+// the theta-derivative of a cosine series, Matrix_Operators.py:711-716, is applied by the prep stage).
+// Transform q of a state packs (cosine-type row | sine-type row): 0 (JT | omega)  1 (DT | Dpsi)  2 (DS | -kT)  3 (- | -kS):
+// rows (2q, 2q + 1), so that what a warp needs for its transforms is contiguous (TMA staging in nlin_fft_staged_kernel).
+SDDC_HD constexpr int row_a(int q) { return q < 3 ? 2 * q : -1; }
+SDDC_HD constexpr int row_b(int q) { return q < 3 ? 2 * q + 1 : 6; }
+
+// TYPE 0: (cosine | sine).  TYPE 1: (sine | sine).  HASA 0: no field a, 1: field a present (both compile time),
+// 2: decided per thread (a == nullptr: none).
 struct PackSrc {
     const double* a;
     const double* b;
-    bool kfac;
 };
-
-// stored rows of one radial point: 0 JT, 1 Dpsi, 2 omega, 3 DT, 4 DS, 5 T, 6 S  (k_prep.cuh, FFTL)
 template <int K>
 SDDC_HD PackSrc pack_src(int q, const double* __restrict__ rows) {
-    // q: 0 (JT | omega)   1 (DT | Dpsi)   2 (DS | -kT)   3 (0 | -kS)
-    const int ra = q == 0 ? 0 : (q == 1 ? 3 : 4);
-    const int rb = q == 0 ? 2 : (q == 1 ? 1 : (q == 2 ? 5 : 6));
-    return PackSrc{q < 3 ? rows + ra * K : nullptr, rows + rb * K, q >= 2};
+    return PackSrc{q < 3 ? rows + row_a(q) * K : nullptr, rows + row_b(q) * K};
 }
-
-template <int TYPE>
+template <int HASA>
 SDDC_HD double ld_a(const PackSrc& s, int k) {
-    if (TYPE == 0) return s.a ? s.a[k] : 0.0;
-    return -(double)k * s.a[k];
-}
-SDDC_HD double ld_b(const PackSrc& s, int k) {
-    const double v = s.b[k];
-    return s.kfac ? -(double)k * v : v;
+    if (HASA == 0) return 0.0;
+    if (HASA == 1) return s.a[k];
+    return s.a ? s.a[k] : 0.0;
 }
 
 // Packed spectrum at kappa and M - kappa (1 <= kappa <= M/2) from the raw coefficients at kappa (a, s) and, when the mirror
 // index lies inside the truncated spectrum (FULL), at M - kappa (ap, sp).  DCT-III inputs: cosine type X_k = c_k, sine
 // type X_k = s_{M-k}; Z_k = w_k [(X^a_k - i X^a_{M-k}) + i (X^b_k - i X^b_{M-k})] / 2 (fft_core.h, build()).
-template <int TYPE, bool FULL>
+template <int TYPE, bool FULL, bool HAS_A>
 SDDC_HD void pack_pair(double a, double s, double ap, double sp, double wc, double ws, C& zk, C& zkp) {
-    if (TYPE == 0) {
+    if (!HAS_A) {
+        // the sine-type field alone (either slot: the other one is identically zero)
+        if (FULL) {
+            zk = C{wc * s - ws * sp, wc * sp + ws * s};
+            zkp = C{ws * sp - wc * s, ws * s + wc * sp};
+        } else {
+            zk = C{wc * s, ws * s};
+            zkp = C{-(wc * s), ws * s};
+        }
+    } else if (TYPE == 0) {
         if (FULL) {
             const double P = a + s, Q = sp - ap, P2 = ap + sp, Q2 = s - a;
             zk = C{wc * P - ws * Q, wc * Q + ws * P};
@@ -98,38 +103,39 @@ SDDC_HD void pack_pair(double a, double s, double ap, double sp, double wc, doub
 }
 
 // ---- bc: packing + inverse radix-8 pass of the block pair (j, NB - j), 1 <= j <= NB/2 ----------------------------------
-template <int M, int TYPE>
+template <int M, int TYPE, int HASA>
 SDDC_HD void bc_unit(int j, const PackSrc& s, double* __restrict__ re, double* __restrict__ im, const Tables& tb) {
     constexpr int NB = Cfg<M>::NBLK, K = Cfg<M>::K;
+    constexpr bool HA = HASA != 0;
     const int jb = NB - j;
     C zA[8], zB[8];
     // pairs whose lower index lies in block j: kappa = j + NB c <= M/2, mirror = element 7 - c of block NB - j
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const int k = j + NB * c, kp = M - k;
-        const double a = ld_a<TYPE>(s, k), b = ld_b(s, k);
+        const double a = ld_a<HASA>(s, k), b = s.b[k];
         const double wc = tb.wkc[k], ws = tb.wks[k];
         if (c == 3) {   // kappa > M/3: the mirror index is inside the truncated spectrum
-            pack_pair<TYPE, true>(a, b, ld_a<TYPE>(s, kp), ld_b(s, kp), wc, ws, zA[c], zB[7 - c]);
+            pack_pair<TYPE, true, HA>(a, b, ld_a<HASA>(s, kp), s.b[kp], wc, ws, zA[c], zB[7 - c]);
         } else {
-            pack_pair<TYPE, false>(a, b, 0.0, 0.0, wc, ws, zA[c], zB[7 - c]);
+            pack_pair<TYPE, false, HA>(a, b, 0.0, 0.0, wc, ws, zA[c], zB[7 - c]);
         }
     }
     // pairs whose lower index lies in block NB - j
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const int k = jb + NB * c, kp = M - k;
-        const double a = ld_a<TYPE>(s, k), b = ld_b(s, k);
+        const double a = ld_a<HASA>(s, k), b = s.b[k];
         const double wc = tb.wkc[k], ws = tb.wks[k];
         if (c == 3) {
-            pack_pair<TYPE, true>(a, b, ld_a<TYPE>(s, kp), ld_b(s, kp), wc, ws, zB[c], zA[7 - c]);
+            pack_pair<TYPE, true, HA>(a, b, ld_a<HASA>(s, kp), s.b[kp], wc, ws, zB[c], zA[7 - c]);
         } else if (c == 2) {
             // kappa = NB - j + 2 NB > M/3 only for j < NB/3: the mirror loads are predicated per thread
             const bool in = kp < K;
-            const double ap = in ? ld_a<TYPE>(s, kp) : 0.0, bp = in ? ld_b(s, kp) : 0.0;
-            pack_pair<TYPE, true>(a, b, ap, bp, wc, ws, zB[c], zA[7 - c]);
+            const double ap = in ? ld_a<HASA>(s, kp) : 0.0, bp = in ? s.b[kp] : 0.0;
+            pack_pair<TYPE, true, HA>(a, b, ap, bp, wc, ws, zB[c], zA[7 - c]);
         } else {
-            pack_pair<TYPE, false>(a, b, 0.0, 0.0, wc, ws, zB[c], zA[7 - c]);
+            pack_pair<TYPE, false, HA>(a, b, 0.0, 0.0, wc, ws, zB[c], zA[7 - c]);
         }
     }
     C y[8];
@@ -140,25 +146,26 @@ SDDC_HD void bc_unit(int j, const PackSrc& s, double* __restrict__ re, double* _
 }
 
 // block 0 (k = NB c): mirror of element c is element 8 - c; k = 0 and k = M/2 are their own mirrors
-template <int M, int TYPE>
+template <int M, int TYPE, int HASA>
 SDDC_HD void bc_block0(const PackSrc& s, double* __restrict__ re, double* __restrict__ im, const Tables& tb) {
     constexpr int NB = Cfg<M>::NBLK;
+    constexpr bool HA = HASA != 0;
     C z[8];
     // V_0 = X_0; index 0 of a sine-type row is ignored (Transforms.py:41-54)
-    z[0] = C{(TYPE == 0 && s.a) ? s.a[0] : 0.0, 0.0};
+    z[0] = C{TYPE == 0 ? ld_a<HASA>(s, 0) : 0.0, 0.0};
 #pragma unroll
     for (int c = 1; c < 4; ++c) {
         const int k = NB * c, kp = M - k;
-        const double a = ld_a<TYPE>(s, k), b = ld_b(s, k);
+        const double a = ld_a<HASA>(s, k), b = s.b[k];
         const double wc = tb.wkc[k], ws = tb.wks[k];
-        if (c == 3) pack_pair<TYPE, true>(a, b, ld_a<TYPE>(s, kp), ld_b(s, kp), wc, ws, z[c], z[8 - c]);
-        else pack_pair<TYPE, false>(a, b, 0.0, 0.0, wc, ws, z[c], z[8 - c]);
+        if (c == 3) pack_pair<TYPE, true, HA>(a, b, ld_a<HASA>(s, kp), s.b[kp], wc, ws, z[c], z[8 - c]);
+        else pack_pair<TYPE, false, HA>(a, b, 0.0, 0.0, wc, ws, z[c], z[8 - c]);
     }
     {
         const int k = M / 2;
-        const double a = ld_a<TYPE>(s, k), b = ld_b(s, k);
+        const double a = ld_a<HASA>(s, k), b = s.b[k];
         C dummy;
-        pack_pair<TYPE, true>(a, b, a, b, tb.wkc[k], tb.wks[k], z[4], dummy);
+        pack_pair<TYPE, true, HA>(a, b, a, b, tb.wkc[k], tb.wks[k], z[4], dummy);
     }
     C y[8];
     Dft<8, +1>::run(z, y);
@@ -170,16 +177,49 @@ SDDC_HD void bc_block0(const PackSrc& s, double* __restrict__ re, double* __rest
 template <int NTH>
 SDDC_HD constexpr int spec_base(int nreg) { return (((nreg % NTH) + 31) / 32 * 32) % NTH; }
 
+// Distribution of the NTR transforms of a phase over the NTH / 32 warps of a worker with the transform index uniform
+// per warp (a compile-time constant inside the branch): no per-lane row selection, no selects.  With fewer warps than
+// transforms warp w takes q = w, w + NWARP, ..; otherwise WPT warps share the block pairs of one transform.
+template <int NTH, int NTR>
+struct WarpMap {
+    static constexpr int NWARP = NTH / 32;
+    static constexpr int WPT = NWARP >= NTR ? NWARP / NTR : 1;
+    static SDDC_HD bool mine(int q, int warp) { return NWARP >= NTR ? (warp / WPT == q) : (q % NWARP == warp); }
+    static SDDC_HD int first(int t) { return (NWARP >= NTR ? ((t >> 5) % WPT) * 32 : 0) + (t & 31); }
+    static constexpr int STEP = 32 * WPT;
+};
+
+// one whole transform by the lanes `id`, id + STEP, ..: block pairs 1..NP, then block 0 by the first lane that would
+// otherwise idle in the last round
+template <int M, int TYPE, int HASA, int STEP>
+SDDC_HD void bc_transform(int id, const PackSrc& s, double* __restrict__ re, double* __restrict__ im, const Tables& tb) {
+    constexpr int NP = Cfg<M>::NBLK / 2;
+    for (int j = id + 1; j <= NP; j += STEP) bc_unit<M, TYPE, HASA>(j, s, re, im, tb);
+    if (id == NP % STEP) bc_block0<M, TYPE, HASA>(s, re, im, tb);
+}
+
 // One-state packing: transforms 0..3 of `rows` into plane pairs 0..3 of buf
 template <int M, int NTH>
 SDDC_HD void bc_inv_fx(int t, const double* __restrict__ rows, double* __restrict__ buf, const Tables& tb) {
     constexpr int NP = Cfg<M>::NBLK / 2, PL = Cfg<M>::PL, K = Cfg<M>::K, NQ = 4;
+    if (M >= 384) {
+        using WM = WarpMap<NTH, NQ>;
+        const int warp = t >> 5, id = WM::first(t);
+#define SDDC_BC_FX(Q, HASA)                                                                                           \
+    if (WM::mine(Q, warp))                                                                                            \
+        bc_transform<M, 0, HASA, WM::STEP>(id, PackSrc{rows + (HASA ? row_a(Q) : 0) * K, rows + row_b(Q) * K},        \
+                                           buf + pair_off<M>(Q), buf + pair_off<M>(Q) + PL, tb);
+        SDDC_BC_FX(0, 1) SDDC_BC_FX(1, 1) SDDC_BC_FX(2, 1) SDDC_BC_FX(3, 0)
+#undef SDDC_BC_FX
+        return;
+    }
+    // small grids: lanes of a warp work on different transforms (row selection per thread)
     for (int u = t; u < NQ * NP; u += NTH) {
         const int q = u / NP, j = u - q * NP + 1;
-        bc_unit<M, 0>(j, pack_src<K>(q, rows), buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, tb);
+        bc_unit<M, 0, 2>(j, pack_src<K>(q, rows), buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, tb);
     }
     const int sp = t - spec_base<NTH>(NQ * NP);
-    if (sp >= 0 && sp < NQ) bc_block0<M, 0>(pack_src<K>(sp, rows), buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, tb);
+    if (sp >= 0 && sp < NQ) bc_block0<M, 0, 2>(pack_src<K>(sp, rows), buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, tb);
 }
 
 // Two-state packing: plane pairs 0..2 base state, 3..5 perturbation, 6 = (-kS | -kS') of both
@@ -187,18 +227,31 @@ template <int M, int NTH>
 SDDC_HD void bc_inv_dfx(int t, const double* __restrict__ rows0, const double* __restrict__ rows1, double* __restrict__ buf,
                         const Tables& tb) {
     constexpr int NP = Cfg<M>::NBLK / 2, PL = Cfg<M>::PL, K = Cfg<M>::K;
-    const PackSrc ss{rows0 + 6 * K, rows1 + 6 * K, true};
+    const PackSrc ss{rows0 + 6 * K, rows1 + 6 * K};
+    if (M >= 384) {
+        using WM = WarpMap<NTH, 7>;
+        const int warp = t >> 5, id = WM::first(t);
+#define SDDC_BC_DFX(Q, QS, ROWS)                                                                                      \
+    if (WM::mine(Q, warp))                                                                                            \
+        bc_transform<M, 0, 1, WM::STEP>(id, PackSrc{ROWS + row_a(QS) * K, ROWS + row_b(QS) * K}, buf + pair_off<M>(Q), \
+                                        buf + pair_off<M>(Q) + PL, tb);
+        SDDC_BC_DFX(0, 0, rows0) SDDC_BC_DFX(1, 1, rows0) SDDC_BC_DFX(2, 2, rows0)
+        SDDC_BC_DFX(3, 0, rows1) SDDC_BC_DFX(4, 1, rows1) SDDC_BC_DFX(5, 2, rows1)
+#undef SDDC_BC_DFX
+        if (WM::mine(6, warp)) bc_transform<M, 1, 1, WM::STEP>(id, ss, buf + pair_off<M>(6), buf + pair_off<M>(6) + PL, tb);
+        return;
+    }
     for (int u = t; u < 7 * NP; u += NTH) {
         const int q = u / NP, j = u - q * NP + 1;
-        if (q < 6) bc_unit<M, 0>(j, pack_src<K>(q < 3 ? q : q - 3, q < 3 ? rows0 : rows1), buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, tb);
-        else bc_unit<M, 1>(j, ss, buf + pair_off<M>(6), buf + pair_off<M>(6) + PL, tb);
+        if (q < 6) bc_unit<M, 0, 1>(j, pack_src<K>(q < 3 ? q : q - 3, q < 3 ? rows0 : rows1), buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, tb);
+        else bc_unit<M, 1, 1>(j, ss, buf + pair_off<M>(6), buf + pair_off<M>(6) + PL, tb);
     }
     const int sp = t - spec_base<NTH>(7 * NP);
     if (sp >= 0 && sp < 6) {
         const PackSrc s = pack_src<K>(sp < 3 ? sp : sp - 3, sp < 3 ? rows0 : rows1);
-        bc_block0<M, 0>(s, buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, tb);
+        bc_block0<M, 0, 1>(s, buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, tb);
     } else if (sp == 6) {
-        bc_block0<M, 1>(ss, buf + pair_off<M>(6), buf + pair_off<M>(6) + PL, tb);
+        bc_block0<M, 1, 1>(ss, buf + pair_off<M>(6), buf + pair_off<M>(6) + PL, tb);
     }
 }
 
@@ -346,7 +399,8 @@ SDDC_HD void i3f1_dfx(int t, double* __restrict__ buf, const Tables& tb) {
 // out: [4][K] = DST(JT*om), DST(kDpsi*om + Dpsi*kom) = -k DCT(Dpsi*om), DCT(N_T), DCT(N_S)  (sinusoid indexing;
 // Transforms.py:28-39,56-70).  (A, Bv) = V at kappa, (Cc, D) = V at M - kappa; C_k = Re[conj(w_k) V_k] of the two packed
 // fields, a sine-type field has its coefficient k at index M - k.
-template <int M, bool BOTH>
+// QM: 0 / 1 = transform index known at compile time, 2 = per thread (argument q)
+template <int M, bool BOTH, int QM>
 SDDC_HD void cp_emit(int q, int k, C vk, C vkp, double* __restrict__ oa, double* __restrict__ ob, bool kp_ok,
                      const Tables& tb) {
     constexpr double sc = 2.0 / M;   // the table holds w_k / 2, which absorbs the 1/2 of the Hermitian split
@@ -354,20 +408,36 @@ SDDC_HD void cp_emit(int q, int k, C vk, C vkp, double* __restrict__ oa, double*
     const double hc = sc * tb.wkc[k], hs = sc * tb.wks[k];
     const double s = vk.r + vkp.r, d = vk.i - vkp.i, e = vk.i + vkp.i, f = vk.r - vkp.r;
     // field a at kappa: cosine type  hc s + hs d ; sine type (its coefficient kappa sits at M - kappa)  hs s - hc d
-    const bool q0 = q == 0;
-    const double al = q0 ? hs : hc, be = q0 ? -hc : hs;
-    oa[k] = al * s + be * d;
+    const bool q0 = QM == 2 ? q == 0 : QM == 0;
     const double cbk = hc * e - hs * f;
-    ob[k] = q0 ? -(double)k * cbk : cbk;
+    if (QM == 2) {
+        const double al = q0 ? hs : hc, be = q0 ? -hc : hs;
+        oa[k] = al * s + be * d;
+        ob[k] = q0 ? -(double)k * cbk : cbk;
+    } else if (QM == 0) {
+        oa[k] = hs * s - hc * d;
+        ob[k] = -(double)k * cbk;
+    } else {
+        oa[k] = hc * s + hs * d;
+        ob[k] = cbk;
+    }
     if (BOTH && kp_ok) {
-        const double al2 = q0 ? hc : hs, be2 = q0 ? hs : -hc;
-        oa[kp] = al2 * s + be2 * d;
         const double cbkp = hs * e + hc * f;
-        ob[kp] = q0 ? -(double)kp * cbkp : cbkp;
+        if (QM == 2) {
+            const double al2 = q0 ? hc : hs, be2 = q0 ? hs : -hc;
+            oa[kp] = al2 * s + be2 * d;
+            ob[kp] = q0 ? -(double)kp * cbkp : cbkp;
+        } else if (QM == 0) {
+            oa[kp] = hc * s + hs * d;
+            ob[kp] = -(double)kp * cbkp;
+        } else {
+            oa[kp] = hs * s - hc * d;
+            ob[kp] = cbkp;
+        }
     }
 }
 
-template <int M>
+template <int M, int QM>
 SDDC_HD void cp_unit(int q, int j, const double* __restrict__ re, const double* __restrict__ im, double* __restrict__ out,
                      const Tables& tb) {
     constexpr int NB = Cfg<M>::NBLK, K = Cfg<M>::K;
@@ -382,21 +452,21 @@ SDDC_HD void cp_unit(int q, int j, const double* __restrict__ re, const double* 
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const int k = j + NB * c;
-        if (c == 3) cp_emit<M, true>(q, k, VA[c], VB[7 - c], oa, ob, true, tb);
-        else cp_emit<M, false>(q, k, VA[c], VB[7 - c], oa, ob, false, tb);
+        if (c == 3) cp_emit<M, true, QM>(q, k, VA[c], VB[7 - c], oa, ob, true, tb);
+        else cp_emit<M, false, QM>(q, k, VA[c], VB[7 - c], oa, ob, false, tb);
     }
     if (j != jb) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int k = jb + NB * c;
-            if (c == 3) cp_emit<M, true>(q, k, VB[c], VA[7 - c], oa, ob, true, tb);
-            else if (c == 2) cp_emit<M, true>(q, k, VB[c], VA[7 - c], oa, ob, M - k < K, tb);
-            else cp_emit<M, false>(q, k, VB[c], VA[7 - c], oa, ob, false, tb);
+            if (c == 3) cp_emit<M, true, QM>(q, k, VB[c], VA[7 - c], oa, ob, true, tb);
+            else if (c == 2) cp_emit<M, true, QM>(q, k, VB[c], VA[7 - c], oa, ob, M - k < K, tb);
+            else cp_emit<M, false, QM>(q, k, VB[c], VA[7 - c], oa, ob, false, tb);
         }
     }
 }
 
-template <int M>
+template <int M, int QM>
 SDDC_HD void cp_block0(int q, const double* __restrict__ re, const double* __restrict__ im, double* __restrict__ out,
                        const Tables& tb) {
     constexpr int NB = Cfg<M>::NBLK, K = Cfg<M>::K;
@@ -410,21 +480,64 @@ SDDC_HD void cp_block0(int q, const double* __restrict__ re, const double* __res
     ob[0] = q == 0 ? 0.0 : V[0].i * (1.0 / M);
 #pragma unroll
     for (int c = 1; c < 4; ++c) {
-        if (c == 3) cp_emit<M, true>(q, NB * c, V[c], V[8 - c], oa, ob, true, tb);
-        else cp_emit<M, false>(q, NB * c, V[c], V[8 - c], oa, ob, false, tb);
+        if (c == 3) cp_emit<M, true, QM>(q, NB * c, V[c], V[8 - c], oa, ob, true, tb);
+        else cp_emit<M, false, QM>(q, NB * c, V[c], V[8 - c], oa, ob, false, tb);
     }
-    cp_emit<M, false>(q, M / 2, V[4], V[4], oa, ob, false, tb);
+    cp_emit<M, false, QM>(q, M / 2, V[4], V[4], oa, ob, false, tb);
+}
+
+template <int M, int Q, int STEP>
+SDDC_HD void cp_transform(int id, const double* __restrict__ re, const double* __restrict__ im, double* __restrict__ out,
+                          const Tables& tb) {
+    constexpr int NP = Cfg<M>::NBLK / 2;
+    for (int j = id + 1; j <= NP; j += STEP) cp_unit<M, Q>(Q, j, re, im, out, tb);
+    if (id == NP % STEP) cp_block0<M, Q>(Q, re, im, out, tb);
 }
 
 template <int M, int NTH>
 SDDC_HD void cp_fwd(int t, const double* __restrict__ buf, double* __restrict__ out, const Tables& tb) {
     constexpr int NP = Cfg<M>::NBLK / 2, PL = Cfg<M>::PL;
+    if (M >= 384) {
+        using WM = WarpMap<NTH, 2>;
+        const int warp = t >> 5, id = WM::first(t);
+        if (WM::mine(0, warp)) cp_transform<M, 0, WM::STEP>(id, buf, buf + PL, out, tb);
+        if (WM::mine(1, warp)) cp_transform<M, 1, WM::STEP>(id, buf + pair_off<M>(1), buf + pair_off<M>(1) + PL, out, tb);
+        return;
+    }
     for (int u = t; u < 2 * NP; u += NTH) {
         const int q = u / NP, j = u - q * NP + 1;
-        cp_unit<M>(q, j, buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, out, tb);
+        cp_unit<M, 2>(q, j, buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, out, tb);
     }
     const int sp = t - spec_base<NTH>(2 * NP);
-    if (sp >= 0 && sp < 2) cp_block0<M>(sp, buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, out, tb);
+    if (sp >= 0 && sp < 2) cp_block0<M, 2>(sp, buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, out, tb);
+}
+
+// ---- staged schedule of the one-state kernel (nlin_fft_staged_kernel): per-warp ownership of transforms ------------------
+// Worker buffer: plane pairs 0..3 (8 PL doubles), then 3 K doubles (DS | -kT | -kS) of the staged row; the rows
+// (JT, omega) / (DT, Dpsi) of the staged row sit in the planes of pair 2 / 3.
+// what warp `warp` of a worker does between two product phases; shared by the kernel and tests/fft_emul.cpp
+template <int M>
+SDDC_HD void staged_pack(int warp, int lane, double* __restrict__ buf, const Tables& tb, const C (&tw)[Cfg<M>::RD], int stage) {
+    constexpr int PL = Cfg<M>::PL, K = Cfg<M>::K;
+    double* extra = buf + 8 * PL;   // DS | -kT | -kS
+    double* own = buf + (4 + 2 * warp) * PL;   // staged rows of transform `warp`, later the planes of transform 2 + warp
+    if (stage == 0) {
+        bc_transform<M, 0, 1, 32>(lane, PackSrc{own, own + K}, buf + 2 * warp * PL, buf + (2 * warp + 1) * PL, tb);
+    } else if (stage == 1) {
+        if (warp == 0) bc_transform<M, 0, 1, 32>(lane, PackSrc{extra, extra + K}, own, own + PL, tb);
+        else bc_transform<M, 0, 0, 32>(lane, PackSrc{nullptr, extra + 2 * K}, own, own + PL, tb);
+    } else {
+        pass_d_warp<M, 2, +1>(lane, buf + 2 * warp * PL, own, tw);
+    }
+}
+template <int M>
+SDDC_HD void staged_unpack(int warp, int lane, double* __restrict__ buf, double* __restrict__ out, const Tables& tb,
+                           const C (&tw)[Cfg<M>::RD], int stage) {
+    constexpr int PL = Cfg<M>::PL;
+    double* re = buf + 2 * warp * PL;
+    if (stage == 0) pass_d_warp<M, 1, -1>(lane, re, re, tw);
+    else if (warp == 0) cp_transform<M, 0, 32>(lane, re, re + PL, out, tb);
+    else cp_transform<M, 1, 32>(lane, re, re + PL, out, tb);
 }
 
 }  // namespace fftp

@@ -95,6 +95,87 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     }
 }
 
+// ---- staged one-state kernel (64-thread workers: M = 384) -----------------------------------------------------------------
+// Same phases, two changes in the schedule:
+//  * Ownership.  Warp w of a worker owns the transforms w and w + 2 on the way in and transform w on the way back: packing,
+//    radix-8 and radix-RD passes of a transform never leave their warp, so only __syncwarp() separates them.  The two
+//    warps meet twice per row -- before and after the radix-6 / product phase, which needs every transform at one grid
+//    column -- instead of six times, and drift freely in between.
+//  * Staging.  The coefficient rows of the NEXT row arrive by TMA bulk copies (cp.async.bulk + mbarrier, one barrier per
+//    warp) while the current row is still being analysed: rows (JT, omega) and (DT, Dpsi) land in the plane pairs 2 and 3,
+//    which are dead after the product phase, rows (DS, -kT, -kS) in 6 KB of their own.  Warp w first packs its transform
+//    w from the dead planes of pair 2 + w, then overwrites exactly those planes with its transform 2 + w: no global
+//    load is left in the packing phase (it was 35 % of all stall samples, most of them on the L2 latency).
+#ifndef NLIN_FFT_STAGED_NW
+#define NLIN_FFT_STAGED_NW 6  // 30 KB per worker at M = 384; 6 workers = 3 warps per scheduler at 168 registers (no spills) measured faster than 7
+#endif
+template <int M>
+__host__ __device__ constexpr size_t nlin_fft_staged_worker_doubles() { return (size_t)8 * fftp::Cfg<M>::PL + 3 * fftp::Cfg<M>::K; }
+template <int M>
+__host__ __device__ constexpr size_t nlin_fft_staged_smem_bytes(int nw) {
+    return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + (size_t)nw * nlin_fft_staged_worker_doubles<M>());
+}
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int M, int NW>
+__global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftParams p) {
+    using namespace fftp;
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NT = 64;
+    static_assert(Cfg<M>::L == NT, "one radix-6 column per thread");
+    extern __shared__ __align__(128) double smem[];
+    __shared__ int s_row[NW];
+    __shared__ __align__(8) uint64_t s_bar[NW][2];
+    double* stab = smem;
+    for (int i = threadIdx.x; i < tab_doubles<M>(); i += NT * NW) stab[i] = p.tab[i];
+    const int w = threadIdx.x / NT, t = threadIdx.x % NT, warp = t >> 5, lane = t & 31;
+    if (lane == 0) mbar_init(&s_bar[w][warp], 1);
+    if (t == 0) s_row[w] = atomicAdd(p.next_row, 1);
+    mbar_fence_init();
+    __syncthreads();
+    const Tables tb = make_tables<M>(stab);
+    double* buf = smem + nlin_fft_tab_pad<M>() + (size_t)w * nlin_fft_staged_worker_doubles<M>();
+    double* extra = buf + 8 * PL;
+    C tw[Cfg<M>::RD];
+    load_tw<M>(t, tb, tw);
+    // lane 0 of a warp fetches what its warp packs: rows (2 warp, 2 warp + 1) and its share of (DS, -kT | -kS)
+    auto fetch = [&](int r) {
+        if (lane != 0 || r >= p.nrows) return;
+        const double* src = p.coef0 + (size_t)r * 7 * K;
+        uint64_t* bar = &s_bar[w][warp];
+        mbar_expect_tx(bar, (warp == 0 ? 4 : 3) * K * (unsigned)sizeof(double));
+        bulk_g2s(buf + (4 + 2 * warp) * PL, src + 2 * warp * K, 2 * K * sizeof(double), bar);
+        if (warp == 0) bulk_g2s(extra, src + 4 * K, 2 * K * sizeof(double), bar);
+        else bulk_g2s(extra + 2 * K, src + 6 * K, K * sizeof(double), bar);
+    };
+    int row = s_row[w];
+    fetch(row);
+    unsigned ph = 0;
+    while (row < p.nrows) {
+        int next = 0;
+        if (t == 0) next = atomicAdd(p.next_row, 1);   // travels to L2 and back while this row is transformed
+        mbar_wait(&s_bar[w][warp], ph);
+        ph ^= 1;
+        staged_pack<M>(warp, lane, buf, tb, tw, 0);
+        __syncwarp();
+        staged_pack<M>(warp, lane, buf, tb, tw, 1);
+        __syncwarp();
+        staged_pack<M>(warp, lane, buf, tb, tw, 2);
+        if (t == 0) s_row[w] = next;
+        worker_sync<NT>(w);
+        const int nrow = s_row[w];
+        i3f1_fx<M, NT>(t, buf, tb);
+        worker_sync<NT>(w);
+        fence_proxy_async();   // the generic-proxy reads of the dead planes precede the bulk copies into them
+        fetch(nrow);
+        staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * 4 * K, tb, tw, 0);
+        __syncwarp();
+        staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * 4 * K, tb, tw, 1);
+        __syncwarp();
+        row = nrow;
+    }
+}
+
 // Kinetic energy on the 3K grid (Main.py:71-134) in the FFT formulation: one complex transform per radial row
 // (J_theta(psi)/r and Dr psi packed), weighted sum of squares in the last pass.  kepart[row] = wr[i] * sum_theta.
 struct KeFftParams {

@@ -83,7 +83,7 @@ __host__ __device__ inline size_t prep_smem_bytes(int n8, int nstage) {
 // GEMM -- one accumulator tile is one contiguous 256-byte A-fragment block there -- and (b) the linear
 // right-hand sides of Step_Python (Main.py:266-280) in the state layout.
 // FFTL selects the output of the FFT formulation (k_nlin_fft.cuh): seven row-major spectral rows per radial point
-// (JT, Dpsi, omega, DT, DS, T, S) and the natural MMA column order, so that a quad writes 64 contiguous bytes.
+// (JT, omega, DT, Dpsi, DS, -kT, -kS: one (cosine | sine) pair per transform of fft_fused.h) and the natural MMA column order, so that a quad writes 64 contiguous bytes.
 template <int NT8, bool FFTL = false>
 __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(PrepParams p, int ntiles) {
     extern __shared__ __align__(128) double smem[];
@@ -196,12 +196,14 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
                     dp.y = dps[nl][1];
                     double* r7 = p.coef + ((long long)b * n + i) * 7 * K + c;
                     *reinterpret_cast<double2*>(r7) = make_double2(j0, j1);                       // JT
-                    *reinterpret_cast<double2*>(r7 + (long long)K) = dp;                          // Dpsi
-                    *reinterpret_cast<double2*>(r7 + 2LL * K) = om;                               // omega
-                    *reinterpret_cast<double2*>(r7 + 3LL * K) = make_double2(dT[nl][0], dT[nl][1]);
+                    *reinterpret_cast<double2*>(r7 + (long long)K) = om;                          // omega
+                    *reinterpret_cast<double2*>(r7 + 2LL * K) = make_double2(dT[nl][0], dT[nl][1]);
+                    *reinterpret_cast<double2*>(r7 + 3LL * K) = dp;                               // Dpsi
                     *reinterpret_cast<double2*>(r7 + 4LL * K) = make_double2(dS[nl][0], dS[nl][1]);
-                    *reinterpret_cast<double2*>(r7 + 5LL * K) = make_double2(sT[col * LDX + i], sT[(col + 1) * LDX + i]);
-                    *reinterpret_cast<double2*>(r7 + 6LL * K) = make_double2(sS[col * LDX + i], sS[(col + 1) * LDX + i]);
+                    // -k T, -k S: the sine series of the theta-derivatives (Matrix_Operators.py:711-716)
+                    const double m0 = -(double)c, m1 = -(double)(c + 1);
+                    *reinterpret_cast<double2*>(r7 + 5LL * K) = make_double2(m0 * sT[col * LDX + i], m1 * sT[(col + 1) * LDX + i]);
+                    *reinterpret_cast<double2*>(r7 + 6LL * K) = make_double2(m0 * sS[col * LDX + i], m1 * sS[(col + 1) * LDX + i]);
                 }
             }
 #pragma unroll

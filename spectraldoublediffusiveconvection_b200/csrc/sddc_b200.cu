@@ -368,6 +368,7 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
     if (set_attr) {
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, true, NWD, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        if (M == 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         return SDDC_OK;
     }
     const int n = pl->g.n, n8 = pl->g.n8;
@@ -378,6 +379,12 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
         if (dfx) {
             const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
             nlin_fft_kernel<M, true, NWD, NT><<<grid, NT * NWD, smem_d, st>>>(np);
+        } else if (M == 384) {
+            // headline shape: per-warp ownership of the transforms, coefficient rows staged by TMA (k_nlin_fft.cuh)
+            constexpr int NWS = NLIN_FFT_STAGED_NW;
+            static_assert(nlin_fft_staged_smem_bytes<384>(NWS) <= SMEM_LIMIT, "staged workers do not fit into shared memory");
+            const int grid = std::min((np.nrows + NWS - 1) / NWS, pl->num_sms);
+            nlin_fft_staged_kernel<384, NWS><<<grid, 64 * NWS, nlin_fft_staged_smem_bytes<384>(NWS), st>>>(np);
         } else {
             const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
             nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
@@ -935,7 +942,7 @@ int sddc_time_step(sddc_plan* pl, const double* Xin, double* Xout, const double*
         double* dst = ((nsteps - s + 1) & 1) ? Xout : pl->xtmp;  // the last step lands in Xout
         if ((rc = run_step_prep(pl, src, Ra, Ras, B, linear != 0, st, s > 1))) return rc;
         if (pending >= 0) {
-            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, pl->g.K, pl->ir, diag_hist + (size_t)pending * B * 6, B, st))) return rc;
+            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, diag_hist + (size_t)pending * B * 6, B, st))) return rc;
             pending = -1;
         }
         if ((rc = run_step_rest(pl, dst, nullptr, B, linear != 0, st, s < nsteps))) return rc;
@@ -1225,7 +1232,7 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
     for (int s = 1; s <= nsteps; ++s) {
         if ((rc = run_step_prep(pl, cur, pl->hRa, pl->hRas, B, linear != 0, cs, s > 1))) return rc;
         if (pending >= 0) {
-            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs))) return rc;
+            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs))) return rc;
             if ((rc = ship_record(pending))) return rc;
             pending = -1;
         }

@@ -7,6 +7,7 @@
 
 #include "../spectraldoublediffusiveconvection_b200/csrc/fft_core.h"
 #include "../spectraldoublediffusiveconvection_b200/csrc/fft_fused.h"
+#include <cstring>
 
 using namespace sddc::fftp;
 
@@ -32,6 +33,39 @@ static void run_rows(const double* coef0, const double* coef1, double* out, int 
         }
         for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
         for (int t = 0; t < NT; ++t) cp_fwd<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
+    }
+}
+
+// staged one-state schedule (nlin_fft_staged_kernel): the two warps of a worker, each running ahead of the other as far
+// as the two worker barriers allow (warp 1 completely before warp 0 in every barrier interval)
+template <int M>
+static void run_rows_staged(const double* coef0, double* out, int nrows) {
+    constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NT = 64;
+    std::vector<double> tab(tab_doubles<M>());
+    fill_tables<M>(tab.data());
+    const Tables tb = make_tables<M>(tab.data());
+    std::vector<double> buf((size_t)8 * PL + 3 * K);
+    for (auto& v : buf) v = 1e300;
+    auto fetch = [&](int row, int warp) {   // the bulk copies lane 0 of `warp` issues
+        const double* src = coef0 + (size_t)row * 7 * K;
+        std::memcpy(buf.data() + (4 + 2 * warp) * PL, src + 2 * warp * K, sizeof(double) * 2 * K);
+        if (warp == 0) std::memcpy(buf.data() + 8 * PL, src + 4 * K, sizeof(double) * 2 * K);
+        else std::memcpy(buf.data() + 8 * PL + 2 * K, src + 6 * K, sizeof(double) * K);
+    };
+    fetch(0, 0); fetch(0, 1);
+    for (int row = 0; row < nrows; ++row) {
+        for (int wi = 0; wi < 2; ++wi) {
+            const int warp = 1 - wi;
+            for (int stage = 0; stage < 3; ++stage)
+                for (int lane = 0; lane < 32; ++lane) { C tw[Cfg<M>::RD]; load_tw<M>(32 * warp + lane, tb, tw); staged_pack<M>(warp, lane, buf.data(), tb, tw, stage); }
+        }
+        for (int t = 0; t < NT; ++t) i3f1_fx<M, NT>(t, buf.data(), tb);
+        for (int wi = 0; wi < 2; ++wi) {
+            const int warp = 1 - wi;
+            if (row + 1 < nrows) fetch(row + 1, warp);
+            for (int stage = 0; stage < 2; ++stage)
+                for (int lane = 0; lane < 32; ++lane) { C tw[Cfg<M>::RD]; load_tw<M>(32 * warp + lane, tb, tw); staged_unpack<M>(warp, lane, buf.data(), out + (size_t)row * 4 * K, tb, tw, stage); }
+        }
     }
 }
 
@@ -105,6 +139,13 @@ double fft_emul_butterfly_error() {
     e = std::max(e, check_dft6<+1>());
     e = std::max(e, check_dft6<-1>());
     return e;
+}
+
+// staged schedule of the one-state kernel (M = 384)
+int fft_emul_rows_staged(int M, const double* coef0, double* out, int nrows) {
+    if (M != 384) return -1;
+    run_rows_staged<384>(coef0, out, nrows);
+    return 0;
 }
 
 // coef0 / coef1: [nrows][7][K]; out: [nrows][4][K].  Returns 0, or -1 for an unsupported grid size.

@@ -23,16 +23,18 @@ def emul(tmp_path_factory):
     dp = ctypes.POINTER(ctypes.c_double)
     lib.fft_emul_rows.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, ctypes.c_int]
     lib.fft_emul_ke_rows.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int]
+    lib.fft_emul_rows_staged.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int]
     return lib
 
 
 def _rows(X3, op, symmetric):
-    """[n][7][K] stored rows (JT, Dpsi, omega, DT, DS, T, S) and the nine grid-ready arrays of the oracle."""
+    """[n][7][K] stored rows (JT, omega, DT, Dpsi, DS, -kT, -kS) and the nine grid-ready arrays of the oracle."""
     c, s = orc._spectral_fields(X3, op, symmetric)
     K, n = op.K, op.n
     if symmetric:
         X3 = X3 * orc.sym_mask(K, n)
-    rows = np.stack([c["JT"], s["Dpsi"], s["om"], c["DT"], c["DS"], X3[1].T, X3[2].T], axis=1)
+    kk = -np.arange(K, dtype=np.float64)[None, :]
+    rows = np.stack([c["JT"], s["om"], c["DT"], s["Dpsi"], c["DS"], kk * X3[1].T, kk * X3[2].T], axis=1)
     return np.ascontiguousarray(rows)
 
 
@@ -81,6 +83,13 @@ def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
     assert np.isfinite(got).all()
     scale = np.abs(exp).max(axis=(0, 2), keepdims=True)
     assert (np.abs(got - exp) / scale).max() < 1e-12  # white spectra times k: the dense sums themselves round at this level
+    if K == 256:
+        # the staged schedule of the headline kernel (per-warp ownership, coefficient rows staged in the dead planes)
+        # performs the same arithmetic: bit-identical
+        got_s = np.full_like(got, np.nan)
+        dp = ctypes.POINTER(ctypes.c_double)
+        assert emul.fft_emul_rows_staged(M, rows.ctypes.data_as(dp), got_s.ctypes.data_as(dp), rows.shape[0]) == 0
+        assert np.array_equal(got_s, got)
     # two-state (Jacobian-vector product) variant
     rows1 = _rows(Y3, op, symmetric)
     h = orc._grid_fields(Y3, op, symmetric)
