@@ -124,8 +124,9 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arms
 def _cpu_worker(args):
-    """One host process: advance one member `nsteps` steps with the oracle port; returns seconds."""
-    N_fm, N_r, seed, nsteps, warm = args
+    """One host process: advance one member with the oracle port in blocks of `nsteps` steps until at least `min_s`
+    seconds have been timed; returns the seconds of every block."""
+    N_fm, N_r, seed, nsteps, warm, min_s = args
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = "1"
     from oracle import sddc_oracle as orc
     orc.set_transform_backend("fft")
@@ -134,10 +135,16 @@ def _cpu_worker(args):
     X = make_ics(seed, 1, 3 * op.n * op.K)[0]
     for _ in range(max(warm, 2)):     # the first call compiles the numba loops in this process: never inside the timing
         X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
-    return time.perf_counter() - t0
+    blocks, total = [], 0.0
+    while total < min_s or not blocks:
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            X = orc.step(X, op, 3750.0, PHYS["Ra_s"])
+        blocks.append(time.perf_counter() - t0)
+        total += blocks[-1]
+        if len(blocks) >= 400:
+            break
+    return blocks
 
 
 def cpu_baseline_single(N_fm, N_r, seconds):
@@ -168,17 +175,21 @@ def run_reference(a):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("spawn")
+    min_s = 2.5   # every worker repeats its K-step block for at least this long: a 20-step block is only ~60 ms
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, 1, 2) for i in range(cores)])          # spawn + JIT warm-up
-        # all workers run concurrently; each times its own K steps after its own W warm-up steps
+        pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, 1, 2, 0.0) for i in range(cores)])          # spawn + JIT warm-up
+        # all workers run concurrently; each repeats its block of K steps (after its own W warm-up steps)
         t0 = time.perf_counter()
-        times = pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, a.steps, a.warmup) for i in range(cores)])
+        blocks = pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, a.steps, a.warmup, min_s) for i in range(cores)])
         wall = time.perf_counter() - t0
-    el = max(times)
+    # one "run" = the r-th block of every worker (they run side by side); its time is the slowest worker's block
+    nrep = min(len(b) for b in blocks)
+    runs = sorted(max(b[r] for b in blocks) for r in range(nrep))
+    el = runs[len(runs) // 2]
     value = cores * a.steps / el
-    sample = ("%d host processes (1 thread each) x 1 member x %d IMEX steps at N_r=%d N_theta=%d; oracle port "
-              "(scipy.fft + numba loops); the reference itself is pure Python and does not travel to the GPU box"
-              % (cores, a.steps, a.N_r, a.N_fm))
+    sample = ("%d host processes (1 thread each) x 1 member x %d IMEX steps at N_r=%d N_theta=%d, block repeated %d times "
+              "(>= %.1f s per worker), median block; oracle port (scipy.fft + numba loops); the reference itself is pure "
+              "Python and does not travel to the GPU box" % (cores, a.steps, a.N_r, a.N_fm, nrep, min_s))
     line = {"impl": "reference", "metric": "member-steps/sec at N_r=%d,N_theta=%d" % (a.N_r, a.N_fm),
             "value": value, "unit": "member-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * el / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -187,7 +198,8 @@ def run_reference(a):
                        "members": cores, **PHYS},
             "cpu_baseline": {"value": value, "unit": "member-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "member-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s_all_workers": wall}
+            "gpu_launches": 0, "wall_s_all_workers": wall, "blocks": nrep,
+            "block_spread": {"min_ms": 1e3 * runs[0], "median_ms": 1e3 * el, "max_ms": 1e3 * runs[-1]}}
     print(json.dumps(line), flush=True)
 
 

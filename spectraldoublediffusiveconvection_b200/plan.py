@@ -96,12 +96,31 @@ class EnsemblePlan:
         return t.contiguous()
 
     def _param(self, v, B):
-        if isinstance(v, torch.Tensor):
-            v = v.to(device=self.device, dtype=torch.float64).reshape(-1)
+        """Per-member parameter [B] (a scalar or 1-element tensor is broadcast); the C ABI trusts the pointer, so any
+        other length is rejected here."""
+        if isinstance(v, (torch.Tensor, np.ndarray, list, tuple)):
+            v = torch.as_tensor(v).to(device=self.device, dtype=torch.float64).reshape(-1)
             if v.numel() == 1:
                 v = v.expand(B)
+            elif v.numel() != B:
+                raise ValueError("per-member parameter has %d entries, the batch has %d members" % (v.numel(), B))
             return v.contiguous()
         return torch.full((B,), float(v), dtype=torch.float64, device=self.device)
+
+    def _out(self, out, shape):
+        """Result tensor: allocated here, or the caller's - which must be exactly what the kernels write into."""
+        shape = tuple(int(x) for x in shape)
+        if out is None:
+            return torch.empty(shape, dtype=torch.float64, device=self.device)
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float64):
+            raise TypeError("out must be a float64 CUDA tensor")
+        if out.device != self.device:
+            raise ValueError("out on %s, plan on %s" % (out.device, self.device))
+        if tuple(out.shape) != shape and not (shape[0] == 1 and tuple(out.shape) == shape[1:]):
+            raise ValueError("out has shape %s, expected %s" % (tuple(out.shape), shape))
+        if not out.is_contiguous():
+            raise ValueError("out must be contiguous")
+        return out
 
     def info(self):
         """Kernel-selection facts: quarter-wave split active, synthesis variant, JVP availability, padded n, grid size
@@ -147,31 +166,31 @@ class EnsemblePlan:
     # ------------------------------------------------------------------ hot path
     def nlin_fx(self, X, out=None):
         X = self._in(X, 3 * self.N)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         self._check(self.lib.sddc_nlin_fx(self._h, X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
         return out
 
     def nlin_dfx(self, dv, X, out=None):
         dv, X = self._in(dv, 3 * self.N), self._in(X, 3 * self.N)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         self._check(self.lib.sddc_nlin_dfx(self._h, dv.data_ptr(), X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
         return out
 
     def linear_op(self, op, f, out=None):
         f = self._in(f, self.N)
-        out = torch.empty_like(f) if out is None else out
+        out = self._out(out, f.shape)
         self._check(self.lib.sddc_linear_op(self._h, int(op), f.data_ptr(), out.data_ptr(), f.shape[0], self._stream()))
         return out
 
     def solve_a4(self, g, out=None):
         g = self._in(g, self.N)
-        out = torch.empty_like(g) if out is None else out
+        out = self._out(out, g.shape)
         self._check(self.lib.sddc_solve_a4(self._h, g.data_ptr(), out.data_ptr(), g.shape[0], self._stream()))
         return out
 
     def solve_nab2(self, g, which, out=None):
         g = self._in(g, self.N)
-        out = torch.empty_like(g) if out is None else out
+        out = self._out(out, g.shape)
         self._check(self.lib.sddc_solve_nab2(self._h, int(which), g.data_ptr(), out.data_ptr(), g.shape[0], self._stream()))
         return out
 
@@ -179,7 +198,7 @@ class EnsemblePlan:
         X = self._in(X, 3 * self.N)
         B = X.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         self._check(self.lib.sddc_step(self._h, X.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
                                        int(nsteps), int(bool(linear)), self._stream()))
         return out
@@ -191,7 +210,7 @@ class EnsemblePlan:
         X = self._in(X, 3 * self.N)
         B = X.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         nrec = int(nsteps) // int(diag_every) if diag_every else 0
         hist = torch.empty((nrec, B, 6), dtype=torch.float64, device=self.device)
         self._check(self.lib.sddc_time_step(self._h, X.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
@@ -203,7 +222,7 @@ class EnsemblePlan:
         X = self._in(X, 3 * self.N)
         B = X.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         self._check(self.lib.sddc_residual(self._h, X.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B, self._stream()))
         return out
 
@@ -211,7 +230,7 @@ class EnsemblePlan:
         dv, X = self._in(dv, 3 * self.N), self._in(X, 3 * self.N)
         B = X.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         self._check(self.lib.sddc_jvp(self._h, dv.data_ptr(), X.data_ptr(), out.data_ptr(), Ra.data_ptr(),
                                       Ra_s.data_ptr(), B, self._stream()))
         return out
@@ -227,22 +246,21 @@ class EnsemblePlan:
         dv = self._in(dv, 3 * self.N)
         B = dv.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
-        out = torch.empty_like(dv) if out is None else out
+        out = self._out(out, dv.shape)
         self._check(self.lib.sddc_jvp_apply(self._h, dv.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
                                             self._stream()))
         return out
 
     def dF_dRa(self, X, out=None):
         X = self._in(X, 3 * self.N)
-        out = torch.empty_like(X) if out is None else out
+        out = self._out(out, X.shape)
         self._check(self.lib.sddc_dF_dRa(self._h, X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
         return out
 
     def diagnostics(self, X, out=None):
         """[B, 6]: ||X||_2, KE, Nu_T, Nu_S, Nu_T(outer wall), Nu_S(outer wall)."""
         X = self._in(X, 3 * self.N)
-        if out is None:
-            out = torch.empty((X.shape[0], 6), dtype=torch.float64, device=self.device)
+        out = self._out(out, (X.shape[0], 6))
         self._check(self.lib.sddc_diagnostics(self._h, X.data_ptr(), out.data_ptr(), X.shape[0], self._stream()))
         return out
 
@@ -277,7 +295,10 @@ class EnsemblePlan:
         B = X.shape[0]
         Ra = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra, dtype=np.float64), (B,)))
         Ra_s = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra_s, dtype=np.float64), (B,)))
-        out = np.empty_like(X) if out is None else out
+        if out is None:
+            out = np.empty_like(X)
+        elif out.shape != X.shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape %s" % (X.shape,))
         nrec = nsteps // diag_every if diag_every else 0
         nck = nsteps // ckpt_every if ckpt_every else 0
         if diag_hist is None:
@@ -286,6 +307,9 @@ class EnsemblePlan:
             ckpt = np.empty((nck, B, 3 * self.N))
         if diag_hist.shape != (nrec, B, 6) or (nck and ckpt.shape != (nck, B, 3 * self.N)):
             raise ValueError("history / checkpoint buffers have the wrong shape")
+        for buf in (diag_hist, ckpt):
+            if buf is not None and (buf.dtype != np.float64 or not buf.flags.c_contiguous):
+                raise ValueError("history / checkpoint buffers must be C-contiguous float64 arrays")
         self._check(self.lib.sddc_time_step_host(
             self._h, X.ctypes.data, out.ctypes.data, Ra.ctypes.data, Ra_s.ctypes.data, B, int(nsteps),
             int(bool(linear)), int(diag_every), diag_hist.ctypes.data if nrec else None, int(ckpt_every),
