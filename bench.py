@@ -41,7 +41,12 @@ def parse():
     ap.add_argument("--members-per-gpu", type=int, default=512)
     ap.add_argument("--N_r", type=int, default=30)
     ap.add_argument("--N_fm", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: the same K as --steps, at most 1000)")
+    ap.add_argument("--e2e-steps", type=int, default=0,
+                    help="steps of the host-buffer leg (0: 1000 - ten checkpoints at the reference's N_save = N_iters/10 "
+                         "cadence, independent of --steps)")
+    ap.add_argument("--e2e-ckpt-every", type=int, default=100)
+    ap.add_argument("--strong-members", type=int, default=4096, help="total members of the strong-scaling leg (0: skip)")
+    ap.add_argument("--parity-steps", type=int, default=20, help="member-steps of the oracle spot check (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -389,8 +394,10 @@ def run_ours(a):
     # ---- end to end through the C ABI with HOST buffers (pinned): the ensemble analogue of Main._Time_Step
     # (Main.py:286-329): state H2D, K_e member-steps, the diagnostics of EVERY step copied back to the host, the
     # state checkpointed to the host every K_e/10 steps (the reference's N_save cadence) and at the end.
-    ne = max(10, a.e2e_steps if a.e2e_steps > 0 else min(a.steps, 1000))   # the same K steps as the device-resident region
-    ck = max(1, ne // 10)
+    # The leg is decoupled from --steps: a 20-step driver run would otherwise checkpoint the full state every 2nd step
+    # (PCIe line rate), which is not the reference's regime (N_save = N_iters/10 with N_iters >= 1000, Main.py:301).
+    ne = a.e2e_steps if a.e2e_steps > 0 else 1000
+    ck = max(1, min(a.e2e_ckpt_every, ne))
     xin, xout = plan.pinned((Bl, W)), plan.pinned((Bl, W))
     hist = plan.pinned((ne, Bl, 6))
     ckp = plan.pinned((ne // ck, Bl, W))
@@ -430,6 +437,57 @@ def run_ours(a):
                      "h2d_bytes_per_step": int(state_b + 2 * Bl * 8) * world, "d2h_bytes_per_step": int(state_b + Bl * 48) * world,
                      "call": "sddc_step_host(nsteps=1) per step: full state H2D + D2H every step (PCIe-bound)"}
 
+    # ---- strong scaling: a FIXED ensemble of `strong_members` split over the ranks ----
+    strong = None
+    if a.strong_members > 0 and a.strong_members % world == 0:
+        Bs = a.strong_members // world
+        ns = max(5, min(a.steps, 50))
+        if Bs == Bl:
+            sp, Xs, Ys, Ra_s_, Ras_s = plan, A, Bf, Ra, Ras
+        else:
+            sp = EnsemblePlan(a.N_fm, a.N_r, PHYS["d"], PHYS["dt"], PHYS["Pr"], PHYS["Tau"], symmetric=False,
+                              max_batch=Bs, device=local, operators=plan.ops)
+            reps = (Bs + Bl - 1) // Bl
+            Xs = A.repeat(reps, 1)[:Bs].contiguous()        # synthetic states: the shard's members, repeated
+            Ys = torch.empty_like(Xs)
+            Ra_s_ = torch.as_tensor(np.linspace(2000.0, 6000.0, a.strong_members)[rank * Bs:(rank + 1) * Bs]).to(dev)
+            Ras_s = torch.full((Bs,), PHYS["Ra_s"], dtype=torch.float64, device=dev)
+        for _ in range(3):
+            sp.step(Xs, Ra_s_, Ras_s, nsteps=2, out=Ys)
+        barrier()
+        e0.record()
+        sp.step(Xs, Ra_s_, Ras_s, nsteps=ns, out=Ys)
+        e1.record()
+        barrier()
+        ms_s = max_over_ranks(e0.elapsed_time(e1))
+        strong = {"members_total": a.strong_members, "members_per_gpu": Bs, "steps": ns,
+                  "value": a.strong_members * ns / (ms_s * 1e-3), "unit": "member-steps/s", "ms_per_step": ms_s / ns,
+                  "scaling": "strong"}
+        if sp is not plan:
+            sp.close()
+            del Xs, Ys
+
+    # ---- parity spot check OUTSIDE every timed region: the benchmarked call shape (full batch, one multi-step call)
+    # from the synthetic initial conditions, first and last member of rank 0 against the oracle ----
+    parity = None
+    if rank == 0 and a.parity_steps > 0:
+        from oracle import sddc_oracle as orc
+        orc.set_transform_backend("fft")
+        orc.set_accel(True)
+        op = orc.Operators(a.N_fm, a.N_r, PHYS["d"], PHYS["dt"], PHYS["Pr"], PHYS["Tau"])
+        Y = plan.step(torch.as_tensor(Xh).to(dev), Ra, Ras, nsteps=a.parity_steps).cpu().numpy()
+        errs = {}
+        for m in (0, Bl - 1):
+            x = Xh[m].copy()
+            for _ in range(a.parity_steps):
+                x = orc.step(x, op, float(Ra_all[m]), PHYS["Ra_s"])
+            errs[str(m)] = float(np.linalg.norm(Y[m] - x) / np.linalg.norm(x))
+        orc.set_accel(False)
+        orc.set_transform_backend("dense")
+        parity = {"steps": a.parity_steps, "members": list(errs), "rel_l2_error": errs, "tolerance": 1e-10,
+                  "ok": bool(max(errs.values()) <= 1e-10),
+                  "against": "oracle/sddc_oracle.py stepped on the host from the same initial conditions"}
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline_single(a.N_fm, a.N_r, a.cpu_seconds)
@@ -452,6 +510,10 @@ def run_ours(a):
                 "stage_ms": stage_ms, "jvp": jvp_rate, "with_diagnostics": {"value": with_diag, "unit": "member-steps/s", "steps": nd,
                                                            "collective": "one all_gather of the [steps, B_local, 6] f64 history" if world > 1 else None,
                                                            "call": "sddc_time_step(nsteps, diag_every=1), device resident"}}
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if parity is not None:
+            line["parity_check"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
