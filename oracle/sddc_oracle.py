@@ -505,6 +505,52 @@ def A4_BSub(g: np.ndarray, Linv: np.ndarray, op: Operators, dt: float, symmetric
     return f
 
 
+def NAB2_BSub_solve(g: np.ndarray, op: Operators, dt: float, symmetric: bool = False) -> np.ndarray:
+    """Second oracle for the T / S solve: the reference's solve-based NAB2_BSub_TSTEP (Matrix_Operators.py:248-323),
+    which factorises A_j = r^2 - dt (Nabla2 + b_j I) per mode instead of applying a pre-computed inverse."""
+    K, n = g.shape
+    f = np.zeros_like(g)
+    R2 = np.diag(op.r ** 2)
+    N2 = nabla2_interior(op.D, op.R)
+    eye = np.eye(n)
+    starts = [K - 2] if symmetric else [K - 1, K - 2]
+    for j0 in starts:
+        b = np.zeros(n)
+        for j in range(j0, -1, -2):
+            A = R2 - dt * (N2 + (-j * (j + 1.0)) * eye)
+            if j < K - 2:
+                b = b + (2.0 * dt * (j + 2.0)) * f[j + 2]
+            f[j] = np.linalg.solve(A, g[j] - (0.5 * b if j == 0 else b))
+    return f
+
+
+def A4_BSub_solve(g: np.ndarray, op: Operators, dt: float, symmetric: bool = False) -> np.ndarray:
+    """Second oracle for the psi solve: the reference's solve-based A4_BSub_TSTEP (Matrix_Operators.py:327-433).
+    dt is Pr*dt."""
+    K, n = g.shape
+    f = np.zeros_like(g)
+    D4 = nabla4_interior(op.D, op.R)
+    starts = [K] if symmetric else [K, K - 1]
+    for j0 in starts:
+        f_e = np.zeros(n)
+        bf_e = np.zeros(n)
+        for j in range(j0, 0, -2):
+            row = j - 1
+            bj = -j * (j + 1.0)
+            bjt = -2.0 * j
+            L1 = op.D2 + bj * op.IR4
+            L = (op.Dsq + bj * op.IR2) - dt * (D4 + bj * L1)
+            if j == j0:
+                f[row] = np.linalg.solve(L, g[row])
+                bf_e = bf_e + bj * f[row]
+            else:
+                f_e = f_e + f[row + 2]
+                b_test = dt * bjt * (L1 @ f_e + op.IR4 @ bf_e) - bjt * (op.IR2 @ f_e)
+                f[row] = np.linalg.solve(L, g[row] + b_test)
+                bf_e = bf_e + bj * f[row] + bjt * f_e
+    return f
+
+
 # --------------------------------------------------------------------------------------
 # Member-step, residual, JVP, d/dRa (Main.py:255-283, 473-521, 779-837)
 # --------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ def _dev(a):
 @pytest.fixture(scope="module", params=CASES)
 def case(request):
     g = load_golden(request.param)
+    g["_name"] = request.param
     pl = _plan(g)
     yield g, pl
     pl.close()
@@ -67,6 +68,20 @@ def test_solves(case):
     assert rel_l2(f, g["NAB2_BSub_T"]) < 1e-11
     f = pl.solve_nab2(_dev(Xb[2 * N:3 * N]), 1).cpu().numpy().ravel()
     assert rel_l2(f, g["NAB2_BSub_S"]) < 1e-11
+
+
+def test_solves_against_solve_based_oracle(case):
+    """Second oracle: the reference's per-mode factorisations (Matrix_Operators.py:248-433, golden/solve.npz)."""
+    g, pl = case
+    name = g["_name"]
+    s2 = load_golden("solve")
+    if name + "_A4" not in s2:
+        pytest.skip("no solve-based vectors for this case")
+    N = pl.N
+    Xb = g["Xb"]
+    assert rel_l2(pl.solve_a4(_dev(Xb[0:N])).cpu().numpy().ravel(), s2[name + "_A4"]) < 1e-9
+    assert rel_l2(pl.solve_nab2(_dev(Xb[N:2 * N]), 0).cpu().numpy().ravel(), s2[name + "_T"]) < 1e-11
+    assert rel_l2(pl.solve_nab2(_dev(Xb[2 * N:3 * N]), 1).cpu().numpy().ravel(), s2[name + "_S"]) < 1e-11
 
 
 def test_step_jvp_dmu(case):
