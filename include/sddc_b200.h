@@ -148,6 +148,21 @@ int sddc_diagnostics(sddc_plan* plan, const double* X, double* out, int B, void*
  * Synthesis kinds zero-pad / truncate to n_out like scipy's n= argument; analysis kinds truncate. */
 int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, int n_out, void* stream);
 
+/* Batched Arnoldi orthogonalisation for the lock-step Newton / pseudo-arc-length drivers: the Krylov algebra SciPy's
+ * LGMRES performs inside Main._Newton (Main.py:530-534) and Main._ContinC (Main.py:917-920, 948), for B independent
+ * solves at once.  V: [B][.][n] bases (member_stride doubles apart), w: [B][n] new directions, device pointers.
+ * Classical Gram-Schmidt, applied twice, in three passes over the basis:
+ *     sddc_gs_dots  (V, w)                         -> part1
+ *     sddc_gs_update(V, w, part1, h1, part2, 1)    w -= V h1, part2 = V^T w
+ *     sddc_gs_update(V, w, part2, h2, part3, 0)    w -= V h2, part3[.][chunk][nvec] = |w_chunk|^2
+ * part buffers: [B][sddc_gs_chunks(n)][ldp] with ldp >= nvec + 1 (slot nvec of sddc_gs_update's output holds the
+ * squared norm of the chunk of the updated w); h buffers: [B][ldp].  Reductions run in a fixed order. */
+int sddc_gs_chunks(int n);
+int sddc_gs_dots(const double* V, long long member_stride, int n, int nvec, const double* w, double* part, int ldp, int B,
+                 void* stream);
+int sddc_gs_update(const double* V, long long member_stride, int n, int nvec, double* w, const double* part_in,
+                   double* h_out, double* part_out, int ldp, int want_dots, int B, void* stream);
+
 /* Per-stage device timing with CUDA events recorded on the caller's stream around each kernel launch.
  * sddc_profile_begin switches recording on; sddc_profile_end synchronises the device, switches it off and
  * returns the summed milliseconds and launch counts per stage (arrays of SDDC_STAGE_COUNT). */

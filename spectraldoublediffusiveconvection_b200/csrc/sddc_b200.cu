@@ -17,6 +17,7 @@
 #include "k_synth.cuh"
 #include "k_synth_wsq.cuh"
 #include "k_nlin_fft.cuh"
+#include "k_krylov.cuh"
 
 using namespace sddc;
 
@@ -1113,6 +1114,40 @@ int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, 
     if (kind >= 2 && n_out > n_in) return SDDC_ERR_INVALID;
     const long long tot = (long long)rows * n_out;
     transform_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, in, out, rows, n_in, n_out);
+    return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
+// ---- batched Arnoldi orthogonalisation (k_krylov.cuh); stateless like sddc_transform ----
+static int gs_fill(GsParams& gp, const double* V, long long member_stride, int n, int nvec, double* w, int ldp, int B) {
+    if (!V || !w || n < 1 || nvec < 1 || B < 1 || ldp < nvec + 1 || member_stride < (long long)nvec * n) return SDDC_ERR_INVALID;
+    gp.V = V; gp.member_stride = member_stride; gp.n = n; gp.nvec = nvec; gp.w = w;
+    gp.nchunk = (n + GS_CHUNK - 1) / GS_CHUNK; gp.ldp = ldp;
+    return SDDC_OK;
+}
+
+int sddc_gs_chunks(int n) { return n < 1 ? 0 : (n + GS_CHUNK - 1) / GS_CHUNK; }
+
+int sddc_gs_dots(const double* V, long long member_stride, int n, int nvec, const double* w, double* part, int ldp, int B,
+                 void* stream) {
+    GsParams gp{};
+    int rc = gs_fill(gp, V, member_stride, n, nvec, const_cast<double*>(w), ldp, B);
+    if (rc || !part) return SDDC_ERR_INVALID;
+    gp.part_out = part;
+    gs_dots_kernel<<<dim3(gp.nchunk, B), GS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(gp);
+    return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
+int sddc_gs_update(const double* V, long long member_stride, int n, int nvec, double* w, const double* part_in,
+                   double* h_out, double* part_out, int ldp, int want_dots, int B, void* stream) {
+    GsParams gp{};
+    int rc = gs_fill(gp, V, member_stride, n, nvec, w, ldp, B);
+    if (rc || !part_in || !h_out || !part_out || part_in == part_out) return SDDC_ERR_INVALID;
+    gp.part_in = part_in; gp.part_out = part_out; gp.h_out = h_out;
+    const size_t smem = sizeof(double) * ((size_t)GS_CHUNK + nvec);
+    if (smem > 48 * 1024) return SDDC_ERR_UNSUPPORTED;   // nvec <= 5120: far beyond any Krylov space in use
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (want_dots) gs_update_kernel<true><<<dim3(gp.nchunk, B), GS_THREADS, smem, st>>>(gp);
+    else gs_update_kernel<false><<<dim3(gp.nchunk, B), GS_THREADS, smem, st>>>(gp);
     return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
 }
 

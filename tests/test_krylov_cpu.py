@@ -22,6 +22,6 @@ def test_batched_gmres_restart_and_absolute_tolerance():
     A = torch.eye(n, dtype=torch.float64)[None] * 2.0 + 0.2 * torch.randn(B, n, n, dtype=torch.float64)
     b = torch.randn(B, n, dtype=torch.float64)
     atol = torch.tensor([1e-3, 1e-6, 1e-9], dtype=torch.float64)
-    x, info = batched_gmres(lambda v: torch.bmm(A, v.unsqueeze(2)).squeeze(2), b, atol=atol, m=8, max_restarts=40)
+    x, info = batched_gmres(lambda v: torch.bmm(A, v.unsqueeze(2)).squeeze(2), b, rtol=0.0, atol=atol, m=8, max_restarts=40)
     r = torch.linalg.vector_norm(torch.bmm(A, x.unsqueeze(2)).squeeze(2) - b, dim=1)
     assert bool((r <= atol * 1.01).all())
