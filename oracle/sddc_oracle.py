@@ -86,10 +86,14 @@ def IDST(g_hat: np.ndarray, n: int | None = None) -> np.ndarray:
         a[..., :-1] = 0.5 * g_hat[..., 1:]
         return dst(a, type=3, n=M, axis=-1)
     # after the shift the scaled array holds modes 1..K-1 in slots 0..K-2; truncation to n keeps slots < n
+    # A TRUNCATING call (n < K) keeps mode n in the last slot, where the DST-III takes its input with half the weight
+    # of the others: + 0.5 g_hat[n] sin(n theta_j) = 0.5 (-1)^j g_hat[n]  (checked against Transforms.IDST)
     Ku = min(K, M + 1)
     _, S = _trig_tables(Ku, M)
     S = S.copy()
     S[0, :] = 0.0
+    if M < K:
+        S[M, :] *= 0.5
     return g_hat[..., :Ku] @ S
 
 

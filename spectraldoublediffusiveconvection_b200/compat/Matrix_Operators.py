@@ -10,9 +10,12 @@ NAB2_TSTEP_MATS are opaque to Main.py and carry the host-built inverse stack plu
 """
 import numpy as np
 
-from ..operators import (RadialOperators, a4_tstep_mats, cheb_radial, nab2_tstep_mats)  # noqa: F401  (cheb_radial re-exported)
+from collections import OrderedDict
 
-_PLANS = {}
+from ..operators import (RadialOperators, a4_tstep_mats, cheb_radial, diff_matrix, nab2_tstep_mats)  # noqa: F401  (cheb_radial re-exported)
+
+_PLANS = OrderedDict()   # least recently used first; evicted plans are closed (a gap sweep builds one per gap)
+MAX_PLANS = 8
 
 
 class OperatorStack(list):
@@ -31,25 +34,35 @@ def _check_even(N_fm):
         raise ValueError('The number of Fourier modes is not even %d' % N_fm)
 
 
-def _plan(N_fm, nr, symmetric, D=None, R=None):
-    """One cached EnsemblePlan per (N_fm, nr, symmetric, grid). d is recovered from the inner radius R[0] = 1/d."""
+def _plan(N_fm, nr, symmetric, D=None, R=None, d=None):
+    """One cached EnsemblePlan per (N_fm, nr, symmetric, grid).  Calls that carry no grid (the back-substitutions, whose
+    operator stacks are uploaded per call and identified by object) take the most recently used plan of that shape.
+    d is the caller's gap where the reference passes one, else recovered from the inner radius R[0] = 1/d."""
     from ..plan import EnsemblePlan
     _check_even(N_fm)
     if R is None:
-        for (k_, p_) in _PLANS.items():
+        for k_ in reversed(_PLANS):
             if k_[:3] == (N_fm, nr, bool(symmetric)):
-                return p_
-        d = 1.0
-        D, R = cheb_radial(nr + 1, d)
+                _PLANS.move_to_end(k_)
+                return _PLANS[k_]
+        D, R = cheb_radial(nr + 1, 1.0)
+    R = np.asarray(R, dtype=np.float64)
     key = (N_fm, nr, bool(symmetric), float(R[0]), float(R[-1]))
     pl = _PLANS.get(key)
     if pl is None:
-        d = 1.0 / float(R[0])
+        if D is None:
+            D = diff_matrix(R)
+        d = 1.0 / float(R[0]) if d is None else float(d)
         eye = np.broadcast_to(np.eye(nr), (N_fm, nr, nr))
         ops = RadialOperators(N_fm, nr + 1, d, 1.0, 1.0, 1.0, L_inv_A4=eye, L_inv_T=eye, L_inv_S=eye, D=D, R=R)
         pl = EnsemblePlan(N_fm, nr + 1, d, 1.0, 1.0, 1.0, symmetric=bool(symmetric), max_batch=1, operators=ops)
         pl._loaded, pl._lru, pl._keep, pl._tick, pl._aux = [None] * 3, [0] * 3, {}, 0, None
         _PLANS[key] = pl
+        while len(_PLANS) > MAX_PLANS:
+            _, old = _PLANS.popitem(last=False)
+            old.close()
+    else:
+        _PLANS.move_to_end(key)
     return pl
 
 
@@ -66,12 +79,13 @@ def _host(t):
 class _DotOperator:
     """Stand-in for the scipy.sparse matrices returned by R2 / kGR_RT: Main.py only ever calls .dot(vector)."""
 
-    def __init__(self, op, N_fm, R):
-        self.op, self.N_fm, self.R = op, N_fm, np.asarray(R, dtype=np.float64)
+    def __init__(self, op, N_fm, R, d=None):
+        self.op, self.N_fm, self.R, self.d = op, N_fm, np.array(R, dtype=np.float64), d
         self.shape = (N_fm * (len(R) - 2),) * 2
 
     def dot(self, v):
-        pl = _plan(self.N_fm, len(self.R) - 2, False, *cheb_radial(len(self.R) - 1, 1.0 / float(self.R[0])))
+        # the grid this operator was built on, as given (no 1 / (1 / x) round trip through d)
+        pl = _plan(self.N_fm, len(self.R) - 2, False, None, self.R, self.d)
         return _host(pl.linear_op(self.op, _dev(v)))
 
 
@@ -82,7 +96,7 @@ def R2(R, N_fm):
 
 def kGR_RT(R, N_fm, d):
     from ..plan import OP_KGR
-    return _DotOperator(OP_KGR, N_fm, R)
+    return _DotOperator(OP_KGR, N_fm, R, d)
 
 
 def NAB2_TSTEP_MATS(dt, N_fm, nr, D, R):

@@ -216,8 +216,13 @@ __global__ void transform_kernel(int kind, const double* __restrict__ in, double
         const int ku = min(n_in, n_out);
         for (int k = 0; k < ku; ++k) { trig_kj(k, o, n_out, c, s); acc = fma(x[k], c, acc); }
     } else if (kind == 1) {   // IDST: g_j = sum_{1 <= k < min(K, M+1)} b_k sin(k theta_j)
+        // a truncating call (n_out < n_in) keeps mode n_out with HALF weight: the reference's shifted, halved array is
+        // cut to n_out entries and the DST-III takes its last input without the factor 2 (Transforms.py:41-54,87-100)
         const int ku = min(n_in, n_out + 1);
-        for (int k = 1; k < ku; ++k) { trig_kj(k, o, n_out, c, s); acc = fma(x[k], s, acc); }
+        for (int k = 1; k < ku; ++k) {
+            trig_kj(k, o, n_out, c, s);
+            acc = fma(k == n_out ? 0.5 * x[k] : x[k], s, acc);
+        }
     } else if (kind == 2) {   // DCT: a_k = (2/M) sum_j f_j cos(k theta_j), a_0 halved, M = n_in
         for (int j = 0; j < n_in; ++j) { trig_kj(o, j, n_in, c, s); acc = fma(x[j], c, acc); }
         acc *= (o == 0 ? 1.0 : 2.0) / n_in;

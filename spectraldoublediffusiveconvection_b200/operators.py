@@ -19,12 +19,21 @@ def cheb_radial(N: int, d: float):
     idx = np.arange(0, N + 1)
     x = np.cos(np.pi * idx / N).reshape(N + 1, 1)
     x = 0.5 * (r_in + r_out) + 0.5 * (r_in - r_out) * x
+    return diff_matrix(x), x.reshape(N + 1)
+
+
+def diff_matrix(R):
+    """The differentiation matrix of cheb_radial for given collocation radii (Matrix_Operators.py:22-26: weights
+    c_i / c_j over the node differences, diagonal by the negative-sum trick)."""
+    N = len(R) - 1
+    x = np.asarray(R, dtype=np.float64).reshape(N + 1, 1)
+    idx = np.arange(0, N + 1)
     c = (np.hstack(([2.0], np.ones(N - 1), [2.0])) * (-1) ** idx).reshape(N + 1, 1)
     X = np.tile(x, (1, N + 1))
     dX = X - X.T
     D = np.dot(c, 1.0 / c.T) / (dX + np.eye(N + 1))
     D -= np.diag(np.sum(D.T, axis=0))
-    return D, x.reshape(N + 1)
+    return D
 
 
 def nabla2(D, R):

@@ -174,6 +174,8 @@ def make_transforms(TR):
         out["IDST_%d" % K] = TR.IDST(a, n=M)
         out["IDCT_same_%d" % K] = TR.IDCT(a)
         out["IDST_same_%d" % K] = TR.IDST(a)
+        out["IDCT_half_%d" % K] = TR.IDCT(a, n=K // 2)      # truncating inverse transforms
+        out["IDST_half_%d" % K] = TR.IDST(a, n=K // 2)
         out["IDCT_3x_%d" % K] = TR.IDCT(a, n=3 * K)
         out["IDST_3x_%d" % K] = TR.IDST(a, n=3 * K)
         out["DCT_%d" % K] = TR.DCT(g)
@@ -203,6 +205,9 @@ if __name__ == "__main__":
     Main, MO, TR = import_reference()
     if "--only-interp" in sys.argv:
         make_interp(MO)
+        sys.exit(0)
+    if "--only-transforms" in sys.argv:
+        make_transforms(TR)
         sys.exit(0)
     make_transforms(TR)
     make_interp(MO)

@@ -175,6 +175,8 @@ def test_transforms_shim():
         assert rel_l2(P.transform(P.T_IDST, a, M).cpu().numpy(), g["IDST_%d" % K]) < 1e-13
         assert rel_l2(P.transform(P.T_IDCT, a).cpu().numpy(), g["IDCT_same_%d" % K]) < 1e-13
         assert rel_l2(P.transform(P.T_IDST, a, 3 * K).cpu().numpy(), g["IDST_3x_%d" % K]) < 1e-13
+        assert rel_l2(P.transform(P.T_IDCT, a, K // 2).cpu().numpy(), g["IDCT_half_%d" % K]) < 1e-13   # truncating
+        assert rel_l2(P.transform(P.T_IDST, a, K // 2).cpu().numpy(), g["IDST_half_%d" % K]) < 1e-13
         assert rel_l2(P.transform(P.T_DCT, gr).cpu().numpy(), g["DCT_%d" % K]) < 1e-13
         assert rel_l2(P.transform(P.T_DST, gr).cpu().numpy(), g["DST_%d" % K]) < 1e-13
         assert rel_l2(P.transform(P.T_DCT, gr, K).cpu().numpy(), g["DCT_trunc_%d" % K]) < 1e-13

@@ -47,6 +47,8 @@ def test_transforms_match_reference(backend):
         assert rel_l2(orc.IDST(a, n=M), g["IDST_%d" % K]) < 1e-13
         assert rel_l2(orc.IDCT(a), g["IDCT_same_%d" % K]) < 1e-13
         assert rel_l2(orc.IDST(a), g["IDST_same_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDCT(a, n=K // 2), g["IDCT_half_%d" % K]) < 1e-13
+        assert rel_l2(orc.IDST(a, n=K // 2), g["IDST_half_%d" % K]) < 1e-13
         assert rel_l2(orc.IDCT(a, n=3 * K), g["IDCT_3x_%d" % K]) < 1e-13
         assert rel_l2(orc.IDST(a, n=3 * K), g["IDST_3x_%d" % K]) < 1e-13
         assert rel_l2(orc.DCT(gr), g["DCT_%d" % K]) < 1e-13
