@@ -28,6 +28,39 @@ import ctypes as C
 import torch
 
 
+# ------------------------------------------------------------------------------------------------ optional device timing
+class _Profile:
+    """CUDA-event timing of the two device-heavy pieces of a solve (operator applications, orthogonalisation)."""
+    enabled = False
+    events = []
+
+    @classmethod
+    def timed(cls, kind, fn, *args):
+        if not cls.enabled:
+            return fn(*args)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn(*args)
+        b.record()
+        cls.events.append((kind, a, b))
+        return out
+
+
+def profile_begin():
+    _Profile.enabled, _Profile.events = True, []
+
+
+def profile_end():
+    """{"matvec_ms", "ortho_ms", "matvec_calls", "ortho_calls"} since profile_begin() (synchronises the device)."""
+    torch.cuda.synchronize()
+    out = {"matvec_ms": 0.0, "ortho_ms": 0.0, "matvec_calls": 0, "ortho_calls": 0}
+    for kind, a, b in _Profile.events:
+        out[kind + "_ms"] += a.elapsed_time(b)
+        out[kind + "_calls"] += 1
+    _Profile.enabled, _Profile.events = False, []
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ orthogonalisation
 class _TorchOrtho:
     """CGS2 with torch.bmm: CPU tensors (tests of the host logic)."""
@@ -108,7 +141,7 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
     one, zero = torch.ones_like(bnorm), torch.zeros_like(bnorm)
     for _ in range(max_restarts):
         if x0 is not None or total > 0:
-            r = b - matvec(x)
+            r = b - _Profile.timed("matvec", matvec, x)
             total += 1
         else:
             r = b.clone()
@@ -129,11 +162,11 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
         gvec[:, 0] = torch.where(live, beta, zero)
         jdone = 0
         for j in range(m):
-            w = matvec(V[:, j].contiguous())
+            w = _Profile.timed("matvec", matvec, V[:, j].contiguous())
             total += 1
             member_iters += live.long()
             w = torch.where(live[:, None], w, torch.zeros_like(w))
-            h, hn, w = ortho(j, w)
+            h, hn, w = _Profile.timed("ortho", ortho, j, w)
             V[:, j + 1] = w / torch.where(hn > 0, hn, one)[:, None]
             col = torch.cat([h, hn[:, None]], dim=1)          # [B, j+2]
             col = torch.bmm(Q[:, :j + 2, :j + 2], col.unsqueeze(2)).squeeze(2)

@@ -117,6 +117,77 @@ def newton(MO, X, Ra, Ra_s, Tau, Pr, d, N_fm, N_r, symmetric, dt=1.0, tol_newton
     return X, np.array(history), n_matvec[0]
 
 
+def continc(MO, Y_0, sign, ds, Ra_s, Tau, Pr, d, N_fm, N_r, symmetric, dt=1.0, tol_newton=1e-8, tol_gmres=1e-4,
+            Krylov_Space_Size=300):
+    """One pseudo-arc-length step as Main._ContinC makes it (Main.py:742-955): Predict (839-876), the bordered Newton
+    corrector with the ds halving rule (885-930), ds doubling (933-935).  SciPy's LGMRES on the host as in the
+    reference.  Returns (Y, ds, history [(err_X, err_mu)], n_matvec)."""
+    import scipy.sparse.linalg as spla
+    ops = build_matrix_operators(MO, N_fm, N_r, d, dt, Pr, Tau)
+    nr = N_r - 1
+    N = N_fm * nr
+    delta = 1.0 / (3.0 * N)
+    mask = np.ones(3 * N)
+    if symmetric:
+        m3 = mask.reshape(3, N_fm, nr)
+        m3[0, 0::2] = 0.0
+        m3[1:, 1::2] = 0.0
+    n_matvec = [0]
+
+    def closures(mu):
+        return make_closures(MO, ops, mu, Ra_s, dt, Pr, Tau, symmetric)
+
+    X_0 = mask * Y_0[0:-1].copy()
+    mu_0 = float(Y_0[-1])
+    _, _, jvp0, dmu0 = closures(mu_0)
+    dfmu = -1.0 * dmu0(X_0)
+
+    def DF0(v):
+        n_matvec[0] += 1
+        return jvp0(v, X_0)
+
+    xi, info = spla.lgmres(spla.LinearOperator((3 * N, 3 * N), matvec=DF0, dtype="float64"), dfmu, maxiter=250,
+                           inner_m=Krylov_Space_Size, atol=tol_newton * np.linalg.norm(dfmu, 2))
+    assert info == 0
+    mu_dot = sign / np.sqrt(1.0 + delta * (np.linalg.norm(xi, 2) - 1.0))
+    X_dot = mu_dot * xi
+    Y = np.hstack((X_0 + X_dot * ds, mu_0 + mu_dot * ds))
+    G = 0.0 * Y
+    err_X = err_mu = 1.0
+    it = 0
+    history = []
+    while (err_X > tol_newton or err_mu > tol_newton) or it < 2:
+        if it >= 5:
+            it = 0
+            ds *= 0.5
+            assert ds >= tol_newton
+            Y = np.hstack((X_0 + X_dot * ds, mu_0 + mu_dot * ds))
+        X = mask * Y[0:-1].copy()
+        mu = float(Y[-1])
+        _, residual, jvp, dmu = closures(mu)
+        DF_mu = dmu(X)
+        G[0:-1] = residual(X)
+        G[-1] = delta * np.dot(X_dot, X - X_0) + (1.0 - delta) * mu_dot * (mu - mu_0) - ds
+
+        def DG(dY, X=X, jvp=jvp, DF_mu=DF_mu):
+            n_matvec[0] += 1
+            return np.hstack((jvp(dY[0:-1], X) + DF_mu * dY[-1],
+                              delta * np.dot(X_dot, dY[0:-1]) + (1.0 - delta) * mu_dot * dY[-1]))
+
+        b_norm = np.sqrt(delta * np.dot(G[0:-1], G[0:-1]) + (1.0 - delta) * (G[-1] ** 2))
+        dY, info = spla.lgmres(spla.LinearOperator((Y.shape[0],) * 2, matvec=DG, dtype="float64"), G, maxiter=250,
+                               inner_m=Krylov_Space_Size, atol=tol_gmres * b_norm)
+        assert info == 0
+        Y = Y - dY
+        err_X = np.linalg.norm(dY[0:-1], 2) / np.linalg.norm(X, 2)
+        err_mu = abs(dY[-1]) / abs(mu)
+        history.append((err_X, err_mu))
+        it += 1
+    if it <= 4:
+        ds *= 2
+    return Y, ds, np.array(history), n_matvec[0]
+
+
 class OracleOperators:
     """The same operator-layer surface as Matrix_Operators, backed by the NumPy oracle (CPU) -- the comparison arm
     for driver-level parity tests."""

@@ -170,3 +170,64 @@ def test_batched_newton_and_arclength_lockstep(modules):
     nrm = torch.sqrt(delta * (Xd ** 2).sum(dim=1) + (1 - delta) * mud ** 2)
     assert torch.allclose(nrm, torch.ones_like(nrm), atol=1e-10) and bool((mud > 0).all())
     pn.close()
+
+
+def _upsample(MO, X, K_o, N_r_o, K, N_r, d):
+    return MO.INTERP_THETAS(K, K_o, MO.INTERP_RADIAL(N_r, N_r_o, X, d))
+
+
+def test_newton_history_at_config4_size(modules):
+    """BASELINE config 4 at its stated size: Main._Newton's iteration (host SciPy LGMRES, matrix-free JVPs) at
+    N_r = 30, N_theta = 256, symmetric, l = 10 parameter set (Main.py:617-624), from the seeded branch state
+    (golden/branch_seeds.npz, interpolated like Main.py:599-601).  The printed error history on the GPU operators must
+    equal the one on the CPU oracle operators to 1e-10 (north_star)."""
+    from oracle import sddc_oracle as orc
+    MO, _ = modules
+    sd = load_golden("branch_seeds")
+    l, d, Ra_c, Ra_s, sym = sd["l10_params"]
+    N_fm, N_r, Pr, Tau = 256, 30, 1.0, 1.0 / 15.0
+    X0 = _upsample(MO, sd["l10_X"], int(sd["N_fm"]), int(sd["N_r"]), N_fm, N_r, d)
+    Ra = float(sd["l10_Ra"]) - 2.0
+    Xg, hg, ng = drv.newton(MO, X0, Ra, Ra_s, Tau, Pr, d, N_fm, N_r, bool(sym))
+    orc.set_transform_backend("fft")
+    orc.set_accel(True)
+    try:
+        Xc, hc, nc = drv.newton(drv.OracleOperators(orc, N_fm, N_r, d, 1.0, Pr, Tau), X0, Ra, Ra_s, Tau, Pr, d, N_fm, N_r,
+                                bool(sym))
+    finally:
+        orc.set_accel(False)
+        orc.set_transform_backend("dense")
+    print("config-4 newton history gpu", hg, "cpu", hc, "matvecs", ng, nc)
+    assert len(hg) == len(hc) and len(hg) < 5 and hg[-1] < 1e-8, (hg, hc)      # converged inside Main._Newton's 5 iterations
+    assert ng == nc
+    assert np.max(np.abs(hg - hc)) < 1e-10, (hg, hc)
+    assert rel_l2(Xg, Xc) < 1e-9
+
+
+def test_arclength_history_at_config5_size(modules):
+    """BASELINE config 5 at its stated size: one branch point's (err_X, err_mu) history (Main.py:929) of Main._ContinC's
+    step at N_r = 40, N_theta = 512, l = 11 parameter set (Main.py:609-614), GPU operators against CPU oracle operators."""
+    from oracle import sddc_oracle as orc
+    MO, _ = modules
+    sd = load_golden("branch_seeds")
+    l, d, Ra_c, Ra_s, sym = sd["l11_params"]
+    N_fm, N_r, Pr, Tau = 512, 40, 1.0, 1.0 / 15.0
+    X0 = _upsample(MO, sd["l11_X"], int(sd["N_fm"]), int(sd["N_r"]), N_fm, N_r, d)
+    Ra = float(sd["l11_Ra"])
+    # polish on the new grid first (the interpolated state is only close to the discrete branch)
+    X0, h0, _ = drv.newton(MO, X0, Ra, Ra_s, Tau, Pr, d, N_fm, N_r, bool(sym), max_it=8)
+    assert h0[-1] < 1e-8, h0
+    Y0 = np.hstack((X0, Ra))
+    Yg, dsg, hg, ng = drv.continc(MO, Y0, float(sd["l11_sign"]), 0.5, Ra_s, Tau, Pr, d, N_fm, N_r, bool(sym))
+    orc.set_transform_backend("fft")
+    orc.set_accel(True)
+    try:
+        Yc, dsc, hc, nc = drv.continc(drv.OracleOperators(orc, N_fm, N_r, d, 1.0, Pr, Tau), Y0, float(sd["l11_sign"]), 0.5,
+                                      Ra_s, Tau, Pr, d, N_fm, N_r, bool(sym))
+    finally:
+        orc.set_accel(False)
+        orc.set_transform_backend("dense")
+    print("config-5 arc-length history gpu", hg.tolist(), "cpu", hc.tolist(), "matvecs", ng, nc, "ds", dsg, dsc)
+    assert hg.shape == hc.shape and dsg == dsc
+    assert np.max(np.abs(hg - hc)) < 1e-10, (hg, hc)
+    assert abs(Yg[-1] - Yc[-1]) < 1e-9 * abs(Yc[-1]) and rel_l2(Yg[:-1], Yc[:-1]) < 1e-9
