@@ -148,6 +148,14 @@ int sddc_diagnostics(sddc_plan* plan, const double* X, double* out, int B, void*
  * Synthesis kinds zero-pad / truncate to n_out like scipy's n= argument; analysis kinds truncate. */
 int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, int n_out, void* stream);
 
+/* Resolution transfer, the step every driver runs right before the hot path (Main.py:414-416, 599-601, 1093-1095;
+ * Gap_Continuation.py:27-31), batched over members (device pointers).
+ * sddc_interp_radial: INTERP_RADIAL (Matrix_Operators.py:901-941) as out[row][i] = sum_j W[i][j] in[row][j] over
+ *   rows = B * 3 * N_fm radial profiles; W [nr_n][nr_o] is the reference's polyfit / polyval map, built on the host.
+ * sddc_interp_thetas: INTERP_THETAS (Matrix_Operators.py:944-1011): [B][3][K_o][nr] -> [B][3][K_n][nr]. */
+int sddc_interp_radial(const double* in, double* out, const double* W, long long rows, int nr_o, int nr_n, void* stream);
+int sddc_interp_thetas(const double* in, double* out, int B, int K_o, int K_n, int nr, void* stream);
+
 /* Batched Arnoldi orthogonalisation for the lock-step Newton / pseudo-arc-length drivers: the Krylov algebra SciPy's
  * LGMRES performs inside Main._Newton (Main.py:530-534) and Main._ContinC (Main.py:917-920, 948), for B independent
  * solves at once.  V: [B][.][n] bases (member_stride doubles apart), w: [B][n] new directions, device pointers.

@@ -233,6 +233,44 @@ __global__ void transform_kernel(int kind, const double* __restrict__ in, double
     out[idx] = acc;
 }
 
+// Resolution transfer in r (INTERP_RADIAL, Matrix_Operators.py:901-941): the reference fits a polynomial through every
+// radial profile and evaluates it on the new grid -- a LINEAR map of the nr_o values, the same for every profile, which
+// the host builds once with the reference's own np.polyfit call (interp.py).  out[row][i] = sum_j W[i][j] in[row][j].
+__global__ void __launch_bounds__(256) interp_radial_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                           const double* __restrict__ W, long long rows, int nr_o, int nr_n) {
+    extern __shared__ double sW[];   // [nr_n][nr_o]
+    for (int i = threadIdx.x; i < nr_n * nr_o; i += 256) sW[i] = W[i];
+    __syncthreads();
+    const long long tot = rows * nr_n;
+    for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < tot; idx += (long long)gridDim.x * 256) {
+        const long long row = idx / nr_n;
+        const int i = (int)(idx - row * nr_n);
+        const double* x = in + row * nr_o;
+        const double* w = sW + i * nr_o;
+        double acc = 0.0;
+        for (int j = 0; j < nr_o; ++j) acc = fma(w[j], x[j], acc);
+        out[idx] = acc;
+    }
+}
+
+// Resolution transfer in theta (INTERP_THETAS, Matrix_Operators.py:944-1011).  The reference goes to the grid and back
+// (IDST / IDCT on max(K_o, K_n) points, DST / DCT truncated to K_n), which on one and the same midpoint grid is the
+// identity on every retained coefficient: the result is spectral zero-padding / truncation -- with one quirk kept, the
+// stream-function block 0 comes back as zero because IDST ignores entry 0 of what it is handed (Transforms.py:41-54).
+__global__ void interp_thetas_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int K_o, int K_n, int nr) {
+    const long long per = 3LL * K_n * nr, tot = per * B;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / per;
+        const long long r = idx - b * per;
+        const int f = (int)(r / ((long long)K_n * nr));
+        const int k = (int)((r - (long long)f * K_n * nr) / nr);
+        const int i = (int)(r % nr);
+        double v = 0.0;
+        if (k < K_o && !(f == 0 && k == 0)) v = in[((b * 3 + f) * K_o + k) * nr + i];
+        out[idx] = v;
+    }
+}
+
 // out = a - b (residual / JVP helper for rows the solve does not touch is not needed; used for host tests)
 __global__ void axpby_kernel(double* out, const double* a, const double* b, double alpha, double beta, long long nel) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nel; i += (long long)gridDim.x * blockDim.x)

@@ -1,4 +1,5 @@
 // Host side of the C ABI (include/sddc_b200.h): plan construction, operator upload / padding, kernel dispatch.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1114,6 +1115,24 @@ int sddc_transform(int kind, const double* in, double* out, int rows, int n_in, 
     if (kind >= 2 && n_out > n_in) return SDDC_ERR_INVALID;
     const long long tot = (long long)rows * n_out;
     transform_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(kind, in, out, rows, n_in, n_out);
+    return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
+int sddc_interp_radial(const double* in, double* out, const double* W, long long rows, int nr_o, int nr_n, void* stream) {
+    if (!in || !out || !W || rows < 1 || nr_o < 1 || nr_n < 1 || in == out) return SDDC_ERR_INVALID;
+    const size_t smem = sizeof(double) * (size_t)nr_o * nr_n;
+    if (smem > 48 * 1024) return SDDC_ERR_UNSUPPORTED;
+    const long long tot = rows * nr_n;
+    const int grid = (int)std::min<long long>((tot + 255) / 256, 148 * 16);
+    interp_radial_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(in, out, W, rows, nr_o, nr_n);
+    return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
+int sddc_interp_thetas(const double* in, double* out, int B, int K_o, int K_n, int nr, void* stream) {
+    if (!in || !out || B < 1 || K_o < 1 || K_n < 1 || nr < 1 || in == out) return SDDC_ERR_INVALID;
+    const long long tot = 3LL * K_n * nr * B;
+    const int grid = (int)std::min<long long>((tot + 255) / 256, 148 * 16);
+    interp_thetas_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, B, K_o, K_n, nr);
     return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
 }
 
