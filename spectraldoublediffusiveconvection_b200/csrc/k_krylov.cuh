@@ -27,17 +27,34 @@ struct GsParams {
     int nchunk, ldp;
 };
 
-// dot products of the CTA's chunk of w (in shared memory) with the same chunk of every basis vector: warp per vector
+// dot products of the CTA's chunk of w (in shared memory) with the same chunk of every basis vector: a warp takes two
+// vectors at a time (eight independent 8-byte loads per lane in flight)
 __device__ __forceinline__ void gs_chunk_dots(const GsParams& p, const double* Vb, const double* ws, int x0, int len,
                                               double* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = warp; i < p.nvec; i += GS_THREADS / 32) {
-        const double* row = Vb + (size_t)i * p.n + x0;
-        double acc = 0.0;
-#pragma unroll 4
-        for (int x = lane; x < len; x += 32) acc = fma(row[x], ws[x], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) out[i] = acc;
+    constexpr int NW = GS_THREADS / 32;
+    for (int i = 2 * warp; i < p.nvec; i += 2 * NW) {
+        const bool two = i + 1 < p.nvec;
+        const double* r0 = Vb + (size_t)i * p.n + x0;
+        const double* r1 = two ? r0 + p.n : r0;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        int x = lane;
+        for (; x + 96 < len; x += 128) {
+            const double w0 = ws[x], w1 = ws[x + 32], w2 = ws[x + 64], w3 = ws[x + 96];
+            const double p0 = r0[x], p1 = r0[x + 32], p2 = r0[x + 64], p3 = r0[x + 96];
+            const double q0 = r1[x], q1 = r1[x + 32], q2 = r1[x + 64], q3 = r1[x + 96];
+            a0 = fma(p0, w0, a0); a1 = fma(p1, w1, a1); a0 = fma(p2, w2, a0); a1 = fma(p3, w3, a1);
+            b0 = fma(q0, w0, b0); b1 = fma(q1, w1, b1); b0 = fma(q2, w2, b0); b1 = fma(q3, w3, b1);
+        }
+        for (; x < len; x += 32) {
+            a0 = fma(r0[x], ws[x], a0);
+            b0 = fma(r1[x], ws[x], b0);
+        }
+        const double sa = warp_sum(a0 + a1), sb = warp_sum(b0 + b1);
+        if (lane == 0) {
+            out[i] = sa;
+            if (two) out[i + 1] = sb;
+        }
     }
 }
 
@@ -69,19 +86,34 @@ __global__ void __launch_bounds__(GS_THREADS) gs_update_kernel(GsParams p) {
     __syncthreads();
     double* wb = p.w + (size_t)b * p.n + x0;
     double nrm = 0.0;
-    for (int x = threadIdx.x; x < len; x += GS_THREADS) {
-        const double* col = Vb + x0 + x;
-        double a0 = wb[x], a1 = 0.0;
-        int i = 0;
-        for (; i + 1 < p.nvec; i += 2) {      // two independent chains
-            a0 = fma(-hs[i], col[(size_t)i * p.n], a0);
-            a1 = fma(-hs[i + 1], col[(size_t)(i + 1) * p.n], a1);
+    // thread t owns the elements t, t + 256, t + 512, t + 768 of the chunk: four independent accumulation chains, the
+    // loads of one basis vector are coalesced across the warp
+    {
+        constexpr int NX = GS_CHUNK / GS_THREADS;
+        double acc[NX];
+        bool in[NX];
+#pragma unroll
+        for (int u = 0; u < NX; ++u) {
+            const int x = threadIdx.x + u * GS_THREADS;
+            in[u] = x < len;
+            acc[u] = in[u] ? wb[x] : 0.0;
         }
-        if (i < p.nvec) a0 = fma(-hs[i], col[(size_t)i * p.n], a0);
-        const double v = a0 + a1;
-        wb[x] = v;
-        ws[x] = v;
-        nrm = fma(v, v, nrm);
+        const double* col = Vb + x0 + threadIdx.x;
+        for (int i = 0; i < p.nvec; ++i, col += p.n) {
+            const double h = hs[i];
+#pragma unroll
+            for (int u = 0; u < NX; ++u)
+                if (in[u]) acc[u] = fma(-h, col[u * GS_THREADS], acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < NX; ++u) {
+            const int x = threadIdx.x + u * GS_THREADS;
+            if (in[u]) {
+                wb[x] = acc[u];
+                ws[x] = acc[u];
+                nrm = fma(acc[u], acc[u], nrm);
+            }
+        }
     }
     double* po = p.part_out + ((size_t)b * p.nchunk + c) * p.ldp;
     nrm = block_sum(nrm, red);       // contains the barrier that publishes ws

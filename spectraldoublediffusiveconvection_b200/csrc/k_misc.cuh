@@ -204,6 +204,27 @@ __global__ void __launch_bounds__(256) diag_kernel(const double* __restrict__ X,
     }
 }
 
+// The same record from partial sums: the back-substitution chains leave sum f^2 and the Nusselt sums of the state they
+// produce in dpart[b][field * 2 + parity][3] (k_solve_hot.cuh, DIAG), the kinetic-energy transform its row sums in kepart.
+// One warp per member; fixed summation order.
+__global__ void __launch_bounds__(128) diag_finish_kernel(const double* __restrict__ dpart, const double* __restrict__ kepart,
+                                                          int nke, double ke_scale, int B, double* __restrict__ out) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= B) return;
+    double ke = 0.0;
+    for (int idx = lane; idx < nke; idx += 32) ke += kepart[(long long)b * nke + idx];
+    ke = warp_sum(ke);
+    if (lane == 0) {
+        const double* d = dpart + (long long)b * 18;
+        double s2 = 0.0;
+        for (int c = 0; c < 6; ++c) s2 += d[c * 3];
+        double* o = out + (long long)b * 6;
+        o[0] = sqrt(s2); o[1] = ke_scale * ke;
+        o[2] = d[2 * 3 + 1] + d[3 * 3 + 1]; o[3] = d[4 * 3 + 1] + d[5 * 3 + 1];
+        o[4] = d[2 * 3 + 2] + d[3 * 3 + 2]; o[5] = d[4 * 3 + 2] + d[5 * 3 + 2];
+    }
+}
+
 // Generic drop-in transforms (Transforms.py:73-129) by direct summation; one thread per output element.
 __global__ void transform_kernel(int kind, const double* __restrict__ in, double* __restrict__ out, int rows,
                                  int n_in, int n_out) {

@@ -36,6 +36,10 @@ struct SolveParams {
     int field_base;         // field index of chain group 0 (for single-field calls)
     double dt_psi, dt_T, dt_S;  // Pr*dt, dt, Tau*dt
     int nsl;                    // pipeline stages in use (2 or 3)
+    double* dpart;              // optional [B][6][3] (k_solve_hot.cuh, DIAG): per chain (field * 2 + parity) the partial sums
+                                // of the NEW state's diagnostics: sum f^2, and for the even T / S chains the Nusselt sums at
+                                // the inner and outer wall (Main.py:41-68, 292)
+    const double *nu_in, *nu_out;   // [n] Nusselt weights (R_w^2 / A_T) D[w, 1:-1]
     double* jj_out;             // optional [B][K+1][n]: theta-coupling brackets of the NEW stream function, exactly what
                                 // scan_kernel would compute from the output (the running sum f_e of the A4 chain is that
                                 // suffix sum), so the next step of a multi-step call skips its scan (k_solve_hot.cuh)

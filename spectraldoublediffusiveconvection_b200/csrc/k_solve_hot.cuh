@@ -33,7 +33,8 @@ __host__ inline size_t solve_hot_smem_bytes(int n8, int nsl) {
 }
 
 // SUB: the call carries a subtrahend (residual / JVP); a compile-time switch so that the plain step keeps its registers
-template <int NT8, int NSL, int NTB, bool PSI, bool SUB = true>
+// DIAG: the chain also accumulates its share of ||X'||^2 and of the Nusselt sums of the state it produces (p.dpart)
+template <int NT8, int NSL, int NTB, bool PSI, bool SUB = true, bool DIAG = false>
 __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* smem, uint64_t* bar_full,
                                                 uint64_t* bar_empty, int fld, int which, int b0) {
     constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
@@ -75,6 +76,10 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     }
 
     if (G.symmetric && which == 1) {   // these modes are identically zero under the equatorial symmetry
+        if (DIAG) {
+            for (int m = tid; m < 3 * BT; m += blockDim.x)
+                if (b0 + m / 3 < p.B) p.dpart[((long long)(b0 + m / 3) * 6 + fld * 2 + which) * 3 + m % 3] = 0.0;
+        }
         if (is_producer) return;
         for (int s = 0; s < nsteps; ++s) {
 #pragma unroll
@@ -139,6 +144,11 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     for (int d = 0; d < 3; ++d)
 #pragma unroll
         for (int e = 0; e < NE; ++e) subq[d][e] = (has_sub && ok[e] && d < nsteps) ? outp[e][sub_delta + d * rstep] : 0.0;
+    double dn2[NE], dni[NE], dno[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { dn2[e] = 0.0; dni[e] = 0.0; dno[e] = 0.0; }
+    const bool nu_chain = DIAG && !PSI && which == 0;   // cosine modes 0, 2, 4, ... of T / S (Main.py:58-63)
+    const double nu_i = (nu_chain && row_ok) ? p.nu_in[i] : 0.0, nu_o = (nu_chain && row_ok) ? p.nu_out[i] : 0.0;
     int st = 0, ph = 0;
     for (int step = 0; step < nsteps; ++step) {
         const int j = j0 - 2 * step;
@@ -217,6 +227,18 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
                 f[e] = s;
             }
         }
+        if (DIAG) {
+            const double wk = 1.0 / (1.0 - (double)j * (double)j);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                dn2[e] = fma(f[e], f[e], dn2[e]);
+                if (nu_chain) {
+                    const double t = f[e] * wk;
+                    dni[e] = fma(nu_i, t, dni[e]);
+                    dno[e] = fma(nu_o, t, dno[e]);
+                }
+            }
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);   // operator + tiles of this stage are consumed
         if (++st == NSL) { st = 0; ph ^= 1; }
@@ -245,20 +267,58 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
         for (int e = 0; e < NE; ++e)
             if (ok[e]) jjp[e][0] = s1[e] + f[e];
     }
+    if (DIAG) {
+        // sum over the radial rows: the eight row groups of a warp by shuffles, the warps through shared memory in a
+        // fixed order; the lanes 0..3 of warp 0 then own the members 2 tq, 2 tq + 1 (+ 8 per member tile)
+        // (scratch: the GEMM operand buffers sR, free once every warp has left the last chain step)
+        static_assert(2 * NM * LDL >= NT8 * 3, "reduction scratch does not fit into the operand buffers");
+        double (*s_dred)[BT][3] = reinterpret_cast<double (*)[BT][3]>(sR);
+        asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            double v0 = dn2[e], v1 = dni[e], v2 = dno[e];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            }
+            if (gq == 0) {
+                const int m = (e >> 1) * 8 + 2 * tq + (e & 1);
+                s_dred[warp][m][0] = v0; s_dred[warp][m][1] = v1; s_dred[warp][m][2] = v2;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
+        if (warp == 0 && gq == 0) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int m = (e >> 1) * 8 + 2 * tq + (e & 1);
+                if (b0 + m < p.B) {
+                    double* d = p.dpart + ((long long)(b0 + m) * 6 + fld * 2 + which) * 3;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        double t = 0.0;
+                        for (int w2 = 0; w2 < NT8; ++w2) t += s_dred[w2][m][q];
+                        d[q] = t;
+                    }
+                }
+            }
+        }
+    }
 }
 
 // grid = 2 * (psi member tiles) + 4 * (T,S member tiles) CTAs, stream-function chains first; block = 32 * (NT8 + 1):
 // compute warp w owns radial rows 8w..8w+7 in MMA accumulator layout, the last warp is the TMA producer.
-template <int NT8, int NSL, bool SUB = false>
+template <int NT8, int NSL, bool SUB = false, bool DIAG = false>
 __global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
     const int bid = blockIdx.x;
     if (bid < 2 * npsi_tiles) {
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, SUB>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, SUB, DIAG>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
     } else {
         const int r = bid - 2 * npsi_tiles;
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, SUB>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, SUB, DIAG>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
                                                           (r >> 2) * 8 * SOLVE_NTB_TS);
     }
 }

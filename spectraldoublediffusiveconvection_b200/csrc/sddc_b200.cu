@@ -26,6 +26,9 @@ namespace {
 
 thread_local std::string g_create_error;
 constexpr size_t SMEM_LIMIT = 227 * 1024 - 1024;  // dynamic shared memory we opt in to (1 KB left for static barriers)
+#ifndef KE_NW768
+#define KE_NW768 8   // (6: 0.093 ms, 8: 0.084 ms, 10: 0.093 ms at (30,256), 512 members)  // workers per CTA of the kinetic-energy transform at M = 768
+#endif
 #ifndef SOLVE_NTB
 #define SOLVE_NTB 2  // members per back-substitution CTA = 8 * SOLVE_NTB (1 and 4 measured slower)
 #endif
@@ -64,6 +67,7 @@ struct sddc_plan {
     double *JJ = nullptr, *coef = nullptr, *prd = nullptr, *lin = nullptr, *rhs = nullptr, *xtmp = nullptr,
            *kepart = nullptr, *zeroRa = nullptr;
     double* coef1 = nullptr;
+    double* dpart = nullptr;   // [max_batch][6][3] diagnostics partial sums written by the back-substitution (DIAG)
     long long coef_member_stride = 0;
     double *lin_sm = nullptr, *f_sm = nullptr;  // solve-major [3][K][bstride][n8+2]
     double *gridc = nullptr, *xbase = nullptr;  // cached base state of sddc_jvp_set_base (lazily allocated)
@@ -425,9 +429,11 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
 
 // gs < 0 selects the solve-major layout for g / fnl
 int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, long long gf, double* out, long long os,
-              long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st, double* jj_out = nullptr) {
+              long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st, double* jj_out = nullptr,
+              double* dpart = nullptr) {
     SolveParams sp{};
     sp.jj_out = jj_out;
+    sp.dpart = dpart; sp.nu_in = pl->nu_in; sp.nu_out = pl->nu_out;
     const bool sm = gs < 0;
     sp.bstride = pl->bstride;
     sp.g = g; sp.fnl = fnl; sp.mdt = -pl->g.dt; sp.g_stride = gs; sp.g_field_off = gf; sp.out = out; sp.out_stride = os; sp.out_field_off = of;
@@ -445,8 +451,10 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
         const size_t smb = pl->solve_hot_smem;
         const bool n3 = pl->solve_hot_nsl == 3;
         const int nblk = 2 * npsi + 4 * nts;
+        if (sub && dpart) { pl->err = "diagnostics partial sums are only produced by plain steps"; return SDDC_ERR_INVALID; }
 #define SDDC_LAUNCH_SOLVE_HOT(NT)                                                                                 \
     if (sub) { if (n3) solve_hot_kernel<NT, 3, true><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, true><<<nblk, nthr, smb, st>>>(sp, npsi); } \
+    else if (dpart) { if (n3) solve_hot_kernel<NT, 3, false, true><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, false, true><<<nblk, nthr, smb, st>>>(sp, npsi); } \
     else { if (n3) solve_hot_kernel<NT, 3, false><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, false><<<nblk, nthr, smb, st>>>(sp, npsi); }
         switch (pl->g.nt8) {
             case 3: SDDC_LAUNCH_SOLVE_HOT(3) break;
@@ -466,7 +474,7 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
 
 // kinetic energy by FFT from coefficient rows + the remaining diagnostics (norm, Nusselt numbers)
 int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row_stride, int b_off, const double* ascale,
-               double* out, int B, cudaStream_t st) {
+               double* out, int B, cudaStream_t st, const double* dpart = nullptr) {
     const Geo& g = pl->g;
     KeFftParams kf{};
     kf.rows = rows; kf.row_stride = row_stride; kf.b_off = b_off; kf.ascale = ascale;
@@ -475,12 +483,14 @@ int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row
     {
         StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
         if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<std::min((kf.nrows + 7) / 8, pl->num_sms), 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
-        else ke_fft_kernel<768, 6><<<std::min((kf.nrows + 5) / 6, pl->num_sms), 384, ke_fft_smem_bytes<768>(6), st>>>(kf);
+        else ke_fft_kernel<768, KE_NW768><<<std::min((kf.nrows + KE_NW768 - 1) / KE_NW768, pl->num_sms), 64 * KE_NW768, ke_fft_smem_bytes<768>(KE_NW768), st>>>(kf);
     }
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     StageTimer tm2(pl, SDDC_STAGE_DIAG, st);
-    diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, g.n, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
+    // norm and Nusselt numbers: from the partial sums the back-substitution that produced X left behind, else from X
+    if (dpart) diag_finish_kernel<<<(B + 3) / 4, 128, 0, st>>>(dpart, pl->kepart, g.n, pl->ke_scale, B, out);
+    else diag_kernel<<<B, 256, 0, st>>>(X, pl->kepart, g.n, pl->nu_in, pl->nu_out, pl->ke_scale, g, out);
     pl->launches++;
     PLAN_CUDA(pl, cudaGetLastError());
     return SDDC_OK;
@@ -494,7 +504,8 @@ int run_step_prep(sddc_plan* pl, const double* X, const double* Ra, const double
     return run_prep(pl, X, 0, !linear, pl->lin_sm, Ra, Ras, B, st, fft ? pl->coef7 : nullptr, have_jj);
 }
 
-int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool linear, cudaStream_t st, bool emit_jj = false) {
+int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool linear, cudaStream_t st, bool emit_jj = false,
+                  bool emit_diag = false) {
     const long long N3 = 3LL * pl->g.N;
     const bool fft = pl->fft_M != 0 && !linear;
     int rc;
@@ -507,7 +518,8 @@ int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool lin
         if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
     }
-    return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, emit_jj ? pl->JJ : nullptr);
+    return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, emit_jj ? pl->JJ : nullptr,
+                     emit_diag ? pl->dpart : nullptr);
 }
 
 // have_jj / emit_jj chain the steps of a multi-step call: the A4 back-substitution of step s writes the suffix-sum
@@ -702,6 +714,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->nke = pl->Mh3p / (8 * pl->synth_nt_ke);
     TRY(dev_alloc(pl, &pl->kepart, Bm * std::max(pl->nke, n), true));
     TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
+    TRY(dev_alloc(pl, &pl->dpart, Bm * 18, true));
     // ---- opt in to large dynamic shared memory ----
     {
         SynthParams sp{};
@@ -768,7 +781,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
                     TRY(set_smem(pl, (ke_fft_kernel<384, 8>), ke_fft_smem_bytes<384>(8)));
                 } else {
                     kt.resize(fftp::tab_doubles<768>()); fftp::fill_tables<768>(kt.data()); fftp::fill_ke_weights<768>(kw.data());
-                    TRY(set_smem(pl, (ke_fft_kernel<768, 6>), ke_fft_smem_bytes<768>(6)));
+                    TRY(set_smem(pl, (ke_fft_kernel<768, KE_NW768>), ke_fft_smem_bytes<768>(KE_NW768)));
                 }
                 TRY(upload(pl, &pl->ke_tab, kt));
                 TRY(upload(pl, &pl->ke_Wn, kw));
@@ -786,18 +799,18 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->solve_smem = solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double);
     pl->solve_hot_nsl = solve_hot_smem_bytes(n8, 3) <= SMEM_LIMIT ? 3 : 2;
     pl->solve_hot_smem = solve_hot_smem_bytes(n8, pl->solve_hot_nsl);
-    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<3, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, true>), pl->solve_hot_smem)); }
-    else { TRY(set_smem(pl, (solve_hot_kernel<3, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, true>), pl->solve_hot_smem)); }
-    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<4, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, true>), pl->solve_hot_smem)); }
-    else { TRY(set_smem(pl, (solve_hot_kernel<4, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 2, true>), pl->solve_hot_smem)); }
-    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<5, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 3, true>), pl->solve_hot_smem)); }
-    else { TRY(set_smem(pl, (solve_hot_kernel<5, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 2, true>), pl->solve_hot_smem)); }
-    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<6, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 3, true>), pl->solve_hot_smem)); }
-    else { TRY(set_smem(pl, (solve_hot_kernel<6, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 2, true>), pl->solve_hot_smem)); }
-    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<7, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 3, true>), pl->solve_hot_smem)); }
-    else { TRY(set_smem(pl, (solve_hot_kernel<7, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 2, true>), pl->solve_hot_smem)); }
-    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<8, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 3, true>), pl->solve_hot_smem)); }
-    else { TRY(set_smem(pl, (solve_hot_kernel<8, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 2, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<3, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, false, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<3, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, false, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<4, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, false, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<4, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 2, false, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<5, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 3, false, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<5, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<5, 2, false, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<6, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 3, false, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<6, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<6, 2, false, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<7, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 3, false, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<7, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<7, 2, false, true>), pl->solve_hot_smem)); }
+    if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<8, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 3, false, true>), pl->solve_hot_smem)); }
+    else { TRY(set_smem(pl, (solve_hot_kernel<8, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<8, 2, false, true>), pl->solve_hot_smem)); }
     TRY(set_smem(pl, solve_kernel<SOLVE_NTB, false>, pl->solve_smem));
     TRY(set_smem(pl, prep_kernel<3>, prep_smem_bytes(n8, 1)));
     TRY(set_smem(pl, prep_kernel<4>, prep_smem_bytes(n8, 1)));
@@ -944,10 +957,12 @@ int sddc_time_step(sddc_plan* pl, const double* Xin, double* Xout, const double*
         double* dst = ((nsteps - s + 1) & 1) ? Xout : pl->xtmp;  // the last step lands in Xout
         if ((rc = run_step_prep(pl, src, Ra, Ras, B, linear != 0, st, s > 1))) return rc;
         if (pending >= 0) {
-            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, diag_hist + (size_t)pending * B * 6, B, st))) return rc;
+            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, diag_hist + (size_t)pending * B * 6, B, st, pl->dpart))) return rc;
             pending = -1;
         }
-        if ((rc = run_step_rest(pl, dst, nullptr, B, linear != 0, st, s < nsteps))) return rc;
+        // the back-substitution also leaves ||X_s||^2 and the Nusselt sums when X_s gets a shared-prep record
+        const bool rec_shared = share && diag_every && s % diag_every == 0 && s < nsteps;
+        if ((rc = run_step_rest(pl, dst, nullptr, B, linear != 0, st, s < nsteps, rec_shared))) return rc;
         src = dst;
         if (diag_every && s % diag_every == 0) {
             const int r = s / diag_every - 1;
@@ -1286,11 +1301,12 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
     for (int s = 1; s <= nsteps; ++s) {
         if ((rc = run_step_prep(pl, cur, pl->hRa, pl->hRas, B, linear != 0, cs, s > 1))) return rc;
         if (pending >= 0) {
-            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs))) return rc;
+            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs, pl->dpart))) return rc;
             if ((rc = ship_record(pending))) return rc;
             pending = -1;
         }
-        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs, s < nsteps))) return rc;
+        const bool rec_shared = share && diag_every && s % diag_every == 0 && s < nsteps;
+        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs, s < nsteps, rec_shared))) return rc;
         std::swap(cur, nxt);
         if (diag_every && s % diag_every == 0) {
             const int r = s / diag_every - 1;

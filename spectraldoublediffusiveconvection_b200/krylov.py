@@ -78,7 +78,11 @@ class _TorchOrtho:
 
 
 class _FusedOrtho:
-    """CGS2 in three passes over the basis with the library's kernels (sddc_gs_dots / sddc_gs_update)."""
+    """Classical Gram-Schmidt with re-orthogonalisation in at most three passes over the basis with the library's
+    kernels (sddc_gs_dots / sddc_gs_update).  The second pass already measures what the first one left behind
+    (part2 = V^T w'): when that is below REORTH_TOL |w'| for every member the third pass is skipped ("twice is enough"
+    applied only where once was not)."""
+    REORTH_TOL = 1e-11
 
     def __init__(self, V):
         from . import _lib
@@ -100,8 +104,14 @@ class _FusedOrtho:
         rc = lib.sddc_gs_dots(*args, w.data_ptr(), self.p1.data_ptr(), self.ldp, self.B, st)
         rc = rc or lib.sddc_gs_update(*args, w.data_ptr(), self.p1.data_ptr(), self.h1.data_ptr(), self.p2.data_ptr(),
                                       self.ldp, 1, self.B, st)
-        rc = rc or lib.sddc_gs_update(*args, w.data_ptr(), self.p2.data_ptr(), self.h2.data_ptr(), self.p3.data_ptr(),
-                                      self.ldp, 0, self.B, st)
+        if rc:
+            raise RuntimeError("libsddc_b200 Gram-Schmidt kernels failed (%d)" % rc)
+        s2 = self.p2.sum(dim=1)                                  # [B, ldp]: V^T w' and |w'|^2 in slot nvec (fixed order)
+        left = torch.linalg.vector_norm(s2[:, :nvec], dim=1)
+        if bool((left <= self.REORTH_TOL * torch.sqrt(s2[:, nvec])).all()):
+            return self.h1[:, :nvec].clone(), torch.sqrt(s2[:, nvec]), w
+        rc = lib.sddc_gs_update(*args, w.data_ptr(), self.p2.data_ptr(), self.h2.data_ptr(), self.p3.data_ptr(),
+                                self.ldp, 0, self.B, st)
         if rc:
             raise RuntimeError("libsddc_b200 Gram-Schmidt kernels failed (%d)" % rc)
         h = self.h1[:, :nvec] + self.h2[:, :nvec]
