@@ -297,30 +297,7 @@ SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, 
 }
 
 // ---- kinetic energy (Main.py:71-134): one complex transform per radial row on the M = 3K grid -----------------------
-// ca: K = M/3 cosine-type coefficients (J_theta(psi)/r), sb: K sine-type coefficients (Dr psi, sinusoid indexing).
-// Same packing as build(); the spectrum is empty between K and M - K.
-template <int M>
-SDDC_HD void build_ke(int t, const double* __restrict__ ca, const double* __restrict__ sb, double asc,
-                      double* __restrict__ buf, const Tables& tb) {   // asc scales the cosine-type row (1/r)
-    constexpr int Kc = M / 3, PL = Cfg<M>::PL;
-    double* re = buf;
-    double* im = buf + PL;
-    for (int k = t; k <= M / 2; k += NTW) {
-        const int kp = M - k, p = kpos<M>(k), pp = kpos<M>(kp % M);
-        if (k >= Kc) {
-            re[p] = 0.0; im[p] = 0.0;
-            if (kp != k) { re[pp] = 0.0; im[pp] = 0.0; }
-        } else if (k == 0) {
-            re[p] = asc * ca[0]; im[p] = 0.0;
-        } else {
-            const double a = asc * ca[k], b = sb[k], wc = tb.wkc[k], ws = tb.wks[k];
-            const double P = a + b, Q2 = b - a;   // Z_k = w_k P / 2,  Z_{M-k} = w_{M-k} (i Q2) / 2
-            re[p] = wc * P;   im[p] = ws * P;
-            re[pp] = -wc * Q2; im[pp] = ws * Q2;
-        }
-    }
-}
-
+// (packing + radix-8 pass: fftp::ke_stage / ke_pack in fft_fused.h)
 // last inverse pass + weighted sum of squares: returns this thread's share of
 //   sum_n Wn[n] (Jpsi(n)^2 + Dpsi(n)^2),  Wn = theta trapezoid weight * sin(theta) in the transform's point order
 template <int M>

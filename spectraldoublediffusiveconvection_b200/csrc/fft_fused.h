@@ -512,6 +512,24 @@ SDDC_HD void cp_fwd(int t, const double* __restrict__ buf, double* __restrict__ 
     if (sp >= 0 && sp < 2) cp_block0<M, 2>(sp, buf + pair_off<M>(sp), buf + pair_off<M>(sp) + PL, out, tb);
 }
 
+// ---- kinetic energy (Main.py:71-134) with the fused packing ----------------------------------------------------------
+// The 3K grid keeps only K = M/3 coefficients per field.  ke_stage copies the cosine-type row (scaled by asc = 1/r) and the
+// sine-type row into shared memory, zero padded to the 2M/3 entries bc_transform reads, so that packing and the radix-8 pass
+// run from registers exactly as for the nonlinear term (one shared-memory round trip less than build_ke + pass_c).
+template <int M>
+SDDC_HD void ke_stage(int t, const double* __restrict__ ca, const double* __restrict__ sb, double asc,
+                      double* __restrict__ rows) {
+    constexpr int Kc = M / 3, K2 = Cfg<M>::K;
+    for (int k = t; k < K2; k += NTW) {
+        rows[k] = k < Kc ? asc * ca[k] : 0.0;
+        rows[K2 + k] = k < Kc ? sb[k] : 0.0;
+    }
+}
+template <int M>
+SDDC_HD void ke_pack(int t, const double* __restrict__ rows, double* __restrict__ buf, const Tables& tb) {
+    bc_transform<M, 0, 1, NTW>(t, PackSrc{rows, rows + Cfg<M>::K}, buf, buf + Cfg<M>::PL, tb);
+}
+
 // ---- staged schedule of the one-state kernel (nlin_fft_staged_kernel): per-warp ownership of transforms ------------------
 // Worker buffer: plane pairs 0..3 (8 PL doubles), then 3 K doubles (DS | -kT | -kS) of the staged row; the rows
 // (JT, omega) / (DT, Dpsi) of the staged row sit in the planes of pair 2 / 3.

@@ -191,9 +191,12 @@ struct KeFftParams {
 };
 template <int M>
 __host__ __device__ constexpr int ke_fft_shared_doubles() { return nlin_fft_tab_pad<M>() + M; }
+// per worker: one plane pair + the two zero-padded coefficient rows (fftp::ke_stage)
+template <int M>
+__host__ __device__ constexpr int ke_fft_worker_doubles() { return 2 * fftp::Cfg<M>::PL + 2 * fftp::Cfg<M>::K; }
 template <int M>
 __host__ __device__ constexpr size_t ke_fft_smem_bytes(int nw) {
-    return sizeof(double) * ((size_t)ke_fft_shared_doubles<M>() + (size_t)nw * 2 * fftp::Cfg<M>::PL);
+    return sizeof(double) * ((size_t)ke_fft_shared_doubles<M>() + (size_t)nw * ke_fft_worker_doubles<M>());
 }
 
 template <int M, int NW>
@@ -209,14 +212,15 @@ __global__ void __launch_bounds__(64 * NW, 1) ke_fft_kernel(KeFftParams p) {
     __syncthreads();
     const Tables tb = make_tables<M>(stab);
     const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
-    double* buf = smem + ke_fft_shared_doubles<M>() + (size_t)w * 2 * PL;
+    double* buf = smem + ke_fft_shared_doubles<M>() + (size_t)w * ke_fft_worker_doubles<M>();
+    double* srow = buf + 2 * PL;
     C tw[Cfg<M>::RD];
     load_tw<M>(t, tb, tw);
     for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
         const double* r = p.rows + (size_t)row * p.row_stride;
-        build_ke<M>(t, r, r + p.b_off, p.ascale ? p.ascale[row % p.n] : 1.0, buf, tb);
+        ke_stage<M>(t, r, r + p.b_off, p.ascale ? p.ascale[row % p.n] : 1.0, srow);
         worker_sync(w);
-        pass_c<M, 1, +1>(t, buf);
+        ke_pack<M>(t, srow, buf, tb);
         worker_sync(w);
         pass_d<M, 1, +1>(t, buf, tw);
         worker_sync(w);

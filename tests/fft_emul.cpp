@@ -103,12 +103,13 @@ static void run_ke_rows(const double* rows, double* out, int nrows) {
     fill_tables<M>(tab.data());
     fill_ke_weights<M>(Wn.data());
     const Tables tb = make_tables<M>(tab.data());
-    std::vector<double> buf((size_t)2 * PL);
+    std::vector<double> buf((size_t)2 * PL), srow((size_t)2 * Cfg<M>::K);
     for (int row = 0; row < nrows; ++row) {
         for (auto& v : buf) v = 1e300;
+        for (auto& v : srow) v = 1e300;
         const double* r = rows + (size_t)row * 2 * Kc;
-        for (int t = 0; t < NTW; ++t) build_ke<M>(t, r, r + Kc, 1.0, buf.data(), tb);
-        for (int t = 0; t < NTW; ++t) pass_c<M, 1, +1>(t, buf.data());
+        for (int t = 0; t < NTW; ++t) ke_stage<M>(t, r, r + Kc, 1.0, srow.data());
+        for (int t = 0; t < NTW; ++t) ke_pack<M>(t, srow.data(), buf.data(), tb);
         for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 1, +1>(t, buf.data(), tw); }
         double s = 0.0;
         for (int t = 0; t < NTW; ++t) s += ke6<M>(t, buf.data(), tb, Wn.data());
