@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "fft_core.h"
 #include "fft_fused.h"
+#include "k_misc.cuh"
 
 namespace sddc {
 
@@ -229,6 +230,90 @@ __global__ void __launch_bounds__(64 * NW, 1) ke_fft_kernel(KeFftParams p) {
         worker_sync(w);
         if (t == 0) p.kepart[row] = p.wr[row % p.n] * (s_part[w][0] + s_part[w][1]);
         worker_sync(w);
+    }
+}
+
+// ---- direct-summation row kernel ---------------------------------------------------------------------------------------
+// The same contract as nlin_fft_kernel -- [rows][7][K] spectral rows in, [rows][4][K] analysed products out, then
+// post_kernel -- for shapes the FFT and the mirror-split DMMA transforms do not cover: N_fm = 2 (mod 4), whose 3/2-padded
+// grid has an odd number of points (the reference only asks for an even N_fm, Matrix_Operators.py:758), and the two-state
+// products at N_r > 41 outside N_fm = 128 / 256 / 512.  One CTA per (member, radial row); thread j synthesises the seven
+// fields at theta_j by direct sums (exact argument reduction, no tables), forms the products of
+// Matrix_Operators.py:791-793 (884-887 for a pair of states), thread k analyses them.  O(K M) per field: a correctness
+// path for small or odd shapes, not a fast one.
+struct NlinDirectParams {
+    const double* coef0;  // [rows][7][K]
+    const double* coef1;  // [rows][7][K] second state, or null
+    double* spec;         // [rows][4][K]
+    int K, M;
+};
+
+__device__ __forceinline__ void direct_fields(const double* __restrict__ r, int K, int M, int j, double (&f)[7]) {
+    // rows: 0 JT (cos), 1 omega (sin), 2 DT (cos), 3 Dpsi (sin), 4 DS (cos), 5 -kT (sin), 6 -kS (sin)
+#pragma unroll
+    for (int q = 0; q < 7; ++q) f[q] = 0.0;
+    for (int k = 0; k < K; ++k) {
+        double c, s;
+        trig_kj(k, j, M, c, s);
+        f[0] = fma(r[k], c, f[0]);
+        f[2] = fma(r[2 * K + k], c, f[2]);
+        f[4] = fma(r[4 * K + k], c, f[4]);
+        if (k) {   // entry 0 of a sine-type row is ignored (Transforms.py:41-54)
+            f[1] = fma(r[K + k], s, f[1]);
+            f[3] = fma(r[3 * K + k], s, f[3]);
+            f[5] = fma(r[5 * K + k], s, f[5]);
+            f[6] = fma(r[6 * K + k], s, f[6]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) nlin_direct_kernel(NlinDirectParams p) {
+    extern __shared__ __align__(128) double smem[];
+    const int K = p.K, M = p.M, row = blockIdx.x, tid = threadIdx.x;
+    const bool two = p.coef1 != nullptr;
+    double* sc0 = smem;                     // [7][K]
+    double* sc1 = sc0 + 7 * K;              // [7][K] (two-state)
+    double* sp = sc1 + (two ? 7 * K : 0);   // [4][M] grid products: JT*om, Dpsi*om, N_T, N_S
+    for (int i = tid; i < 7 * K; i += 128) {
+        sc0[i] = p.coef0[(size_t)row * 7 * K + i];
+        if (two) sc1[i] = p.coef1[(size_t)row * 7 * K + i];
+    }
+    __syncthreads();
+    for (int j = tid; j < M; j += 128) {
+        double a[7];
+        direct_fields(sc0, K, M, j, a);
+        if (!two) {
+            sp[j] = a[0] * a[1];
+            sp[M + j] = a[3] * a[1];
+            sp[2 * M + j] = a[0] * a[2] - a[3] * a[5];     // JT DT - Dpsi kT: the rows -k T, -k S ARE the sine series kT, kS
+            sp[3 * M + j] = a[0] * a[4] - a[3] * a[6];
+        } else {
+            double b[7];
+            direct_fields(sc1, K, M, j, b);
+            sp[j] = a[0] * b[1] + b[0] * a[1];
+            sp[M + j] = a[3] * b[1] + b[3] * a[1];
+            sp[2 * M + j] = (a[0] * b[2] + b[0] * a[2]) - (a[3] * b[5] + b[3] * a[5]);
+            sp[3 * M + j] = (a[0] * b[4] + b[0] * a[4]) - (a[3] * b[6] + b[3] * a[6]);
+        }
+    }
+    __syncthreads();
+    // out: [0] DST(JT om), [1] DST(kDpsi om + Dpsi kom) = -k DCT(Dpsi om), [2] DCT(N_T), [3] DCT(N_S)  (as cp_emit)
+    double* o = p.spec + (size_t)row * 4 * K;
+    for (int k = tid; k < K; k += 128) {
+        double s0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+        for (int j = 0; j < M; ++j) {
+            double c, s;
+            trig_kj(k, j, M, c, s);
+            s0 = fma(sp[j], s, s0);
+            c1 = fma(sp[M + j], c, c1);
+            c2 = fma(sp[2 * M + j], c, c2);
+            c3 = fma(sp[3 * M + j], c, c3);
+        }
+        const double sc = (k == 0 ? 1.0 : 2.0) / M;
+        o[k] = k ? s0 * (2.0 / M) : 0.0;
+        o[K + k] = -(double)k * (c1 * sc);
+        o[2 * K + k] = c2 * sc;
+        o[3 * K + k] = c3 * sc;
     }
 }
 

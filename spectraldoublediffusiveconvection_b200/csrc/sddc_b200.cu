@@ -72,8 +72,10 @@ struct sddc_plan {
     double *lin_sm = nullptr, *f_sm = nullptr;  // solve-major [3][K][bstride][n8+2]
     double *gridc = nullptr, *xbase = nullptr;  // cached base state of sddc_jvp_set_base (lazily allocated)
     // FFT formulation of the nonlinear term (k_nlin_fft.cuh): available for N_fm = 128, 256, 512
-    int fft_M = 0;              // 3 N_fm / 2 when the FFT path is active, else 0
-    bool fft_dfx = false;       // two-state (JVP) variant available
+    int fft_M = 0;              // 3 N_fm / 2 when the row pipeline (prep -> row kernel -> post) is active, else 0
+    bool fft_dfx = false;       // two-state (JVP) products through the row pipeline
+    bool fft_direct = false;    // row kernel = nlin_direct_kernel (N_fm = 2 mod 4) instead of the FFT kernels
+    bool dfx_direct = false;    // only the two-state products take the (direct) row pipeline: dense shapes beyond N_r = 41
     int ke_M = 0;               // 3 N_fm when the kinetic-energy synthesis runs as an FFT (N_fm = 128, 256), else 0
     double *ke_tab = nullptr, *ke_Wn = nullptr;
     int* fft_row = nullptr;     // dynamic row counter of nlin_fft_kernel (zeroed before every launch)
@@ -419,6 +421,30 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
     np.coef0 = c0; np.coef1 = c1; np.spec = pl->spec4; np.tab = pl->fft_tab; np.nrows = B * pl->g.n;
     const long long bstride = solve_major ? pl->bstride : 0;
     const bool dfx = c1 != nullptr;
+    if (pl->fft_direct || (dfx && pl->dfx_direct)) {
+        if (set_attr) return SDDC_OK;
+        NlinDirectParams dp{};
+        dp.coef0 = c0; dp.coef1 = c1; dp.spec = pl->spec4; dp.K = pl->g.K; dp.M = pl->g.M;
+        const size_t dsm = sizeof(double) * ((size_t)(dfx ? 14 : 7) * pl->g.K + 4 * (size_t)pl->g.M);
+        {
+            StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
+            nlin_direct_kernel<<<np.nrows, 128, dsm, st>>>(dp);
+        }
+        pl->launches++;
+        PLAN_CUDA(pl, cudaGetLastError());
+        if (out) {
+            PostParams pp{};
+            pp.spec = pl->spec4; pp.DrT = pl->DrT; pp.out = out; pp.bstride = bstride; pp.g = pl->g;
+            const int ntiles = ((pl->g.K + POST_TC - 1) / POST_TC) * B;
+            const size_t psm = post_smem_bytes(pl->g.n, pl->g.n8);
+            const int per_sm = std::max(1, std::min(4, (int)((SMEM_LIMIT + 1024) / (psm + 1024))));
+            StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
+            post_kernel<<<std::min(ntiles, per_sm * pl->num_sms), 256, psm, st>>>(pp, ntiles);
+            pl->launches++;
+            PLAN_CUDA(pl, cudaGetLastError());
+        }
+        return SDDC_OK;
+    }
     switch (pl->fft_M) {
         case 192: return launch_nlin_fft<192>(pl, np, out, bstride, dfx, st, set_attr);
         case 384: return launch_nlin_fft<384>(pl, np, out, bstride, dfx, st, set_attr);
@@ -570,9 +596,10 @@ int sddc_plan_info(const sddc_plan* plan, int what) {
         case 1: return plan->ws_ok ? 1 : 0;         // dense path: 0 generic synthesis kernel, 1 persistent warp-specialised
         case 2: return plan->dfx_ok ? 1 : 0;        // two-state JVP synthesis available
         case 3: return plan->g.n8;
-        case 4: return plan->fft_M;                 // grid size of the FFT formulation of the nonlinear term (0: dense DMMA path)
+        case 4: return plan->fft_direct ? 0 : plan->fft_M;   // grid size of the FFT formulation of the nonlinear term (0: not active)
         case 5: return plan->fft_dfx ? 1 : 0;       // FFT formulation also used for the two-state (JVP) products
         case 6: return plan->ke_M;                  // grid size of the kinetic-energy FFT (0: dense synthesis)
+        case 7: return plan->fft_direct ? 1 : (plan->dfx_direct ? 2 : 0);   // direct-summation row kernel: 1 every product, 2 two-state products only
         default: return -1;
     }
 }
@@ -599,10 +626,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
         g_create_error = "The number of Fourier modes is not even " + std::to_string(cfg->N_fm);
         return SDDC_ERR_INVALID;
     }
-    if (cfg->N_fm % 4 != 0 || cfg->N_fm < 8) {
-        g_create_error = "N_fm must be a multiple of 4 and >= 8 (mirror-pair split of the 3/2-padded grid)";
-        return SDDC_ERR_UNSUPPORTED;
-    }
+    if (cfg->N_fm < 8) { g_create_error = "N_fm must be >= 8"; return SDDC_ERR_UNSUPPORTED; }
     if (cfg->N_r < 4 || cfg->N_r - 1 > 64) { g_create_error = "N_r must satisfy 4 <= N_r <= 65"; return SDDC_ERR_UNSUPPORTED; }
     if (cfg->max_batch < 1) { g_create_error = "max_batch must be >= 1"; return SDDC_ERR_INVALID; }
     int ndev = 0;
@@ -786,6 +810,32 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
                 TRY(upload(pl, &pl->ke_tab, kt));
                 TRY(upload(pl, &pl->ke_Wn, kw));
             }
+            TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<5, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<6, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<7, true>), prep_smem_bytes(n8, 1)));
+            TRY(set_smem(pl, (prep_kernel<8, true>), prep_smem_bytes(n8, 1)));
+        }
+    }
+    {
+        // shapes neither the FFT kernels nor the mirror-split DMMA transforms cover go through the same row pipeline with
+        // the direct-summation row kernel (k_nlin_fft.cuh): every product for N_fm = 2 (mod 4), the two-state products only
+        // where the dense two-state synthesis does not fit into shared memory (N_r > 41)
+        const bool all_direct = K % 4 != 0;
+        const bool jvp_direct = !all_direct && pl->fft_M == 0 && !pl->dfx_ok;
+        if (all_direct || jvp_direct) {
+            if ((size_t)(14 * K + 4 * g.M) * sizeof(double) > 48 * 1024) {
+                pl->err = "direct-summation path: N_fm too large";
+                return fail(SDDC_ERR_UNSUPPORTED);
+            }
+            pl->fft_direct = all_direct; pl->dfx_direct = jvp_direct;
+            if (all_direct) pl->fft_M = g.M;
+            pl->fft_dfx = true;
+            TRY(dev_alloc(pl, &pl->coef7, Bm * 7 * g.N, false));
+            TRY(dev_alloc(pl, &pl->coef7b, Bm * 7 * g.N, false));
+            TRY(dev_alloc(pl, &pl->spec4, Bm * 4 * g.N, false));
+            TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
             TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8, 1)));
             TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8, 1)));
             TRY(set_smem(pl, (prep_kernel<5, true>), prep_smem_bytes(n8, 1)));

@@ -195,7 +195,8 @@ def test_error_behaviour():
 
 @pytest.mark.parametrize("K,N_r,sym", [(128, 20, False), (512, 40, False), (64, 33, True), (40, 50, False),
                                         (24, 65, False), (8, 18, True), (128, 26, True), (256, 12, True),
-                                        (512, 9, True), (256, 50, False)])
+                                        (512, 9, True), (256, 50, False),
+                                        (50, 12, False), (30, 10, True), (42, 45, False), (10, 8, False)])
 def test_other_shapes_against_oracle(K, N_r, sym):
     """Every kernel instantiation (radial tile counts 3..8, BASELINE configs 2 and 5 shapes, ragged mode counts):
     one step, one JVP, diagnostics and the nonlinear term against the NumPy oracle on seeded inputs."""
@@ -212,15 +213,15 @@ def test_other_shapes_against_oracle(K, N_r, sym):
     Xd, dvd = _dev(X), _dev(dv)
     F = pl.nlin_fx(Xd).cpu().numpy()
     st = pl.step(Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
-    # the dense two-state synthesis needs 2x the staging shared memory; the FFT formulation
-    # (N_fm = 128, 256) has no such limit
-    has_jvp = N_r <= 41 or K in (128, 256)
-    if has_jvp:
-        jv = pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
-    else:
-        from spectraldoublediffusiveconvection_b200.plan import SddcError
-        with pytest.raises(SddcError):
-            pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s))
+    # every shape has its two-state products: FFT kernels (N_fm = 128, 256, 512), dense two-state synthesis (N_r <= 41), or
+    # the direct-summation row kernel (N_r > 41 elsewhere, and everything at N_fm = 2 mod 4, whose padded grid is odd)
+    info = pl.info()
+    assert info["direct_rows"] == (1 if K % 4 else (2 if (N_r > 41 and K not in (128, 256, 512)) else 0)), info
+    has_jvp = True
+    jv = pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
+    Fd = pl.nlin_dfx(dvd, Xd).cpu().numpy()
+    for m in range(B):
+        assert rel_l2(Fd[m], orc.NLIN_DFX(dv[m], X[m], op, sym)) < 1e-11
     dg = pl.diagnostics(Xd).cpu().numpy()
     mask = orc.sym_mask(K, N_r - 1).reshape(-1) if sym else 1.0
     for m in range(B):
