@@ -180,7 +180,7 @@ def run_reference(a):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     ctx = mp.get_context("spawn")
-    min_s = 2.5   # every worker repeats its K-step block for at least this long: a 20-step block is only ~60 ms
+    min_s = 4.0   # every worker repeats its K-step block for at least this long: a 20-step block is only ~60 ms
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_worker, [(a.N_fm, a.N_r, i, 1, 2, 0.0) for i in range(cores)])          # spawn + JIT warm-up
         # all workers run concurrently; each repeats its block of K steps (after its own W warm-up steps)
@@ -308,10 +308,22 @@ def run_ours(a):
     synth_tflops = Bl * synth_flops / (stage_ms["synth"] * 1e-3) / 1e12 if stage_ms["synth"] > 0 else 0.0
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
-    traffic = None
+    # DRAM bytes per launch from the committed ncu capture of this very configuration (tools/profile_step.py under
+    # `ncu --set full`, summarised by tools/summarize_ncu.py): only quoted when the capture's kernel is the one that ran
+    traffic, step_traffic = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "synth_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_summary_traffic.json")) as f:
+            cap = json.load(f)
+        if Bl == 512 and (a.N_fm, a.N_r) == (256, 30):
+            in_step = [k for k in cap["kernels"] if not k["kernel"].startswith("scan_kernel")]   # no scan inside a multi-step call
+            step_traffic = {"dram_bytes_per_step": sum(k["dram_read"] + k["dram_write"] for k in in_step),
+                            "algorithmic_bytes_per_step": 48.0 * (a.N_r - 1) * a.N_fm * Bl,
+                            "per_kernel": {k["kernel"]: k["dram_read"] + k["dram_write"] for k in in_step},
+                            "source": "profiles/" + cap["source"].replace(".ncu-rep", "") + " (ncu --set full, one step of 512 members)"}
+            step_traffic["ratio"] = step_traffic["dram_bytes_per_step"] / step_traffic["algorithmic_bytes_per_step"]
+            for k in in_step:
+                if k["kernel"].startswith("nlin_fft"):
+                    traffic = k["dram_read"] + k["dram_write"]
     except Exception:
         pass
     kname = ("synth_wsq_kernel" if info["quarter_wave"] else "synth_ws_kernel" if info["synth_variant"] == 1 else "synth_kernel")
@@ -328,10 +340,10 @@ def run_ours(a):
         # keeps every transform in shared memory -> graded against HBM: 11 * 8 * nr * K bytes
         # per member.  Its fp64 work: 7 complex length-M FFTs per row (5 inverse, 2 forward) + packing + products.
         fft_bytes = 88.0 * nr * K
-        fft_flops = nr * (7 * 5.0 * M * math.log2(M) + 60.0 * M)
+        fft_flops = nr * (6 * 5.0 * M * math.log2(M) + 60.0 * M)
         gbs = Bl * fft_bytes / (stage_ms["synth"] * 1e-3) / 1e9 if stage_ms["synth"] > 0 else 0.0
-        roofline = {"kernel": "nlin_fft_kernel (5 inverse + 2 forward complex FFTs per radial row in shared memory, "
-                              "Jacobian products fused between the radix-6 passes)",
+        roofline = {"kernel": "nlin_fft_staged_kernel / nlin_fft_kernel (4 inverse + 2 forward complex FFTs per radial row in "
+                              "shared memory, Jacobian products fused between the radix-6 passes)",
                     "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                     "traffic": traffic, "peak_kind": peak_kind,
                     "launch_ms": stage_ms["synth"], "members_per_launch": Bl, "bytes_per_member": fft_bytes,
@@ -506,7 +518,7 @@ def run_ours(a):
                            "l2": "state + scratch working set (~%.1f GB/GPU) exceeds the 126 MB L2" %
                                  (Bl * (W * 5 + 9 * 2 * 32 * 256 + 3 * 2 * 32 * 192) * 8 / 1e9), **PHYS},
                 "clocks": clocks, "e2e": e2e, "e2e_state_roundtrip_every_step": e2e_roundtrip, "gpu_launches": launches,
-                "roofline": roofline, "roofline_hbm_step": hbm_view,
+                "roofline": roofline, "roofline_hbm_step": hbm_view, "step_traffic": step_traffic,
                 "stage_ms": stage_ms, "jvp": jvp_rate, "with_diagnostics": {"value": with_diag, "unit": "member-steps/s", "steps": nd,
                                                            "collective": "one all_gather of the [steps, B_local, 6] f64 history" if world > 1 else None,
                                                            "call": "sddc_time_step(nsteps, diag_every=1), device resident"}}

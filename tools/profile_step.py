@@ -1,7 +1,7 @@
 """One member-step of the headline configuration between cudaProfilerStart/Stop, for
     ncu --profile-from-start off --set full --clock-control none --import-source on -o out python tools/profile_step.py
 (the capture then holds exactly scan, prep, synth, analysis, solve of one step; add `jvp` as argv[1] for the cached
-Jacobian-vector product instead)."""
+Jacobian-vector product instead, `diag` for three steps of the device-resident time loop with per-step diagnostics)."""
 import sys; sys.path.insert(0, '.')
 import torch
 from spectraldoublediffusiveconvection_b200 import EnsemblePlan
@@ -23,6 +23,8 @@ torch.cuda.synchronize()
 torch.cuda.profiler.start()
 if mode == 'jvp':
     pl.jvp_apply(dv, Ra, Ras, out=out)
+elif mode == 'diag':
+    pl.time_step(X, Ra, Ras, 3, diag_every=1, out=out)      # steps with the shared-prep diagnostics (KE transform, finish)
 else:
     pl.step(X, Ra, Ras, out=out)
 torch.cuda.synchronize()

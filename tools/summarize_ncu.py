@@ -1,5 +1,5 @@
 """Summarise an ncu report (run here, no GPU needed): per-kernel key metrics -> text, and the dominant kernel's
-DRAM traffic per launch -> profiles/synth_traffic.json (read by bench.py for roofline.traffic).
+DRAM traffic per launch of every kernel -> <out>_traffic.json (read by bench.py for roofline.traffic / step_traffic).
 
     python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/r01_ncu_summary.txt
 """
@@ -42,6 +42,7 @@ def main(rep, out):
     hdr, units = rows[0], rows[1]
     lines = ["ncu summary of %s (--set full --clock-control none; per launch)" % os.path.basename(rep), ""]
     traffic = None
+    per_kernel = []
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         lines.append("== " + name)
@@ -56,18 +57,26 @@ def main(rep, out):
         top = sorted(stalls.items(), key=lambda kv: -kv[1])[:6]
         lines.append("   top warp stalls (per issue): " + ", ".join("%s %.2f" % kv for kv in top))
         import re
-        if "nlin_fft_kernel" in name:
+        if "nlin_fft_kernel" in name or "nlin_fft_staged_kernel" in name:
             traffic = None   # the FFT formulation's kernel is the dominant one when present
         if (re.search(r"synth_kernel<(\(int\))?\d+, *(\(int\))?0>", name) or "synth_ws_kernel" in name or "synth_wsq_kernel" in name
-                or "nlin_fft_kernel" in name) and traffic is None:
+                or "nlin_fft_kernel" in name or "nlin_fft_staged_kernel" in name) and traffic is None:
             rd = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
             wr = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
             traffic = {"kernel": name, "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr,
                        "source": os.path.basename(rep)}
         lines.append("")
+        try:
+            rd_ = to_bytes(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
+            wr_ = to_bytes(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
+            per_kernel.append({"kernel": name.split("(")[0].replace("void ", ""), "dram_read": rd_, "dram_write": wr_,
+                               "duration_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", ""))})
+        except Exception:
+            pass
     open(out, "w").write("\n".join(lines))
-    if traffic:
-        json.dump(traffic, open(os.path.join(os.path.dirname(out), "synth_traffic.json"), "w"), indent=1)
+    json.dump({"source": os.path.basename(rep), "kernels": per_kernel,
+               "dram_bytes_total": sum(k["dram_read"] + k["dram_write"] for k in per_kernel)},
+              open(os.path.splitext(out)[0] + "_traffic.json", "w"), indent=1)
     print("\n".join(lines[:60]))
 
 
