@@ -198,6 +198,12 @@ int sddc_step_host(sddc_plan* plan, const double* Xin, double* Xout, const doubl
  * Xout. Blocking. */
 int sddc_time_step_host(sddc_plan* plan, const double* Xin, double* Xout, const double* Ra, const double* Ra_s, int B,
                         int nsteps, int linear, int diag_every, double* diag_hist, int ckpt_every, double* ckpt);
+/* Step of the first checkpoint of sddc_time_step_host: checkpoints are taken after the steps first, first + ckpt_every, ...
+ * (ckpt needs (nsteps - first) / ckpt_every + 1 records).  0 (default) = ckpt_every: after every ckpt_every-th step.
+ * The reference's X_DATA is saved after the steps 1, 1 + N_save, 1 + 2 N_save, ... (`iteration % N_save == 0` with the
+ * iteration counter starting at 0, Main.py:286-321): first_step = 1 reproduces exactly those checkpoints. */
+int sddc_plan_set_ckpt_phase(sddc_plan* plan, int first_step);
+
 int sddc_jvp_host(sddc_plan* plan, const double* dv, const double* X, double* out, const double* Ra,
                   const double* Ra_s, int B);
 

@@ -55,6 +55,7 @@ SYMBOLS = {
     "sddc_dF_dRa": (_i, [_vp, _dp, _dp, _i, _vp]),
     "sddc_diagnostics": (_i, [_vp, _dp, _dp, _i, _vp]),
     "sddc_transform": (_i, [_i, _dp, _dp, _i, _i, _i, _vp]),
+    "sddc_plan_set_ckpt_phase": (_i, [_vp, _i]),
     "sddc_interp_radial": (_i, [_dp, _dp, _dp, _ll, _i, _i, _vp]),
     "sddc_interp_thetas": (_i, [_dp, _dp, _i, _i, _i, _i, _vp]),
     "sddc_gs_chunks": (_i, [_i]),

@@ -86,6 +86,7 @@ struct sddc_plan {
     double *hX0 = nullptr, *hX1 = nullptr, *hX2 = nullptr, *hRa = nullptr, *hRas = nullptr, *hDiag = nullptr;
     double* hHist = nullptr;  // [hist_cap][max_batch][6] diagnostics history of sddc_time_step_host
     int hist_cap = 0;
+    int ckpt_phase = 0;       // sddc_plan_set_ckpt_phase: checkpoints after the steps phase, phase + every, ... (0: every, 2 every, ...)
     cudaEvent_t ev_ckpt = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
@@ -1367,8 +1368,9 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
                 if ((rc = ship_record(r))) return rc;
             }
         }
-        if (ckpt_every && s % ckpt_every == 0) {
-            const int r = s / ckpt_every - 1;
+        const int cph = pl->ckpt_phase > 0 ? pl->ckpt_phase : ckpt_every;   // step of the first checkpoint
+        if (ckpt_every && s >= cph && (s - cph) % ckpt_every == 0) {
+            const int r = (s - cph) / ckpt_every;
             if (ckpt_pending) PLAN_CUDA(pl, cudaStreamWaitEvent(cs, pl->ev_ckpt, 0));  // staging buffer free again
             PLAN_CUDA(pl, cudaMemcpyAsync(pl->hX2, cur, bytes, cudaMemcpyDeviceToDevice, cs));
             PLAN_CUDA(pl, cudaEventRecord(pl->ev_in[0], cs));
@@ -1381,6 +1383,12 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
     PLAN_CUDA(pl, cudaMemcpyAsync(Xout, cur, bytes, cudaMemcpyDeviceToHost, cs));
     PLAN_CUDA(pl, cudaStreamSynchronize(cs));
     PLAN_CUDA(pl, cudaStreamSynchronize(pl->out_stream));
+    return SDDC_OK;
+}
+
+int sddc_plan_set_ckpt_phase(sddc_plan* pl, int first_step) {
+    if (!pl || first_step < 0) return SDDC_ERR_INVALID;
+    pl->ckpt_phase = first_step;
     return SDDC_OK;
 }
 

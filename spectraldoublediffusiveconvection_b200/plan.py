@@ -288,9 +288,11 @@ class EnsemblePlan:
         return (out, diag) if want_diag else out
 
     def time_step_host(self, X, Ra, Ra_s, nsteps, diag_every=1, ckpt_every=0, linear=False, out=None, diag_hist=None,
-                       ckpt=None):
+                       ckpt=None, ckpt_first=None):
         """Ensemble analogue of Main._Time_Step from NumPy buffers: returns (X_final, diag_hist[, checkpoints]) with
-        diag_hist [nsteps // diag_every, B, 6] and checkpoints [nsteps // ckpt_every, B, 3N]."""
+        diag_hist [nsteps // diag_every, B, 6] and checkpoints after the steps ckpt_first, ckpt_first + ckpt_every, ...
+        ckpt_first defaults to ckpt_every ([nsteps // ckpt_every, B, 3N] records); ckpt_first=1 gives the reference's own
+        checkpoints, which Main._Time_Step takes after the steps 1, 1 + N_save, ... (Main.py:301-303)."""
         X = np.ascontiguousarray(X, dtype=np.float64).reshape(-1, 3 * self.N)
         B = X.shape[0]
         Ra = np.ascontiguousarray(np.broadcast_to(np.asarray(Ra, dtype=np.float64), (B,)))
@@ -300,7 +302,11 @@ class EnsemblePlan:
         elif out.shape != X.shape or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float64 array of shape %s" % (X.shape,))
         nrec = nsteps // diag_every if diag_every else 0
-        nck = nsteps // ckpt_every if ckpt_every else 0
+        first = int(ckpt_every if ckpt_first is None else ckpt_first)
+        if ckpt_every and not (1 <= first):
+            raise ValueError("ckpt_first must be >= 1")
+        nck = ((nsteps - first) // ckpt_every + 1 if nsteps >= first else 0) if ckpt_every else 0
+        self._check(self.lib.sddc_plan_set_ckpt_phase(self._h, first if ckpt_every else 0))
         if diag_hist is None:
             diag_hist = np.empty((nrec, B, 6))
         if ckpt is None and nck:

@@ -257,6 +257,22 @@ def test_time_step_host_matches_device_loop():
     pl.close()
 
 
+def test_time_step_host_reference_checkpoint_cadence():
+    """ckpt_first=1: checkpoints after the steps 1, 1 + N_save, ... as Main._Time_Step takes them (Main.py:301-303); with
+    the golden config-1 run: first checkpoint = X_step1, and the run's last state = X_step100."""
+    g = load_golden("cfg1_nosym")
+    pl = _plan(g, max_batch=2)
+    X0 = np.stack([g["X0"], g["X0"]])
+    out, hist, ck = pl.time_step_host(X0, float(g["Ra"]), float(g["Ra_s"]), 100, diag_every=1, ckpt_every=10, ckpt_first=1)
+    assert ck.shape == (10, 2, 3 * pl.N)                                   # steps 1, 11, ..., 91
+    assert rel_l2(ck[0, 0], g["X_step1"]) < 1e-12 and rel_l2(ck[1, 1], load_golden("cfg1_nosym")["X_step10"]) > 1e-6
+    assert rel_l2(out[0], g["X_step100"]) < TOL_STEPS
+    assert np.allclose(hist[:, 0, :4], g["diag_hist"], rtol=1e-9, atol=0)
+    cur = pl.step(_dev(X0), float(g["Ra"]), float(g["Ra_s"]), nsteps=11).cpu().numpy()
+    assert np.array_equal(ck[1], cur)
+    pl.close()
+
+
 @pytest.mark.parametrize("sym", [False, True])
 def test_time_step_host_shares_prep_with_diagnostics(sym):
     """FFT formulation: inside sddc_time_step_host the kinetic energy of X_s comes from the spectral rows that the prep
