@@ -3,6 +3,10 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#ifndef SDDC_SM_PAD
+#define SDDC_SM_PAD 2   // solve-major rows: n8 + SDDC_SM_PAD doubles per member (k_solve.cuh)
+#endif
+
 namespace sddc {
 
 // D(8x8) += A(8x4, row) * B(4x8, col).  Fragment ownership (lane = 4*g + t):

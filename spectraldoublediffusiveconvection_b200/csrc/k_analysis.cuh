@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(416, (NT8 <= 5 && ANA_NT == 2) ? 2 : 1) analys
     const int kt = blockIdx.x, par = blockIdx.y, b = blockIdx.z;
     const int n = g.n, K = g.K, N = g.N, Mhp = g.Mhp;
     const bool sm = p.bstride != 0;
-    const int LDG = NT8 * 8 + 2;
+    const int LDG = NT8 * 8 + SDDC_SM_PAD;
     // element (field f, block blk, radial i) of member b
     auto out_at = [&](int f, int blk, int i) -> double& {
         return sm ? p.out[(((long long)f * K + blk) * p.bstride + b) * LDG + i]

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p, int ntiles) {
         }
     };
     const bool sm = p.bstride != 0;
-    const int LDG = n8 + 2;
+    const int LDG = n8 + SDDC_SM_PAD;
     int tile = blockIdx.x, stage = 0;
     if (tile < ntiles) issue(tile, 0);
     cp_async_commit();

@@ -52,7 +52,7 @@ constexpr int SOLVE_NSL = SOLVE_NSL_MAX;  // maximum pipeline stages (operator +
 
 template <int NTB>
 __host__ __device__ inline size_t solve_smem_doubles(int n8, int nsl) {
-    const int LDL = n8 + 4, LDG = n8 + 2;
+    const int LDL = n8 + 4, LDG = n8 + SDDC_SM_PAD;
     return (size_t)(2 * nsl) * n8 * LDL + (size_t)4 * (8 * NTB) * LDL + (size_t)nsl * 2 * (8 * NTB) * LDG;
 }
 
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(288) solve_kernel(SolveParams p) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[SOLVE_NSL], bar_empty[SOLVE_NSL];
     const Geo& G = p.geo;
-    const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, GT = BT * LDG;
+    const int n = G.n, n8 = G.n8, K = G.K, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + SDDC_SM_PAD, GT = BT * LDG;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const int nthr = blockDim.x - 32;          // compute threads (the last warp only streams operands)
     const int ncw = nthr >> 5;

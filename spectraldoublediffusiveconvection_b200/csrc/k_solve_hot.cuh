@@ -23,7 +23,7 @@ namespace sddc {
 
 template <int NTB, bool PSI>
 __host__ __device__ constexpr size_t solve_hot_doubles(int n8, int nsl) {
-    const int LDL = n8 + 4, LDG = n8 + 2, NM = PSI ? 2 : 1;
+    const int LDL = n8 + 4, LDG = n8 + SDDC_SM_PAD, NM = PSI ? 2 : 1;
     return (size_t)nsl * NM * n8 * LDL + (size_t)2 * NM * (8 * NTB) * LDL + (size_t)nsl * 2 * (8 * NTB) * LDG;
 }
 // nsl = pipeline stages (operator + right-hand-side tiles): 3, or 2 when three do not fit an SM
@@ -37,7 +37,7 @@ __host__ inline size_t solve_hot_smem_bytes(int n8, int nsl) {
 template <int NT8, int NSL, int NTB, bool PSI, bool SUB = true, bool DIAG = false>
 __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* smem, uint64_t* bar_full,
                                                 uint64_t* bar_empty, int fld, int which, int b0) {
-    constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + 2, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
+    constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + SDDC_SM_PAD, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
     constexpr int NM = PSI ? 2 : 1, NTHR = 32 * NT8;
     constexpr int NCH = NTB >= 2 ? 1 : 2;   // accumulator chains per product and member tile (k-steps interleaved)
     const Geo& G = p.geo;
