@@ -731,8 +731,8 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(dev_alloc(pl, &pl->coef1, Bm * pl->coef_member_stride, true));  // second set: dv (JVP) or KE rows
     TRY(dev_alloc(pl, &pl->prd, Bm * 3 * 2 * n8 * g.Mhp, true));
     pl->bstride = (long long)round_up(cfg->max_batch, 32);   // a cluster pair of 16-member tiles never leaves its slab
-    TRY(dev_alloc(pl, &pl->lin_sm, (size_t)3 * K * pl->bstride * (n8 + 2), true));
-    TRY(dev_alloc(pl, &pl->f_sm, (size_t)3 * K * pl->bstride * (n8 + 2), true));
+    TRY(dev_alloc(pl, &pl->lin_sm, (size_t)3 * K * pl->bstride * (n8 + SDDC_SM_PAD), true));
+    TRY(dev_alloc(pl, &pl->f_sm, (size_t)3 * K * pl->bstride * (n8 + SDDC_SM_PAD), true));
     TRY(dev_alloc(pl, &pl->lin, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->rhs, Bm * 3 * g.N, false));
     TRY(dev_alloc(pl, &pl->xtmp, Bm * 3 * g.N, false));
