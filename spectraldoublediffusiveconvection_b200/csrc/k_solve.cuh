@@ -40,6 +40,7 @@ struct SolveParams {
                                 // of the NEW state's diagnostics: sum f^2, and for the even T / S chains the Nusselt sums at
                                 // the inner and outer wall (Main.py:41-68, 292)
     const double *nu_in, *nu_out;   // [n] Nusselt weights (R_w^2 / A_T) D[w, 1:-1]
+    const double* nu_w;             // [K] 1 / (1 - k^2) (Main.py:58-63; only even k are used)
     double* jj_out;             // optional [B][K+1][n]: theta-coupling brackets of the NEW stream function, exactly what
                                 // scan_kernel would compute from the output (the running sum f_e of the A4 chain is that
                                 // suffix sum), so the next step of a multi-step call skips its scan (k_solve_hot.cuh)

@@ -228,7 +228,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
             }
         }
         if (DIAG) {
-            const double wk = 1.0 / (1.0 - (double)j * (double)j);
+            const double wk = nu_chain ? __ldg(p.nu_w + j) : 0.0;   // 1 / (1 - j^2), tabulated: a division per chain step showed
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 dn2[e] = fma(f[e], f[e], dn2[e]);

@@ -67,6 +67,7 @@ struct sddc_plan {
     double *JJ = nullptr, *coef = nullptr, *prd = nullptr, *lin = nullptr, *rhs = nullptr, *xtmp = nullptr,
            *kepart = nullptr, *zeroRa = nullptr;
     double* coef1 = nullptr;
+    double* nu_w = nullptr;    // [K] 1 / (1 - k^2)
     double* dpart = nullptr;   // [max_batch][6][3] diagnostics partial sums written by the back-substitution (DIAG)
     long long coef_member_stride = 0;
     double *lin_sm = nullptr, *f_sm = nullptr;  // solve-major [3][K][bstride][n8+2]
@@ -460,7 +461,7 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
               double* dpart = nullptr) {
     SolveParams sp{};
     sp.jj_out = jj_out;
-    sp.dpart = dpart; sp.nu_in = pl->nu_in; sp.nu_out = pl->nu_out;
+    sp.dpart = dpart; sp.nu_in = pl->nu_in; sp.nu_out = pl->nu_out; sp.nu_w = pl->nu_w;
     const bool sm = gs < 0;
     sp.bstride = pl->bstride;
     sp.g = g; sp.fnl = fnl; sp.mdt = -pl->g.dt; sp.g_stride = gs; sp.g_field_off = gf; sp.out = out; sp.out_stride = os; sp.out_field_off = of;
@@ -740,6 +741,11 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     TRY(dev_alloc(pl, &pl->kepart, Bm * std::max(pl->nke, n), true));
     TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
     TRY(dev_alloc(pl, &pl->dpart, Bm * 18, true));
+    {
+        std::vector<double> w(K);
+        for (int k = 0; k < K; ++k) w[k] = k == 1 ? 0.0 : 1.0 / (1.0 - (double)k * (double)k);
+        TRY(upload(pl, &pl->nu_w, w));
+    }
     // ---- opt in to large dynamic shared memory ----
     {
         SynthParams sp{};

@@ -77,3 +77,21 @@ def test_checkpoint_schema_roundtrip(tmp_path):
     assert float(back["Parameters/Ra"]) == 2.0
     for key in ("Scalar_Data/Norm", "Scalar_Data/Nu_T", "Scalar_Data/Nu_S", "Scalar_Data/Time", "Parameters/N_fm"):
         assert key in back
+
+
+def test_plan_validates_parameters_and_outputs_before_the_abi():
+    """Per-member parameter lengths and caller-supplied `out` tensors are checked in Python: the C ABI trusts pointers."""
+    import torch
+    from spectraldoublediffusiveconvection_b200.plan import EnsemblePlan
+    pl = EnsemblePlan.__new__(EnsemblePlan)          # no library / device needed for the host-side checks
+    pl.device = torch.device("cpu")
+    assert pl._param(3.0, 4).tolist() == [3.0] * 4
+    assert pl._param(torch.tensor([2.0]), 3).tolist() == [2.0] * 3
+    assert pl._param(np.arange(3.0), 3).tolist() == [0.0, 1.0, 2.0]
+    with pytest.raises(ValueError):
+        pl._param(torch.arange(5.0, dtype=torch.float64), 4)       # a globally sized Ra with a local shard
+    # (_out insists on CUDA tensors: everything else is rejected before a pointer is taken)
+    with pytest.raises(TypeError):
+        pl._out(torch.zeros((2, 6), dtype=torch.float64), (2, 6))
+    with pytest.raises(TypeError):
+        pl._out(np.zeros((2, 6)), (2, 6))

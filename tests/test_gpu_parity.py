@@ -190,6 +190,15 @@ def test_error_behaviour():
     pl = EnsemblePlan(16, 10, 0.4, 1e-2, 1.0, 1.0, max_batch=2)
     with pytest.raises(ValueError):
         pl.nlin_fx(torch.zeros((3, 3 * pl.N), dtype=torch.float64, device="cuda"))   # B > max_batch
+    X = torch.zeros((2, 3 * pl.N), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        pl.step(X, torch.zeros(3, dtype=torch.float64, device="cuda"), 0.0)          # Ra of the wrong length
+    with pytest.raises(ValueError):
+        pl.step(X, 3000.0, 0.0, out=torch.zeros((2, 3 * pl.N + 1), dtype=torch.float64, device="cuda"))   # too large
+    with pytest.raises(ValueError):
+        pl.step(X, 3000.0, 0.0, out=torch.zeros((3 * pl.N, 2), dtype=torch.float64, device="cuda").t())   # strided
+    with pytest.raises(TypeError):
+        pl.step(X, 3000.0, 0.0, out=torch.zeros((2, 3 * pl.N), dtype=torch.float32, device="cuda"))
     pl.close()
 
 
