@@ -48,8 +48,9 @@ def gather_rows(local: torch.Tensor, n_members: int, group=None) -> torch.Tensor
 class Ensemble:
     """B members of one (N_fm, N_r, d, dt, Pr, Tau, symmetric) with per-member Ra, Ra_s, sharded over ranks."""
 
-    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, Ra, Ra_s, symmetric=False, device=None, group=None):
-        from .plan import EnsemblePlan
+    def __init__(self, N_fm, N_r, d, dt, Pr, Tau, Ra, Ra_s, symmetric=False, device=None, group=None, plan_factory=None):
+        """plan_factory(max_batch) -> plan replaces the EnsemblePlan of this rank (tests of the sharding logic on CPU
+        tensors with an oracle-backed plan; the product path always builds the CUDA plan)."""
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -58,9 +59,13 @@ class Ensemble:
         self.n_members = int(Ra.shape[0])
         self.lo, self.hi = partition(self.n_members, self.world, self.rank)
         self.n_local = self.hi - self.lo
-        self.plan = EnsemblePlan(N_fm, N_r, d, dt, Pr, Tau, symmetric=symmetric, max_batch=max(1, self.n_local),
-                                 device=device)
-        dev = self.plan.device
+        if plan_factory is not None:
+            self.plan = plan_factory(max(1, self.n_local))
+        else:
+            from .plan import EnsemblePlan
+            self.plan = EnsemblePlan(N_fm, N_r, d, dt, Pr, Tau, symmetric=symmetric, max_batch=max(1, self.n_local),
+                                     device=device)
+        dev = getattr(self.plan, "device", torch.device("cpu"))
         self.Ra = torch.as_tensor(np.ascontiguousarray(Ra[self.lo:self.hi])).to(dev)
         self.Ra_s = torch.as_tensor(np.ascontiguousarray(Ra_s[self.lo:self.hi])).to(dev)
         self.dt = float(dt)
@@ -68,7 +73,30 @@ class Ensemble:
     def shard(self, X_all):
         """Local rows of a global [B, 3N] host array, uploaded to this rank's GPU."""
         X_all = np.asarray(X_all, dtype=np.float64).reshape(self.n_members, -1)
-        return torch.as_tensor(np.ascontiguousarray(X_all[self.lo:self.hi])).to(self.plan.device)
+        return torch.as_tensor(np.ascontiguousarray(X_all[self.lo:self.hi])).to(self.Ra.device)
+
+    # ---- lock-step Newton / continuation over the whole ensemble: every rank drives its own members (krylov.py), no
+    # communication while the solves run (members are independent, ranks need not even agree on iteration counts); the
+    # per-member outcomes are all-gathered at the end
+    def newton(self, X, **kw):
+        """Main._Newton for every local member.  Returns (X_local, summary [n_members, 4] on every rank: converged,
+        Newton iterations, member JVPs, last error)."""
+        from . import krylov
+        Xn, info = krylov.newton_batched(self.plan, X, self.Ra, self.Ra_s, **kw)
+        hist = info["history"]
+        last = torch.stack([hist[max(int(i) - 1, 0), m] for m, i in enumerate(info["iterations"].tolist())]) \
+            if hist.numel() else torch.zeros(self.n_local, dtype=torch.float64, device=X.device)
+        local = torch.stack([info["converged"].double(), info["iterations"].double(), info["member_jvps"].double(), last], dim=1)
+        return Xn, gather_rows(local, self.n_members, self.group)
+
+    def continuation(self, X, N_steps, sign=1.0, **kw):
+        """Main._Continuation for every local member, mu = Ra.  Returns (BranchResult of the local members, history
+        [N_steps, n_members, 3] on every rank: Ra, KE, Nu_T per branch step)."""
+        from . import krylov
+        res = krylov.continuation_batched(self.plan, X, self.Ra, N_steps, self.Ra_s, sign=sign, **kw)
+        local = torch.stack([torch.stack(res.Ra), torch.stack(res.KE), torch.stack(res.NuT)], dim=2)   # [steps, B_local, 3]
+        hist = gather_rows(local.permute(1, 0, 2).contiguous(), self.n_members, self.group).permute(1, 0, 2).contiguous()
+        return res, hist
 
     def time_step(self, X, n_steps, diag_every=1, linear=False):
         """Advance the local members n_steps; every `diag_every` steps (0 = never) compute the diagnostics of all
