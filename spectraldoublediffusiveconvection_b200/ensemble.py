@@ -50,7 +50,7 @@ class Ensemble:
 
     def __init__(self, N_fm, N_r, d, dt, Pr, Tau, Ra, Ra_s, symmetric=False, device=None, group=None, plan_factory=None):
         """plan_factory(max_batch) -> plan replaces the EnsemblePlan of this rank (tests of the sharding logic on CPU
-        tensors with an oracle-backed plan; the product path always builds the CUDA plan)."""
+        tensors with a CPU test double; the product path always builds the CUDA plan)."""
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
