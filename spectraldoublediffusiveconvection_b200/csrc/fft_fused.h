@@ -395,6 +395,89 @@ SDDC_HD void i3f1_dfx(int t, double* __restrict__ buf, const Tables& tb) {
     }
 }
 
+// ---- cached base state (sddc_jvp_set_base / sddc_jvp_apply) ----------------------------------------------------------------
+// Inside one linear solve the base state X of PDFX(dv, X) is fixed, so its seven grid fields are synthesised ONCE
+// (i3f1_grid) and kept in HBM in exactly the order the product phase consumes them: grid[field][m][n1], the value of
+// `field` at grid point n1 + L m held by thread n1 (512 contiguous bytes per (field, m) at M = 384).  Every product then
+// transforms only the perturbation -- four inverse transforms like the one-state kernel instead of the seven of a pair of
+// states -- and reads 7 M doubles per row (i3f1_jvpc).  Field order: 0 JT, 1 omega, 2 DT, 3 Dpsi, 4 DS, 5 kT, 6 kS.
+template <int M, int NTH>
+SDDC_HD void i3f1_grid(int t, const double* __restrict__ buf, const Tables& tb, double* __restrict__ grid) {
+    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
+    for (int n1 = t; n1 < L; n1 += NTH) {
+        int pos[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
+        C t6[5];
+        load_tw6<M>(n1, tb, t6);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            C z[6];
+            inv6t(buf + pair_off<M>(q), buf + pair_off<M>(q) + PL, pos, t6, z);
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                if (q < 3) grid[((2 * q) * 6 + m) * L + n1] = z[m].r;
+                grid[((q < 3 ? 2 * q + 1 : 6) * 6 + m) * L + n1] = z[m].i;
+            }
+        }
+    }
+}
+
+// in : plane pairs 0..3 = the perturbation's (JT'|om') (DT'|Dpsi') (DS'|-kT') (0|-kS'); grid = the base state's fields
+// out: as i3f1_fx, with the bilinear products of Matrix_Operators.py:884-887
+template <int M, int NTH>
+SDDC_HD void i3f1_jvpc(int t, double* __restrict__ buf, const Tables& tb, const double* __restrict__ grid) {
+    constexpr int L = Cfg<M>::L, PL = Cfg<M>::PL;
+    for (int n1 = t; n1 < L; n1 += NTH) {
+        int pos[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
+        C t6[5];
+        load_tw6<M>(n1, tb, t6);
+        const double* g = grid + n1;
+        double jt[6], dp[6], jtp[6], dpp[6], NT[6];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+            jt[m] = g[(0 * 6 + m) * L];
+            dp[m] = g[(3 * 6 + m) * L];
+        }
+        {
+            C z0[6], z1[6];
+            inv6t(buf, buf + PL, pos, t6, z0);                                       // JT' | omega'
+            inv6t(buf + pair_off<M>(1), buf + pair_off<M>(1) + PL, pos, t6, z1);    // DT' | Dpsi'
+            double P1[6], Q[6];
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const double om = g[(1 * 6 + m) * L], dT = g[(2 * 6 + m) * L];
+                jtp[m] = z0[m].r;
+                dpp[m] = z1[m].i;
+                P1[m] = jt[m] * z0[m].i + jtp[m] * om;
+                Q[m] = dp[m] * z0[m].i + dpp[m] * om;
+                NT[m] = jt[m] * z1[m].r + jtp[m] * dT;
+            }
+            fwd6t(P1, Q, buf, buf + PL, pos, t6);
+        }
+        double NS[6];
+        {
+            C z2[6];
+            inv6t(buf + pair_off<M>(2), buf + pair_off<M>(2) + PL, pos, t6, z2);    // DS' | -kT'
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const double dS = g[(4 * 6 + m) * L], kT = g[(5 * 6 + m) * L];
+                NT[m] -= dp[m] * z2[m].i + dpp[m] * kT;
+                NS[m] = jt[m] * z2[m].r + jtp[m] * dS;
+            }
+        }
+        {
+            C z3[6];
+            inv6t(buf + pair_off<M>(3), buf + pair_off<M>(3) + PL, pos, t6, z3);    // 0 | -kS'
+#pragma unroll
+            for (int m = 0; m < 6; ++m) NS[m] -= dp[m] * z3[m].i + dpp[m] * g[(6 * 6 + m) * L];
+        }
+        fwd6t(NT, NS, buf + pair_off<M>(1), buf + pair_off<M>(1) + PL, pos, t6);
+    }
+}
+
 // ---- cp: forward radix-8 pass + separation of the packed sequences, scaling, truncation to K ---------------------------
 // out: [4][K] = DST(JT*om), DST(kDpsi*om + Dpsi*kom) = -k DCT(Dpsi*om), DCT(N_T), DCT(N_S)  (sinusoid indexing;
 // Transforms.py:28-39,56-70).  (A, Bv) = V at kappa, (Cc, D) = V at M - kappa; C_k = Re[conj(w_k) V_k] of the two packed

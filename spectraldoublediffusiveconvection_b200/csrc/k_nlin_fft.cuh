@@ -23,6 +23,7 @@ struct NlinFftParams {
     const double* coef1;  // [rows][7][K] rows of the perturbation (two-state mode)
     double* spec;         // [rows][4][K] analysed products
     const double* tab;    // fftp::tab_doubles<M>() table doubles (fftp::fill_tables)
+    double* grid;         // [rows][7][M] cached grid fields of the base state (MODE 1 writes, MODE 2 reads; fft_fused.h)
     int nrows;
     int* next_row;        // row counter, zeroed before every launch: workers claim rows dynamically
 };
@@ -48,8 +49,11 @@ __device__ __forceinline__ void worker_sync(int w) {
 }
 
 // NT = threads per worker: 64, or 128 where the radix-6 pass has 128 columns (M = 768)
-template <int M, bool DFX, int NW, int NT = 64>
+// MODE (one-state instantiations): 0 products of coef0; 1 GRID: grid fields of coef0 -> p.grid, no analysis;
+//                                  2 JVPC: bilinear products of the perturbation rows coef1 with the cached p.grid
+template <int M, bool DFX, int NW, int NT = 64, int MODE = 0>
 __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
+    static_assert(!DFX || MODE == 0, "the cached-base modes are one-state kernels");
     using namespace fftp;
     constexpr int K = Cfg<M>::K, NF = DFX ? 7 : 4;
     extern __shared__ __align__(128) double smem[];
@@ -70,13 +74,17 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
         // the next claim travels to L2 and back while this row is transformed
         int next = 0;
         if (t == 0) next = atomicAdd(p.next_row, 1);
-        const double* r0 = p.coef0 + (size_t)row * 7 * K;
+        const double* r0 = (MODE == 2 ? p.coef1 : p.coef0) + (size_t)row * 7 * K;
         if (DFX) bc_inv_dfx<M, NT>(t, r0, p.coef1 + (size_t)row * 7 * K, buf, tb);
         else bc_inv_fx<M, NT>(t, r0, buf, tb);
         // pull the row that will be claimed one round from now from HBM into L2 while this one is transformed
         if (row + stride < p.nrows) {
-            const char* nx = reinterpret_cast<const char*>(p.coef0 + (size_t)(row + stride) * 7 * K);
+            const char* nx = reinterpret_cast<const char*>((MODE == 2 ? p.coef1 : p.coef0) + (size_t)(row + stride) * 7 * K);
             for (int o = t * 128; o < 7 * K * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+            if (MODE == 2) {
+                const char* ng = reinterpret_cast<const char*>(p.grid + (size_t)(row + stride) * 7 * M);
+                for (int o = t * 128; o < 7 * M * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ng + o));
+            }
             if (DFX) {
                 const char* nx1 = reinterpret_cast<const char*>(p.coef1 + (size_t)(row + stride) * 7 * K);
                 for (int o = t * 128; o < 7 * K * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx1 + o));
@@ -85,7 +93,14 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
         worker_sync<NT>(w);
         pass_d<M, NF, +1, NT>(t, buf, tw);
         worker_sync<NT>(w);
+        if (MODE == 1) {
+            i3f1_grid<M, NT>(t, buf, tb, p.grid + (size_t)row * 7 * M);
+            if (t == 0) s_row[w] = next;
+            worker_sync<NT>(w);
+            continue;
+        }
         if (DFX) i3f1_dfx<M, NT>(t, buf, tb);
+        else if (MODE == 2) i3f1_jvpc<M, NT>(t, buf, tb, p.grid + (size_t)row * 7 * M);
         else i3f1_fx<M, NT>(t, buf, tb);
         worker_sync<NT>(w);
         pass_d<M, 2, -1, NT>(t, buf, tw);
@@ -119,7 +134,7 @@ __host__ __device__ constexpr size_t nlin_fft_staged_smem_bytes(int nw) {
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int M, int NW>
+template <int M, int NW, int MODE = 0>
 __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftParams p) {
     using namespace fftp;
     constexpr int K = Cfg<M>::K, PL = Cfg<M>::PL, NT = 64;
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftPara
     // lane 0 of a warp fetches what its warp packs: rows (2 warp, 2 warp + 1) and its share of (DS, -kT | -kS)
     auto fetch = [&](int r) {
         if (lane != 0 || r >= p.nrows) return;
-        const double* src = p.coef0 + (size_t)r * 7 * K;
+        const double* src = (MODE == 2 ? p.coef1 : p.coef0) + (size_t)r * 7 * K;
         uint64_t* bar = &s_bar[w][warp];
         mbar_expect_tx(bar, (warp == 0 ? 4 : 3) * K * (unsigned)sizeof(double));
         bulk_g2s(buf + (4 + 2 * warp) * PL, src + 2 * warp * K, 2 * K * sizeof(double), bar);
@@ -165,10 +180,17 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftPara
         if (t == 0) s_row[w] = next;
         worker_sync<NT>(w);
         const int nrow = s_row[w];
-        i3f1_fx<M, NT>(t, buf, tb);
+        if (MODE == 1) i3f1_grid<M, NT>(t, buf, tb, p.grid + (size_t)row * 7 * M);
+        else if (MODE == 2) i3f1_jvpc<M, NT>(t, buf, tb, p.grid + (size_t)row * 7 * M);
+        else i3f1_fx<M, NT>(t, buf, tb);
         worker_sync<NT>(w);
         fence_proxy_async();   // the generic-proxy reads of the dead planes precede the bulk copies into them
         fetch(nrow);
+        if (MODE == 1) { row = nrow; continue; }
+        if (MODE == 2 && nrow < p.nrows) {   // the next row's cached grid fields on their way into L2 while this row is analysed
+            const char* ng = reinterpret_cast<const char*>(p.grid + (size_t)nrow * 7 * M);
+            for (int o = t * 128; o < 7 * M * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ng + o));
+        }
         staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * 4 * K, tb, tw, 0);
         __syncwarp();
         staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * 4 * K, tb, tw, 1);

@@ -81,6 +81,7 @@ struct sddc_plan {
     double *ke_tab = nullptr, *ke_Wn = nullptr;
     int* fft_row = nullptr;     // dynamic row counter of nlin_fft_kernel (zeroed before every launch)
     double *coef7 = nullptr, *coef7b = nullptr, *coef7base = nullptr, *spec4 = nullptr, *fft_tab = nullptr;
+    double* grid7 = nullptr;    // [max_batch n][7][M] grid fields of the base state of sddc_jvp_set_base (FFT kernels; lazily allocated)
     int base_B = 0;
     long long bstride = 0;
     // host-API staging
@@ -369,8 +370,10 @@ int run_analysis(sddc_plan* pl, double* out, bool solve_major, int B, cudaStream
 template <int M>
 constexpr int nlin_fft_nw(bool dfx) { return dfx ? (M == 768 ? 2 : (M == 384 ? 5 : 8)) : (M == 768 ? 4 : NLIN_FFT_NW); }
 
+// mode: 0 products of c0 (and c1: two-state kernel); 1 grid fields of c0 -> pl->grid7; 2 products of c1 with the cached grid
 template <int M>
-int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bstride, bool dfx, cudaStream_t st, bool set_attr) {
+int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bstride, bool dfx, cudaStream_t st, bool set_attr,
+                    int mode = 0) {
     constexpr int NW = nlin_fft_nw<M>(false), NWD = nlin_fft_nw<M>(true);
     constexpr int NT = M == 768 ? 128 : 64;   // threads per worker = columns of the radix-6 pass at M = 768
     constexpr size_t smem = nlin_fft_smem_bytes<M, false>(NW), smem_d = nlin_fft_smem_bytes<M, true>(NWD);
@@ -378,7 +381,13 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
     if (set_attr) {
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, true, NWD, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        if (M == 384) PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        if (M == 384) {
+            PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+            PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+            PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        }
         return SDDC_OK;
     }
     const int n = pl->g.n, n8 = pl->g.n8;
@@ -386,7 +395,7 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
     PLAN_CUDA(pl, cudaMemsetAsync(pl->fft_row, 0, sizeof(int), st));
     {
         StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
-        if (dfx) {
+        if (dfx && mode == 0) {
             const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
             nlin_fft_kernel<M, true, NWD, NT><<<grid, NT * NWD, smem_d, st>>>(np);
         } else if (M == 384) {
@@ -394,10 +403,15 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
             constexpr int NWS = NLIN_FFT_STAGED_NW;
             static_assert(nlin_fft_staged_smem_bytes<384>(NWS) <= SMEM_LIMIT, "staged workers do not fit into shared memory");
             const int grid = std::min((np.nrows + NWS - 1) / NWS, pl->num_sms);
-            nlin_fft_staged_kernel<384, NWS><<<grid, 64 * NWS, nlin_fft_staged_smem_bytes<384>(NWS), st>>>(np);
+            const size_t ssm = nlin_fft_staged_smem_bytes<384>(NWS);
+            if (mode == 1) nlin_fft_staged_kernel<384, NWS, 1><<<grid, 64 * NWS, ssm, st>>>(np);
+            else if (mode == 2) nlin_fft_staged_kernel<384, NWS, 2><<<grid, 64 * NWS, ssm, st>>>(np);
+            else nlin_fft_staged_kernel<384, NWS><<<grid, 64 * NWS, ssm, st>>>(np);
         } else {
             const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
-            nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
+            if (mode == 1) nlin_fft_kernel<M, false, NW, NT, 1><<<grid, NT * NW, smem, st>>>(np);
+            else if (mode == 2) nlin_fft_kernel<M, false, NW, NT, 2><<<grid, NT * NW, smem, st>>>(np);
+            else nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
         }
     }
     pl->launches++;
@@ -418,9 +432,9 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
 
 // nonlinear term of the rows c0 (and, two-state, c1) into `out` (state layout or solve-major)
 int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out, bool solve_major, int B, cudaStream_t st,
-                 bool set_attr = false) {
+                 bool set_attr = false, int mode = 0) {
     NlinFftParams np{};
-    np.coef0 = c0; np.coef1 = c1; np.spec = pl->spec4; np.tab = pl->fft_tab; np.nrows = B * pl->g.n;
+    np.coef0 = c0; np.coef1 = c1; np.spec = pl->spec4; np.tab = pl->fft_tab; np.nrows = B * pl->g.n; np.grid = pl->grid7;
     const long long bstride = solve_major ? pl->bstride : 0;
     const bool dfx = c1 != nullptr;
     if (pl->fft_direct || (dfx && pl->dfx_direct)) {
@@ -448,9 +462,9 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
         return SDDC_OK;
     }
     switch (pl->fft_M) {
-        case 192: return launch_nlin_fft<192>(pl, np, out, bstride, dfx, st, set_attr);
-        case 384: return launch_nlin_fft<384>(pl, np, out, bstride, dfx, st, set_attr);
-        case 768: return launch_nlin_fft<768>(pl, np, out, bstride, dfx, st, set_attr);
+        case 192: return launch_nlin_fft<192>(pl, np, out, bstride, dfx, st, set_attr, mode);
+        case 384: return launch_nlin_fft<384>(pl, np, out, bstride, dfx, st, set_attr, mode);
+        case 768: return launch_nlin_fft<768>(pl, np, out, bstride, dfx, st, set_attr, mode);
         default: pl->err = "FFT path not available for this N_fm"; return SDDC_ERR_UNSUPPORTED;
     }
 }
@@ -1080,14 +1094,22 @@ int sddc_jvp_set_base(sddc_plan* pl, const double* X, int B, void* stream) {
     const Geo& g = pl->g;
     if (!pl->xbase) {
         if ((rc = dev_alloc(pl, &pl->xbase, (size_t)pl->cfg.max_batch * 3 * g.N, false))) return rc;
-        if (pl->fft_dfx) {
+        if (pl->fft_dfx && pl->fft_M != 0 && !pl->fft_direct) {
+            if ((rc = dev_alloc(pl, &pl->grid7, (size_t)pl->cfg.max_batch * g.n * 7 * g.M, false))) return rc;
+        } else if (pl->fft_dfx) {
             if ((rc = dev_alloc(pl, &pl->coef7base, (size_t)pl->cfg.max_batch * 7 * g.N, false))) return rc;
         } else if (pl->ws_ok && (rc = dev_alloc(pl, &pl->gridc, (size_t)pl->cfg.max_batch * 9 * 2 * g.n8 * g.Mhp, true))) return rc;
     }
     PLAN_CUDA(pl, cudaMemcpyAsync(pl->xbase, X, sizeof(double) * (size_t)B * 3 * g.N, cudaMemcpyDeviceToDevice, st));
     pl->base_B = B;
-    // FFT formulation: the base state is kept as its seven spectral rows; its grid values are re-synthesised inside
-    // every product kernel (cheaper than reading 9 n M cached grid values per member back from HBM)
+    // FFT kernels: the seven grid fields of the base state are synthesised once and cached in the order the product phase
+    // reads them (fft_fused.h, i3f1_grid / i3f1_jvpc): every product then needs the four inverse transforms of the
+    // perturbation only, not the seven of a pair of states
+    if (pl->grid7) {
+        if ((rc = run_prep(pl, pl->xbase, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
+        return run_nlin_fft(pl, pl->coef7, nullptr, nullptr, false, B, st, false, 1);
+    }
+    // direct-summation rows: the base state is kept as its seven spectral rows
     if (pl->fft_dfx) return run_prep(pl, pl->xbase, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7base);
     if (pl->ws_ok) {
         if ((rc = run_prep(pl, pl->xbase, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
@@ -1103,6 +1125,11 @@ int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* R
     if (dv == out) { pl->err = "out must not alias dv"; return SDDC_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long N3 = 3LL * pl->g.N;
+    if (pl->grid7) {
+        if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
+        if ((rc = run_nlin_fft(pl, nullptr, pl->coef7b, pl->f_sm, true, B, st, false, 2))) return rc;
+        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+    }
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
         if ((rc = run_nlin_fft(pl, pl->coef7base, pl->coef7b, pl->f_sm, true, B, st))) return rc;

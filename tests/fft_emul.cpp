@@ -36,6 +36,29 @@ static void run_rows(const double* coef0, const double* coef1, double* out, int 
     }
 }
 
+// cached base state: grid fields of rows0 by the GRID mode, then the bilinear products of (rows0, rows1) by the JVPC mode
+template <int M>
+static void run_rows_cached(const double* coef0, const double* coef1, double* out, int nrows) {
+    constexpr int K = Cfg<M>::K, NT = M == 768 ? 128 : 64;
+    std::vector<double> tab(tab_doubles<M>());
+    fill_tables<M>(tab.data());
+    const Tables tb = make_tables<M>(tab.data());
+    std::vector<double> buf((size_t)pairs_doubles<M>(4)), grid((size_t)7 * M);
+    for (int row = 0; row < nrows; ++row) {
+        for (auto& v : buf) v = 1e300;
+        for (auto& v : grid) v = 1e300;
+        for (int t = 0; t < NT; ++t) bc_inv_fx<M, NT>(t, coef0 + (size_t)row * 7 * K, buf.data(), tb);
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 4, +1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) i3f1_grid<M, NT>(t, buf.data(), tb, grid.data());
+        for (auto& v : buf) v = 1e300;
+        for (int t = 0; t < NT; ++t) bc_inv_fx<M, NT>(t, coef1 + (size_t)row * 7 * K, buf.data(), tb);
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 4, +1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) i3f1_jvpc<M, NT>(t, buf.data(), tb, grid.data());
+        for (int t = 0; t < NT; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 2, -1, NT>(t, buf.data(), tw); }
+        for (int t = 0; t < NT; ++t) cp_fwd<M, NT>(t, buf.data(), out + (size_t)row * 4 * K, tb);
+    }
+}
+
 // staged one-state schedule (nlin_fft_staged_kernel): the two warps of a worker, each running ahead of the other as far
 // as the two worker barriers allow (warp 1 completely before warp 0 in every barrier interval)
 template <int M>
@@ -151,6 +174,14 @@ int fft_emul_rows_staged(int M, const double* coef0, double* out, int nrows) {
 
 // coef0 / coef1: [nrows][7][K]; out: [nrows][4][K].  Returns 0, or -1 for an unsupported grid size.
 int fft_emul_rows(int M, int dfx, const double* coef0, const double* coef1, double* out, int nrows) {
+    if (dfx == 2) {   // two-state products through the cached base grid (GRID + JVPC modes)
+        switch (M) {
+            case 192: run_rows_cached<192>(coef0, coef1, out, nrows); return 0;
+            case 384: run_rows_cached<384>(coef0, coef1, out, nrows); return 0;
+            case 768: run_rows_cached<768>(coef0, coef1, out, nrows); return 0;
+            default: return -1;
+        }
+    }
     switch (M) {
         case 192: dfx ? run_rows<192, true>(coef0, coef1, out, nrows) : run_rows<192, false>(coef0, coef1, out, nrows); return 0;
         case 384: dfx ? run_rows<384, true>(coef0, coef1, out, nrows) : run_rows<384, false>(coef0, coef1, out, nrows); return 0;

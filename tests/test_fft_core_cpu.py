@@ -54,12 +54,12 @@ def _expected(g, h=None):
     return np.stack([orc.DST(P1)[:, :K], orc.DST(P2)[:, :K], orc.DCT(NT)[:, :K], orc.DCT(NS)[:, :K]], axis=1)
 
 
-def _call(lib, M, rows0, rows1=None):
+def _call(lib, M, rows0, rows1=None, cached=False):
     n, _, K = rows0.shape
     out = np.full((n, 4, K), np.nan)
     dp = ctypes.POINTER(ctypes.c_double)
     r1 = rows1 if rows1 is not None else rows0
-    rc = lib.fft_emul_rows(M, int(rows1 is not None), rows0.ctypes.data_as(dp), r1.ctypes.data_as(dp),
+    rc = lib.fft_emul_rows(M, 2 if cached else int(rows1 is not None), rows0.ctypes.data_as(dp), r1.ctypes.data_as(dp),
                            out.ctypes.data_as(dp), n)
     assert rc == 0
     return out
@@ -97,6 +97,9 @@ def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
     got2 = _call(emul, M, rows, rows1)
     scale2 = np.abs(exp2).max(axis=(0, 2), keepdims=True)
     assert (np.abs(got2 - exp2) / scale2).max() < 1e-12
+    # the same products with the base state's grid fields synthesised once and cached (sddc_jvp_set_base / _apply)
+    got3 = _call(emul, M, rows, rows1, cached=True)
+    assert (np.abs(got3 - exp2) / scale2).max() < 1e-12
 
 
 @pytest.mark.parametrize("K", [128, 256])
