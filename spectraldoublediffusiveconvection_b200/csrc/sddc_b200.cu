@@ -375,6 +375,10 @@ template <int M>
 int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bstride, bool dfx, cudaStream_t st, bool set_attr,
                     int mode = 0) {
     constexpr int NW = nlin_fft_nw<M>(false), NWD = nlin_fft_nw<M>(true);
+#ifndef NLIN_JVPC_NW768
+#define NLIN_JVPC_NW768 3   // 4 workers (512 threads) cap the registers at 128: 360 bytes of spills, 0.71 ms against 0.61 ms at (40,512)
+#endif
+    constexpr int NWJ = M == 768 ? NLIN_JVPC_NW768 : NW;   // workers of the cached-base product kernel
     constexpr int NT = M == 768 ? 128 : 64;   // threads per worker = columns of the radix-6 pass at M = 768
     constexpr size_t smem = nlin_fft_smem_bytes<M, false>(NW), smem_d = nlin_fft_smem_bytes<M, true>(NWD);
     static_assert(smem <= SMEM_LIMIT && smem_d <= SMEM_LIMIT, "workers do not fit into shared memory");
@@ -382,7 +386,7 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, true, NWD, NT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
-        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NW, NT, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+        PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_kernel<M, false, NWJ, NT, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
         if (M == 384) {
             PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
             PLAN_CUDA(pl, cudaFuncSetAttribute((nlin_fft_staged_kernel<384, NLIN_FFT_STAGED_NW, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
@@ -410,7 +414,7 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
         } else {
             const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
             if (mode == 1) nlin_fft_kernel<M, false, NW, NT, 1><<<grid, NT * NW, smem, st>>>(np);
-            else if (mode == 2) nlin_fft_kernel<M, false, NW, NT, 2><<<grid, NT * NW, smem, st>>>(np);
+            else if (mode == 2) nlin_fft_kernel<M, false, NWJ, NT, 2><<<std::min((np.nrows + NWJ - 1) / NWJ, pl->num_sms), NT * NWJ, nlin_fft_smem_bytes<M, false>(NWJ), st>>>(np);
             else nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
         }
     }
