@@ -229,8 +229,11 @@ def test_other_shapes_against_oracle(K, N_r, sym):
     has_jvp = True
     jv = pl.jvp(dvd, Xd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
     Fd = pl.nlin_dfx(dvd, Xd).cpu().numpy()
+    pl.jvp_set_base(Xd)                                     # cached base state: grid fields (FFT kernels) or spectral rows
+    jc = pl.jvp_apply(dvd, _dev(Ra), _dev(Ra_s)).cpu().numpy()
     for m in range(B):
         assert rel_l2(Fd[m], orc.NLIN_DFX(dv[m], X[m], op, sym)) < 1e-11
+        assert rel_l2(jc[m], jv[m]) < 1e-12
     dg = pl.diagnostics(Xd).cpu().numpy()
     mask = orc.sym_mask(K, N_r - 1).reshape(-1) if sym else 1.0
     for m in range(B):
