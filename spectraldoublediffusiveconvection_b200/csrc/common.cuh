@@ -70,6 +70,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                  : "memory");
 }
 
+// Programmatic dependent launch (the kernels of a member-step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel lets its successor's CTAs become resident as soon as all
+// of its own have started, and itself touches nothing its predecessors produced before pdl_wait() -- the successor's
+// prologue (tables / operators into shared memory, barrier initialisation) then overlaps the predecessor's tail.  Both
+// are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

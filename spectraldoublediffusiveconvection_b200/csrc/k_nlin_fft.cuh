@@ -25,7 +25,8 @@ struct NlinFftParams {
     const double* tab;    // fftp::tab_doubles<M>() table doubles (fftp::fill_tables)
     double* grid;         // [rows][7][M] cached grid fields of the base state (MODE 1 writes, MODE 2 reads; fft_fused.h)
     int nrows;
-    int* next_row;        // row counter, zeroed before every launch: workers claim rows dynamically
+    int* next_row;        // [0] row counter: workers claim rows dynamically; [1] CTAs that have finished -- the last one
+                          // zeroes both for the next launch (no memset between the kernels of a step)
 };
 
 #ifndef NLIN_FFT_NW
@@ -41,6 +42,15 @@ __host__ __device__ constexpr size_t nlin_fft_worker_doubles() { return (size_t)
 template <int M, bool DFX>
 __host__ __device__ constexpr size_t nlin_fft_smem_bytes(int nw) {
     return sizeof(double) * ((size_t)nlin_fft_tab_pad<M>() + (size_t)nw * nlin_fft_worker_doubles<M, DFX>());
+}
+
+// every claim of this CTA has been made: the last CTA of the launch to get here resets the counters for the next launch
+__device__ __forceinline__ void rows_done(int* cnt) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(cnt + 1, 1) == (int)gridDim.x - 1) {
+        cnt[0] = 0;
+        cnt[1] = 0;
+    }
 }
 
 template <int NT = 64>
@@ -59,8 +69,10 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
     extern __shared__ __align__(128) double smem[];
     __shared__ int s_row[NW];
     double* stab = smem;
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < tab_doubles<M>(); i += NT * NW) stab[i] = p.tab[i];
     const int w = threadIdx.x / NT, t = threadIdx.x % NT;
+    pdl_wait();   // coefficient rows (prep_kernel) and the row counter (reset by the previous launch's last CTA)
     if (t == 0) s_row[w] = atomicAdd(p.next_row, 1);
     __syncthreads();
     const Tables tb = make_tables<M>(stab);
@@ -109,6 +121,7 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
         if (t == 0) s_row[w] = next;
         worker_sync<NT>(w);   // the planes are free again and the next row index is visible
     }
+    rows_done(p.next_row);
 }
 
 // ---- staged one-state kernel (64-thread workers: M = 384) -----------------------------------------------------------------
@@ -143,9 +156,11 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftPara
     __shared__ int s_row[NW];
     __shared__ __align__(8) uint64_t s_bar[NW][2];
     double* stab = smem;
+    pdl_launch_dependents();
     for (int i = threadIdx.x; i < tab_doubles<M>(); i += NT * NW) stab[i] = p.tab[i];
     const int w = threadIdx.x / NT, t = threadIdx.x % NT, warp = t >> 5, lane = t & 31;
     if (lane == 0) mbar_init(&s_bar[w][warp], 1);
+    pdl_wait();   // coefficient rows (prep_kernel) and the row counter (reset by the previous launch's last CTA)
     if (t == 0) s_row[w] = atomicAdd(p.next_row, 1);
     mbar_fence_init();
     __syncthreads();
@@ -197,6 +212,7 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftPara
         __syncwarp();
         row = nrow;
     }
+    rows_done(p.next_row);
 }
 
 // Kinetic energy on the 3K grid (Main.py:71-134) in the FFT formulation: one complex transform per radial row
@@ -361,7 +377,9 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p, int ntiles) {
     const int n = g.n, n8 = g.n8, K = g.K, N = g.N, LDT = POST_TC + 1;
     const int tid = threadIdx.x, nkt = (K + POST_TC - 1) / POST_TC, TS = 4 * n * LDT;
     double* sD = smem + 2 * TS;   // [n][n8]
+    pdl_launch_dependents();
     for (int idx = tid; idx < n * n8; idx += 256) sD[idx] = p.DrT[idx];
+    pdl_wait();   // the analysed products come from the row kernel
     auto issue = [&](int tile, int stage) {
         const int b = tile / nkt, k0 = (tile - b * nkt) * POST_TC;
         const double* sb = p.spec + (size_t)b * n * 4 * K;

@@ -120,11 +120,13 @@ __global__ void __launch_bounds__(64 * NT8, (NT8 <= 4) ? 3 : 1) prep_kernel(Prep
             cp_async8_zfill(&sJ[idx], okj ? Jb + (long long)bt * n + i : Jb, okj);
         }
     };
+    pdl_launch_dependents();
     for (int idx = tid; idx < n8 * LDX / 2; idx += nthr) {
         cp_async16(&mDr[2 * idx], p.DrP + 2 * idx);
         cp_async16(&mD2r[2 * idx], p.D2rP + 2 * idx);
         cp_async16(&mDsq[2 * idx], p.DsqP + 2 * idx);
     }
+    pdl_wait();   // the state and its suffix sums come from the previous back-substitution
     int tile = blockIdx.x, stage = 0;
     if (tile < ntiles) issue(tile, 0);
     cp_async_commit();

@@ -76,6 +76,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     }
 
     if (G.symmetric && which == 1) {   // these modes are identically zero under the equatorial symmetry
+        pdl_wait();
         if (DIAG) {
             for (int m = tid; m < 3 * BT; m += blockDim.x)
                 if (b0 + m / 3 < p.B) p.dpart[((long long)(b0 + m / 3) * 6 + fld * 2 + which) * 3 + m % 3] = 0.0;
@@ -100,6 +101,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     }
     for (int idx = tid; idx < 2 * NM * BT * LDL; idx += blockDim.x) sR[idx] = 0.0;   // padded rows stay zero
     __syncthreads();
+    pdl_wait();   // right-hand sides from prep_kernel / post_kernel
 
     if (is_producer) {
       if (lane == 0) {
@@ -313,6 +315,7 @@ template <int NT8, int NSL, bool SUB = false, bool DIAG = false>
 __global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
+    pdl_launch_dependents();
     const int bid = blockIdx.x;
     if (bid < 2 * npsi_tiles) {
         solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, SUB, DIAG>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);

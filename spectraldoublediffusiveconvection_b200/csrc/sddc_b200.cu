@@ -79,7 +79,7 @@ struct sddc_plan {
     bool dfx_direct = false;    // only the two-state products take the (direct) row pipeline: dense shapes beyond N_r = 41
     int ke_M = 0;               // 3 N_fm when the kinetic-energy synthesis runs as an FFT (N_fm = 128, 256), else 0
     double *ke_tab = nullptr, *ke_Wn = nullptr;
-    int* fft_row = nullptr;     // dynamic row counter of nlin_fft_kernel (zeroed before every launch)
+    int* fft_row = nullptr;     // [2] row counter / finished-CTA counter of the row kernels (self-resetting: k_nlin_fft.cuh)
     double *coef7 = nullptr, *coef7b = nullptr, *coef7base = nullptr, *spec4 = nullptr, *fft_tab = nullptr;
     double* grid7 = nullptr;    // [max_batch n][7][M] grid fields of the base state of sddc_jvp_set_base (FFT kernels; lazily allocated)
     int base_B = 0;
@@ -135,6 +135,19 @@ namespace {
             return SDDC_ERR_CUDA;                                                                      \
         }                                                                                              \
     } while (0)
+
+// Launch with programmatic stream serialization (common.cuh, pdl_*): the kernels of a member-step overlap their
+// prologues with the tail of their predecessor.
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 int dev_alloc(sddc_plan* pl, double** out, size_t count, bool zero) {
     void* p = nullptr;
@@ -310,21 +323,21 @@ int run_prep(sddc_plan* pl, const double* X, int set, bool want_coef, double* li
     StageTimer tm(pl, SDDC_STAGE_PREP, st);
     if (fftl) {
         switch (pl->g.nt8) {
-            case 3: prep_kernel<3, true><<<grid, 192, smem, st>>>(pp, ntiles); break;
-            case 4: prep_kernel<4, true><<<grid, 256, smem, st>>>(pp, ntiles); break;
-            case 5: prep_kernel<5, true><<<grid, 320, smem, st>>>(pp, ntiles); break;
-            case 6: prep_kernel<6, true><<<grid, 384, smem, st>>>(pp, ntiles); break;
-            case 7: prep_kernel<7, true><<<grid, 448, smem, st>>>(pp, ntiles); break;
-            default: prep_kernel<8, true><<<grid, 512, smem, st>>>(pp, ntiles); break;
+            case 3: launch_pdl(prep_kernel<3, true>, dim3(grid), dim3(192), smem, st, pp, ntiles); break;
+            case 4: launch_pdl(prep_kernel<4, true>, dim3(grid), dim3(256), smem, st, pp, ntiles); break;
+            case 5: launch_pdl(prep_kernel<5, true>, dim3(grid), dim3(320), smem, st, pp, ntiles); break;
+            case 6: launch_pdl(prep_kernel<6, true>, dim3(grid), dim3(384), smem, st, pp, ntiles); break;
+            case 7: launch_pdl(prep_kernel<7, true>, dim3(grid), dim3(448), smem, st, pp, ntiles); break;
+            default: launch_pdl(prep_kernel<8, true>, dim3(grid), dim3(512), smem, st, pp, ntiles); break;
         }
     } else {
         switch (pl->g.nt8) {
-            case 3: prep_kernel<3><<<grid, 192, smem, st>>>(pp, ntiles); break;
-            case 4: prep_kernel<4><<<grid, 256, smem, st>>>(pp, ntiles); break;
-            case 5: prep_kernel<5><<<grid, 320, smem, st>>>(pp, ntiles); break;
-            case 6: prep_kernel<6><<<grid, 384, smem, st>>>(pp, ntiles); break;
-            case 7: prep_kernel<7><<<grid, 448, smem, st>>>(pp, ntiles); break;
-            default: prep_kernel<8><<<grid, 512, smem, st>>>(pp, ntiles); break;
+            case 3: launch_pdl(prep_kernel<3, false>, dim3(grid), dim3(192), smem, st, pp, ntiles); break;
+            case 4: launch_pdl(prep_kernel<4, false>, dim3(grid), dim3(256), smem, st, pp, ntiles); break;
+            case 5: launch_pdl(prep_kernel<5, false>, dim3(grid), dim3(320), smem, st, pp, ntiles); break;
+            case 6: launch_pdl(prep_kernel<6, false>, dim3(grid), dim3(384), smem, st, pp, ntiles); break;
+            case 7: launch_pdl(prep_kernel<7, false>, dim3(grid), dim3(448), smem, st, pp, ntiles); break;
+            default: launch_pdl(prep_kernel<8, false>, dim3(grid), dim3(512), smem, st, pp, ntiles); break;
         }
     }
     pl->launches++;
@@ -396,26 +409,25 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
     }
     const int n = pl->g.n, n8 = pl->g.n8;
     np.next_row = pl->fft_row;
-    PLAN_CUDA(pl, cudaMemsetAsync(pl->fft_row, 0, sizeof(int), st));
     {
         StageTimer tm(pl, SDDC_STAGE_SYNTH, st);
         if (dfx && mode == 0) {
             const int grid = std::min((np.nrows + NWD - 1) / NWD, pl->num_sms);
-            nlin_fft_kernel<M, true, NWD, NT><<<grid, NT * NWD, smem_d, st>>>(np);
+            launch_pdl(nlin_fft_kernel<M, true, NWD, NT, 0>, dim3(grid), dim3(NT * NWD), smem_d, st, np);
         } else if (M == 384) {
             // headline shape: per-warp ownership of the transforms, coefficient rows staged by TMA (k_nlin_fft.cuh)
             constexpr int NWS = NLIN_FFT_STAGED_NW;
             static_assert(nlin_fft_staged_smem_bytes<384>(NWS) <= SMEM_LIMIT, "staged workers do not fit into shared memory");
             const int grid = std::min((np.nrows + NWS - 1) / NWS, pl->num_sms);
             const size_t ssm = nlin_fft_staged_smem_bytes<384>(NWS);
-            if (mode == 1) nlin_fft_staged_kernel<384, NWS, 1><<<grid, 64 * NWS, ssm, st>>>(np);
-            else if (mode == 2) nlin_fft_staged_kernel<384, NWS, 2><<<grid, 64 * NWS, ssm, st>>>(np);
-            else nlin_fft_staged_kernel<384, NWS><<<grid, 64 * NWS, ssm, st>>>(np);
+            if (mode == 1) launch_pdl(nlin_fft_staged_kernel<384, NWS, 1>, dim3(grid), dim3(64 * NWS), ssm, st, np);
+            else if (mode == 2) launch_pdl(nlin_fft_staged_kernel<384, NWS, 2>, dim3(grid), dim3(64 * NWS), ssm, st, np);
+            else launch_pdl(nlin_fft_staged_kernel<384, NWS, 0>, dim3(grid), dim3(64 * NWS), ssm, st, np);
         } else {
             const int grid = std::min((np.nrows + NW - 1) / NW, pl->num_sms);
-            if (mode == 1) nlin_fft_kernel<M, false, NW, NT, 1><<<grid, NT * NW, smem, st>>>(np);
-            else if (mode == 2) nlin_fft_kernel<M, false, NWJ, NT, 2><<<std::min((np.nrows + NWJ - 1) / NWJ, pl->num_sms), NT * NWJ, nlin_fft_smem_bytes<M, false>(NWJ), st>>>(np);
-            else nlin_fft_kernel<M, false, NW, NT><<<grid, NT * NW, smem, st>>>(np);
+            if (mode == 1) launch_pdl(nlin_fft_kernel<M, false, NW, NT, 1>, dim3(grid), dim3(NT * NW), smem, st, np);
+            else if (mode == 2) launch_pdl(nlin_fft_kernel<M, false, NWJ, NT, 2>, dim3(std::min((np.nrows + NWJ - 1) / NWJ, pl->num_sms)), dim3(NT * NWJ), nlin_fft_smem_bytes<M, false>(NWJ), st, np);
+            else launch_pdl(nlin_fft_kernel<M, false, NW, NT, 0>, dim3(grid), dim3(NT * NW), smem, st, np);
         }
     }
     pl->launches++;
@@ -427,7 +439,7 @@ int launch_nlin_fft(sddc_plan* pl, NlinFftParams& np, double* out, long long bst
         const size_t psm = post_smem_bytes(n, n8);
         const int per_sm = std::max(1, std::min(4, (int)((SMEM_LIMIT + 1024) / (psm + 1024))));
         StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
-        post_kernel<<<std::min(ntiles, per_sm * pl->num_sms), 256, psm, st>>>(pp, ntiles);
+        launch_pdl(post_kernel, dim3(std::min(ntiles, per_sm * pl->num_sms)), dim3(256), psm, st, pp, ntiles);
         pl->launches++;
         PLAN_CUDA(pl, cudaGetLastError());
     }
@@ -459,7 +471,7 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
             const size_t psm = post_smem_bytes(pl->g.n, pl->g.n8);
             const int per_sm = std::max(1, std::min(4, (int)((SMEM_LIMIT + 1024) / (psm + 1024))));
             StageTimer tm(pl, SDDC_STAGE_ANALYSIS, st);
-            post_kernel<<<std::min(ntiles, per_sm * pl->num_sms), 256, psm, st>>>(pp, ntiles);
+            launch_pdl(post_kernel, dim3(std::min(ntiles, per_sm * pl->num_sms)), dim3(256), psm, st, pp, ntiles);
             pl->launches++;
             PLAN_CUDA(pl, cudaGetLastError());
         }
@@ -499,9 +511,9 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
         const int nblk = 2 * npsi + 4 * nts;
         if (sub && dpart) { pl->err = "diagnostics partial sums are only produced by plain steps"; return SDDC_ERR_INVALID; }
 #define SDDC_LAUNCH_SOLVE_HOT(NT)                                                                                 \
-    if (sub) { if (n3) solve_hot_kernel<NT, 3, true><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, true><<<nblk, nthr, smb, st>>>(sp, npsi); } \
-    else if (dpart) { if (n3) solve_hot_kernel<NT, 3, false, true><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, false, true><<<nblk, nthr, smb, st>>>(sp, npsi); } \
-    else { if (n3) solve_hot_kernel<NT, 3, false><<<nblk, nthr, smb, st>>>(sp, npsi); else solve_hot_kernel<NT, 2, false><<<nblk, nthr, smb, st>>>(sp, npsi); }
+    if (sub) { if (n3) launch_pdl(solve_hot_kernel<NT, 3, true, false>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); else launch_pdl(solve_hot_kernel<NT, 2, true, false>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); } \
+    else if (dpart) { if (n3) launch_pdl(solve_hot_kernel<NT, 3, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); else launch_pdl(solve_hot_kernel<NT, 2, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); } \
+    else { if (n3) launch_pdl(solve_hot_kernel<NT, 3, false, false>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); else launch_pdl(solve_hot_kernel<NT, 2, false, false>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); }
         switch (pl->g.nt8) {
             case 3: SDDC_LAUNCH_SOLVE_HOT(3) break;
             case 4: SDDC_LAUNCH_SOLVE_HOT(4) break;
