@@ -146,3 +146,70 @@ def test_tight_tangent_equals_the_secant():
     sec = (out["X"][0] - X0[0]) / (out["mu"][0] - Ra)
     tan = out["X_dot"][0] / out["mu_dot"][0]
     assert float(torch.linalg.vector_norm(tan - sec) / torch.linalg.vector_norm(sec)) < 2e-2
+
+
+class _FoldPlan:
+    """Saddle-node normal form G(x, mu) = mu - a - x^2 (componentwise, a per member): steady branches
+    x = +-sqrt(mu - a) meet in a fold at mu = a.  Exposes what the drivers use of an EnsemblePlan."""
+    symmetric = False
+    N_fm, nr = 2, 1
+
+    def __init__(self, a):
+        self.a = torch.as_tensor(a, dtype=torch.float64)
+        self.base = None
+
+    def _param(self, v, B):
+        v = torch.as_tensor(v, dtype=torch.float64).reshape(-1)
+        return (v.expand(B) if v.numel() == 1 else v).contiguous()
+
+    def residual(self, X, mu, Ra_s):
+        return self._param(mu, X.shape[0])[:, None] - self.a[:X.shape[0], None] - X * X
+
+    def jvp_set_base(self, X):
+        self.base = X.clone()
+
+    def jvp_apply(self, dv, mu, Ra_s):
+        return -2.0 * self.base * dv
+
+    def dF_dRa(self, X):
+        return torch.ones_like(X)
+
+    def diagnostics(self, X):
+        out = torch.zeros((X.shape[0], 6), dtype=torch.float64)
+        out[:, 0] = torch.linalg.vector_norm(X, dim=1)
+        out[:, 1] = X[:, 0]                        # "KE" slot: the signed amplitude, to see which branch a member is on
+        return out
+
+
+def test_branch_loop_detects_folds_per_member():
+    """Two members with folds at different parameter values walk down their upper branches (sign = -1), go round the
+    saddle node by arc-length steps and come back up on the lower branch: the sign change of mu_dot is recorded as a fold
+    for each member where ITS fold is (Main.py:996-997), and the walk continues with mu increasing."""
+    a = torch.tensor([10.0, 10.5], dtype=torch.float64)
+
+    class Plan(_FoldPlan):
+        def residual(self, X, mu, Ra_s):           # sub-batches of the branch loop carry their own a through Ra_s
+            return self._param(mu, X.shape[0])[:, None] - self._param(Ra_s, X.shape[0])[:, None] - X * X
+
+    pl = Plan(a)
+    mu0 = torch.tensor([10.6, 11.0], dtype=torch.float64)
+    X0 = torch.sqrt(mu0 - a)[:, None].repeat(1, 4)
+    # ds_min above every step size: always the arc-length branch of the loop, the only one in which the reference looks
+    # for folds and re-decides the direction (with Newton steps enabled and a failed one falling back to an arc-length step,
+    # Main.py:976-988 neither records the fold nor flips `sign`, and the walk oscillates around the saddle node -- the
+    # batched loop reproduces that too)
+    res = krylov.continuation_batched(pl, X0, mu0, 14, a, sign=-1.0, ds=0.01, ds_min=1e9, krylov=6, lgmres_rtol=0.0)
+    h = res.stacked()
+    assert bool(res.alive.all())
+    for m in range(2):
+        assert len(res.folds[m]) >= 1, (m, h["Ra"][:, m])
+        it, mu_f, X_f = res.folds[m][0]
+        assert abs(mu_f - float(a[m])) < 0.1                      # the fold sits at mu = a
+        amp = h["KE"][:, m]
+        assert amp[0] > 0 and amp[it] * amp[it - 1] < 0            # the step that found the fold changed branches
+        assert np.all(np.diff(h["Ra"][:it, m]) < 0)                # mu decreased up to the fold ...
+        assert np.all(np.diff(h["Ra"][it + 1:it + 4, m]) > 0)      # ... and increases afterwards (sign re-decided, 1000-1003)
+        assert h["Ra"][:, m].min() >= float(a[m]) - 1e-6           # no steady state below the fold
+        # every recorded point is a steady state of ITS member
+        r = pl.residual(res.X, res.mu, a)
+        assert float(r.abs().max()) < 1e-7
