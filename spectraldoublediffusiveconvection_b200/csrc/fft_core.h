@@ -41,7 +41,8 @@ struct Cfg {
     static constexpr int RD = L / 8;
     static constexpr int NBLK = M_ / 8;  // = 6 RD
     static constexpr int PL = M_;        // doubles per plane
-    static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16), "supported grids: M = 192, 384, 768");
+    // RD = 32 (M = 1536) exists for the kinetic-energy transform only: its middle pass runs in two steps (pass_d32_*)
+    static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16 || RD == 32), "supported grids: M = 192, 384, 768 (1536: KE)");
 };
 SDDC_HD int at(int j, int c) { return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7)); }
 // offset of the (re, im) plane pair of transform q inside a worker's buffer.  On the small grid (M = 192), where the lanes
@@ -282,6 +283,78 @@ SDDC_HD void pass_d_warp(int lane, double* __restrict__ pa, double* __restrict__
     }
 }
 
+// ---- radix-32 middle pass (M = 1536, inverse only), in place in two steps ----------------------------------------------
+// 32 complex values do not fit into registers next to their twiddles, so the DFT over d = d1 + 4 d2 is split as
+//   y[8 b1 + b2] = sum_d1 e^{2 pi i d1 b1 / 4} [ e^{2 pi i d1 b2 / 32} sum_d2 X[d1 + 4 d2] e^{2 pi i d2 b2 / 8} ],   X[d] = x[d] e^{2 pi i d a / L}
+// step a: per (k2, a, d1) an 8-point DFT over d2, written back to the positions it read (d1 + 4 b2);
+// step b: per (k2, a, b2) a 4-point DFT over d1 on the positions 4 b2 + d1, in place: position 4 b2 + b1 then holds
+// y[8 b1 + b2], i.e. the pass leaves its output in the order dperm() and the last pass reads it through that map.
+template <int M>
+SDDC_HD constexpr int dperm(int b) { return Cfg<M>::RD == 32 ? (((b & 7) << 2) | (b >> 3)) : b; }
+
+SDDC_HD void root32(int k, double& c, double& s) {   // e^{2 pi i k / 32}, 0 <= k < 32
+    constexpr double q[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                             0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                             0.19509032201612826785, 0.0};
+    auto cosq = [&](int m) {   // cos(2 pi m / 32) for any m >= 0
+        m &= 31;
+        if (m > 16) m = 32 - m;
+        return m <= 8 ? q[m] : -q[16 - m];
+    };
+    c = cosq(k);
+    s = cosq(k + 24);          // sin x = cos(x - pi/2) = cos(x + 3 pi/2)
+}
+
+template <int M>
+SDDC_HD void pass_d32_a(int t, double* __restrict__ buf, const Tables& tb) {
+    constexpr int PL = Cfg<M>::PL;
+    static_assert(Cfg<M>::RD == 32, "two-step middle pass");
+    double* re = buf;
+    double* im = buf + PL;
+    for (int u = t; u < 4 * 48; u += NTW) {
+        const int d1 = u / 48, rem = u - d1 * 48, k2 = rem >> 3, a = rem & 7;
+        int o[8];
+        C x[8], y[8];
+#pragma unroll
+        for (int d2 = 0; d2 < 8; ++d2) {
+            const int d = d1 + 4 * d2;
+            o[d2] = at(6 * d + k2, a);
+            x[d2] = cmul(C{re[o[d2]], im[o[d2]]}, tb.tLc[d * 9 + a], tb.tLs[d * 9 + a]);
+        }
+        Dft<8, +1>::run(x, y);
+#pragma unroll
+        for (int b2 = 0; b2 < 8; ++b2) {
+            double c, s;
+            root32(d1 * b2, c, s);
+            const C v = cmul(y[b2], c, s);
+            re[o[b2]] = v.r;
+            im[o[b2]] = v.i;
+        }
+    }
+}
+template <int M>
+SDDC_HD void pass_d32_b(int t, double* __restrict__ buf) {
+    constexpr int PL = Cfg<M>::PL;
+    double* re = buf;
+    double* im = buf + PL;
+    for (int u = t; u < 8 * 48; u += NTW) {
+        const int b2 = u / 48, rem = u - b2 * 48, k2 = rem >> 3, a = rem & 7;
+        int o[4];
+        C x[4], y[4];
+#pragma unroll
+        for (int d1 = 0; d1 < 4; ++d1) {
+            o[d1] = at(6 * (4 * b2 + d1) + k2, a);
+            x[d1] = C{re[o[d1]], im[o[d1]]};
+        }
+        Dft<4, +1>::run(x, y);
+#pragma unroll
+        for (int b1 = 0; b1 < 4; ++b1) {
+            re[o[b1]] = y[b1].r;
+            im[o[b1]] = y[b1].i;
+        }
+    }
+}
+
 // last inverse pass of one transform at column n1: six grid values z[n2] <-> grid point n = n1 + L n2
 template <int M>
 SDDC_HD void inv6(const double* __restrict__ re, const double* __restrict__ im, const int (&pos)[6], int n1,
@@ -307,7 +380,7 @@ SDDC_HD double ke6(int t, const double* __restrict__ buf, const Tables& tb, cons
     for (int n1 = t; n1 < L; n1 += NTW) {
         int pos[6];
 #pragma unroll
-        for (int m = 0; m < 6; ++m) pos[m] = at(6 * (n1 >> 3) + m, n1 & 7);
+        for (int m = 0; m < 6; ++m) pos[m] = at(6 * dperm<M>(n1 >> 3) + m, n1 & 7);
         C z[6];
         inv6<M>(buf, buf + PL, pos, n1, tb, z);
 #pragma unroll

@@ -253,15 +253,22 @@ __global__ void __launch_bounds__(64 * NW, 1) ke_fft_kernel(KeFftParams p) {
     const int w = threadIdx.x >> 6, t = threadIdx.x & 63;
     double* buf = smem + ke_fft_shared_doubles<M>() + (size_t)w * ke_fft_worker_doubles<M>();
     double* srow = buf + 2 * PL;
-    C tw[Cfg<M>::RD];
-    load_tw<M>(t, tb, tw);
+    constexpr bool TWO_STEP = Cfg<M>::RD == 32;   // M = 1536: radix-32 middle pass in two in-place steps (fft_core.h)
+    C tw[TWO_STEP ? 1 : Cfg<M>::RD];
+    if constexpr (!TWO_STEP) load_tw<M>(t, tb, tw);
     for (int row = blockIdx.x * NW + w; row < p.nrows; row += gridDim.x * NW) {
         const double* r = p.rows + (size_t)row * p.row_stride;
         ke_stage<M>(t, r, r + p.b_off, p.ascale ? p.ascale[row % p.n] : 1.0, srow);
         worker_sync(w);
         ke_pack<M>(t, srow, buf, tb);
         worker_sync(w);
-        pass_d<M, 1, +1>(t, buf, tw);
+        if constexpr (TWO_STEP) {
+            pass_d32_a<M>(t, buf, tb);
+            worker_sync(w);
+            pass_d32_b<M>(t, buf);
+        } else {
+            pass_d<M, 1, +1>(t, buf, tw);
+        }
         worker_sync(w);
         const double part = warp_sum(ke6<M>(t, buf, tb, sW));
         if ((t & 31) == 0) s_part[w][t >> 5] = part;

@@ -29,6 +29,9 @@ constexpr size_t SMEM_LIMIT = 227 * 1024 - 1024;  // dynamic shared memory we op
 #ifndef KE_NW768
 #define KE_NW768 8   // (6: 0.093 ms, 8: 0.084 ms, 10: 0.093 ms at (30,256), 512 members)  // workers per CTA of the kinetic-energy transform at M = 768
 #endif
+#ifndef KE_NW1536
+#define KE_NW1536 4  // 40 KB of planes + rows per worker at M = 1536 (N_fm = 512)
+#endif
 #ifndef SOLVE_NTB
 #define SOLVE_NTB 2  // members per back-substitution CTA = 8 * SOLVE_NTB (1 and 4 measured slower)
 #endif
@@ -541,6 +544,7 @@ int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row
     {
         StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
         if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<std::min((kf.nrows + 7) / 8, pl->num_sms), 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
+        else if (pl->ke_M == 1536) ke_fft_kernel<1536, KE_NW1536><<<std::min((kf.nrows + KE_NW1536 - 1) / KE_NW1536, pl->num_sms), 64 * KE_NW1536, ke_fft_smem_bytes<1536>(KE_NW1536), st>>>(kf);
         else ke_fft_kernel<768, KE_NW768><<<std::min((kf.nrows + KE_NW768 - 1) / KE_NW768, pl->num_sms), 64 * KE_NW768, ke_fft_smem_bytes<768>(KE_NW768), st>>>(kf);
     }
     pl->launches++;
@@ -833,13 +837,17 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             }
             TRY(run_nlin_fft(pl, nullptr, nullptr, nullptr, false, 1, nullptr, true));
             TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
-            if (K <= 256) {
-                // kinetic energy on the 3K grid with the same transform code (M = 384 or 768)
+            {
+                // kinetic energy on the 3K grid with the same transform code (M = 384, 768 or 1536)
                 pl->ke_M = 3 * K;
                 std::vector<double> kt, kw(pl->ke_M);
                 if (pl->ke_M == 384) {
                     kt.resize(fftp::tab_doubles<384>()); fftp::fill_tables<384>(kt.data()); fftp::fill_ke_weights<384>(kw.data());
                     TRY(set_smem(pl, (ke_fft_kernel<384, 8>), ke_fft_smem_bytes<384>(8)));
+                } else if (pl->ke_M == 1536) {
+                    kt.resize(fftp::tab_doubles<1536>()); fftp::fill_tables<1536>(kt.data()); fftp::fill_ke_weights<1536>(kw.data());
+                    static_assert(ke_fft_smem_bytes<1536>(KE_NW1536) <= SMEM_LIMIT, "KE workers do not fit into shared memory");
+                    TRY(set_smem(pl, (ke_fft_kernel<1536, KE_NW1536>), ke_fft_smem_bytes<1536>(KE_NW1536)));
                 } else {
                     kt.resize(fftp::tab_doubles<768>()); fftp::fill_tables<768>(kt.data()); fftp::fill_ke_weights<768>(kw.data());
                     TRY(set_smem(pl, (ke_fft_kernel<768, KE_NW768>), ke_fft_smem_bytes<768>(KE_NW768)));

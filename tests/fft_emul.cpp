@@ -133,7 +133,12 @@ static void run_ke_rows(const double* rows, double* out, int nrows) {
         const double* r = rows + (size_t)row * 2 * Kc;
         for (int t = 0; t < NTW; ++t) ke_stage<M>(t, r, r + Kc, 1.0, srow.data());
         for (int t = 0; t < NTW; ++t) ke_pack<M>(t, srow.data(), buf.data(), tb);
-        for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 1, +1>(t, buf.data(), tw); }
+        if constexpr (Cfg<M>::RD == 32) {
+            for (int t = 0; t < NTW; ++t) pass_d32_a<M>(t, buf.data(), tb);
+            for (int t = 0; t < NTW; ++t) pass_d32_b<M>(t, buf.data());
+        } else {
+            for (int t = 0; t < NTW; ++t) { C tw[Cfg<M>::RD]; load_tw<M>(t, tb, tw); pass_d<M, 1, +1>(t, buf.data(), tw); }
+        }
         double s = 0.0;
         for (int t = 0; t < NTW; ++t) s += ke6<M>(t, buf.data(), tb, Wn.data());
         out[row] = s;
@@ -147,6 +152,7 @@ int fft_emul_ke_rows(int M, const double* rows, double* out, int nrows) {
     switch (M) {
         case 384: run_ke_rows<384>(rows, out, nrows); return 0;
         case 768: run_ke_rows<768>(rows, out, nrows); return 0;
+        case 1536: run_ke_rows<1536>(rows, out, nrows); return 0;
         default: return -1;
     }
 }

@@ -102,7 +102,7 @@ def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
     assert (np.abs(got3 - exp2) / scale2).max() < 1e-12
 
 
-@pytest.mark.parametrize("K", [128, 256])
+@pytest.mark.parametrize("K", [128, 256, 512])
 def test_fft_kinetic_energy_rows(emul, K):
     """Weighted sum of squares of the two Kinetic_Energy fields on the 3K grid (Main.py:104-130)."""
     rng = np.random.default_rng(K)
