@@ -164,12 +164,14 @@ int sddc_interp_thetas(const double* in, double* out, int B, int K_o, int K_n, i
  *     sddc_gs_update(V, w, part1, h1, part2, 1)    w -= V h1, part2 = V^T w
  *     sddc_gs_update(V, w, part2, h2, part3, 0)    w -= V h2, part3[.][chunk][nvec] = |w_chunk|^2
  * part buffers: [B][sddc_gs_chunks(n)][ldp] with ldp >= nvec + 1 (slot nvec of sddc_gs_update's output holds the
- * squared norm of the chunk of the updated w); h buffers: [B][ldp].  Reductions run in a fixed order. */
+ * squared norm of the chunk of the updated w); h buffers: [B][ldp].  Reductions run in a fixed order.
+ * member_mask (optional, [B] ints): members with 0 are skipped by sddc_gs_update -- the third pass only runs for the
+ * members whose second pass found something left. */
 int sddc_gs_chunks(int n);
 int sddc_gs_dots(const double* V, long long member_stride, int n, int nvec, const double* w, double* part, int ldp, int B,
                  void* stream);
 int sddc_gs_update(const double* V, long long member_stride, int n, int nvec, double* w, const double* part_in,
-                   double* h_out, double* part_out, int ldp, int want_dots, int B, void* stream);
+                   double* h_out, double* part_out, int ldp, int want_dots, const int* member_mask, int B, void* stream);
 
 /* Per-stage device timing with CUDA events recorded on the caller's stream around each kernel launch.
  * sddc_profile_begin switches recording on; sddc_profile_end synchronises the device, switches it off and

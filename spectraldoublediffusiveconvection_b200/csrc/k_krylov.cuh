@@ -25,6 +25,7 @@ struct GsParams {
     double* part_out;         // [B][nchunk][ldp]: per-chunk partial dot products produced; slot nvec = |w_chunk|^2
     double* h_out;            // [B][ldp]: the summed coefficients this pass subtracts (column of the Hessenberg matrix)
     int nchunk, ldp;
+    const int* member_mask;   // optional [B]: members with 0 are skipped by the update kernel (their w stays as it is)
 };
 
 // dot products of the CTA's chunk of w (in shared memory) with the same chunk of every basis vector: a warp takes two
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(GS_THREADS) gs_update_kernel(GsParams p) {
     double* hs = sm + GS_CHUNK;      // [nvec]
     __shared__ double red[32];
     const int b = blockIdx.y, c = blockIdx.x, x0 = c * GS_CHUNK, len = min(GS_CHUNK, p.n - x0);
+    if (p.member_mask && p.member_mask[b] == 0) return;
     const double* Vb = p.V + (size_t)b * p.member_stride;
     // coefficients: partial sums of the previous pass, added in chunk order
     for (int i = threadIdx.x; i < p.nvec; i += GS_THREADS) {

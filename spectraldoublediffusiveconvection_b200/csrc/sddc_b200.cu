@@ -1280,11 +1280,11 @@ int sddc_gs_dots(const double* V, long long member_stride, int n, int nvec, cons
 }
 
 int sddc_gs_update(const double* V, long long member_stride, int n, int nvec, double* w, const double* part_in,
-                   double* h_out, double* part_out, int ldp, int want_dots, int B, void* stream) {
+                   double* h_out, double* part_out, int ldp, int want_dots, const int* member_mask, int B, void* stream) {
     GsParams gp{};
     int rc = gs_fill(gp, V, member_stride, n, nvec, w, ldp, B);
     if (rc || !part_in || !h_out || !part_out || part_in == part_out) return SDDC_ERR_INVALID;
-    gp.part_in = part_in; gp.part_out = part_out; gp.h_out = h_out;
+    gp.part_in = part_in; gp.part_out = part_out; gp.h_out = h_out; gp.member_mask = member_mask;
     const size_t smem = sizeof(double) * ((size_t)GS_CHUNK + nvec);
     if (smem > 48 * 1024) return SDDC_ERR_UNSUPPORTED;   // nvec <= 5120: far beyond any Krylov space in use
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -80,9 +80,11 @@ class _TorchOrtho:
 class _FusedOrtho:
     """Classical Gram-Schmidt with re-orthogonalisation in at most three passes over the basis with the library's
     kernels (sddc_gs_dots / sddc_gs_update).  The second pass already measures what the first one left behind
-    (part2 = V^T w'): when that is below REORTH_TOL |w'| for every member the third pass is skipped ("twice is enough"
-    applied only where once was not)."""
-    REORTH_TOL = 1e-11
+    (part2 = V^T w'): when that is below reorth_tol |w'| for every member the third pass is skipped ("twice is enough"
+    applied only where once was not).  reorth_tol follows the accuracy the solve asks for (batched_gmres sets it to a
+    thousandth of the smallest relative residual tolerance, between 1e-13 and 1e-8)."""
+    reorth_tol = 1e-11
+    calls = third_passes = 0      # process-wide counters (tools/run_configs45.py reports them)
 
     def __init__(self, V):
         from . import _lib
@@ -103,19 +105,24 @@ class _FusedOrtho:
         args = (self.V.data_ptr(), self.stride, self.n, nvec)
         rc = lib.sddc_gs_dots(*args, w.data_ptr(), self.p1.data_ptr(), self.ldp, self.B, st)
         rc = rc or lib.sddc_gs_update(*args, w.data_ptr(), self.p1.data_ptr(), self.h1.data_ptr(), self.p2.data_ptr(),
-                                      self.ldp, 1, self.B, st)
+                                      self.ldp, 1, None, self.B, st)
         if rc:
             raise RuntimeError("libsddc_b200 Gram-Schmidt kernels failed (%d)" % rc)
         s2 = self.p2.sum(dim=1)                                  # [B, ldp]: V^T w' and |w'|^2 in slot nvec (fixed order)
         left = torch.linalg.vector_norm(s2[:, :nvec], dim=1)
-        if bool((left <= self.REORTH_TOL * torch.sqrt(s2[:, nvec])).all()):
-            return self.h1[:, :nvec].clone(), torch.sqrt(s2[:, nvec]), w
+        need = left > self.reorth_tol * torch.sqrt(s2[:, nvec])   # members whose first pass left something behind
+        _FusedOrtho.calls += 1
+        hn2 = torch.sqrt(s2[:, nvec])
+        if not bool(need.any()):
+            return self.h1[:, :nvec].clone(), hn2, w
+        _FusedOrtho.third_passes += 1
+        mask = need.to(torch.int32)
         rc = lib.sddc_gs_update(*args, w.data_ptr(), self.p2.data_ptr(), self.h2.data_ptr(), self.p3.data_ptr(),
-                                self.ldp, 0, self.B, st)
+                                self.ldp, 0, mask.data_ptr(), self.B, st)
         if rc:
             raise RuntimeError("libsddc_b200 Gram-Schmidt kernels failed (%d)" % rc)
-        h = self.h1[:, :nvec] + self.h2[:, :nvec]
-        hn = torch.sqrt(self.p3[:, :, nvec].sum(dim=1))
+        h = self.h1[:, :nvec] + torch.where(need[:, None], self.h2[:, :nvec], torch.zeros_like(self.h2[:, :nvec]))
+        hn = torch.where(need, torch.sqrt(self.p3[:, :, nvec].sum(dim=1)), hn2)
         return h, hn, w
 
 
@@ -145,6 +152,9 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
     x = torch.zeros_like(b) if x0 is None else x0.clone()
     V = torch.zeros((B, m + 1, n), dtype=dt, device=dev)
     ortho = _make_ortho(V)
+    if isinstance(ortho, _FusedOrtho):
+        rel = torch.where(act & (bnorm > 0), tol / torch.where(bnorm > 0, bnorm, torch.ones_like(bnorm)), torch.ones_like(bnorm))
+        ortho.reorth_tol = float(min(1e-8, max(1e-13, 1e-3 * float(rel.min()))))
     total = 0
     member_iters = torch.zeros(B, dtype=torch.long, device=dev)
     resid = torch.where(act, bnorm, torch.zeros_like(bnorm))

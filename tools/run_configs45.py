@@ -122,6 +122,7 @@ if __name__ == "__main__":
         out["config4"] = config4(seeds, a.b4, a.krylov)
     if a.only in (0, 5):
         out["config5"] = config5(seeds, a.b5, a.krylov)
+    out["gram_schmidt"] = {"arnoldi_steps": krylov._FusedOrtho.calls, "third_passes": krylov._FusedOrtho.third_passes}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs45.json"), "w") as f:
         json.dump(out, f, indent=1)
