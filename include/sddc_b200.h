@@ -138,6 +138,12 @@ int sddc_jvp(sddc_plan* plan, const double* dv, const double* X, double* out, co
 int sddc_jvp_set_base(sddc_plan* plan, const double* X, int B, void* stream);
 int sddc_jvp_apply(sddc_plan* plan, const double* dv, double* out, const double* Ra, const double* Ra_s, int B,
                    void* stream);
+/* PDFX(dv, X) + dv: the linearised member-step applied to dv, i.e. PDFX without the "- delta" that ends each of its
+ * three solves (Main.py:511, 515, 519).  For Krylov solvers that work with the shifted operator A + I and correct the
+ * Hessenberg diagonal themselves (krylov.py): the back-substitution then needs no subtrahend (its scattered state-layout
+ * loads cost a quarter of the solve).  SDDC_ERR_UNSUPPORTED on the dense paths that fall back to sddc_jvp. */
+int sddc_jvp_apply_plus(sddc_plan* plan, const double* dv, double* out, const double* Ra, const double* Ra_s, int B,
+                        void* stream);
 /* PDFmu(X) (Main.py:829-837) */
 int sddc_dF_dRa(sddc_plan* plan, const double* X, double* out, int B, void* stream);
 /* per member [ ||X||_2, KE, Nu_T, Nu_S, Nu_T(outer wall), Nu_S(outer wall) ]: Main.py:292-295, Kinetic_Energy

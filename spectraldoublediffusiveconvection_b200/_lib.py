@@ -52,6 +52,7 @@ SYMBOLS = {
     "sddc_jvp": (_i, [_vp, _dp, _dp, _dp, _dp, _dp, _i, _vp]),
     "sddc_jvp_set_base": (_i, [_vp, _dp, _i, _vp]),
     "sddc_jvp_apply": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _vp]),
+    "sddc_jvp_apply_plus": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _vp]),
     "sddc_dF_dRa": (_i, [_vp, _dp, _dp, _i, _vp]),
     "sddc_diagnostics": (_i, [_vp, _dp, _dp, _i, _vp]),
     "sddc_transform": (_i, [_i, _dp, _dp, _i, _i, _i, _vp]),

@@ -1142,28 +1142,41 @@ int sddc_jvp_set_base(sddc_plan* pl, const double* X, int B, void* stream) {
     return SDDC_OK;
 }
 
-int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* Ra, const double* Ras, int B, void* stream) {
+static int jvp_apply_impl(sddc_plan* pl, const double* dv, double* out, const double* Ra, const double* Ras, int B, void* stream,
+                          bool plus_identity) {
     int rc = check_batch(pl, B);
     if (rc) return rc;
     if (!pl->xbase || B != pl->base_B) { pl->err = "sddc_jvp_apply: call sddc_jvp_set_base with the same batch first"; return SDDC_ERR_INVALID; }
     if (dv == out) { pl->err = "out must not alias dv"; return SDDC_ERR_INVALID; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long N3 = 3LL * pl->g.N;
+    const double* sub = plus_identity ? nullptr : dv;   // PDFX subtracts dv at the end (Main.py:511-519)
     if (pl->grid7) {
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
         if ((rc = run_nlin_fft(pl, nullptr, pl->coef7b, pl->f_sm, true, B, st, false, 2))) return rc;
-        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
     }
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
         if ((rc = run_nlin_fft(pl, pl->coef7base, pl->coef7b, pl->f_sm, true, B, st))) return rc;
-        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
     }
-    if (!pl->ws_ok) return sddc_jvp(pl, dv, pl->xbase, out, Ra, Ras, B, stream);
+    if (!pl->ws_ok) {
+        if (plus_identity) { pl->err = "sddc_jvp_apply_plus is not available on this path"; return SDDC_ERR_UNSUPPORTED; }
+        return sddc_jvp(pl, dv, pl->xbase, out, Ra, Ras, B, stream);
+    }
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
     if ((rc = run_synth_ws_mode(pl, SWS_JVPC, pl->coef1, B, st))) return rc;
     if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
-    return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+    return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
+}
+
+int sddc_jvp_apply(sddc_plan* pl, const double* dv, double* out, const double* Ra, const double* Ras, int B, void* stream) {
+    return jvp_apply_impl(pl, dv, out, Ra, Ras, B, stream, false);
+}
+
+int sddc_jvp_apply_plus(sddc_plan* pl, const double* dv, double* out, const double* Ra, const double* Ras, int B, void* stream) {
+    return jvp_apply_impl(pl, dv, out, Ra, Ras, B, stream, true);
 }
 
 int sddc_dF_dRa(sddc_plan* pl, const double* X, double* out, int B, void* stream) {

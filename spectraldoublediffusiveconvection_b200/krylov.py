@@ -134,11 +134,14 @@ def _make_ortho(V):
 LGMRES_RTOL = 1e-5   # SciPy's default rtol: the reference passes only atol, so every solve stops at max(atol, 1e-5 |b|)
 
 
-def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None, active=None):
+def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None, active=None, shifted=False):
     """Solve A_k x_k = b_k for every row k of b [B, n] in lock step.  matvec maps [B, n] -> [B, n] (row-wise
     independent operators).  Member k stops when |r_k| <= max(atol_k, rtol * |b_k|) (SciPy's convention; atol = None
     means 0); from then on it is masked: its Krylov vectors are zero, its Hessenberg columns the identity, its solution untouched.  Members
     with active[k] == False are never touched (x_k = x0_k or 0).
+    shifted=True: matvec applies A + I instead of A (EnsemblePlan.jvp_apply(plus_identity=True): the back-substitution
+    then carries no subtrahend); orthogonalising (A + I) v_j against a basis that contains v_j leaves the same new
+    direction, and the Hessenberg column of A is the one of A + I minus e_j.
     Returns (x, info), info = {"iters": batched matvec calls, "member_iters": Krylov vectors per member [B],
     "converged": bool [B], "resid": |r_k| [B]}."""
     B, n = b.shape
@@ -162,6 +165,8 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
     for _ in range(max_restarts):
         if x0 is not None or total > 0:
             r = b - _Profile.timed("matvec", matvec, x)
+            if shifted:
+                r = r + x
             total += 1
         else:
             r = b.clone()
@@ -187,6 +192,9 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
             member_iters += live.long()
             w = torch.where(live[:, None], w, torch.zeros_like(w))
             h, hn, w = _Profile.timed("ortho", ortho, j, w)
+            if shifted:
+                h = h.clone()
+                h[:, j] -= live.to(dt)
             V[:, j + 1] = w / torch.where(hn > 0, hn, one)[:, None]
             col = torch.cat([h, hn[:, None]], dim=1)          # [B, j+2]
             col = torch.bmm(Q[:, :j + 2, :j + 2], col.unsqueeze(2)).squeeze(2)
@@ -264,8 +272,10 @@ def newton_batched(plan, X, Ra, Ra_s, tol_newton=1e-8, tol_gmres=1e-4, krylov=10
         fx = plan.residual(X, Ra, Ra_s)                                  # PFX (Main.py:473-496)
         plan.jvp_set_base(X)                                             # X is fixed during the linear solve
         b_norm = torch.linalg.vector_norm(fx, dim=1)
-        dv, info = batched_gmres(lambda v: plan.jvp_apply(v, Ra, Ra_s), fx, rtol=lgmres_rtol, atol=tol_gmres * b_norm,
-                                 m=krylov, max_restarts=max_restarts, active=active)      # Main.py:533-534
+        plus = bool(getattr(plan, "has_jvp_plus", False))
+        mv = (lambda v: plan.jvp_apply(v, Ra, Ra_s, plus_identity=True)) if plus else (lambda v: plan.jvp_apply(v, Ra, Ra_s))
+        dv, info = batched_gmres(mv, fx, rtol=lgmres_rtol, atol=tol_gmres * b_norm, m=krylov, max_restarts=max_restarts,
+                                 active=active, shifted=plus)                                  # Main.py:533-534
         njvp += info["iters"]
         mj += info["member_iters"]
         dv = torch.where(active[:, None], dv, torch.zeros_like(dv))
@@ -294,8 +304,10 @@ def predict_batched(plan, X0, mu0, sign, ds, Ra_s, tol_newton=1e-8, krylov=100, 
     X0 = _masked(X0, mask)
     dfmu = -plan.dF_dRa(X0)                                              # (-1) PDFmu (Main.py:848)
     plan.jvp_set_base(X0)
-    xi, info = batched_gmres(lambda v: plan.jvp_apply(v, mu0, Ra_s), dfmu, rtol=lgmres_rtol,
-                             atol=tol_newton * torch.linalg.vector_norm(dfmu, dim=1), m=krylov, max_restarts=max_restarts)
+    plus = bool(getattr(plan, "has_jvp_plus", False))
+    mv = (lambda v: plan.jvp_apply(v, mu0, Ra_s, plus_identity=True)) if plus else (lambda v: plan.jvp_apply(v, mu0, Ra_s))
+    xi, info = batched_gmres(mv, dfmu, rtol=lgmres_rtol, atol=tol_newton * torch.linalg.vector_norm(dfmu, dim=1), m=krylov,
+                             max_restarts=max_restarts, shifted=plus)
     mu_dot = sign / torch.sqrt(1.0 + delta * (torch.linalg.vector_norm(xi, dim=1) - 1.0))
     X_dot = mu_dot[:, None] * xi
     return X0 + X_dot * ds[:, None], mu0 + mu_dot * ds, X0, X_dot, mu_dot, info["converged"], info["iters"]
@@ -334,10 +346,16 @@ def continc_batched(plan, X0, mu0, sign, ds, Ra_s, tol_newton=1e-8, tol_gmres=1e
     hist = []
     Xe = mue = dfmu = None
 
+    plus = bool(getattr(plan, "has_jvp_plus", False))
+
     def DG(dY):
+        """The bordered operator (Main.py:914-915); with `plus`, DG + I (every batched_gmres call below is shifted then)."""
         dX, dmu = dY[:, :n].contiguous(), dY[:, n]
-        top = plan.jvp_apply(dX, mue, Ra_s) + dfmu * dmu[:, None]                         # Main.py:914
-        bot = delta * (X_dot * dX).sum(dim=1) + (1.0 - delta) * mu_dot * dmu              # Main.py:915
+        top = plan.jvp_apply(dX, mue, Ra_s, plus_identity=True) if plus else plan.jvp_apply(dX, mue, Ra_s)
+        top = top + dfmu * dmu[:, None]
+        bot = delta * (X_dot * dX).sum(dim=1) + (1.0 - delta) * mu_dot * dmu
+        if plus:
+            bot = bot + dmu
         return torch.cat([top, bot[:, None]], dim=1)
 
     for _ in range(max_rounds):
@@ -364,7 +382,7 @@ def continc_batched(plan, X0, mu0, sign, ds, Ra_s, tol_newton=1e-8, tol_gmres=1e
         G[:, n] = delta * (X_dot * (Xe - X0)).sum(dim=1) + (1.0 - delta) * mu_dot * (mue - mu0) - ds
         b_norm = _wnorm(G[:, :n], G[:, n], delta)                                         # Main.py:919
         dY, info = batched_gmres(DG, G, rtol=lgmres_rtol, atol=tol_gmres * b_norm, m=krylov, max_restarts=max_restarts,
-                                 active=active)
+                                 active=active, shifted=plus)
         njvp += info["iters"]
         mj += info["member_iters"]
         lin_fail = active & ~info["converged"]                                            # raises in the reference (923)
@@ -391,7 +409,8 @@ def continc_batched(plan, X0, mu0, sign, ds, Ra_s, tol_newton=1e-8, tol_gmres=1e
         Yd = torch.zeros_like(e)
         tangent_ok = torch.zeros(B, dtype=torch.bool, device=dev)
     else:
-        Yd, info = batched_gmres(DG, e, rtol=max(lgmres_rtol, tol_newton), m=krylov, max_restarts=max_restarts, active=ok)
+        Yd, info = batched_gmres(DG, e, rtol=max(lgmres_rtol, tol_newton), m=krylov, max_restarts=max_restarts, active=ok,
+                                 shifted=plus)
         njvp += info["iters"]
         mj += info["member_iters"]
         tangent_ok = ok & info["converged"]

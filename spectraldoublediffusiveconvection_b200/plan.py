@@ -241,15 +241,23 @@ class EnsemblePlan:
         self._check(self.lib.sddc_jvp_set_base(self._h, X.data_ptr(), X.shape[0], self._stream()))
         self._base_B = X.shape[0]
 
-    def jvp_apply(self, dv, Ra, Ra_s, out=None):
-        """PDFX(dv, X_base) for the state given to jvp_set_base."""
+    def jvp_apply(self, dv, Ra, Ra_s, out=None, plus_identity=False):
+        """PDFX(dv, X_base) for the state given to jvp_set_base; plus_identity=True returns PDFX(dv) + dv (the
+        linearised step itself: no subtrahend in the back-substitution), for Krylov solvers that handle the shift."""
         dv = self._in(dv, 3 * self.N)
         B = dv.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
         out = self._out(out, dv.shape)
-        self._check(self.lib.sddc_jvp_apply(self._h, dv.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B,
-                                            self._stream()))
+        fn = self.lib.sddc_jvp_apply_plus if plus_identity else self.lib.sddc_jvp_apply
+        self._check(fn(self._h, dv.data_ptr(), out.data_ptr(), Ra.data_ptr(), Ra_s.data_ptr(), B, self._stream()))
         return out
+
+    @property
+    def has_jvp_plus(self):
+        """True when jvp_apply(plus_identity=True) is available (every shape with the row pipeline for two-state products
+        or the dense persistent synthesis)."""
+        i = self.info()
+        return bool(i["fft_jvp"] or i["synth_variant"])
 
     def dF_dRa(self, X, out=None):
         X = self._in(X, 3 * self.N)

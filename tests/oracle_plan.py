@@ -36,12 +36,15 @@ class OraclePlan:
     def jvp_set_base(self, X):
         self._base = X.clone()
 
-    def jvp_apply(self, dv, Ra, Ra_s):
+    has_jvp_plus = True
+
+    def jvp_apply(self, dv, Ra, Ra_s, plus_identity=False):
         B = dv.shape[0]
         Ra, Ra_s = self._param(Ra, B), self._param(Ra_s, B)
         self.jvps += B
-        return self._rows(lambda v, x, ra, ras: orc.jvp(v, x, self.op, float(ra), float(ras), self.symmetric),
-                          dv, self._base, Ra, Ra_s)
+        out = self._rows(lambda v, x, ra, ras: orc.jvp(v, x, self.op, float(ra), float(ras), self.symmetric),
+                         dv, self._base, Ra, Ra_s)
+        return out + dv if plus_identity else out
 
     def dF_dRa(self, X):
         return self._rows(lambda x: orc.dF_dRa(x, self.op, self.symmetric), X)

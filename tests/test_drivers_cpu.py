@@ -168,7 +168,7 @@ class _FoldPlan:
     def jvp_set_base(self, X):
         self.base = X.clone()
 
-    def jvp_apply(self, dv, mu, Ra_s):
+    def jvp_apply(self, dv, mu, Ra_s):           # no has_jvp_plus: this double exercises the unshifted path
         return -2.0 * self.base * dv
 
     def dF_dRa(self, X):

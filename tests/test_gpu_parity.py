@@ -394,6 +394,9 @@ def test_cached_base_jvp_equals_jvp(name):
     assert rel_l2(j1, g["jvp_Xb"]) < 1e-10
     assert rel_l2(j2, 2.0 * g["jvp_Xb"]) < 1e-10
     assert rel_l2(j1, pl.jvp(dv, Xb, Ra, Ra_s).cpu().numpy().ravel()) < 1e-12
+    if pl.has_jvp_plus:      # the linearised step itself: PDFX(dv) + dv, no subtrahend in the back-substitution
+        jp = pl.jvp_apply(dv, Ra, Ra_s, plus_identity=True).cpu().numpy().ravel()
+        assert rel_l2(jp, g["jvp_Xb"] + g["dv"]) < 1e-10
     pl.close()
 
 
