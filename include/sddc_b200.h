@@ -179,6 +179,14 @@ int sddc_gs_dots(const double* V, long long member_stride, int n, int nvec, cons
 int sddc_gs_update(const double* V, long long member_stride, int n, int nvec, double* w, const double* part_in,
                    double* h_out, double* part_out, int ldp, int want_dots, const int* member_mask, int B, void* stream);
 
+/* Hessenberg column of one Arnoldi step for all members of a batched GMRES (krylov.py): previous Givens rotations applied
+ * to (h[0..j], hn), new rotation, rotated right-hand side g, residual estimate, retirement of the members that reached
+ * tol (live[b] -> 0; any_live = OR of the new flags).  shifted != 0: the operator applied was A + I, so 1 is subtracted
+ * from h[j].  H [B][m+1][m], cs / sn [B][m], g [B][m+1], device pointers; one small kernel instead of two dozen tensor
+ * operations per Arnoldi step. */
+int sddc_gmres_column(const double* h, int ldh, const double* hn, double* H, double* cs, double* sn, double* g, double* resid,
+                      const double* tol, int* live, int* any_live, int B, int j, int m, int shifted, void* stream);
+
 /* Per-stage device timing with CUDA events recorded on the caller's stream around each kernel launch.
  * sddc_profile_begin switches recording on; sddc_profile_end synchronises the device, switches it off and
  * returns the summed milliseconds and launch counts per stage (arrays of SDDC_STAGE_COUNT). */

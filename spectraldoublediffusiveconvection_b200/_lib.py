@@ -62,6 +62,7 @@ SYMBOLS = {
     "sddc_gs_chunks": (_i, [_i]),
     "sddc_gs_dots": (_i, [_dp, _ll, _i, _i, _dp, _dp, _i, _i, _vp]),
     "sddc_gs_update": (_i, [_dp, _ll, _i, _i, _dp, _dp, _dp, _dp, _i, _i, _vp, _i, _vp]),
+    "sddc_gmres_column": (_i, [_dp, _i, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sddc_profile_begin": (_i, [_vp]),
     "sddc_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sddc_time_step": (_i, [_vp, _dp, _dp, _dp, _dp, _i, _i, _i, _i, _dp, _vp]),

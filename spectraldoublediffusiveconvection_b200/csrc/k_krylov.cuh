@@ -123,4 +123,71 @@ __global__ void __launch_bounds__(GS_THREADS) gs_update_kernel(GsParams p) {
     if (DOTS) gs_chunk_dots(p, Vb, ws, x0, len, po);
 }
 
+// ---- Hessenberg column of one Arnoldi step, all members (batched_gmres in krylov.py) -----------------------------------------
+// One thread per member: takes the projection coefficients h[0..j] and the norm of the orthogonalised vector, applies
+// the member's previous Givens rotations, forms the new one, updates the rotated right-hand side g and the residual
+// estimate, and retires the member when it has reached its tolerance.  Masked members (live = 0) get an identity column
+// and a zero right-hand-side entry, so that the triangular solve at the end of the cycle leaves their solution untouched.
+// O(j) work per member per step: this replaces two dozen tiny tensor operations per Arnoldi step, not arithmetic.
+struct GmresColParams {
+    const double* h;      // [B][ldh] projection coefficients of this step (ldh >= j + 1)
+    const double* hn;     // [B] norm of the orthogonalised vector
+    double* H;            // [B][m+1][m] rotated Hessenberg matrix (upper triangular part is R)
+    double* cs;           // [B][m]
+    double* sn;           // [B][m]
+    double* g;            // [B][m+1] rotated right-hand side
+    double* resid;        // [B]
+    const double* tol;    // [B]
+    int* live;            // [B] in / out
+    int* any_live;        // [1] out: OR of the new live flags (zeroed by the caller)
+    int B, j, m, ldh, shifted;
+};
+
+__global__ void gmres_column_kernel(GmresColParams p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int j = p.j, m = p.m;
+    double* Hb = p.H + (size_t)b * (m + 1) * m;
+    double* gb = p.g + (size_t)b * (m + 1);
+    if (!p.live[b]) {
+        for (int i = 0; i < j; ++i) Hb[(size_t)i * m + j] = 0.0;
+        Hb[(size_t)j * m + j] = 1.0;
+        Hb[(size_t)(j + 1) * m + j] = 0.0;
+        p.cs[(size_t)b * m + j] = 1.0;
+        p.sn[(size_t)b * m + j] = 0.0;
+        gb[j] = 0.0;
+        gb[j + 1] = 0.0;
+        return;
+    }
+    const double* hb = p.h + (size_t)b * p.ldh;
+    const double* csb = p.cs + (size_t)b * m;
+    const double* snb = p.sn + (size_t)b * m;
+    // column after the previous rotations, written as it is produced (element i is final once rotation i has acted)
+    double lo = hb[0] - ((p.shifted && j == 0) ? 1.0 : 0.0);
+    for (int i = 0; i < j; ++i) {
+        const double hi = hb[i + 1] - ((p.shifted && i + 1 == j) ? 1.0 : 0.0);
+        const double c = csb[i], s = snb[i];
+        Hb[(size_t)i * m + j] = c * lo + s * hi;
+        lo = -s * lo + c * hi;
+    }
+    const double hnb = p.hn[b];
+    const double den = sqrt(lo * lo + hnb * hnb);
+    double c = 1.0, s = 0.0, diag = 1.0;
+    if (den > 0.0) { c = lo / den; s = hnb / den; diag = c * lo + s * hnb; }
+    Hb[(size_t)j * m + j] = diag;
+    Hb[(size_t)(j + 1) * m + j] = 0.0;
+    p.cs[(size_t)b * m + j] = c;
+    p.sn[(size_t)b * m + j] = s;
+    const double gj = gb[j];
+    double gn = -s * gj;
+    gb[j] = c * gj;
+    const double r = fabs(gn);
+    p.resid[b] = r;
+    const bool still = r > p.tol[b];
+    if (!still) gn = 0.0;              // a member that stops here
+    gb[j + 1] = gn;
+    p.live[b] = still ? 1 : 0;
+    if (still) atomicOr(p.any_live, 1);
+}
+
 }  // namespace sddc

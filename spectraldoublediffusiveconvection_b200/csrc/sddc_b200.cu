@@ -1306,6 +1306,19 @@ int sddc_gs_update(const double* V, long long member_stride, int n, int nvec, do
     return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
 }
 
+int sddc_gmres_column(const double* h, int ldh, const double* hn, double* H, double* cs, double* sn, double* g, double* resid,
+                      const double* tol, int* live, int* any_live, int B, int j, int m, int shifted, void* stream) {
+    if (!h || !hn || !H || !cs || !sn || !g || !resid || !tol || !live || !any_live || B < 1 || j < 0 || j >= m || ldh < j + 1)
+        return SDDC_ERR_INVALID;
+    GmresColParams gp{};
+    gp.h = h; gp.hn = hn; gp.H = H; gp.cs = cs; gp.sn = sn; gp.g = g; gp.resid = resid; gp.tol = tol; gp.live = live;
+    gp.any_live = any_live; gp.B = B; gp.j = j; gp.m = m; gp.ldh = ldh; gp.shifted = shifted;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cudaMemsetAsync(any_live, 0, sizeof(int), st) != cudaSuccess) return SDDC_ERR_CUDA;
+    gmres_column_kernel<<<(B + 127) / 128, 128, 0, st>>>(gp);
+    return cudaGetLastError() == cudaSuccess ? SDDC_OK : SDDC_ERR_CUDA;
+}
+
 int sddc_profile_begin(sddc_plan* pl) {
     if (!pl) return SDDC_ERR_INVALID;
     pl->profiling = true;

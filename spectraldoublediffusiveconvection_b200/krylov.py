@@ -155,6 +155,10 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
     x = torch.zeros_like(b) if x0 is None else x0.clone()
     V = torch.zeros((B, m + 1, n), dtype=dt, device=dev)
     ortho = _make_ortho(V)
+    fused = isinstance(ortho, _FusedOrtho)
+    lib = ortho.lib if fused else None
+    if fused:
+        tol = tol.contiguous()
     if isinstance(ortho, _FusedOrtho):
         rel = torch.where(act & (bnorm > 0), tol / torch.where(bnorm > 0, bnorm, torch.ones_like(bnorm)), torch.ones_like(bnorm))
         ortho.reorth_tol = float(min(1e-8, max(1e-13, 1e-3 * float(rel.min()))))
@@ -178,24 +182,43 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
         safe_beta = torch.where(beta > 0, beta, one)
         V[:, 0] = torch.where(live[:, None], r / safe_beta[:, None], torch.zeros_like(r))
         H = torch.zeros((B, m + 1, m), dtype=dt, device=dev)
-        # Q = G_{j-1} .. G_0, the product of the Givens rotations so far: one small bmm applies them all to a new column
-        # (a Python loop over the rotations would cost O(m^2) kernel launches per solve)
-        Q = torch.eye(m + 1, dtype=dt, device=dev).repeat(B, 1, 1)
         cs = torch.zeros((B, m), dtype=dt, device=dev)
         sn = torch.zeros((B, m), dtype=dt, device=dev)
         gvec = torch.zeros((B, m + 1), dtype=dt, device=dev)
         gvec[:, 0] = torch.where(live, beta, zero)
         jdone = 0
+        if fused:
+            # the Hessenberg / Givens bookkeeping of a step is one kernel over the members (sddc_gmres_column)
+            live_i = live.to(torch.int32)
+            any_live = torch.zeros(1, dtype=torch.int32, device=dev)
+            resid = resid.contiguous()
+        else:
+            # Q = G_{j-1} .. G_0, the product of the Givens rotations so far: one small bmm applies them all to a new column
+            # (a Python loop over the rotations would cost O(m^2) kernel launches per solve)
+            Q = torch.eye(m + 1, dtype=dt, device=dev).repeat(B, 1, 1)
         for j in range(m):
             w = _Profile.timed("matvec", matvec, V[:, j].contiguous())
             total += 1
             member_iters += live.long()
             w = torch.where(live[:, None], w, torch.zeros_like(w))
             h, hn, w = _Profile.timed("ortho", ortho, j, w)
+            V[:, j + 1] = w / torch.where(hn > 0, hn, one)[:, None]
+            jdone = j + 1
+            if fused:
+                hn = hn.contiguous()
+                rc = lib.sddc_gmres_column(h.data_ptr(), h.stride(0), hn.data_ptr(), H.data_ptr(), cs.data_ptr(), sn.data_ptr(),
+                                           gvec.data_ptr(), resid.data_ptr(), tol.data_ptr(), live_i.data_ptr(),
+                                           any_live.data_ptr(), B, j, m, int(shifted),
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                if rc:
+                    raise RuntimeError("sddc_gmres_column failed (%d)" % rc)
+                live = live_i.bool()
+                if int(any_live.item()) == 0:
+                    break
+                continue
             if shifted:
                 h = h.clone()
                 h[:, j] -= live.to(dt)
-            V[:, j + 1] = w / torch.where(hn > 0, hn, one)[:, None]
             col = torch.cat([h, hn[:, None]], dim=1)          # [B, j+2]
             col = torch.bmm(Q[:, :j + 2, :j + 2], col.unsqueeze(2)).squeeze(2)
             den = torch.sqrt(col[:, j] ** 2 + col[:, j + 1] ** 2)
@@ -213,7 +236,6 @@ def batched_gmres(matvec, b, rtol=1e-4, atol=None, m=60, max_restarts=8, x0=None
             Q[:, j + 1, :] = -sn[:, j, None] * qj + cs[:, j, None] * qj1
             gvec[:, j + 1] = -sn[:, j] * gvec[:, j]
             gvec[:, j] = torch.where(live, cs[:, j] * gvec[:, j], zero)
-            jdone = j + 1
             resid = torch.where(live, gvec[:, j + 1].abs(), resid)
             gvec[:, j + 1] = torch.where(live & (resid > tol), gvec[:, j + 1], zero)   # a member that stops here
             live = live & (resid > tol)

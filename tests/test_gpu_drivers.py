@@ -94,3 +94,29 @@ def test_branch_loop_matches_reference_driver():
     assert rel_l2(res.X_DATA[-1][0].cpu().numpy(), G["branch_X_DATA"][-1]) < 1e-5
     assert np.all(np.diff(h["Ra"][:7, 1]) < 0)            # the second member walks down the branch
     pl.close()
+
+
+@pytest.mark.parametrize("shifted", [False, True])
+def test_fused_gmres_bookkeeping_matches_torch_path(shifted):
+    """CUDA tensors: Gram-Schmidt and the Hessenberg / Givens bookkeeping run in the library's kernels; CPU tensors: plain
+    torch.  Same systems, same tolerances (per-member, so that members retire at different steps) -> same solutions
+    and the same per-member iteration counts."""
+    from spectraldoublediffusiveconvection_b200 import krylov
+    torch.manual_seed(5)
+    B, n = 6, 300
+    A = torch.eye(n, dtype=torch.float64)[None] * 3.0 + 0.04 * torch.randn(B, n, n, dtype=torch.float64)
+    b = torch.randn(B, n, dtype=torch.float64)
+    b[4] = 0.0
+    atol = torch.tensor([1e-3, 1e-6, 1e-9, 1e-12, 1e-6, 1e-4], dtype=torch.float64)
+    active = torch.tensor([True, True, True, True, True, False])
+    off = 1.0 if shifted else 0.0
+    Ad = A.cuda()
+    xc, ic = krylov.batched_gmres(lambda v: torch.bmm(A, v.unsqueeze(2)).squeeze(2) + off * v, b, rtol=0.0, atol=atol, m=25,
+                                  max_restarts=6, active=active, shifted=shifted)
+    xg, ig = krylov.batched_gmres(lambda v: torch.bmm(Ad, v.unsqueeze(2)).squeeze(2) + off * v, b.cuda(), rtol=0.0,
+                                  atol=atol.cuda(), m=25, max_restarts=6, active=active.cuda(), shifted=shifted)
+    assert torch.equal(ig["member_iters"].cpu(), ic["member_iters"]) and ig["iters"] == ic["iters"]
+    assert torch.allclose(xg.cpu(), xc, rtol=1e-9, atol=1e-12)
+    assert bool(ig["converged"].all()) and float(xg[5].abs().max()) == 0.0 and float(xg[4].abs().max()) == 0.0
+    r = torch.linalg.vector_norm(torch.bmm(A, xg.cpu().unsqueeze(2)).squeeze(2) - b, dim=1)
+    assert bool((r[:5] <= atol[:5] * 1.001).all())
