@@ -200,9 +200,14 @@ def INTERP_RADIAL(N_n, N_o, X_o, d):
     K = len(X_o) // (3 * nr_o)
     Xo = np.asarray(X_o, dtype=np.float64).reshape(3 * K, nr_o)
     Xn = np.empty((3 * K, nr_n))
-    for row in range(3 * K):
-        coeff = np.polyfit(R_o, np.hstack(([0.0], Xo[row], [0.0])), len(R_o))
-        Xn[row] = np.polyval(coeff, R_n[1:-1])
+    import warnings
+    with warnings.catch_warnings():
+        # one unknown more than equations: np.polyfit warns about the rank on every call; the reference silences the
+        # warning for the whole module (Matrix_Operators.py:5-6)
+        warnings.simplefilter("ignore")
+        for row in range(3 * K):
+            coeff = np.polyfit(R_o, np.hstack(([0.0], Xo[row], [0.0])), len(R_o))
+            Xn[row] = np.polyval(coeff, R_n[1:-1])
     return Xn.reshape(-1)
 
 
