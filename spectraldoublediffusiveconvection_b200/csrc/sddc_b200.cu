@@ -93,6 +93,9 @@ struct sddc_plan {
     int hist_cap = 0;
     int ckpt_phase = 0;       // sddc_plan_set_ckpt_phase: checkpoints after the steps phase, phase + every, ... (0: every, 2 every, ...)
     cudaEvent_t ev_ckpt = nullptr;
+    // kinetic energy of a record under the next step's back-substitution (sddc_time_step*): side stream + events
+    cudaStream_t ke_stream = nullptr;
+    cudaEvent_t ev_rows = nullptr, ev_ke = nullptr;
     cudaStream_t own_stream = nullptr, in_stream = nullptr, out_stream = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
     // kernel configuration
@@ -535,7 +538,7 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
 
 // kinetic energy by FFT from coefficient rows + the remaining diagnostics (norm, Nusselt numbers)
 int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row_stride, int b_off, const double* ascale,
-               double* out, int B, cudaStream_t st, const double* dpart = nullptr) {
+               double* out, int B, cudaStream_t st, const double* dpart = nullptr, bool side = false) {
     const Geo& g = pl->g;
     KeFftParams kf{};
     kf.rows = rows; kf.row_stride = row_stride; kf.b_off = b_off; kf.ascale = ascale;
@@ -543,7 +546,8 @@ int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row
     kf.nrows = B * g.n; kf.n = g.n;
     {
         StageTimer tm(pl, SDDC_STAGE_KE_SYNTH, st);
-        if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<std::min((kf.nrows + 7) / 8, pl->num_sms), 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
+        if (side && pl->ke_M == 768) ke_fft_kernel<768, 2><<<std::min((kf.nrows + 1) / 2, 3 * pl->num_sms), 128, ke_fft_smem_bytes<768>(2), st>>>(kf);
+        else if (pl->ke_M == 384) ke_fft_kernel<384, 8><<<std::min((kf.nrows + 7) / 8, pl->num_sms), 512, ke_fft_smem_bytes<384>(8), st>>>(kf);
         else if (pl->ke_M == 1536) ke_fft_kernel<1536, KE_NW1536><<<std::min((kf.nrows + KE_NW1536 - 1) / KE_NW1536, pl->num_sms), 64 * KE_NW1536, ke_fft_smem_bytes<1536>(KE_NW1536), st>>>(kf);
         else ke_fft_kernel<768, KE_NW768><<<std::min((kf.nrows + KE_NW768 - 1) / KE_NW768, pl->num_sms), 64 * KE_NW768, ke_fft_smem_bytes<768>(KE_NW768), st>>>(kf);
     }
@@ -567,7 +571,7 @@ int run_step_prep(sddc_plan* pl, const double* X, const double* Ra, const double
 }
 
 int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool linear, cudaStream_t st, bool emit_jj = false,
-                  bool emit_diag = false) {
+                  double* emit_diag = nullptr) {
     const long long N3 = 3LL * pl->g.N;
     const bool fft = pl->fft_M != 0 && !linear;
     int rc;
@@ -581,7 +585,7 @@ int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool lin
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
     }
     return run_solve(pl, pl->lin_sm, fnl, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, emit_jj ? pl->JJ : nullptr,
-                     emit_diag ? pl->dpart : nullptr);
+                     emit_diag);
 }
 
 // have_jj / emit_jj chain the steps of a multi-step call: the A4 back-substitution of step s writes the suffix-sum
@@ -649,6 +653,9 @@ void sddc_plan_destroy(sddc_plan* plan) {
     if (plan->in_stream) cudaStreamDestroy(plan->in_stream);
     if (plan->out_stream) cudaStreamDestroy(plan->out_stream);
     if (plan->ev_ckpt) cudaEventDestroy(plan->ev_ckpt);
+    if (plan->ke_stream) cudaStreamDestroy(plan->ke_stream);
+    if (plan->ev_rows) cudaEventDestroy(plan->ev_rows);
+    if (plan->ev_ke) cudaEventDestroy(plan->ev_ke);
     for (auto e : plan->ev_in) cudaEventDestroy(e);
     for (auto e : plan->ev_done) cudaEventDestroy(e);
     delete plan;
@@ -774,7 +781,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->nke = pl->Mh3p / (8 * pl->synth_nt_ke);
     TRY(dev_alloc(pl, &pl->kepart, Bm * std::max(pl->nke, n), true));
     TRY(dev_alloc(pl, &pl->zeroRa, Bm, true));
-    TRY(dev_alloc(pl, &pl->dpart, Bm * 18, true));
+    TRY(dev_alloc(pl, &pl->dpart, 2 * Bm * 18, true));   // two records in flight (sddc_time_step*)
     {
         std::vector<double> w(K);
         for (int k = 0; k < K; ++k) w[k] = k == 1 ? 0.0 : 1.0 / (1.0 - (double)k * (double)k);
@@ -854,6 +861,15 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
                 }
                 TRY(upload(pl, &pl->ke_tab, kt));
                 TRY(upload(pl, &pl->ke_Wn, kw));
+                if (pl->ke_M == 768) {
+                    // side-stream variant: two workers per CTA (65 KB), so that it fits next to the back-substitution's CTAs
+                    TRY(set_smem(pl, (ke_fft_kernel<768, 2>), ke_fft_smem_bytes<768>(2)));
+                    int lo = 0, hi = 0;
+                    TRYC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    TRYC(cudaStreamCreateWithPriority(&pl->ke_stream, cudaStreamNonBlocking, lo));
+                    TRYC(cudaEventCreateWithFlags(&pl->ev_rows, cudaEventDisableTiming));
+                    TRYC(cudaEventCreateWithFlags(&pl->ev_ke, cudaEventDisableTiming));
+                }
             }
             TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8, 1)));
             TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8, 1)));
@@ -1048,23 +1064,44 @@ int sddc_time_step(sddc_plan* pl, const double* Xin, double* Xout, const double*
     const bool share = pl->fft_M != 0 && pl->ke_M != 0 && !linear;   // see sddc_time_step_host
     const double* src = Xin;
     int pending = -1;
+    // The kinetic-energy transform of record r only needs the spectral rows of the prep stage that follows it; on a
+    // low-priority side stream it runs under the latency-bound back-substitution of the same step instead of in front
+    // of it (two-worker CTAs fit next to the back-substitution's).  The compute stream waits for it before the next
+    // prep stage overwrites the rows.
+    const bool side = share && pl->ke_stream != nullptr;
+    bool ke_inflight = false;
+    const size_t dstride = (size_t)pl->cfg.max_batch * 18;
     for (int s = 1; s <= nsteps; ++s) {
         double* dst = ((nsteps - s + 1) & 1) ? Xout : pl->xtmp;  // the last step lands in Xout
+        if (ke_inflight) { PLAN_CUDA(pl, cudaStreamWaitEvent(st, pl->ev_ke, 0)); ke_inflight = false; }
         if ((rc = run_step_prep(pl, src, Ra, Ras, B, linear != 0, st, s > 1))) return rc;
-        if (pending >= 0) {
-            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, diag_hist + (size_t)pending * B * 6, B, st, pl->dpart))) return rc;
-            pending = -1;
-        }
+        double* rec = pending >= 0 ? diag_hist + (size_t)pending * B * 6 : nullptr;
+        const double* dp = pl->dpart + ((s - 1) & 1) * dstride;     // written by the back-substitution of step s - 1
+        if (rec && side) PLAN_CUDA(pl, cudaEventRecord(pl->ev_rows, st));
+        if (rec && !side && (rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, rec, B, st, dp))) return rc;
         // the back-substitution also leaves ||X_s||^2 and the Nusselt sums when X_s gets a shared-prep record
         const bool rec_shared = share && diag_every && s % diag_every == 0 && s < nsteps;
-        if ((rc = run_step_rest(pl, dst, nullptr, B, linear != 0, st, s < nsteps, rec_shared))) return rc;
+        if ((rc = run_step_rest(pl, dst, nullptr, B, linear != 0, st, s < nsteps, rec_shared ? pl->dpart + (s & 1) * dstride : nullptr))) return rc;
+        if (rec && side) {
+            // submitted after the step's own kernels: with equal stream priorities the transform then takes what the
+            // row kernel, the finishing stage and the back-substitution leave free
+            PLAN_CUDA(pl, cudaStreamWaitEvent(pl->ke_stream, pl->ev_rows, 0));
+            if ((rc = run_ke_fft(pl, src, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, rec, B, pl->ke_stream, dp, true))) return rc;
+            PLAN_CUDA(pl, cudaEventRecord(pl->ev_ke, pl->ke_stream));
+            ke_inflight = true;
+        }
+        pending = -1;
         src = dst;
         if (diag_every && s % diag_every == 0) {
             const int r = s / diag_every - 1;
             if (share && s < nsteps) pending = r;
-            else if ((rc = sddc_diagnostics(pl, src, diag_hist + (size_t)r * B * 6, B, stream))) return rc;
+            else {
+                if (ke_inflight) { PLAN_CUDA(pl, cudaStreamWaitEvent(st, pl->ev_ke, 0)); ke_inflight = false; }   // kepart is shared
+                if ((rc = sddc_diagnostics(pl, src, diag_hist + (size_t)r * B * 6, B, stream))) return rc;
+            }
         }
     }
+    if (ke_inflight) PLAN_CUDA(pl, cudaStreamWaitEvent(st, pl->ev_ke, 0));
     return SDDC_OK;
 }
 
@@ -1424,31 +1461,47 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
     // stand-alone diagnostics.  (Symmetric runs: stepped states are masked already, so the masked prep loads are exact.)
     const bool share = pl->fft_M != 0 && pl->ke_M != 0 && !linear;
     int pending = -1;   // diagnostics record of the current state still to be produced
-    auto ship_record = [&](int r) -> int {
+    auto ship_record = [&](int r, cudaStream_t from) -> int {
         double* drec = pl->hHist + (size_t)r * B * 6;
-        PLAN_CUDA(pl, cudaEventRecord(pl->ev_done[0], cs));
+        PLAN_CUDA(pl, cudaEventRecord(pl->ev_done[0], from));
         PLAN_CUDA(pl, cudaStreamWaitEvent(pl->out_stream, pl->ev_done[0], 0));
         PLAN_CUDA(pl, cudaMemcpyAsync(diag_hist + (size_t)r * B * 6, drec, sizeof(double) * B * 6,
                                       cudaMemcpyDeviceToHost, pl->out_stream));
         return SDDC_OK;
     };
+    // kinetic energy of a record on the side stream, under the back-substitution of the following step (see sddc_time_step)
+    const bool side = share && pl->ke_stream != nullptr;
+    bool ke_inflight = false;
+    const size_t dstride = (size_t)pl->cfg.max_batch * 18;
     for (int s = 1; s <= nsteps; ++s) {
+        if (ke_inflight) { PLAN_CUDA(pl, cudaStreamWaitEvent(cs, pl->ev_ke, 0)); ke_inflight = false; }
         if ((rc = run_step_prep(pl, cur, pl->hRa, pl->hRas, B, linear != 0, cs, s > 1))) return rc;
-        if (pending >= 0) {
-            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, pl->hHist + (size_t)pending * B * 6, B, cs, pl->dpart))) return rc;
-            if ((rc = ship_record(pending))) return rc;
-            pending = -1;
+        double* rec = pending >= 0 ? pl->hHist + (size_t)pending * B * 6 : nullptr;
+        const double* dp = pl->dpart + ((s - 1) & 1) * dstride;
+        if (rec && side) PLAN_CUDA(pl, cudaEventRecord(pl->ev_rows, cs));
+        if (rec && !side) {
+            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, rec, B, cs, dp))) return rc;
+            if ((rc = ship_record(pending, cs))) return rc;
         }
         const bool rec_shared = share && diag_every && s % diag_every == 0 && s < nsteps;
-        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs, s < nsteps, rec_shared))) return rc;
+        if ((rc = run_step_rest(pl, nxt, nullptr, B, linear != 0, cs, s < nsteps, rec_shared ? pl->dpart + (s & 1) * dstride : nullptr))) return rc;
+        if (rec && side) {
+            PLAN_CUDA(pl, cudaStreamWaitEvent(pl->ke_stream, pl->ev_rows, 0));
+            if ((rc = run_ke_fft(pl, cur, pl->coef7, 7LL * pl->g.K, 3 * pl->g.K, pl->ir, rec, B, pl->ke_stream, dp, true))) return rc;
+            PLAN_CUDA(pl, cudaEventRecord(pl->ev_ke, pl->ke_stream));
+            ke_inflight = true;
+            if ((rc = ship_record(pending, pl->ke_stream))) return rc;
+        }
+        pending = -1;
         std::swap(cur, nxt);
         if (diag_every && s % diag_every == 0) {
             const int r = s / diag_every - 1;
             if (share && s < nsteps) {
                 pending = r;
             } else {
+                if (ke_inflight) { PLAN_CUDA(pl, cudaStreamWaitEvent(cs, pl->ev_ke, 0)); ke_inflight = false; }   // kepart is shared
                 if ((rc = sddc_diagnostics(pl, cur, pl->hHist + (size_t)r * B * 6, B, cs))) return rc;
-                if ((rc = ship_record(r))) return rc;
+                if ((rc = ship_record(r, cs))) return rc;
             }
         }
         const int cph = pl->ckpt_phase > 0 ? pl->ckpt_phase : ckpt_every;   // step of the first checkpoint
@@ -1465,6 +1518,7 @@ int sddc_time_step_host(sddc_plan* pl, const double* Xin, double* Xout, const do
     }
     PLAN_CUDA(pl, cudaMemcpyAsync(Xout, cur, bytes, cudaMemcpyDeviceToHost, cs));
     PLAN_CUDA(pl, cudaStreamSynchronize(cs));
+    if (pl->ke_stream) PLAN_CUDA(pl, cudaStreamSynchronize(pl->ke_stream));
     PLAN_CUDA(pl, cudaStreamSynchronize(pl->out_stream));
     return SDDC_OK;
 }
