@@ -44,6 +44,10 @@ struct Cfg {
     // RD = 32 (M = 1536) exists for the kinetic-energy transform only: its middle pass runs in two steps (pass_d32_*)
     static_assert(M_ % 48 == 0 && (RD == 4 || RD == 8 || RD == 16 || RD == 32), "supported grids: M = 192, 384, 768 (1536: KE)");
 };
+// Position of sinusoid index k inside a [K] row of the analysed products: even indices first, then the odd ones.  A
+// back-substitution chain walks one parity, so the coefficients it needs two chain steps apart are 16 contiguous bytes
+// (k_solve_hot.cuh gathers them with one cp.async).
+SDDC_HD constexpr int spec_pos(int k, int K) { return (k & 1) * (K >> 1) + (k >> 1); }
 SDDC_HD int at(int j, int c) { return ((j ^ ((j >> 3) & 1)) << 3) | (c ^ (j & 7)); }
 // offset of the (re, im) plane pair of transform q inside a worker's buffer.  On the small grid (M = 192), where the lanes
 // of a half-warp straddle two transforms (blocks .., 11, 12 of pair q | blocks 1, 2, .. of pair q + 1), odd pairs are

@@ -488,6 +488,7 @@ SDDC_HD void cp_emit(int q, int k, C vk, C vkp, double* __restrict__ oa, double*
                      const Tables& tb) {
     constexpr double sc = 2.0 / M;   // the table holds w_k / 2, which absorbs the 1/2 of the Hermitian split
     const int kp = M - k;
+    const int pk = spec_pos(k, Cfg<M>::K), pkp = spec_pos(kp, Cfg<M>::K);   // parity-split row (fft_core.h)
     const double hc = sc * tb.wkc[k], hs = sc * tb.wks[k];
     const double s = vk.r + vkp.r, d = vk.i - vkp.i, e = vk.i + vkp.i, f = vk.r - vkp.r;
     // field a at kappa: cosine type  hc s + hs d ; sine type (its coefficient kappa sits at M - kappa)  hs s - hc d
@@ -495,27 +496,27 @@ SDDC_HD void cp_emit(int q, int k, C vk, C vkp, double* __restrict__ oa, double*
     const double cbk = hc * e - hs * f;
     if (QM == 2) {
         const double al = q0 ? hs : hc, be = q0 ? -hc : hs;
-        oa[k] = al * s + be * d;
-        ob[k] = q0 ? -(double)k * cbk : cbk;
+        oa[pk] = al * s + be * d;
+        ob[pk] = q0 ? -(double)k * cbk : cbk;
     } else if (QM == 0) {
-        oa[k] = hs * s - hc * d;
-        ob[k] = -(double)k * cbk;
+        oa[pk] = hs * s - hc * d;
+        ob[pk] = -(double)k * cbk;
     } else {
-        oa[k] = hc * s + hs * d;
-        ob[k] = cbk;
+        oa[pk] = hc * s + hs * d;
+        ob[pk] = cbk;
     }
     if (BOTH && kp_ok) {
         const double cbkp = hs * e + hc * f;
         if (QM == 2) {
             const double al2 = q0 ? hc : hs, be2 = q0 ? hs : -hc;
-            oa[kp] = al2 * s + be2 * d;
-            ob[kp] = q0 ? -(double)kp * cbkp : cbkp;
+            oa[pkp] = al2 * s + be2 * d;
+            ob[pkp] = q0 ? -(double)kp * cbkp : cbkp;
         } else if (QM == 0) {
-            oa[kp] = hc * s + hs * d;
-            ob[kp] = -(double)kp * cbkp;
+            oa[pkp] = hc * s + hs * d;
+            ob[pkp] = -(double)kp * cbkp;
         } else {
-            oa[kp] = hs * s - hc * d;
-            ob[kp] = cbkp;
+            oa[pkp] = hs * s - hc * d;
+            ob[pkp] = cbkp;
         }
     }
 }
@@ -559,7 +560,7 @@ SDDC_HD void cp_block0(int q, const double* __restrict__ re, const double* __res
     double* oa = out + 2 * q * K;
     double* ob = oa + K;
     // k = 0: DCT mean (Transforms.py:28-39); a sine-type coefficient 0 does not exist and -k DCT(.) vanishes
-    oa[0] = q == 0 ? 0.0 : V[0].r * (1.0 / M);
+    oa[0] = q == 0 ? 0.0 : V[0].r * (1.0 / M);   // spec_pos(0) = 0
     ob[0] = q == 0 ? 0.0 : V[0].i * (1.0 / M);
 #pragma unroll
     for (int c = 1; c < 4; ++c) {

@@ -21,7 +21,7 @@ namespace sddc {
 struct NlinFftParams {
     const double* coef0;  // [rows][7][K] spectral rows of the (base) state, rows = B * n
     const double* coef1;  // [rows][7][K] rows of the perturbation (two-state mode)
-    double* spec;         // [rows][4][K] analysed products
+    double* spec;         // [rows][4][K] analysed products, every row parity-split (fft_core.h: spec_pos)
     const double* tab;    // fftp::tab_doubles<M>() table doubles (fftp::fill_tables)
     double* grid;         // [rows][7][M] cached grid fields of the base state (MODE 1 writes, MODE 2 reads; fft_fused.h)
     int nrows;
@@ -355,15 +355,16 @@ __global__ void __launch_bounds__(128) nlin_direct_kernel(NlinDirectParams p) {
             c3 = fma(sp[3 * M + j], c, c3);
         }
         const double sc = (k == 0 ? 1.0 : 2.0) / M;
-        o[k] = k ? s0 * (2.0 / M) : 0.0;
-        o[K + k] = -(double)k * (c1 * sc);
-        o[2 * K + k] = c2 * sc;
-        o[3 * K + k] = c3 * sc;
+        const int pk = fftp::spec_pos(k, K);   // parity-split row, as the FFT kernels write it
+        o[pk] = k ? s0 * (2.0 / M) : 0.0;
+        o[K + pk] = -(double)k * (c1 * sc);
+        o[2 * K + pk] = c2 * sc;
+        o[3 * K + pk] = c3 * sc;
     }
 }
 
 struct PostParams {
-    const double* spec;  // [B][n][4][K]
+    const double* spec;  // [B][n][4][K], rows parity-split (spec_pos)
     const double* DrT;   // [n][n8]: DrT[i'][i] = Dr[i][i']
     double* out;         // F(X): state layout [B][3N] (bstride == 0) or solve-major [3][K][bstride][n8+2]
     long long bstride;
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p, int ntiles) {
         for (int idx = tid; idx < 4 * n * POST_TC; idx += 256) {
             const int c = idx & (POST_TC - 1), fi = idx / POST_TC, f = fi & 3, i = fi >> 2;
             const bool ok = k0 + c < K;
-            cp_async8_zfill(&sT[(f * n + i) * LDT + c], ok ? sb + ((size_t)i * 4 + f) * K + k0 + c : sb, ok);
+            cp_async8_zfill(&sT[(f * n + i) * LDT + c], ok ? sb + ((size_t)i * 4 + f) * K + fftp::spec_pos(k0 + c, K) : sb, ok);
         }
     };
     const bool sm = p.bstride != 0;

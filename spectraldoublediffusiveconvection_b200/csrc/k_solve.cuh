@@ -16,6 +16,9 @@ struct SolveParams {
     //    order by prep_kernel / analysis_kernel)
     const double* g;
     const double* fnl;      // optional nonlinear term F(X), same layout as g: rhs = g + mdt * fnl  (Main.py:262,271)
+    const double* spec;     // gather mode of the hot kernel (k_solve_hot.cuh, GATH): analysed products [B][n][4][K] of the row
+                            // kernels, rows parity-split; F(X) is formed from them inside the chain (fnl unused)
+    const double* DrT;      // gather mode: [n][n8], DrT[i'][i] = Dr[i][i']
     double mdt;             // -dt
     long long g_stride;     // state layout: member stride (doubles)
     long long g_field_off;  // state layout: offset between fields inside a member (N, or 0 for single-field calls)

@@ -21,6 +21,32 @@ namespace sddc {
 #define SOLVE_NTB_TS 2
 #endif
 
+// GATH (FFT formulation, n8 <= 32, K a multiple of 8): the nonlinear term is not read as a solve-major tile that a separate
+// kernel (post_kernel) transposed; the chain gathers the analysed products of the row kernel itself.  spec[b][i][field][K]
+// holds every row parity-split (fft_core.h: spec_pos), so the four coefficients a chain needs in four consecutive steps
+// are one 32-byte sector: the producer warp fetches a GROUP (four chain steps x members x radial rows x fields) with two
+// adjacent 16-byte cp.async per (member, row, field) -- a lane pair covers the sector -- completion on an mbarrier
+// (cp.async.mbarrier.arrive.noinc), SOLVE_NSF groups in flight.  The stream-function chains apply Dr @ to the first
+// product with the operator's A fragments held in registers (F_psi = Dr @ DST(JT*om) - DST(..),
+// Matrix_Operators.py:776-802) one chain step AHEAD, between the issue of the current step's MMAs and the use of their
+// results, so that none of it sits on the dependent chain.
+// Shared-memory layout of a group: [16-byte half][member][row][2 steps]; the Dr @ operand is read as MMA B fragments (member = lane
+// group, row = lane in group: row pitch n8 + 4 makes the 16-byte reads of a quarter warp conflict free), everything
+// else in accumulator layout (member pair = lane in group, row = lane group: pitch n8 + 1).
+constexpr int SOLVE_NSF = 2;   // gather groups in flight
+constexpr int SOLVE_GSTEPS = 4;   // chain steps per group
+
+template <int NTB, bool PSI>
+__host__ __device__ constexpr size_t solve_gath_slot_doubles(int n8) {
+    return (size_t)(8 * NTB) * ((PSI ? (n8 + 4) : 0) + (n8 + 1)) * SOLVE_GSTEPS;
+}
+template <int NTB, bool PSI>
+__host__ __device__ constexpr size_t solve_gath_doubles(int n8, int nsl) {
+    const int LDL = n8 + 4, LDG = n8 + SDDC_SM_PAD, NM = PSI ? 2 : 1;
+    return (size_t)nsl * NM * n8 * LDL + (size_t)2 * NM * (8 * NTB) * LDL + (size_t)nsl * (8 * NTB) * LDG +
+           (size_t)SOLVE_NSF * solve_gath_slot_doubles<NTB, PSI>(n8);
+}
+
 template <int NTB, bool PSI>
 __host__ __device__ constexpr size_t solve_hot_doubles(int n8, int nsl) {
     const int LDL = n8 + 4, LDG = n8 + SDDC_SM_PAD, NM = PSI ? 2 : 1;
@@ -32,29 +58,45 @@ __host__ inline size_t solve_hot_smem_bytes(int n8, int nsl) {
     return sizeof(double) * (a > b ? a : b);
 }
 
+__host__ inline size_t solve_gath_smem_bytes(int n8) {
+    const size_t a = solve_gath_doubles<SOLVE_NTB_PSI, true>(n8, 3), b = solve_gath_doubles<SOLVE_NTB_TS, false>(n8, 3);
+    return sizeof(double) * (a > b ? a : b);
+}
+
 // SUB: the call carries a subtrahend (residual / JVP); a compile-time switch so that the plain step keeps its registers
 // DIAG: the chain also accumulates its share of ||X'||^2 and of the Nusselt sums of the state it produces (p.dpart)
-template <int NT8, int NSL, int NTB, bool PSI, bool SUB = true, bool DIAG = false>
+// GATH: the nonlinear term comes from p.spec (see above) instead of the solve-major tile p.fnl
+template <int NT8, int NSL, int NTB, bool PSI, bool SUB = true, bool DIAG = false, bool GATH = false>
 __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* smem, uint64_t* bar_full,
-                                                uint64_t* bar_empty, int fld, int which, int b0) {
+                                                uint64_t* bar_empty, uint64_t* bar_gfull, uint64_t* bar_gempty, int fld,
+                                                int which, int b0) {
     constexpr int n8 = 8 * NT8, LDL = n8 + 4, MAT = n8 * LDL, LDG = n8 + SDDC_SM_PAD, BT = 8 * NTB, GT = BT * LDG, NE = 2 * NTB;
     constexpr int NM = PSI ? 2 : 1, NTHR = 32 * NT8;
     constexpr int NCH = NTB >= 2 ? 1 : 2;   // accumulator chains per product and member tile (k-steps interleaved)
+    constexpr int NGT = GATH ? 1 : 2;       // right-hand-side tiles per ring stage (lin [, F])
+    constexpr int LDF1 = n8 + 4, LDF2 = n8 + 1, GS = SOLVE_GSTEPS;
+    constexpr int F2OFF = PSI ? BT * LDF1 * 2 : 0, SLOT = (int)solve_gath_slot_doubles<NTB, PSI>(n8), HSZ = SLOT / 2;
+    static_assert(!GATH || (NSL == 3 && n8 <= 32), "gather mode: three ring stages, n8 <= 32");
     const Geo& G = p.geo;
     const int n = G.n, K = G.K;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
     const bool is_producer = warp == NT8;
     double* sL = smem;                              // [NSL][NM][n8][LDL]
     double* sR = sL + (size_t)NSL * NM * MAT;       // [2 step parities][NM][BT][LDL]
-    double* sG = sR + (size_t)2 * NM * BT * LDL;    // [NSL][2][BT][LDG]   (lin, F)
+    double* sG = sR + (size_t)2 * NM * BT * LDL;    // [NSL][NGT][BT][LDG]   (lin [, F])
+    double* sF = sG + (size_t)NSL * NGT * GT;       // GATH: [SOLVE_NSF][2 halves][{P1: [BT][LDF1][2]}, [BT][LDF2][2]]
     const int i = warp * 8 + gq;
     const bool row_ok = i < n;
-    const bool has_f = p.fnl != nullptr, has_sub = SUB && p.sub != nullptr;
+    const bool has_f = !GATH && p.fnl != nullptr, has_sub = SUB && p.sub != nullptr;
 
     const int j0 = PSI ? (K - which) : (which == 0 ? K - 2 : K - 1);
     const int jend = PSI ? 1 : 0;
     const int row0 = PSI ? j0 - 1 : j0;
     const int nsteps = (j0 - jend) / 2 + 1;
+    // GATH: chain step s >= so0 reads the parity-split position ptop - (s - so0); the block K-1 of the stream function
+    // (first step of the even chain) has no nonlinear term (Matrix_Operators.py:802)
+    const int so0 = (PSI && which == 0) ? 1 : 0, ptop = which * (K >> 1) + (K >> 1) - 1;
+    const int ngroups = (nsteps - so0 + GS - 1) / GS;
 
     double* outp[NE];
     bool ok[NE];
@@ -97,30 +139,69 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     }
     if (tid == 0) {
         for (int s = 0; s < NSL; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NT8); }
+        if (GATH)
+            for (int s = 0; s < SOLVE_NSF; ++s) { mbar_init(&bar_gfull[s], 32); mbar_init(&bar_gempty[s], NT8); }
         mbar_fence_init();
     }
     for (int idx = tid; idx < 2 * NM * BT * LDL; idx += blockDim.x) sR[idx] = 0.0;   // padded rows stay zero
+    if (GATH)
+        for (int idx = tid; idx < SOLVE_NSF * SLOT; idx += blockDim.x) sF[idx] = 0.0;   // padded rows / absent members stay zero
     __syncthreads();
     pdl_wait();   // right-hand sides from prep_kernel / post_kernel
 
     if (is_producer) {
-      if (lane == 0) {
-        const double* Lg = PSI ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
-        constexpr unsigned tile_bytes = GT * sizeof(double), mat_bytes = NM * MAT * sizeof(double);
-        const unsigned bytes = mat_bytes + tile_bytes * (has_f ? 2u : 1u);
-        int st = 0, ph = 0;
-        for (int step = 0; step < nsteps; ++step) {
+      if (!GATH && lane != 0) return;
+      const double* Lg = PSI ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
+      constexpr unsigned tile_bytes = GT * sizeof(double), mat_bytes = NM * MAT * sizeof(double);
+      const unsigned bytes = mat_bytes + tile_bytes * (has_f ? 2u : 1u);
+      // gather group g: positions ptop - 4g - 3 .. ptop - 4g of (member, row, field); lane = (row & 15, 16-byte half)
+      const int gh = lane & 1, gi = lane >> 1;
+      const double* gsrc = GATH ? p.spec + ((long long)b0 * n * 4 + (PSI ? 0 : fld + 1)) * K + (ptop - 3 + 2 * gh) : nullptr;
+      auto issue_group = [&](int g) {
+          const int slot = g & (SOLVE_NSF - 1);
+          if (g >= SOLVE_NSF) mbar_wait(&bar_gempty[slot], ((g / SOLVE_NSF) - 1) & 1);
+          double* dst0 = sF + slot * SLOT + gh * HSZ;
+          const double* src0 = gsrc - 4 * g;
+#pragma unroll
+          for (int q = 0; q < NM; ++q)
+#pragma unroll 4
+              for (int m = 0; m < BT; ++m) {
+                  if (b0 + m < p.B) {
+#pragma unroll
+                      for (int ip = 0; ip < (n8 + 15) / 16; ++ip) {
+                          const int ii = gi + 16 * ip;
+                          if (ii < n)
+                              cp_async16(dst0 + (q == 0 && PSI ? 0 : F2OFF) + (m * (q == 0 && PSI ? LDF1 : LDF2) + ii) * 2,
+                                         src0 + ((long long)(m * n + ii) * 4 + q) * K);
+                      }
+                  }
+              }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_gfull[slot])) : "memory");
+      };
+      if (GATH)
+          for (int g = 0; g < SOLVE_NSF && g < ngroups; ++g) issue_group(g);
+      int st = 0, ph = 0;
+      for (int step = 0; step < nsteps; ++step) {
+          if (GATH) {
+              // group g is first read in chain step 4g + so0 - 1 and its slot was released in step 4g + so0 - 6, which the
+              // operator ring (NSL stages ahead of the consumers) has passed when it reaches step 4g + so0 - 6 + NSL
+              const int t = step + 6 - NSL - so0;
+              if ((t & 3) == 0 && (t >> 2) >= SOLVE_NSF && (t >> 2) < ngroups) issue_group(t >> 2);
+          }
+          if (lane == 0) {
             const int j = j0 - 2 * step;
             const int jj = PSI ? (K - j) : (K - 1 - j), row = PSI ? j - 1 : j;
             if (step >= NSL) mbar_wait(&bar_empty[st], ph ^ 1);
             mbar_expect_tx(&bar_full[st], bytes);
             bulk_g2s(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st]);
             const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
-            bulk_g2s(sG + (size_t)st * 2 * GT, p.g + o, tile_bytes, &bar_full[st]);
-            if (has_f) bulk_g2s(sG + (size_t)st * 2 * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
-            if (++st == NSL) { st = 0; ph ^= 1; }
-        }
+            bulk_g2s(sG + (size_t)st * NGT * GT, p.g + o, tile_bytes, &bar_full[st]);
+            if (has_f) bulk_g2s(sG + (size_t)st * NGT * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
+          }
+          if (GATH) __syncwarp();
+          if (++st == NSL) { st = 0; ph ^= 1; }
       }
+      if (GATH) asm volatile("cp.async.wait_all;" ::: "memory");
       return;
     }
 
@@ -151,6 +232,59 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     for (int e = 0; e < NE; ++e) { dn2[e] = 0.0; dni[e] = 0.0; dno[e] = 0.0; }
     const bool nu_chain = DIAG && !PSI && which == 0;   // cosine modes 0, 2, 4, ... of T / S (Main.py:58-63)
     const double nu_i = (nu_chain && row_ok) ? p.nu_in[i] : 0.0, nu_o = (nu_chain && row_ok) ? p.nu_out[i] : 0.0;
+    // GATH: A fragments of Dr (rows 8w..8w+7 of this warp), and the nonlinear term of chain step s from the gathered group
+    double aDr[GATH && PSI ? n8 / 4 : 1];
+    if (GATH && PSI) {
+#pragma unroll
+        for (int ks = 0; ks < n8 / 4; ++ks)
+            aDr[ks] = (row_ok && 4 * ks + tq < n) ? p.DrT[(4 * ks + tq) * n8 + i] : 0.0;
+    }
+    double fn[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) fn[e] = 0.0;
+    auto load_fn = [&](int s) {
+        const int d = s - so0;
+        if (d < 0 || s >= nsteps) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) fn[e] = 0.0;
+            return;
+        }
+        const int g = d >> 2, r = d & 3, slot = g & (SOLVE_NSF - 1);
+        if (r == 0) mbar_wait(&bar_gfull[slot], (g / SOLVE_NSF) & 1);
+        // element 3 - r of the group: 16-byte half (r < 2 ? 1 : 0), second double of it when r is even
+        const double* fs = sF + slot * SLOT + (r < 2 ? HSZ : 0);
+        const bool hi = !(r & 1);
+        const double* f2 = fs + F2OFF + ((2 * tq) * LDF2 + i) * 2;
+        if (PSI) {
+            double dacc[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) dacc[e] = 0.0;
+            const double* f1 = fs + (gq * LDF1 + tq) * 2;
+#pragma unroll
+            for (int ks = 0; ks < n8 / 4; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NTB; ++nt) {
+                    const double2 v = *reinterpret_cast<const double2*>(f1 + (nt * 8 * LDF1 + 4 * ks) * 2);
+                    mma884(dacc[2 * nt], dacc[2 * nt + 1], aDr[ks], hi ? v.y : v.x);
+                }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double2 v = *reinterpret_cast<const double2*>(f2 + ((e >> 1) * 8 + (e & 1)) * LDF2 * 2);
+                fn[e] = dacc[e] - (hi ? v.y : v.x);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double2 v = *reinterpret_cast<const double2*>(f2 + ((e >> 1) * 8 + (e & 1)) * LDF2 * 2);
+                fn[e] = hi ? v.y : v.x;
+            }
+        }
+        if (r == 3 || s == nsteps - 1) {   // last use of this group
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_gempty[slot]);
+        }
+    };
+    if (GATH) load_fn(0);
     int st = 0, ph = 0;
     for (int step = 0; step < nsteps; ++step) {
         const int j = j0 - 2 * step;
@@ -164,13 +298,14 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
             }
         }
         mbar_wait(&bar_full[st], ph);
-        const double* gt = gT + st * (2 * GT);
+        const double* gt = gT + st * (NGT * GT);
         double gv[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
             const int off = ((e >> 1) * 8 + (e & 1)) * LDG;
             gv[e] = gt[off];
-            if (has_f) gv[e] = fma(p.mdt, gt[GT + off], gv[e]);
+            if (GATH) gv[e] = fma(p.mdt, fn[e], gv[e]);
+            else if (has_f) gv[e] = fma(p.mdt, gt[GT + off], gv[e]);
         }
         double* buf = rW + (step & 1) * (NM * BT * LDL);
         if (!PSI) {
@@ -219,6 +354,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
                                b[q * BT * LDL + nt * 8 * LDL + ks * 4]);
                 }
             }
+            if (GATH) load_fn(step + 1);   // independent of this step's result: fills the MMA latency
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 double s = 0.0;
@@ -311,18 +447,19 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
 
 // grid = 2 * (psi member tiles) + 4 * (T,S member tiles) CTAs, stream-function chains first; block = 32 * (NT8 + 1):
 // compute warp w owns radial rows 8w..8w+7 in MMA accumulator layout, the last warp is the TMA producer.
-template <int NT8, int NSL, bool SUB = false, bool DIAG = false>
+template <int NT8, int NSL, bool SUB = false, bool DIAG = false, bool GATH = false>
 __global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
     extern __shared__ __align__(128) double smem[];
-    __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL];
+    __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL], bar_gfull[SOLVE_NSF], bar_gempty[SOLVE_NSF];
     pdl_launch_dependents();
     const int bid = blockIdx.x;
     if (bid < 2 * npsi_tiles) {
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, SUB, DIAG>(p, smem, bar_full, bar_empty, 0, bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_PSI, true, SUB, DIAG, GATH>(p, smem, bar_full, bar_empty, bar_gfull, bar_gempty, 0,
+                                                                        bid & 1, (bid >> 1) * 8 * SOLVE_NTB_PSI);
     } else {
         const int r = bid - 2 * npsi_tiles;
-        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, SUB, DIAG>(p, smem, bar_full, bar_empty, 1 + ((r >> 1) & 1), r & 1,
-                                                          (r >> 2) * 8 * SOLVE_NTB_TS);
+        solve_chain_hot<NT8, NSL, SOLVE_NTB_TS, false, SUB, DIAG, GATH>(p, smem, bar_full, bar_empty, bar_gfull, bar_gempty,
+                                                                        1 + ((r >> 1) & 1), r & 1, (r >> 2) * 8 * SOLVE_NTB_TS);
     }
 }
 

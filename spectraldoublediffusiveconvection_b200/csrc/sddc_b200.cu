@@ -107,7 +107,8 @@ struct sddc_plan {
     size_t synth_smem_fx = 0, synth_smem_dfx = 0, synth_smem_ke = 0;
     int ana_nt = 0, ana_stage = 0;
     size_t ana_smem = 0;
-    size_t solve_smem = 0, solve_hot_smem = 0;
+    size_t solve_smem = 0, solve_hot_smem = 0, solve_gath_smem = 0;
+    bool solve_gath = false;   // the hot back-substitution gathers the nonlinear term from spec4 (no post_kernel launch)
     int solve_nsl = 3, solve_hot_nsl = 3;
     double dt_psi = 0, dt_T = 0, dt_S = 0;  // effective time steps of the three operator stacks
     // optional per-stage CUDA-event timing (sddc_profile_begin / sddc_profile_end)
@@ -494,8 +495,9 @@ int run_nlin_fft(sddc_plan* pl, const double* c0, const double* c1, double* out,
 // gs < 0 selects the solve-major layout for g / fnl
 int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, long long gf, double* out, long long os,
               long long of, const double* sub, int field_base, int nfields, int B, cudaStream_t st, double* jj_out = nullptr,
-              double* dpart = nullptr) {
+              double* dpart = nullptr, const double* spec = nullptr) {
     SolveParams sp{};
+    sp.spec = spec; sp.DrT = pl->DrT;
     sp.jj_out = jj_out;
     sp.dpart = dpart; sp.nu_in = pl->nu_in; sp.nu_out = pl->nu_out; sp.nu_w = pl->nu_w;
     const bool sm = gs < 0;
@@ -512,10 +514,22 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
         // hot path: all three fields from the solve-major buffers (k_solve_hot.cuh)
         const int npsi = (B + 8 * SOLVE_NTB_PSI - 1) / (8 * SOLVE_NTB_PSI), nts = (B + 8 * SOLVE_NTB_TS - 1) / (8 * SOLVE_NTB_TS);
         const int nthr = 32 * (pl->g.nt8 + 1);
-        const size_t smb = pl->solve_hot_smem;
+        const size_t smb = spec ? pl->solve_gath_smem : pl->solve_hot_smem;
         const bool n3 = pl->solve_hot_nsl == 3;
         const int nblk = 2 * npsi + 4 * nts;
         if (sub && dpart) { pl->err = "diagnostics partial sums are only produced by plain steps"; return SDDC_ERR_INVALID; }
+        if (spec) {
+            if (!pl->solve_gath || fnl) { pl->err = "gather mode of the back-substitution is not available for this plan"; return SDDC_ERR_INVALID; }
+#define SDDC_LAUNCH_SOLVE_GATH(NT)                                                                                  \
+    if (sub) launch_pdl(solve_hot_kernel<NT, 3, true, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi);   \
+    else if (dpart) launch_pdl(solve_hot_kernel<NT, 3, false, true, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); \
+    else launch_pdl(solve_hot_kernel<NT, 3, false, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi);
+            if (pl->g.nt8 == 3) { SDDC_LAUNCH_SOLVE_GATH(3) } else { SDDC_LAUNCH_SOLVE_GATH(4) }
+#undef SDDC_LAUNCH_SOLVE_GATH
+            pl->launches++;
+            PLAN_CUDA(pl, cudaGetLastError());
+            return SDDC_OK;
+        }
 #define SDDC_LAUNCH_SOLVE_HOT(NT)                                                                                 \
     if (sub) { if (n3) launch_pdl(solve_hot_kernel<NT, 3, true, false>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); else launch_pdl(solve_hot_kernel<NT, 2, true, false>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); } \
     else if (dpart) { if (n3) launch_pdl(solve_hot_kernel<NT, 3, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); else launch_pdl(solve_hot_kernel<NT, 2, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); } \
@@ -576,7 +590,12 @@ int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool lin
     const bool fft = pl->fft_M != 0 && !linear;
     int rc;
     const double* fnl = nullptr;
-    if (fft) {
+    if (fft && pl->solve_gath) {
+        // the back-substitution reads the analysed products itself: no post_kernel, no F(X) round trip
+        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, nullptr, true, B, st))) return rc;
+        return run_solve(pl, pl->lin_sm, nullptr, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, emit_jj ? pl->JJ : nullptr,
+                         emit_diag, pl->spec4);
+    } else if (fft) {
         if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, pl->f_sm, true, B, st))) return rc;
         fnl = pl->f_sm;
     } else if (!linear) {
@@ -640,6 +659,7 @@ int sddc_plan_info(const sddc_plan* plan, int what) {
         case 5: return plan->fft_dfx ? 1 : 0;       // FFT formulation also used for the two-state (JVP) products
         case 6: return plan->ke_M;                  // grid size of the kinetic-energy FFT (0: dense synthesis)
         case 7: return plan->fft_direct ? 1 : (plan->dfx_direct ? 2 : 0);   // direct-summation row kernel: 1 every product, 2 two-state products only
+        case 8: return plan->solve_gath ? 1 : 0;    // hot back-substitution gathers the analysed products itself (no post_kernel)
         default: return -1;
     }
 }
@@ -910,6 +930,20 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->solve_smem = solve_smem_doubles<SOLVE_NTB>(n8, pl->solve_nsl) * sizeof(double);
     pl->solve_hot_nsl = solve_hot_smem_bytes(n8, 3) <= SMEM_LIMIT ? 3 : 2;
     pl->solve_hot_smem = solve_hot_smem_bytes(n8, pl->solve_hot_nsl);
+    // gather mode (k_solve_hot.cuh): FFT formulation, sector-aligned parity halves, at most four radial row tiles
+    pl->solve_gath = pl->fft_M != 0 && !pl->fft_direct && n8 <= 32 && K % 8 == 0 && pl->solve_hot_nsl == 3;
+    if (pl->solve_gath) {
+        pl->solve_gath_smem = solve_gath_smem_bytes(n8);
+        if (n8 == 24) {
+            TRY(set_smem(pl, (solve_hot_kernel<3, 3, false, false, true>), pl->solve_gath_smem));
+            TRY(set_smem(pl, (solve_hot_kernel<3, 3, true, false, true>), pl->solve_gath_smem));
+            TRY(set_smem(pl, (solve_hot_kernel<3, 3, false, true, true>), pl->solve_gath_smem));
+        } else {
+            TRY(set_smem(pl, (solve_hot_kernel<4, 3, false, false, true>), pl->solve_gath_smem));
+            TRY(set_smem(pl, (solve_hot_kernel<4, 3, true, false, true>), pl->solve_gath_smem));
+            TRY(set_smem(pl, (solve_hot_kernel<4, 3, false, true, true>), pl->solve_gath_smem));
+        }
+    }
     if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<3, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 3, false, true>), pl->solve_hot_smem)); }
     else { TRY(set_smem(pl, (solve_hot_kernel<3, 2, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<3, 2, false, true>), pl->solve_hot_smem)); }
     if (pl->solve_hot_nsl == 3) { TRY(set_smem(pl, (solve_hot_kernel<4, 3, false>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, true>), pl->solve_hot_smem)); TRY(set_smem(pl, (solve_hot_kernel<4, 3, false, true>), pl->solve_hot_smem)); }

@@ -125,7 +125,8 @@ class EnsemblePlan:
     def info(self):
         """Kernel-selection facts: quarter-wave split active, synthesis variant, JVP availability, padded n, grid size
         of the FFT formulation of the nonlinear term (0 = dense DMMA transforms), FFT formulation used for JVPs."""
-        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8", "fft_M", "fft_jvp", "ke_fft_M", "direct_rows")
+        names = ("quarter_wave", "synth_variant", "jvp_two_state", "n8", "fft_M", "fft_jvp", "ke_fft_M", "direct_rows",
+                 "solve_gather")
         return {nm: int(self.lib.sddc_plan_info(self._h, i)) for i, nm in enumerate(names)}
 
     @property

@@ -62,7 +62,14 @@ def _call(lib, M, rows0, rows1=None, cached=False):
     rc = lib.fft_emul_rows(M, 2 if cached else int(rows1 is not None), rows0.ctypes.data_as(dp), r1.ctypes.data_as(dp),
                            out.ctypes.data_as(dp), n)
     assert rc == 0
-    return out
+    return _natural(out)
+
+
+def _natural(out):
+    """The kernels store every [K] row parity-split (even sinusoid indices first; fft_core.h: spec_pos)."""
+    K = out.shape[-1]
+    k = np.arange(K)
+    return np.ascontiguousarray(out[..., (k & 1) * (K // 2) + (k >> 1)])
 
 
 def test_register_butterflies(emul):
@@ -86,10 +93,10 @@ def test_fft_rows_match_dense_transforms(emul, K, N_r, symmetric):
     if K == 256:
         # the staged schedule of the headline kernel (per-warp ownership, coefficient rows staged in the dead planes)
         # performs the same arithmetic: bit-identical
-        got_s = np.full_like(got, np.nan)
+        got_s = np.full(got.shape, np.nan)
         dp = ctypes.POINTER(ctypes.c_double)
         assert emul.fft_emul_rows_staged(M, rows.ctypes.data_as(dp), got_s.ctypes.data_as(dp), rows.shape[0]) == 0
-        assert np.array_equal(got_s, got)
+        assert np.array_equal(_natural(got_s), got)
     # two-state (Jacobian-vector product) variant
     rows1 = _rows(Y3, op, symmetric)
     h = orc._grid_fields(Y3, op, symmetric)
