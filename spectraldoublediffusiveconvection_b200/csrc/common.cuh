@@ -61,6 +61,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// non-blocking variant: mbarrier.test_wait polled in a loop (try_wait may suspend the warp for an implementation-defined
+// time; a hand-off that is on the critical path wants the shortest reaction time instead)
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_SPIN:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_SPIN;\n"
+        "bra LAB_SPIN;\n"
+        "DONE_SPIN:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 // contiguous global -> shared copy by the TMA engine; completion is signalled on `bar` (complete_tx::bytes).
 // dst, src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
@@ -68,6 +81,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// L2 prefetch of a contiguous global range by the TMA engine (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 
 // Programmatic dependent launch (the kernels of a member-step are launched with
@@ -112,6 +130,15 @@ __host__ __device__ __forceinline__ int chunk_pos_inv(int pos, int par) {
     const int r = pos & 7;
     return (pos & ~7) | (par == 0 ? (((r & 3) << 1) | (r >> 2)) : r);
 }
+
+// Analysed products of the row kernels: spec[b * n + i] is a block of four parity-split rows [4][K] (fft_core.h: spec_pos),
+// the blocks SPEC_PAD doubles apart.  Measured on B200 with pads of 4 and 20 doubles (so that the sectors a
+// back-substitution chain gathers from the rows of its members do not sit a power of two apart): no difference for the
+// gather, post_kernel 10 % slower -- the pad stays 0.
+#ifndef SPEC_PAD
+#define SPEC_PAD 0
+#endif
+__host__ __device__ constexpr long long spec_pitch(int K) { return 4LL * K + SPEC_PAD; }
 
 // Geometry shared by all kernels.
 struct Geo {

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(NT * NW, 1) nlin_fft_kernel(NlinFftParams p) {
         worker_sync<NT>(w);
         pass_d<M, 2, -1, NT>(t, buf, tw);
         worker_sync<NT>(w);
-        cp_fwd<M, NT>(t, buf, p.spec + (size_t)row * 4 * K, tb);
+        cp_fwd<M, NT>(t, buf, p.spec + (size_t)row * spec_pitch(K), tb);
         if (t == 0) s_row[w] = next;
         worker_sync<NT>(w);   // the planes are free again and the next row index is visible
     }
@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(64 * NW, 1) nlin_fft_staged_kernel(NlinFftPara
             const char* ng = reinterpret_cast<const char*>(p.grid + (size_t)nrow * 7 * M);
             for (int o = t * 128; o < 7 * M * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ng + o));
         }
-        staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * 4 * K, tb, tw, 0);
+        staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * spec_pitch(K), tb, tw, 0);
         __syncwarp();
-        staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * 4 * K, tb, tw, 1);
+        staged_unpack<M>(warp, lane, buf, p.spec + (size_t)row * spec_pitch(K), tb, tw, 1);
         __syncwarp();
         row = nrow;
     }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(128) nlin_direct_kernel(NlinDirectParams p) {
     }
     __syncthreads();
     // out: [0] DST(JT om), [1] DST(kDpsi om + Dpsi kom) = -k DCT(Dpsi om), [2] DCT(N_T), [3] DCT(N_S)  (as cp_emit)
-    double* o = p.spec + (size_t)row * 4 * K;
+    double* o = p.spec + (size_t)row * spec_pitch(K);
     for (int k = tid; k < K; k += 128) {
         double s0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
         for (int j = 0; j < M; ++j) {
@@ -390,12 +390,12 @@ __global__ void __launch_bounds__(256) post_kernel(PostParams p, int ntiles) {
     pdl_wait();   // the analysed products come from the row kernel
     auto issue = [&](int tile, int stage) {
         const int b = tile / nkt, k0 = (tile - b * nkt) * POST_TC;
-        const double* sb = p.spec + (size_t)b * n * 4 * K;
+        const double* sb = p.spec + (size_t)b * n * spec_pitch(K);
         double* sT = smem + stage * TS;
         for (int idx = tid; idx < 4 * n * POST_TC; idx += 256) {
             const int c = idx & (POST_TC - 1), fi = idx / POST_TC, f = fi & 3, i = fi >> 2;
             const bool ok = k0 + c < K;
-            cp_async8_zfill(&sT[(f * n + i) * LDT + c], ok ? sb + ((size_t)i * 4 + f) * K + fftp::spec_pos(k0 + c, K) : sb, ok);
+            cp_async8_zfill(&sT[(f * n + i) * LDT + c], ok ? sb + (size_t)i * spec_pitch(K) + f * K + fftp::spec_pos(k0 + c, K) : sb, ok);
         }
     };
     const bool sm = p.bstride != 0;

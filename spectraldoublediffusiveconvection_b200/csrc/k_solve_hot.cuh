@@ -33,8 +33,15 @@ namespace sddc {
 // Shared-memory layout of a group: [16-byte half][member][row][2 steps]; the Dr @ operand is read as MMA B fragments (member = lane
 // group, row = lane in group: row pitch n8 + 4 makes the 16-byte reads of a quarter warp conflict free), everything
 // else in accumulator layout (member pair = lane in group, row = lane group: pitch n8 + 1).
-constexpr int SOLVE_NSF = 2;   // gather groups in flight
-constexpr int SOLVE_GSTEPS = 4;   // chain steps per group
+#ifndef SOLVE_GATH_NSF
+#define SOLVE_GATH_NSF 2
+#endif
+#ifndef SOLVE_GATH_GS
+#define SOLVE_GATH_GS 4
+#endif
+constexpr int SOLVE_NSF = SOLVE_GATH_NSF;   // gather groups in flight
+constexpr int SOLVE_GSTEPS = SOLVE_GATH_GS;   // chain steps per group: 4 (a 32-byte sector per row) or 2 (16 bytes)
+static_assert((SOLVE_GSTEPS == 2 || SOLVE_GSTEPS == 4) && (SOLVE_NSF & (SOLVE_NSF - 1)) == 0, "gather ring geometry");
 
 template <int NTB, bool PSI>
 __host__ __device__ constexpr size_t solve_gath_slot_doubles(int n8) {
@@ -75,12 +82,12 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     constexpr int NCH = NTB >= 2 ? 1 : 2;   // accumulator chains per product and member tile (k-steps interleaved)
     constexpr int NGT = GATH ? 1 : 2;       // right-hand-side tiles per ring stage (lin [, F])
     constexpr int LDF1 = n8 + 4, LDF2 = n8 + 1, GS = SOLVE_GSTEPS;
-    constexpr int F2OFF = PSI ? BT * LDF1 * 2 : 0, SLOT = (int)solve_gath_slot_doubles<NTB, PSI>(n8), HSZ = SLOT / 2;
+    constexpr int F2OFF = PSI ? BT * LDF1 * 2 : 0, SLOT = (int)solve_gath_slot_doubles<NTB, PSI>(n8), HSZ = GS == 4 ? SLOT / 2 : 0;
     static_assert(!GATH || (NSL == 3 && n8 <= 32), "gather mode: three ring stages, n8 <= 32");
     const Geo& G = p.geo;
     const int n = G.n, K = G.K;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
-    const bool is_producer = warp == NT8;
+    const bool is_producer = warp >= NT8;   // warp NT8: operator / right-hand-side ring (TMA); warp NT8 + 1 (GATH): gathers
     double* sL = smem;                              // [NSL][NM][n8][LDL]
     double* sR = sL + (size_t)NSL * NM * MAT;       // [2 step parities][NM][BT][LDL]
     double* sG = sR + (size_t)2 * NM * BT * LDL;    // [NSL][NGT][BT][LDG]   (lin [, F])
@@ -149,59 +156,54 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     __syncthreads();
     pdl_wait();   // right-hand sides from prep_kernel / post_kernel
 
-    if (is_producer) {
-      if (!GATH && lane != 0) return;
+    if (is_producer && warp == NT8) {
+      if (lane != 0) return;
       const double* Lg = PSI ? p.LinvA4 : (fld == 1 ? p.LinvT : p.LinvS);
       constexpr unsigned tile_bytes = GT * sizeof(double), mat_bytes = NM * MAT * sizeof(double);
       const unsigned bytes = mat_bytes + tile_bytes * (has_f ? 2u : 1u);
-      // gather group g: positions ptop - 4g - 3 .. ptop - 4g of (member, row, field); lane = (row & 15, 16-byte half)
-      const int gh = lane & 1, gi = lane >> 1;
-      const double* gsrc = GATH ? p.spec + ((long long)b0 * n * 4 + (PSI ? 0 : fld + 1)) * K + (ptop - 3 + 2 * gh) : nullptr;
-      auto issue_group = [&](int g) {
+      int st = 0, ph = 0;
+      for (int step = 0; step < nsteps; ++step) {
+          const int j = j0 - 2 * step;
+          const int jj = PSI ? (K - j) : (K - 1 - j), row = PSI ? j - 1 : j;
+          if (step >= NSL) mbar_wait(&bar_empty[st], ph ^ 1);
+          mbar_expect_tx(&bar_full[st], bytes);
+          bulk_g2s(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st]);
+          const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
+          bulk_g2s(sG + (size_t)st * NGT * GT, p.g + o, tile_bytes, &bar_full[st]);
+          if (has_f) bulk_g2s(sG + (size_t)st * NGT * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
+          if (++st == NSL) { st = 0; ph ^= 1; }
+      }
+      return;
+    }
+    if (is_producer) {
+      // GATH, second producer warp: group g = positions ptop - 4g - 3 .. ptop - 4g of every (member, row, field) of the
+      // tile; lane = (row & 15, 16-byte half); a slot is refilled as soon as the consumers have released it
+      constexpr int RPP = GS == 4 ? 16 : 32;   // rows per pass of the warp
+      const int gh = GS == 4 ? (lane & 1) : 0, gi = GS == 4 ? (lane >> 1) : lane;
+      const long long SP = spec_pitch(K);
+      const double* gsrc = p.spec + (long long)b0 * n * SP + (PSI ? 0 : fld + 1) * K + (ptop - (GS - 1) + 2 * gh);
+      for (int g = 0; g < ngroups; ++g) {
           const int slot = g & (SOLVE_NSF - 1);
           if (g >= SOLVE_NSF) mbar_wait(&bar_gempty[slot], ((g / SOLVE_NSF) - 1) & 1);
           double* dst0 = sF + slot * SLOT + gh * HSZ;
-          const double* src0 = gsrc - 4 * g;
+          const double* src0 = gsrc - GS * g;
 #pragma unroll
           for (int q = 0; q < NM; ++q)
 #pragma unroll 4
               for (int m = 0; m < BT; ++m) {
                   if (b0 + m < p.B) {
 #pragma unroll
-                      for (int ip = 0; ip < (n8 + 15) / 16; ++ip) {
-                          const int ii = gi + 16 * ip;
+                      for (int ip = 0; ip < (n8 + RPP - 1) / RPP; ++ip) {
+                          const int ii = gi + RPP * ip;
                           if (ii < n)
                               cp_async16(dst0 + (q == 0 && PSI ? 0 : F2OFF) + (m * (q == 0 && PSI ? LDF1 : LDF2) + ii) * 2,
-                                         src0 + ((long long)(m * n + ii) * 4 + q) * K);
+                                         src0 + (long long)(m * n + ii) * SP + q * K);
                       }
                   }
               }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bar_gfull[slot])) : "memory");
-      };
-      if (GATH)
-          for (int g = 0; g < SOLVE_NSF && g < ngroups; ++g) issue_group(g);
-      int st = 0, ph = 0;
-      for (int step = 0; step < nsteps; ++step) {
-          if (GATH) {
-              // group g is first read in chain step 4g + so0 - 1 and its slot was released in step 4g + so0 - 6, which the
-              // operator ring (NSL stages ahead of the consumers) has passed when it reaches step 4g + so0 - 6 + NSL
-              const int t = step + 6 - NSL - so0;
-              if ((t & 3) == 0 && (t >> 2) >= SOLVE_NSF && (t >> 2) < ngroups) issue_group(t >> 2);
-          }
-          if (lane == 0) {
-            const int j = j0 - 2 * step;
-            const int jj = PSI ? (K - j) : (K - 1 - j), row = PSI ? j - 1 : j;
-            if (step >= NSL) mbar_wait(&bar_empty[st], ph ^ 1);
-            mbar_expect_tx(&bar_full[st], bytes);
-            bulk_g2s(sL + (size_t)st * NM * MAT, Lg + (long long)jj * NM * MAT, mat_bytes, &bar_full[st]);
-            const long long o = (((long long)fld * K + row) * p.bstride + b0) * LDG;
-            bulk_g2s(sG + (size_t)st * NGT * GT, p.g + o, tile_bytes, &bar_full[st]);
-            if (has_f) bulk_g2s(sG + (size_t)st * NGT * GT + GT, p.fnl + o, tile_bytes, &bar_full[st]);
-          }
-          if (GATH) __syncwarp();
-          if (++st == NSL) { st = 0; ph ^= 1; }
       }
-      if (GATH) asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("cp.async.wait_all;" ::: "memory");
       return;
     }
 
@@ -239,52 +241,58 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
         for (int ks = 0; ks < n8 / 4; ++ks)
             aDr[ks] = (row_ok && 4 * ks + tq < n) ? p.DrT[(4 * ks + tq) * n8 + i] : 0.0;
     }
-    double fn[NE];
+    // fetch_fn(s): the operands of F at chain step s from the gathered group into registers (issued early in the
+    // previous step, so that the shared-memory latency is covered by the right-hand-side arithmetic and the barrier);
+    // finish_fn(): fn = Dr @ P1 - P2 (stream function) or the product itself, after the chain step's MMAs are issued
+    double fn[NE], fb[GATH && PSI ? (n8 / 4) * NTB : 1], fp[NE];
 #pragma unroll
-    for (int e = 0; e < NE; ++e) fn[e] = 0.0;
-    auto load_fn = [&](int s) {
+    for (int e = 0; e < NE; ++e) { fn[e] = 0.0; fp[e] = 0.0; }
+    bool fn_ok = false;
+    auto fetch_fn = [&](int s) {
         const int d = s - so0;
-        if (d < 0 || s >= nsteps) {
-#pragma unroll
-            for (int e = 0; e < NE; ++e) fn[e] = 0.0;
-            return;
-        }
-        const int g = d >> 2, r = d & 3, slot = g & (SOLVE_NSF - 1);
+        fn_ok = d >= 0 && s < nsteps;
+        if (!fn_ok) return;
+        const int g = d / GS, r = d & (GS - 1), slot = g & (SOLVE_NSF - 1);
         if (r == 0) mbar_wait(&bar_gfull[slot], (g / SOLVE_NSF) & 1);
-        // element 3 - r of the group: 16-byte half (r < 2 ? 1 : 0), second double of it when r is even
-        const double* fs = sF + slot * SLOT + (r < 2 ? HSZ : 0);
-        const bool hi = !(r & 1);
+        // element GS - 1 - r of the group: 16-byte half (r < 2 ? 1 : 0 when there are two), second double of it when r is even
+        const double* fs = sF + slot * SLOT + (r < GS - 2 ? HSZ : 0) + ((r & 1) ? 0 : 1);
         const double* f2 = fs + F2OFF + ((2 * tq) * LDF2 + i) * 2;
         if (PSI) {
-            double dacc[NE];
-#pragma unroll
-            for (int e = 0; e < NE; ++e) dacc[e] = 0.0;
             const double* f1 = fs + (gq * LDF1 + tq) * 2;
 #pragma unroll
             for (int ks = 0; ks < n8 / 4; ++ks)
 #pragma unroll
-                for (int nt = 0; nt < NTB; ++nt) {
-                    const double2 v = *reinterpret_cast<const double2*>(f1 + (nt * 8 * LDF1 + 4 * ks) * 2);
-                    mma884(dacc[2 * nt], dacc[2 * nt + 1], aDr[ks], hi ? v.y : v.x);
-                }
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const double2 v = *reinterpret_cast<const double2*>(f2 + ((e >> 1) * 8 + (e & 1)) * LDF2 * 2);
-                fn[e] = dacc[e] - (hi ? v.y : v.x);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const double2 v = *reinterpret_cast<const double2*>(f2 + ((e >> 1) * 8 + (e & 1)) * LDF2 * 2);
-                fn[e] = hi ? v.y : v.x;
-            }
+                for (int nt = 0; nt < NTB; ++nt) fb[ks * NTB + nt] = f1[(nt * 8 * LDF1 + 4 * ks) * 2];
         }
-        if (r == 3 || s == nsteps - 1) {   // last use of this group
+#pragma unroll
+        for (int e = 0; e < NE; ++e) fp[e] = f2[((e >> 1) * 8 + (e & 1)) * LDF2 * 2];
+        if (r == GS - 1 || s == nsteps - 1) {   // last use of this group
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gempty[slot]);
         }
     };
-    if (GATH) load_fn(0);
+    auto finish_fn = [&]() {
+        if (!fn_ok) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) fn[e] = 0.0;
+            return;
+        }
+        if (PSI) {
+            double dacc[NE];
+#pragma unroll
+            for (int e = 0; e < NE; ++e) dacc[e] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < n8 / 4; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NTB; ++nt) mma884(dacc[2 * nt], dacc[2 * nt + 1], aDr[ks], fb[ks * NTB + nt]);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) fn[e] = dacc[e] - fp[e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) fn[e] = fp[e];
+        }
+    };
+    if (GATH) { fetch_fn(0); finish_fn(); }
     int st = 0, ph = 0;
     for (int step = 0; step < nsteps; ++step) {
         const int j = j0 - 2 * step;
@@ -307,6 +315,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
             if (GATH) gv[e] = fma(p.mdt, fn[e], gv[e]);
             else if (has_f) gv[e] = fma(p.mdt, gt[GT + off], gv[e]);
         }
+        if (GATH) fetch_fn(step + 1);
         double* buf = rW + (step & 1) * (NM * BT * LDL);
         if (!PSI) {
             // b += 2 dt (j+2) f_{j+2};  rhs = g_j - b   (halved for mode 0)       (Matrix_Operators.py:1063-1079)
@@ -354,7 +363,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
                                b[q * BT * LDL + nt * 8 * LDL + ks * 4]);
                 }
             }
-            if (GATH) load_fn(step + 1);   // independent of this step's result: fills the MMA latency
+            if (GATH) finish_fn();   // independent of this step's result: fills the MMA latency
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
                 double s = 0.0;
@@ -448,7 +457,7 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
 // grid = 2 * (psi member tiles) + 4 * (T,S member tiles) CTAs, stream-function chains first; block = 32 * (NT8 + 1):
 // compute warp w owns radial rows 8w..8w+7 in MMA accumulator layout, the last warp is the TMA producer.
 template <int NT8, int NSL, bool SUB = false, bool DIAG = false, bool GATH = false>
-__global__ void __launch_bounds__(32 * (NT8 + 1)) solve_hot_kernel(SolveParams p, int npsi_tiles) {
+__global__ void __launch_bounds__(32 * (NT8 + (GATH ? 2 : 1))) solve_hot_kernel(SolveParams p, int npsi_tiles) {
     extern __shared__ __align__(128) double smem[];
     __shared__ __align__(8) uint64_t bar_full[NSL], bar_empty[NSL], bar_gfull[SOLVE_NSF], bar_gempty[SOLVE_NSF];
     pdl_launch_dependents();

@@ -524,6 +524,7 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     if (sub) launch_pdl(solve_hot_kernel<NT, 3, true, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi);   \
     else if (dpart) launch_pdl(solve_hot_kernel<NT, 3, false, true, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi); \
     else launch_pdl(solve_hot_kernel<NT, 3, false, false, true>, dim3(nblk), dim3(nthr), smb, st, sp, npsi);
+            const int nthr = 32 * (pl->g.nt8 + 2);   // + the gather warp
             if (pl->g.nt8 == 3) { SDDC_LAUNCH_SOLVE_GATH(3) } else { SDDC_LAUNCH_SOLVE_GATH(4) }
 #undef SDDC_LAUNCH_SOLVE_GATH
             pl->launches++;
@@ -856,7 +857,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             TRY(upload(pl, &pl->fft_tab, tab));
             TRY(dev_alloc(pl, &pl->coef7, Bm * 7 * g.N, false));
             if (pl->fft_dfx) TRY(dev_alloc(pl, &pl->coef7b, Bm * 7 * g.N, false));
-            TRY(dev_alloc(pl, &pl->spec4, Bm * 4 * g.N, false));
+            TRY(dev_alloc(pl, &pl->spec4, Bm * g.n * (size_t)spec_pitch(K), false));
             {
                 double* cnt = nullptr;
                 TRY(dev_alloc(pl, &cnt, 2, true));
@@ -915,7 +916,7 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
             pl->fft_dfx = true;
             TRY(dev_alloc(pl, &pl->coef7, Bm * 7 * g.N, false));
             TRY(dev_alloc(pl, &pl->coef7b, Bm * 7 * g.N, false));
-            TRY(dev_alloc(pl, &pl->spec4, Bm * 4 * g.N, false));
+            TRY(dev_alloc(pl, &pl->spec4, Bm * g.n * (size_t)spec_pitch(K), false));
             TRY(set_smem(pl, post_kernel, post_smem_bytes(n, n8)));
             TRY(set_smem(pl, (prep_kernel<3, true>), prep_smem_bytes(n8, 1)));
             TRY(set_smem(pl, (prep_kernel<4, true>), prep_smem_bytes(n8, 1)));
