@@ -551,6 +551,20 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
     return SDDC_OK;
 }
 
+// row kernels on (c0, c1, mode) followed by the hot back-substitution: through the gather mode where the plan has it (the
+// chain reads the analysed products itself), else through post_kernel and the solve-major F(X) buffer
+int run_rows_and_solve(sddc_plan* pl, const double* c0, const double* c1, int mode, double* out, const double* sub, int B,
+                       cudaStream_t st, double* jj_out = nullptr, double* dpart = nullptr) {
+    const long long N3 = 3LL * pl->g.N;
+    int rc;
+    if (pl->solve_gath) {
+        if ((rc = run_nlin_fft(pl, c0, c1, nullptr, true, B, st, false, mode))) return rc;
+        return run_solve(pl, pl->lin_sm, nullptr, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, jj_out, dpart, pl->spec4);
+    }
+    if ((rc = run_nlin_fft(pl, c0, c1, pl->f_sm, true, B, st, false, mode))) return rc;
+    return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, jj_out, dpart);
+}
+
 // kinetic energy by FFT from coefficient rows + the remaining diagnostics (norm, Nusselt numbers)
 int run_ke_fft(sddc_plan* pl, const double* X, const double* rows, long long row_stride, int b_off, const double* ascale,
                double* out, int B, cudaStream_t st, const double* dpart = nullptr, bool side = false) {
@@ -591,15 +605,8 @@ int run_step_rest(sddc_plan* pl, double* out, const double* sub, int B, bool lin
     const bool fft = pl->fft_M != 0 && !linear;
     int rc;
     const double* fnl = nullptr;
-    if (fft && pl->solve_gath) {
-        // the back-substitution reads the analysed products itself: no post_kernel, no F(X) round trip
-        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, nullptr, true, B, st))) return rc;
-        return run_solve(pl, pl->lin_sm, nullptr, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, emit_jj ? pl->JJ : nullptr,
-                         emit_diag, pl->spec4);
-    } else if (fft) {
-        if ((rc = run_nlin_fft(pl, pl->coef7, nullptr, pl->f_sm, true, B, st))) return rc;
-        fnl = pl->f_sm;
-    } else if (!linear) {
+    if (fft) return run_rows_and_solve(pl, pl->coef7, nullptr, 0, out, sub, B, st, emit_jj ? pl->JJ : nullptr, emit_diag);
+    if (!linear) {
         if ((rc = run_synth_nl(pl, false, B, st))) return rc;
         if ((rc = run_analysis(pl, pl->f_sm, true, B, st, pl->quarter))) return rc;
         fnl = pl->f_sm;  // F(X); the solve kernel forms lin - dt * F
@@ -1157,8 +1164,7 @@ int sddc_jvp(sddc_plan* pl, const double* dv, const double* X, double* out, cons
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st, pl->coef7))) return rc;
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
-        if ((rc = run_nlin_fft(pl, pl->coef7, pl->coef7b, pl->f_sm, true, B, st))) return rc;
-        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, dv, 0, 3, B, st);
+        return run_rows_and_solve(pl, pl->coef7, pl->coef7b, 0, out, dv, B, st);
     }
     if ((rc = run_prep(pl, X, 0, true, nullptr, nullptr, nullptr, B, st))) return rc;
     if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st))) return rc;
@@ -1225,13 +1231,11 @@ static int jvp_apply_impl(sddc_plan* pl, const double* dv, double* out, const do
     const double* sub = plus_identity ? nullptr : dv;   // PDFX subtracts dv at the end (Main.py:511-519)
     if (pl->grid7) {
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
-        if ((rc = run_nlin_fft(pl, nullptr, pl->coef7b, pl->f_sm, true, B, st, false, 2))) return rc;
-        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
+        return run_rows_and_solve(pl, nullptr, pl->coef7b, 2, out, sub, B, st);
     }
     if (pl->fft_dfx) {
         if ((rc = run_prep(pl, dv, 1, true, pl->lin_sm, Ra, Ras, B, st, pl->coef7b))) return rc;
-        if ((rc = run_nlin_fft(pl, pl->coef7base, pl->coef7b, pl->f_sm, true, B, st))) return rc;
-        return run_solve(pl, pl->lin_sm, pl->f_sm, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st);
+        return run_rows_and_solve(pl, pl->coef7base, pl->coef7b, 0, out, sub, B, st);
     }
     if (!pl->ws_ok) {
         if (plus_identity) { pl->err = "sddc_jvp_apply_plus is not available on this path"; return SDDC_ERR_UNSUPPORTED; }
