@@ -514,8 +514,10 @@ def run_ours(a):
                            "members_total": Btot, "members_per_gpu": Bl, "N_r": a.N_r, "N_theta": a.N_fm,
                            "parallelism": "ensemble members sharded over %d GPU(s), no data-path collective" % world,
                            "call": "sddc_step(X_dev, nsteps=K): one stream-ordered C-ABI call per timed region, "
-                                   "4 kernels per member-step, launched with programmatic stream serialization "
-                                   "(scan only before the first step)",
+                                   "%s, launched with programmatic stream serialization "
+                                   "(scan only before the first step)" %
+                                   ("3 kernels per member-step (derivatives / row transforms / back-substitution reading the "
+                                    "analysed products itself)" if info.get("solve_gather") else "4 kernels per member-step"),
                            "l2": "state + scratch working set (~%.1f GB/GPU) exceeds the 126 MB L2" %
                                  (Bl * (W * 5 + 9 * 2 * 32 * 256 + 3 * 2 * 32 * 192) * 8 / 1e9), **PHYS},
                 "clocks": clocks, "e2e": e2e, "e2e_state_roundtrip_every_step": e2e_roundtrip, "gpu_launches": launches,
