@@ -552,12 +552,16 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
 }
 
 // row kernels on (c0, c1, mode) followed by the hot back-substitution: through the gather mode where the plan has it (the
-// chain reads the analysed products itself), else through post_kernel and the solve-major F(X) buffer
+// chain reads the analysed products itself), else through post_kernel and the solve-major F(X) buffer.
+// The gather mode trades a throughput-bound kernel (post_kernel: 0.075 ms per 512 members at (30,256)) for a longer chain
+// step of the latency-bound one (0.099 -> 0.134 ms at 512 members, ~0.07 -> ~0.10 ms for a few members): it pays from
+// about 256 members on (measured: 64 concurrent Newton solves ran 20 % slower through it).
+constexpr int SOLVE_GATH_MIN_B = 256;
 int run_rows_and_solve(sddc_plan* pl, const double* c0, const double* c1, int mode, double* out, const double* sub, int B,
                        cudaStream_t st, double* jj_out = nullptr, double* dpart = nullptr) {
     const long long N3 = 3LL * pl->g.N;
     int rc;
-    if (pl->solve_gath) {
+    if (pl->solve_gath && B >= SOLVE_GATH_MIN_B) {
         if ((rc = run_nlin_fft(pl, c0, c1, nullptr, true, B, st, false, mode))) return rc;
         return run_solve(pl, pl->lin_sm, nullptr, -1, 0, out, N3, pl->g.N, sub, 0, 3, B, st, jj_out, dpart, pl->spec4);
     }

@@ -507,3 +507,51 @@ def test_config2_ensemble_parity():
                 assert np.allclose(hist[(s + 1) // 10 - 1, m, :4], orc.diagnostics(ref, op), rtol=1e-9, atol=0)
         assert rel_l2(out[m], ref) < TOL_STEPS, m
     pl.close()
+
+
+@pytest.mark.parametrize("K,N_r,sym,B", [(128, 12, False, 259), (256, 30, True, 261)])
+def test_gather_mode_ragged_batch(K, N_r, sym, B):
+    """From 256 members on the back-substitution reads the analysed products of the row kernels itself (k_solve_hot.cuh,
+    gather mode; smaller batches go through post_kernel).  A ragged batch through it -- plain steps, a multi-step call,
+    residual, JVP, cached JVP, the time loop with diagnostics -- equals the same members run in small batches through
+    the other path, and the oracle on a few members (first / last of a member tile, last of the batch)."""
+    from oracle import sddc_oracle as orc
+    from spectraldoublediffusiveconvection_b200 import EnsemblePlan
+    d, dt, Pr, Tau = 0.353, 2e-3, 1.0, 1.0 / 15.0
+    pl = EnsemblePlan(K, N_r, d, dt, Pr, Tau, symmetric=sym, max_batch=B)
+    assert pl.info()["solve_gather"] == 1
+    op = orc.Operators(K, N_r, d, dt, Pr, Tau)
+    rng = np.random.default_rng(B)
+    X = rng.random((B, 3 * pl.N)) * 1e-2
+    dv = rng.standard_normal((B, 3 * pl.N))
+    Ra, Ra_s = np.linspace(3000.0, 9000.0, B), np.linspace(0.0, 500.0, B)
+    Xd, dvd, Rad, Rasd = _dev(X), _dev(dv), _dev(Ra), _dev(Ra_s)
+    big = {"step": pl.step(Xd, Rad, Rasd), "step3": pl.step(Xd, Rad, Rasd, nsteps=3), "res": pl.residual(Xd, Rad, Rasd),
+           "jvp": pl.jvp(dvd, Xd, Rad, Rasd)}
+    pl.jvp_set_base(Xd)
+    big["jvpc"] = pl.jvp_apply(dvd, Rad, Rasd)
+    out_t, hist_t = pl.time_step(Xd, Rad, Rasd, 3, diag_every=1)
+    big["loop"] = out_t
+    small = {k: [] for k in big}
+    hist_s = []
+    for lo in range(0, B, 100):
+        sl = slice(lo, min(B, lo + 100))
+        small["step"].append(pl.step(Xd[sl], Rad[sl], Rasd[sl]))
+        small["step3"].append(pl.step(Xd[sl], Rad[sl], Rasd[sl], nsteps=3))
+        small["res"].append(pl.residual(Xd[sl], Rad[sl], Rasd[sl]))
+        small["jvp"].append(pl.jvp(dvd[sl], Xd[sl], Rad[sl], Rasd[sl]))
+        pl.jvp_set_base(Xd[sl].contiguous())
+        small["jvpc"].append(pl.jvp_apply(dvd[sl].contiguous(), Rad[sl], Rasd[sl]))
+        o, h = pl.time_step(Xd[sl].contiguous(), Rad[sl], Rasd[sl], 3, diag_every=1)
+        small["loop"].append(o)
+        hist_s.append(h)
+    for k in big:
+        a, b = big[k].cpu().numpy(), torch.cat(small[k]).cpu().numpy()
+        for m in range(B):
+            assert rel_l2(a[m], b[m]) < 1e-12, (k, m)
+    assert np.allclose(hist_t.cpu().numpy(), torch.cat(hist_s, dim=1).cpu().numpy(), rtol=1e-10, atol=1e-300)
+    st, jv = big["step"].cpu().numpy(), big["jvp"].cpu().numpy()
+    for m in (0, 7, 8, 15, 16, 255, 256, B - 1):
+        assert rel_l2(st[m], orc.step(X[m], op, Ra[m], Ra_s[m], sym)) < 1e-9
+        assert rel_l2(jv[m], orc.jvp(dv[m], X[m], op, Ra[m], Ra_s[m], sym)) < 1e-9
+    pl.close()
