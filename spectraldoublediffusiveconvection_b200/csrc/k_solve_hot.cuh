@@ -21,27 +21,22 @@ namespace sddc {
 #define SOLVE_NTB_TS 2
 #endif
 
-// GATH (FFT formulation, n8 <= 32, K a multiple of 8): the nonlinear term is not read as a solve-major tile that a separate
-// kernel (post_kernel) transposed; the chain gathers the analysed products of the row kernel itself.  spec[b][i][field][K]
-// holds every row parity-split (fft_core.h: spec_pos), so the four coefficients a chain needs in four consecutive steps
-// are one 32-byte sector: the producer warp fetches a GROUP (four chain steps x members x radial rows x fields) with two
-// adjacent 16-byte cp.async per (member, row, field) -- a lane pair covers the sector -- completion on an mbarrier
-// (cp.async.mbarrier.arrive.noinc), SOLVE_NSF groups in flight.  The stream-function chains apply Dr @ to the first
-// product with the operator's A fragments held in registers (F_psi = Dr @ DST(JT*om) - DST(..),
-// Matrix_Operators.py:776-802) one chain step AHEAD, between the issue of the current step's MMAs and the use of their
-// results, so that none of it sits on the dependent chain.
-// Shared-memory layout of a group: [16-byte half][member][row][2 steps]; the Dr @ operand is read as MMA B fragments (member = lane
-// group, row = lane in group: row pitch n8 + 4 makes the 16-byte reads of a quarter warp conflict free), everything
-// else in accumulator layout (member pair = lane in group, row = lane group: pitch n8 + 1).
-#ifndef SOLVE_GATH_NSF
-#define SOLVE_GATH_NSF 2
-#endif
-#ifndef SOLVE_GATH_GS
-#define SOLVE_GATH_GS 4
-#endif
-constexpr int SOLVE_NSF = SOLVE_GATH_NSF;   // gather groups in flight
-constexpr int SOLVE_GSTEPS = SOLVE_GATH_GS;   // chain steps per group: 4 (a 32-byte sector per row) or 2 (16 bytes)
-static_assert((SOLVE_GSTEPS == 2 || SOLVE_GSTEPS == 4) && (SOLVE_NSF & (SOLVE_NSF - 1)) == 0, "gather ring geometry");
+// GATH (FFT formulation, n8 <= 32, K a multiple of 8; used from 256 members on): the nonlinear term is not read as a
+// solve-major tile that a separate kernel (post_kernel) transposed; the chain gathers the analysed products of the row
+// kernel itself.  spec[b][i][field][K] holds every row parity-split (fft_core.h: spec_pos), so the four coefficients a
+// chain needs in four consecutive steps are one 32-byte sector: a producer warp of its own (the warp behind the TMA
+// producer) fetches a GROUP (four chain steps x members x radial rows x fields) with two adjacent 16-byte cp.async per
+// (member, row, field) -- a lane pair covers the sector -- completion on an mbarrier (cp.async.mbarrier.arrive.noinc),
+// SOLVE_NSF groups in flight; the consumers hand a slot back through a second mbarrier.  The stream-function chains apply
+// Dr @ to the first product with the operator's A fragments held in registers (F_psi = Dr @ DST(JT*om) - DST(..),
+// Matrix_Operators.py:776-802) one chain step AHEAD: the operands are loaded early in the previous step, the MMAs issued
+// behind that step's own, so that none of it sits on the dependent chain.
+// Shared-memory layout of a group: [16-byte half][member][row][2 steps] (half 1 = the first two of the four steps, each
+// half [later step, earlier step]); the Dr @ operand is read as MMA B fragments (member = lane group, row = lane in
+// group: row pitch n8 + 4), everything else in accumulator layout (member pair = lane in group, row = lane group:
+// pitch n8 + 1).  What else was measured (ring depths, TMA bulk copies, auxiliary warps, pre-tiled spectra): DESIGN.md.
+constexpr int SOLVE_NSF = 2;      // gather groups in flight
+constexpr int SOLVE_GSTEPS = 4;   // chain steps per group (a 32-byte sector per member, row and field)
 
 template <int NTB, bool PSI>
 __host__ __device__ constexpr size_t solve_gath_slot_doubles(int n8) {
@@ -82,7 +77,8 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     constexpr int NCH = NTB >= 2 ? 1 : 2;   // accumulator chains per product and member tile (k-steps interleaved)
     constexpr int NGT = GATH ? 1 : 2;       // right-hand-side tiles per ring stage (lin [, F])
     constexpr int LDF1 = n8 + 4, LDF2 = n8 + 1, GS = SOLVE_GSTEPS;
-    constexpr int F2OFF = PSI ? BT * LDF1 * 2 : 0, SLOT = (int)solve_gath_slot_doubles<NTB, PSI>(n8), HSZ = GS == 4 ? SLOT / 2 : 0;
+    constexpr int F2OFF = PSI ? BT * LDF1 * 2 : 0, SLOT = (int)solve_gath_slot_doubles<NTB, PSI>(n8), HSZ = SLOT / 2;
+    static_assert(GS == 4 && SOLVE_NSF == 2, "group geometry");
     static_assert(!GATH || (NSL == 3 && n8 <= 32), "gather mode: three ring stages, n8 <= 32");
     const Geo& G = p.geo;
     const int n = G.n, K = G.K;
@@ -178,8 +174,8 @@ __device__ __forceinline__ void solve_chain_hot(const SolveParams& p, double* sm
     if (is_producer) {
       // GATH, second producer warp: group g = positions ptop - 4g - 3 .. ptop - 4g of every (member, row, field) of the
       // tile; lane = (row & 15, 16-byte half); a slot is refilled as soon as the consumers have released it
-      constexpr int RPP = GS == 4 ? 16 : 32;   // rows per pass of the warp
-      const int gh = GS == 4 ? (lane & 1) : 0, gi = GS == 4 ? (lane >> 1) : lane;
+      constexpr int RPP = 16;   // rows per pass of the warp
+      const int gh = lane & 1, gi = lane >> 1;
       const long long SP = spec_pitch(K);
       const double* gsrc = p.spec + (long long)b0 * n * SP + (PSI ? 0 : fld + 1) * K + (ptop - (GS - 1) + 2 * gh);
       for (int g = 0; g < ngroups; ++g) {
