@@ -517,7 +517,7 @@ def run_ours(a):
                                    "%s, launched with programmatic stream serialization "
                                    "(scan only before the first step)" %
                                    ("3 kernels per member-step (derivatives / row transforms / back-substitution reading the "
-                                    "analysed products itself)" if info.get("solve_gather") and Bl >= 256 else "4 kernels per member-step"),
+                                    "analysed products itself)" if info.get("solve_gather") and Bl >= 128 else "4 kernels per member-step"),
                            "l2": "state + scratch working set (~%.1f GB/GPU) exceeds the 126 MB L2" %
                                  (Bl * (W * 5 + 9 * 2 * 32 * 256 + 3 * 2 * 32 * 192) * 8 / 1e9), **PHYS},
                 "clocks": clocks, "e2e": e2e, "e2e_state_roundtrip_every_step": e2e_roundtrip, "gpu_launches": launches,

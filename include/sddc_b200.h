@@ -99,7 +99,7 @@ long long sddc_launch_count(const sddc_plan* plan);
  * 3 padded radial size, 4 grid size M of the FFT formulation of the nonlinear term (N_fm = 128, 256, 512; 0: dense
  * DMMA transforms), 5 FFT formulation also used for the two-state (JVP) products, 6 grid size of the kinetic-energy
  * FFT (0: dense synthesis), 7 direct-summation row kernel (1 every product, 2 two-state products only), 8 the hot
- * back-substitution can read the analysed products of the row kernels itself (used from 256 members on: three kernels
+ * back-substitution can read the analysed products of the row kernels itself (used from 128 members on: three kernels
  * per member-step instead of four) */
 int sddc_plan_info(const sddc_plan* plan, int what);
 

@@ -554,9 +554,13 @@ int run_solve(sddc_plan* pl, const double* g, const double* fnl, long long gs, l
 // row kernels on (c0, c1, mode) followed by the hot back-substitution: through the gather mode where the plan has it (the
 // chain reads the analysed products itself), else through post_kernel and the solve-major F(X) buffer.
 // The gather mode trades a throughput-bound kernel (post_kernel: 0.075 ms per 512 members at (30,256)) for a longer chain
-// step of the latency-bound one (0.099 -> 0.134 ms at 512 members, ~0.07 -> ~0.10 ms for a few members): it pays from
-// about 256 members on (measured: 64 concurrent Newton solves ran 20 % slower through it).
-constexpr int SOLVE_GATH_MIN_B = 256;
+// step of the latency-bound one (0.099 -> 0.134 ms at 512 members, 0.080 -> 0.103 ms for a few members): it pays from
+// 128 members on (tools/batch_scaling.py on both builds; 64 concurrent Newton solves ran 20 % slower
+// through it).
+#ifndef SOLVE_GATH_MIN_MEMBERS
+#define SOLVE_GATH_MIN_MEMBERS 128   // compile-time only (tools/batch_scaling.py compares builds)
+#endif
+constexpr int SOLVE_GATH_MIN_B = SOLVE_GATH_MIN_MEMBERS;
 int run_rows_and_solve(sddc_plan* pl, const double* c0, const double* c1, int mode, double* out, const double* sub, int B,
                        cudaStream_t st, double* jj_out = nullptr, double* dpart = nullptr) {
     const long long N3 = 3LL * pl->g.N;

@@ -509,9 +509,9 @@ def test_config2_ensemble_parity():
     pl.close()
 
 
-@pytest.mark.parametrize("K,N_r,sym,B", [(128, 12, False, 259), (256, 30, True, 261)])
+@pytest.mark.parametrize("K,N_r,sym,B", [(128, 12, False, 259), (256, 30, True, 261), (128, 26, True, 131)])
 def test_gather_mode_ragged_batch(K, N_r, sym, B):
-    """From 256 members on the back-substitution reads the analysed products of the row kernels itself (k_solve_hot.cuh,
+    """From 128 members on the back-substitution reads the analysed products of the row kernels itself (k_solve_hot.cuh,
     gather mode; smaller batches go through post_kernel).  A ragged batch through it -- plain steps, a multi-step call,
     residual, JVP, cached JVP, the time loop with diagnostics -- equals the same members run in small batches through
     the other path, and the oracle on a few members (first / last of a member tile, last of the batch)."""
@@ -551,7 +551,7 @@ def test_gather_mode_ragged_batch(K, N_r, sym, B):
             assert rel_l2(a[m], b[m]) < 1e-12, (k, m)
     assert np.allclose(hist_t.cpu().numpy(), torch.cat(hist_s, dim=1).cpu().numpy(), rtol=1e-10, atol=1e-300)
     st, jv = big["step"].cpu().numpy(), big["jvp"].cpu().numpy()
-    for m in (0, 7, 8, 15, 16, 255, 256, B - 1):
+    for m in sorted({0, 7, 8, 15, 16, min(255, B - 2), min(256, B - 2), B - 1}):
         assert rel_l2(st[m], orc.step(X[m], op, Ra[m], Ra_s[m], sym)) < 1e-9
         assert rel_l2(jv[m], orc.jvp(dv[m], X[m], op, Ra[m], Ra_s[m], sym)) < 1e-9
     pl.close()

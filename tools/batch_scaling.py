@@ -2,8 +2,9 @@
 import sys; sys.path.insert(0, '.')
 import torch
 from spectraldoublediffusiveconvection_b200 import EnsemblePlan
-for B in (64, 128, 256, 512, 1024, 2048):
-    pl = EnsemblePlan(256, 30, 0.31325, 1e-3, 1.0, 1.0, max_batch=B)
+sym = len(sys.argv) > 1 and sys.argv[1] == "sym"
+for B in (64, 128, 192, 256, 384, 512, 1024, 2048):
+    pl = EnsemblePlan(256, 30, 0.31325, 1e-3, 1.0, 1.0, symmetric=sym, max_batch=B)
     X = torch.rand((B, 3 * pl.N), dtype=torch.float64, device='cuda') * 1e-3
     Ra = torch.full((B,), 3000.0, dtype=torch.float64, device='cuda'); Ras = torch.zeros_like(Ra)
     out = torch.empty_like(X)

@@ -6,7 +6,7 @@ import os
 SHAPES = [(16, 10, False, 3), (32, 30, True, 17), (24, 41, False, 2), (16, 65, False, 2), (10, 9, False, 2), (30, 12, True, 3)]
 if os.environ.get('SANITIZE_FFT'):   # the FFT formulation (k_nlin_fft.cuh): N_fm = 128 / 256 / 512
     SHAPES = [(128, 10, False, 3), (256, 8, True, 2), (512, 6, False, 1)]
-if os.environ.get('SANITIZE_FFT') == '3':   # batches of 256 members and more: gather mode of the back-substitution (k_solve_hot.cuh)
+if os.environ.get('SANITIZE_FFT') == '3':   # batches of 128 members and more: gather mode of the back-substitution (k_solve_hot.cuh)
     SHAPES = [(128, 9, False, 259), (128, 30, True, 257)]
 for (K, N_r, sym, B) in SHAPES:
     pl = EnsemblePlan(K, N_r, 0.4, 1e-2, 1.0, 0.5, symmetric=sym, max_batch=B)
