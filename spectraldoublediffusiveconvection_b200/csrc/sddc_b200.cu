@@ -947,10 +947,16 @@ int sddc_plan_create(sddc_plan** out, const sddc_config* cfg, const sddc_operato
     pl->solve_hot_nsl = solve_hot_smem_bytes(n8, 3) <= SMEM_LIMIT ? 3 : 2;
     pl->solve_hot_smem = solve_hot_smem_bytes(n8, pl->solve_hot_nsl);
     // gather mode (k_solve_hot.cuh): FFT formulation, sector-aligned parity halves, at most four radial row tiles
-    // Not for equatorially symmetric plans: an experimental build of the gather kernel (four accumulator sets for Dr @)
-    // gave run-to-run differences of 1e-8 in T / S member tiles there -- never without the symmetry, never in the shipped
-    // schedule (tools/determinism_probe.py), cause not found -- so those plans keep the four-kernel path.
-    pl->solve_gath = pl->fft_M != 0 && !pl->fft_direct && n8 <= 32 && K % 8 == 0 && pl->solve_hot_nsl == 3 && !g.symmetric;
+    // The gather mode is NOT part of the shipped configuration (compile with -DSDDC_EXPERIMENTAL_GATHER to get it): it is
+    // 5 % faster per step, but its results were not bit-reproducible from run to run -- whole T / S member tiles off by
+    // 1e-8 in a few runs out of forty at 512 members, in every run of one experimental schedule on equatorially symmetric
+    // plans (tools/determinism_probe.py) -- and the race was not found.  The four-kernel path is
+    // bit-reproducible in every probe.
+#ifdef SDDC_EXPERIMENTAL_GATHER
+    pl->solve_gath = pl->fft_M != 0 && !pl->fft_direct && n8 <= 32 && K % 8 == 0 && pl->solve_hot_nsl == 3;
+#else
+    pl->solve_gath = false;
+#endif
     if (pl->solve_gath) {
         pl->solve_gath_smem = solve_gath_smem_bytes(n8);
         if (n8 == 24) {
