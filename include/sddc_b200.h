@@ -99,8 +99,8 @@ long long sddc_launch_count(const sddc_plan* plan);
  * 3 padded radial size, 4 grid size M of the FFT formulation of the nonlinear term (N_fm = 128, 256, 512; 0: dense
  * DMMA transforms), 5 FFT formulation also used for the two-state (JVP) products, 6 grid size of the kinetic-energy
  * FFT (0: dense synthesis), 7 direct-summation row kernel (1 every product, 2 two-state products only), 8 the hot
- * back-substitution can read the analysed products of the row kernels itself (used from 128 members on: three kernels
- * per member-step instead of four) */
+ * back-substitution reads the analysed products of the row kernels itself (three kernels per member-step instead of
+ * four; experimental builds with -DSDDC_EXPERIMENTAL_GATHER only, 0 in the shipped library: DESIGN.md section 4) */
 int sddc_plan_info(const sddc_plan* plan, int what);
 
 /* Replace one pre-inverted operator stack (which: 0 = A4 / psi, 1 = NAB2 / T, 2 = NAB2 / S) and the effective

@@ -21,7 +21,9 @@ namespace sddc {
 #define SOLVE_NTB_TS 2
 #endif
 
-// GATH (FFT formulation, n8 <= 32, K a multiple of 8; used from 128 members on): the nonlinear term is not read as a
+// GATH -- EXPERIMENTAL, compiled in but only selected by plans of builds with -DSDDC_EXPERIMENTAL_GATHER (its results were
+// not bit-reproducible run to run and the race was not found: DESIGN.md section 4) -- (FFT formulation, n8 <= 32, K a
+// multiple of 8; from 128 members on): the nonlinear term is not read as a
 // solve-major tile that a separate kernel (post_kernel) transposed; the chain gathers the analysed products of the row
 // kernel itself.  spec[b][i][field][K] holds every row parity-split (fft_core.h: spec_pos), so the four coefficients a
 // chain needs in four consecutive steps are one 32-byte sector: a producer warp of its own (the warp behind the TMA
